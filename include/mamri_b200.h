@@ -1,0 +1,170 @@
+/*
+ * mamri_b200.h -- C ABI of the B200-native fiducial-detection path.
+ *
+ * Drop-in boundary for ONE path of PaulSchlabach/mamri-pose-estimation: what
+ * MamriLogic.volume_threshold_segmentation (Mamri/Mamri.py:1304-1323) asks
+ * SimpleITK to do, and the candidate loop of MamriLogic.findAndSetEntryPoint
+ * (Mamri/Mamri.py:1008-1023).  The reference has no FFI of its own (it is a
+ * Python method body calling SimpleITK); each entry point below cites the
+ * reference lines it replaces.  INTEGRATION.md shows the ctypes stub a
+ * maintainer would put behind those two methods.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types;
+ *   - every function returns an int status (MAMRI_OK == 0, negative = error) and
+ *     never aborts the host process; mamri_last_error() gives the text;
+ *   - volumes are x-fastest: linear index = x + nx*(y + ny*z) (ITK buffer order);
+ *   - "d_" pointers are device memory owned by the caller, "h_" pointers host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - a context is not thread-safe and serves one scan at a time; use one per
+ *     (device, stream).  No allocation happens on the hot calls.
+ */
+#ifndef MAMRI_B200_H
+#define MAMRI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MAMRI_API __attribute__((visibility("default")))
+#else
+#define MAMRI_API
+#endif
+
+#define MAMRI_OK                0
+#define MAMRI_ERR_INVALID_ARG  -1
+#define MAMRI_ERR_CUDA         -2
+#define MAMRI_ERR_CAPACITY     -3   /* run table or marker table too small for this scan */
+#define MAMRI_ERR_NO_DEVICE    -4
+#define MAMRI_ERR_STATE        -5   /* collect without a pending detect, ... */
+
+/* voxel types PullVolumeFromSlicer can hand over (Mamri.py:1306) */
+#define MAMRI_U8   0
+#define MAMRI_I16  1
+#define MAMRI_U16  2
+#define MAMRI_I32  3
+#define MAMRI_F32  4
+
+typedef struct mamri_ctx mamri_ctx;
+
+/* Geometry of a SimpleITK image (LPS): physical = origin + direction * (spacing .* index). */
+typedef struct mamri_volume_desc {
+    int32_t nx, ny, nz;
+    int32_t dtype;            /* MAMRI_U8 .. MAMRI_F32 */
+    double  spacing[3];
+    double  origin[3];
+    double  direction[9];     /* row-major 3x3 */
+} mamri_volume_desc;
+
+/* The constants of MamriLogic.__init__ (Mamri.py:810-812) and of the call at :1308-1309.
+ * mamri_default_params() fills in the reference's values. */
+typedef struct mamri_params {
+    double  lower;            /* INTENSITY_THRESHOLD = 65.0            Mamri.py:810  */
+    double  upper;            /* 65535                                 Mamri.py:1308 */
+    int32_t close_radius;     /* [2]*3 sitkBall -> 2 (0..3 supported)  Mamri.py:1308 */
+    int32_t connectivity;     /* 6 = SimpleITK default, or 26          Mamri.py:1309 */
+    double  min_volume;       /* MIN_VOLUME_THRESHOLD = 50.0 mm^3      Mamri.py:811  */
+    double  max_volume;       /* MAX_VOLUME_THRESHOLD = 1500.0 mm^3    Mamri.py:812  */
+} mamri_params;
+
+/* One label kept by the list comprehension at Mamri.py:1310, in ascending label order
+ * (= the control-point order of "DetectedFiducials", :1316-1317), plus what
+ * LabelShapeStatisticsImageFilter computes for it. */
+typedef struct mamri_marker {
+    uint32_t label;                 /* "id": ITK-consecutive label (rank of the min linear index) */
+    uint32_t reserved;
+    uint64_t count;                 /* voxels */
+    uint64_t sum_idx[3];            /* exact: sum x, sum y, sum z */
+    uint64_t sum_mom[6];            /* exact: sum xx, yy, zz, xy, xz, yz */
+    double   volume_mm3;            /* "vol": GetPhysicalSize */
+    double   centroid_index[3];     /* mean voxel index (x,y,z) */
+    double   centroid_lps[3];       /* "centroid": GetCentroid (LPS) */
+    double   centroid_ras[3];       /* [-x,-y,z], Mamri.py:1317 */
+    double   principal_moments[3];  /* ascending */
+    double   principal_axes[9];     /* row-major, rows = axes (ITK GetPrincipalAxes) */
+} mamri_marker;
+
+typedef struct mamri_summary {
+    uint32_t n_labels;        /* K = len(stats.GetLabels())                         */
+    uint32_t n_runs;          /* x-runs of the closed mask (internal CCL nodes)      */
+    uint32_t n_markers;       /* labels kept by the volume filter (may exceed the
+                                 caller's array: then MAMRI_ERR_CAPACITY)            */
+    uint32_t body_label;      /* largest non-fiducial label, 0 = none (Mamri.py:1318-1322) */
+    uint64_t body_count;      /* its voxel count                                     */
+    uint64_t n_foreground;    /* voxels set in the closed mask                       */
+    int32_t  device_status;   /* MAMRI_OK or MAMRI_ERR_CAPACITY raised on the device  */
+    int32_t  reserved;
+    mamri_marker body;        /* shape statistics of the body label (count == 0 if none) */
+} mamri_summary;
+
+/* Result of the entry-point search (Mamri.py:1023-1024). index == -1: no suitable point
+ * (the reference's warning + return at :1020-1022). */
+typedef struct mamri_entry_result {
+    int64_t index;
+    double  distance;
+    double  point[3];
+    uint64_t n_in_radius;     /* candidates inside the search radius                */
+    uint64_t n_suitable;      /* ... that also pass the normal score (and the path check) */
+} mamri_entry_result;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+/* Allocates every scratch buffer for volumes up to max_nx x max_ny x max_nz.  max_runs bounds the
+ * number of x-runs of the closed mask (0 = default: voxels/16, at least 1M); max_markers bounds the
+ * labels passing the volume filter (0 = default 4096). */
+MAMRI_API int mamri_create(mamri_ctx** ctx, int device, int32_t max_nx, int32_t max_ny, int32_t max_nz,
+                 uint32_t max_runs, uint32_t max_markers);
+MAMRI_API int mamri_destroy(mamri_ctx* ctx);
+MAMRI_API const char* mamri_last_error(const mamri_ctx* ctx);   /* ctx may be NULL: last create() error */
+MAMRI_API const char* mamri_version(void);
+MAMRI_API void mamri_default_params(mamri_params* p);
+
+/* ---- stages 1-4a: replaces Mamri.py:1308-1323 ------------------------------------------- */
+/* Enqueues threshold -> ball closing -> connected components -> label statistics -> volume
+ * filter -> body selection on `stream`.  Optional device outputs (NULL = not materialised):
+ *   d_mask_out   uint8  [nz*ny*nx]  closed binary mask            (`closed`,  :1308)
+ *   d_labels_out uint32 [nz*ny*nx]  ITK-consecutive label volume  (`labeled`, :1309)
+ *   d_body_out   uint8  [nz*ny*nx]  1 where label == body label   (`largest_object_img`, :1323)
+ * Returns as soon as the work is enqueued. */
+MAMRI_API int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* d_volume,
+                       const mamri_params* params, uint8_t* d_mask_out, uint32_t* d_labels_out,
+                       uint8_t* d_body_out, void* stream);
+/* Same, from/to HOST buffers (pinned for full PCIe speed): copies the volume in, and the body mask
+ * out when h_body_out != NULL.  This is the call a MamriLogic adapter makes. */
+MAMRI_API int mamri_detect_host_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* h_volume,
+                            const mamri_params* params, uint8_t* h_body_out, void* stream);
+/* Waits for the pending detect, then writes the summary and up to max_markers markers
+ * (ascending label).  "No markers" is MAMRI_OK with n_markers == 0 (Mamri.py:1312). */
+MAMRI_API int mamri_detect_collect(mamri_ctx* ctx, mamri_summary* summary, mamri_marker* h_markers,
+                         uint32_t max_markers);
+/* Voxel count of every label 1..K of the last collected scan (GetPhysicalSize / voxel volume). */
+MAMRI_API int mamri_label_counts(mamri_ctx* ctx, uint32_t* h_counts, uint32_t max_labels);
+
+/* ---- stage 4b: replaces the loop at Mamri.py:1008-1023 ---------------------------------- */
+/* d_points / d_normals: float32 [n][3] (RAS mm / unit normals), as vtkPolyData stores them.
+ * Keeps points with |p - target|^2 <= radius^2 and wx*|nx| + wy*|ny| > cutoff (reference:
+ * radius 80, wx 1, wy -2, cutoff -0.5), returns the closest (lowest index on ties).
+ * Needle-path sampling (north_star extension, no reference counterpart; off when
+ * n_path_samples == 0): a candidate is also rejected when any of n_path_samples points spaced
+ * evenly strictly between it and the target lies on a voxel of d_path_mask whose value is
+ * != path_free_value.  ras_to_index is the row-major 3x4 affine from RAS mm to voxel index of
+ * that mask (nx,ny,nz from mask_desc). */
+MAMRI_API int mamri_entry_search(mamri_ctx* ctx, const float* d_points, const float* d_normals, int64_t n,
+                       const double target[3], double radius, double wx, double wy, double cutoff,
+                       int32_t n_path_samples, const uint8_t* d_path_mask,
+                       const mamri_volume_desc* mask_desc, const double ras_to_index[12],
+                       int32_t path_free_value, mamri_entry_result* result, void* stream);
+
+/* ---- synthetic phantoms (benchmark utility, not part of the reference path) -------------- */
+/* Paints `n_ellipsoids` (7 floats each: cx,cy,cz,ax,ay,az,intensity; index units; in order)
+ * into a zeroed uint16 volume, then adds Rician noise (Philox4x32-10; see phantom.py). */
+MAMRI_API int mamri_phantom_generate(uint16_t* d_volume, int32_t nx, int32_t ny, int32_t nz,
+                           const float* h_ellipsoids, int32_t n_ellipsoids, float sigma,
+                           uint64_t seed, uint32_t scan_index, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAMRI_B200_H */

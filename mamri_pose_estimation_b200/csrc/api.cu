@@ -1,0 +1,308 @@
+// C ABI of the fiducial-detection path (include/mamri_b200.h).  Host-side orchestration only: it
+// validates arguments, enqueues the stage kernels on the caller's stream and moves the small result
+// tables.  No allocation on the hot calls; errors become status codes, never aborts.
+#include "common.cuh"
+
+#include <new>
+
+static char g_create_err[512] = "";
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t _e = (call);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            snprintf(ctx->err, sizeof(ctx->err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                              \
+            return MAMRI_ERR_CUDA;                                                                     \
+        }                                                                                              \
+    } while (0)
+
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+constexpr uint32_t EAGER_MARKERS = 64;   // marker records copied back together with the summary
+
+size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case MAMRI_U8: return 1;
+        case MAMRI_I16: case MAMRI_U16: return 2;
+        case MAMRI_I32: case MAMRI_F32: return 4;
+        default: return 0;
+    }
+}
+
+int fail(mamri_ctx* ctx, int code, const char* msg) {
+    snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
+    return code;
+}
+}  // namespace
+
+extern "C" const char* mamri_version(void) { return "mamri_b200 0.1 (sm_100a)"; }
+
+extern "C" void mamri_default_params(mamri_params* p) {
+    if (!p) return;
+    p->lower = 65.0;          // Mamri.py:810
+    p->upper = 65535.0;       // Mamri.py:1308
+    p->close_radius = 2;      // Mamri.py:1308
+    p->connectivity = 6;      // Mamri.py:1309 (SimpleITK default fullyConnected=False)
+    p->min_volume = 50.0;     // Mamri.py:811
+    p->max_volume = 1500.0;   // Mamri.py:812
+}
+
+extern "C" const char* mamri_last_error(const mamri_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" int mamri_destroy(mamri_ctx* ctx) {
+    if (!ctx) return MAMRI_OK;
+    DeviceGuard g(ctx->device);
+    cudaFree(ctx->d_raw); cudaFree(ctx->d_dil); cudaFree(ctx->d_closed); cudaFree(ctx->d_word_base);
+    cudaFree(ctx->d_parent); cudaFree(ctx->d_run_label); cudaFree(ctx->d_label_count); cudaFree(ctx->d_label_slot);
+    cudaFree(ctx->d_block_sums); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
+    cudaFree(ctx->d_summary); cudaFree(ctx->d_scalars); cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
+    cudaFree(ctx->d_entry_dist); cudaFree(ctx->d_entry_idx); cudaFree(ctx->d_entry_cnt); cudaFree(ctx->d_entry_res);
+    cudaFreeHost(ctx->h_markers); cudaFreeHost(ctx->h_summary); cudaFreeHost(ctx->h_entry_res);
+    delete ctx;
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t max_ny, int32_t max_nz,
+                            uint32_t max_runs, uint32_t max_markers) {
+    if (!out) { snprintf(g_create_err, sizeof(g_create_err), "ctx output pointer is NULL"); return MAMRI_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (max_nx <= 0 || max_ny <= 0 || max_nz <= 0) {
+        snprintf(g_create_err, sizeof(g_create_err), "max dimensions must be positive");
+        return MAMRI_ERR_INVALID_ARG;
+    }
+    const unsigned long long voxels = (unsigned long long)max_nx * max_ny * max_nz;
+    if (voxels >= (1ull << 32)) {
+        snprintf(g_create_err, sizeof(g_create_err), "volumes of 2^32 voxels or more are not supported");
+        return MAMRI_ERR_INVALID_ARG;
+    }
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0 || device < 0 || device >= n_dev) {
+        snprintf(g_create_err, sizeof(g_create_err), "no usable CUDA device %d (%d visible); there is no CPU fallback",
+                 device, n_dev);
+        cudaGetLastError();
+        return MAMRI_ERR_NO_DEVICE;
+    }
+    mamri_ctx* ctx = new (std::nothrow) mamri_ctx();
+    if (!ctx) { snprintf(g_create_err, sizeof(g_create_err), "out of host memory"); return MAMRI_ERR_CUDA; }
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->max_nx = max_nx; ctx->max_ny = max_ny; ctx->max_nz = max_nz;
+    if (max_runs == 0) {
+        unsigned long long d = voxels / 16;
+        if (d < (1u << 20)) d = 1u << 20;
+        max_runs = uint32_t(d);
+    }
+    if (max_markers == 0) max_markers = 4096;
+    ctx->max_runs = max_runs;
+    ctx->max_markers = max_markers;
+    const size_t W = (size_t(max_nx) + 31) / 32;
+    ctx->cap_words = W * max_ny * max_nz;
+    ctx->cap_pad_words = (W + 2) * (size_t(max_ny) + 2 * MAMRI_RMAX) * (size_t(max_nz) + 2 * MAMRI_RMAX);
+    DeviceGuard g(device);
+    auto bail = [&](cudaError_t e, const char* what) {
+        snprintf(g_create_err, sizeof(g_create_err), "allocating %s failed: %s", what, cudaGetErrorString(e));
+        mamri_destroy(ctx);
+        return MAMRI_ERR_CUDA;
+    };
+    cudaError_t e;
+#define ALLOC(ptr, bytes, what) if ((e = cudaMalloc((void**)&(ptr), (bytes))) != cudaSuccess) return bail(e, what)
+    ALLOC(ctx->d_raw, ctx->cap_words * 4, "raw mask");
+    ALLOC(ctx->d_dil, ctx->cap_pad_words * 4, "dilated mask");
+    ALLOC(ctx->d_closed, ctx->cap_words * 4, "closed mask");
+    ALLOC(ctx->d_word_base, ctx->cap_words * 4, "run bases");
+    ALLOC(ctx->d_parent, size_t(max_runs) * 4, "union-find parents");
+    ALLOC(ctx->d_run_label, size_t(max_runs) * 4, "run labels");
+    ALLOC(ctx->d_label_count, size_t(max_runs) * 4, "label counts");
+    ALLOC(ctx->d_label_slot, size_t(max_runs) * 4, "label slots");
+    ALLOC(ctx->d_block_sums, 2048 * 4, "scan partials");
+    ALLOC(ctx->d_cand_label, (size_t(max_markers) + 1) * 4, "candidate labels");
+    ALLOC(ctx->d_cand_sums, (size_t(max_markers) + 1) * 9 * 8, "candidate sums");
+    ALLOC(ctx->d_markers, size_t(max_markers) * sizeof(mamri_marker), "marker table");
+    ALLOC(ctx->d_summary, sizeof(mamri_summary), "summary");
+    ALLOC(ctx->d_scalars, sizeof(DevScalars), "scalars");
+    ALLOC(ctx->d_entry_dist, MAMRI_SCAN_CTAS * sizeof(double), "entry partials");
+    ALLOC(ctx->d_entry_idx, MAMRI_SCAN_CTAS * sizeof(long long), "entry partials");
+    ALLOC(ctx->d_entry_cnt, 2 * sizeof(unsigned long long), "entry counters");
+    ALLOC(ctx->d_entry_res, sizeof(mamri_entry_result), "entry result");
+#undef ALLOC
+    if ((e = cudaMallocHost((void**)&ctx->h_markers, size_t(max_markers) * sizeof(mamri_marker))) != cudaSuccess)
+        return bail(e, "pinned marker table");
+    if ((e = cudaMallocHost((void**)&ctx->h_summary, sizeof(mamri_summary))) != cudaSuccess) return bail(e, "pinned summary");
+    if ((e = cudaMallocHost((void**)&ctx->h_entry_res, sizeof(mamri_entry_result))) != cudaSuccess)
+        return bail(e, "pinned entry result");
+    *out = ctx;
+    return MAMRI_OK;
+}
+
+static int validate(mamri_ctx* ctx, const mamri_volume_desc* d, const mamri_params* p) {
+    if (!d || !p) return fail(ctx, MAMRI_ERR_INVALID_ARG, "desc/params is NULL");
+    if (d->nx <= 0 || d->ny <= 0 || d->nz <= 0) return fail(ctx, MAMRI_ERR_INVALID_ARG, "volume dimensions must be positive");
+    if (d->nx > ctx->max_nx || d->ny > ctx->max_ny || d->nz > ctx->max_nz)
+        return fail(ctx, MAMRI_ERR_INVALID_ARG, "volume larger than the context was created for");
+    if (dtype_size(d->dtype) == 0) return fail(ctx, MAMRI_ERR_INVALID_ARG, "unsupported voxel type");
+    if (p->close_radius < 0 || p->close_radius > MAMRI_RMAX)
+        return fail(ctx, MAMRI_ERR_INVALID_ARG, "close_radius must be 0..3");
+    if (p->connectivity != 6 && p->connectivity != 26) return fail(ctx, MAMRI_ERR_INVALID_ARG, "connectivity must be 6 or 26");
+    for (int i = 0; i < 3; ++i)
+        if (!(d->spacing[i] > 0.0)) return fail(ctx, MAMRI_ERR_INVALID_ARG, "spacing must be positive");
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* d_volume,
+                                  const mamri_params* params, uint8_t* d_mask_out, uint32_t* d_labels_out,
+                                  uint8_t* d_body_out, void* stream) {
+    if (!ctx) return MAMRI_ERR_INVALID_ARG;
+    int rc = validate(ctx, desc, params);
+    if (rc != MAMRI_OK) return rc;
+    if (!d_volume) return fail(ctx, MAMRI_ERR_INVALID_ARG, "volume pointer is NULL");
+    if (ctx->pending) return fail(ctx, MAMRI_ERR_STATE, "a detect is already pending on this context; collect it first");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int nx = desc->nx, ny = desc->ny, nz = desc->nz;
+    CK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(DevScalars), s));
+    CK(launch_threshold_pack(d_volume, desc->dtype, nx, ny, nz, params->lower, params->upper, ctx->d_raw, s));
+    const uint32_t* mask = ctx->d_raw;
+    if (params->close_radius > 0) {
+        CK(launch_closing(ctx, nx, ny, nz, params->close_radius, s));
+        mask = ctx->d_closed;
+    }
+    CK(launch_ccl(ctx, mask, nx, ny, nz, params->connectivity, s));
+    CK(launch_stats(ctx, mask, desc, params, s));
+    CK(launch_materialise(ctx, mask, nx, ny, nz, d_mask_out, d_labels_out, d_body_out, s));
+    CK(cudaMemcpyAsync(ctx->h_summary, ctx->d_summary, sizeof(mamri_summary), cudaMemcpyDeviceToHost, s));
+    const uint32_t eager = ctx->max_markers < EAGER_MARKERS ? ctx->max_markers : EAGER_MARKERS;
+    CK(cudaMemcpyAsync(ctx->h_markers, ctx->d_markers, size_t(eager) * sizeof(mamri_marker), cudaMemcpyDeviceToHost, s));
+    ctx->pending = true;
+    ctx->pending_stream = s;
+    ctx->last_desc = *desc;
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_detect_host_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* h_volume,
+                                       const mamri_params* params, uint8_t* h_body_out, void* stream) {
+    if (!ctx) return MAMRI_ERR_INVALID_ARG;
+    int rc = validate(ctx, desc, params);
+    if (rc != MAMRI_OK) return rc;
+    if (!h_volume) return fail(ctx, MAMRI_ERR_INVALID_ARG, "volume pointer is NULL");
+    if (ctx->pending) return fail(ctx, MAMRI_ERR_STATE, "a detect is already pending on this context; collect it first");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n = size_t(desc->nx) * desc->ny * desc->nz;
+    const size_t in_bytes = n * dtype_size(desc->dtype);
+    if (ctx->stage_in_bytes < in_bytes) {            // first host call at this size: grow the staging buffer
+        CK(cudaStreamSynchronize(s));
+        cudaFree(ctx->d_stage_in);
+        ctx->d_stage_in = nullptr; ctx->stage_in_bytes = 0;
+        CK(cudaMalloc(&ctx->d_stage_in, in_bytes));
+        ctx->stage_in_bytes = in_bytes;
+    }
+    if (h_body_out && ctx->stage_body_bytes < n) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(ctx->d_stage_body);
+        ctx->d_stage_body = nullptr; ctx->stage_body_bytes = 0;
+        CK(cudaMalloc((void**)&ctx->d_stage_body, n));
+        ctx->stage_body_bytes = n;
+    }
+    CK(cudaMemcpyAsync(ctx->d_stage_in, h_volume, in_bytes, cudaMemcpyHostToDevice, s));
+    rc = mamri_detect_async(ctx, desc, ctx->d_stage_in, params, nullptr, nullptr, h_body_out ? ctx->d_stage_body : nullptr,
+                            stream);
+    if (rc != MAMRI_OK) return rc;
+    if (h_body_out) CK(cudaMemcpyAsync(h_body_out, ctx->d_stage_body, n, cudaMemcpyDeviceToHost, s));
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_detect_collect(mamri_ctx* ctx, mamri_summary* summary, mamri_marker* h_markers, uint32_t max_markers) {
+    if (!ctx) return MAMRI_ERR_INVALID_ARG;
+    if (!ctx->pending) return fail(ctx, MAMRI_ERR_STATE, "no detect pending on this context");
+    DeviceGuard g(ctx->device);
+    ctx->pending = false;
+    CK(cudaStreamSynchronize(ctx->pending_stream));
+    const mamri_summary* hs = ctx->h_summary;
+    ctx->last_n_labels = hs->n_labels;
+    if (summary) *summary = *hs;
+    if (hs->device_status != MAMRI_OK) {
+        snprintf(ctx->err, sizeof(ctx->err),
+                 "scan exceeds the context's capacity (runs limit %u, markers limit %u, %u markers found); "
+                 "create the context with larger max_runs/max_markers",
+                 ctx->max_runs, ctx->max_markers, hs->n_markers);
+        return MAMRI_ERR_CAPACITY;
+    }
+    const uint32_t n = hs->n_markers;
+    const uint32_t eager = ctx->max_markers < EAGER_MARKERS ? ctx->max_markers : EAGER_MARKERS;
+    if (n > eager) {
+        CK(cudaMemcpyAsync(ctx->h_markers + eager, ctx->d_markers + eager, size_t(n - eager) * sizeof(mamri_marker),
+                           cudaMemcpyDeviceToHost, ctx->pending_stream));
+        CK(cudaStreamSynchronize(ctx->pending_stream));
+    }
+    if (n > max_markers || (n && !h_markers)) {
+        if (h_markers && max_markers) memcpy(h_markers, ctx->h_markers, size_t(max_markers) * sizeof(mamri_marker));
+        return fail(ctx, MAMRI_ERR_CAPACITY, "caller's marker array is smaller than n_markers");
+    }
+    if (n) memcpy(h_markers, ctx->h_markers, size_t(n) * sizeof(mamri_marker));
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_label_counts(mamri_ctx* ctx, uint32_t* h_counts, uint32_t max_labels) {
+    if (!ctx || !h_counts) return MAMRI_ERR_INVALID_ARG;
+    if (ctx->pending) return fail(ctx, MAMRI_ERR_STATE, "collect the pending detect first");
+    DeviceGuard g(ctx->device);
+    uint32_t n = ctx->last_n_labels < max_labels ? ctx->last_n_labels : max_labels;
+    if (n) CK(cudaMemcpy(h_counts, ctx->d_label_count, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    return ctx->last_n_labels <= max_labels ? MAMRI_OK : fail(ctx, MAMRI_ERR_CAPACITY, "h_counts smaller than n_labels");
+}
+
+extern "C" int mamri_entry_search(mamri_ctx* ctx, const float* d_points, const float* d_normals, int64_t n,
+                                  const double target[3], double radius, double wx, double wy, double cutoff,
+                                  int32_t n_path_samples, const uint8_t* d_path_mask, const mamri_volume_desc* mask_desc,
+                                  const double ras_to_index[12], int32_t path_free_value, mamri_entry_result* result,
+                                  void* stream) {
+    if (!ctx) return MAMRI_ERR_INVALID_ARG;
+    if (!result || !target) return fail(ctx, MAMRI_ERR_INVALID_ARG, "result/target is NULL");
+    if (n < 0 || (n > 0 && (!d_points || !d_normals))) return fail(ctx, MAMRI_ERR_INVALID_ARG, "bad candidate arrays");
+    if (n_path_samples > 0 && d_path_mask && (!mask_desc || !ras_to_index))
+        return fail(ctx, MAMRI_ERR_INVALID_ARG, "path sampling needs mask_desc and ras_to_index");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n == 0) {
+        memset(result, 0, sizeof(*result));
+        result->index = -1;
+        result->distance = INFINITY;
+        return MAMRI_OK;
+    }
+    const bool sample = n_path_samples > 0 && d_path_mask;
+    CK(launch_entry_search(ctx, d_points, d_normals, n, target, radius, wx, wy, cutoff, sample ? n_path_samples : 0,
+                           sample ? d_path_mask : nullptr, sample ? mask_desc->nx : 0, sample ? mask_desc->ny : 0,
+                           sample ? mask_desc->nz : 0, ras_to_index, path_free_value, s));
+    CK(cudaMemcpyAsync(ctx->h_entry_res, ctx->d_entry_res, sizeof(mamri_entry_result), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *result = *ctx->h_entry_res;
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_phantom_generate(uint16_t* d_volume, int32_t nx, int32_t ny, int32_t nz, const float* h_ellipsoids,
+                                      int32_t n_ellipsoids, float sigma, uint64_t seed, uint32_t scan_index, void* stream) {
+    if (!d_volume || nx <= 0 || ny <= 0 || nz <= 0 || n_ellipsoids < 0 || (n_ellipsoids && !h_ellipsoids)) {
+        snprintf(g_create_err, sizeof(g_create_err), "mamri_phantom_generate: invalid argument");
+        return MAMRI_ERR_INVALID_ARG;
+    }
+    cudaError_t e = launch_phantom(d_volume, nx, ny, nz, h_ellipsoids, n_ellipsoids, sigma, seed, scan_index,
+                                   static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) {
+        snprintf(g_create_err, sizeof(g_create_err), "mamri_phantom_generate: %s", cudaGetErrorString(e));
+        return MAMRI_ERR_CUDA;
+    }
+    return MAMRI_OK;
+}

@@ -1,0 +1,103 @@
+// Internal declarations shared by the kernels and the C ABI (include/mamri_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mamri_b200.h"
+
+#define MAMRI_RMAX 3                 // largest closing radius the scratch layout is sized for
+#define MAMRI_SCAN_CTAS 592          // 148 SMs x 4: CTA count of the chunked scans
+#define MAMRI_NONE 0xFFFFFFFFu
+
+// Device-side scalars of one scan (one cudaMemsetAsync clears them).
+struct DevScalars {
+    unsigned int n_runs;
+    unsigned int n_labels;
+    unsigned int n_cand;             // labels passing the volume filter (may exceed max_markers)
+    int          status;             // MAMRI_OK / MAMRI_ERR_CAPACITY
+    unsigned long long body_packed;  // (count << 32) | (0xFFFFFFFF - label): atomicMax picks largest, lowest label
+    unsigned long long n_foreground;
+};
+
+// Bit-packed volume: `w` 32-voxel words per row, `h` rows per slice, `d` slices.
+struct BitVol {
+    uint32_t* p;
+    int w, h, d;
+};
+
+struct mamri_ctx {
+    int device;
+    int max_nx, max_ny, max_nz;
+    uint32_t max_runs, max_markers;
+    size_t cap_words, cap_pad_words;
+
+    // scratch (device)
+    uint32_t* d_raw;        // thresholded mask, bit-packed            [cap_words]
+    uint32_t* d_dil;        // dilation on the r-grown domain           [cap_pad_words]
+    uint32_t* d_closed;     // closed mask, bit-packed                  [cap_words]
+    uint32_t* d_word_base;  // runs that start before each word         [cap_words]
+    uint32_t* d_parent;     // union-find over runs                     [max_runs]
+    uint32_t* d_run_label;  // final label of each run                  [max_runs]
+    uint32_t* d_label_count;// voxels per label                         [max_runs]
+    uint32_t* d_label_slot; // marker-table slot of each label / NONE   [max_runs]
+    uint32_t* d_block_sums; // scan partials                            [2 * 1024]
+    uint32_t* d_cand_label; // label of each slot                       [max_markers + 1]
+    unsigned long long* d_cand_sums; // 9 sums per slot (sx sy sz xx yy zz xy xz yz) [(max_markers+1)*9]
+    mamri_marker* d_markers;         // sorted marker table              [max_markers]
+    mamri_summary* d_summary;
+    DevScalars* d_scalars;
+    void* d_stage_in;       // staging for mamri_detect_host_async (lazy)
+    size_t stage_in_bytes;
+    uint8_t* d_stage_body;  // staging for the body mask (lazy)
+    size_t stage_body_bytes;
+    // entry search scratch
+    double* d_entry_dist;   // per-CTA best                              [MAMRI_SCAN_CTAS]
+    long long* d_entry_idx;
+    unsigned long long* d_entry_cnt; // [2]
+    mamri_entry_result* d_entry_res;
+
+    // pinned host mirrors
+    mamri_marker* h_markers;
+    mamri_summary* h_summary;
+    mamri_entry_result* h_entry_res;
+
+    // state of the pending scan
+    bool pending;
+    cudaStream_t pending_stream;
+    mamri_volume_desc last_desc;
+    uint32_t last_n_labels;
+
+    char err[512];
+};
+
+// ---- stage launchers (each enqueues on `s`; returns cudaError_t) -------------------------------
+cudaError_t launch_threshold_pack(const void* d_vol, int dtype, int nx, int ny, int nz, double lo, double hi,
+                                  uint32_t* d_bits, cudaStream_t s);
+cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s);
+cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int connectivity, cudaStream_t s);
+cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volume_desc* desc,
+                         const mamri_params* prm, cudaStream_t s);
+cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, uint8_t* d_mask_out,
+                               uint32_t* d_labels_out, uint8_t* d_body_out, cudaStream_t s);
+cudaError_t launch_entry_search(mamri_ctx* c, const float* d_points, const float* d_normals, long long n,
+                                const double target[3], double radius, double wx, double wy, double cutoff,
+                                int n_path_samples, const uint8_t* d_path_mask, int mnx, int mny, int mnz,
+                                const double ras_to_index[12], int path_free_value, cudaStream_t s);
+cudaError_t launch_phantom(uint16_t* d_volume, int nx, int ny, int nz, const float* h_ell, int n_ell, float sigma,
+                           unsigned long long seed, unsigned int scan_index, cudaStream_t s);
+
+// ---- small device helpers ---------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// Run-start bits of word `m` given the previous word of the same row (0 at the row start).
+__device__ __forceinline__ uint32_t run_starts(uint32_t m, uint32_t prev) { return m & ~((m << 1) | (prev >> 31)); }
+
+// Id of the run that contains bit `bit` of a word: `base` runs start before the word.
+__device__ __forceinline__ uint32_t run_id_in_word(uint32_t base, uint32_t starts, int bit) {
+    return base + __popc(starts & (0xFFFFFFFFu >> (31 - bit))) - 1u;
+}
+#endif

@@ -1,0 +1,257 @@
+"""Host-side driver of the CUDA fiducial-detection path.
+
+`FiducialDetector` wraps one ``mamri_ctx`` (one GPU, one scan in flight).  PyTorch
+is used only for device memory and streams: tensors are passed to the C ABI as raw
+pointers.  Results come back as plain Python/NumPy objects shaped like what
+``MamriLogic.volume_threshold_segmentation`` builds (Mamri/Mamri.py:1310-1323).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import EntryResult, Marker, Params, Summary, VolumeDesc, check
+
+_TORCH_DTYPES = {torch.uint8: "uint8", torch.int16: "int16", torch.uint16: "uint16",
+                 torch.int32: "int32", torch.float32: "float32"}
+
+IDENTITY = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)
+
+
+@dataclasses.dataclass
+class DetectParams:
+    """Constants of the reference (Mamri.py:810-812, :1308-1309)."""
+    lower: float = 65.0
+    upper: float = 65535.0
+    close_radius: int = 2
+    connectivity: int = 6
+    min_volume: float = 50.0
+    max_volume: float = 1500.0
+
+    def to_c(self) -> Params:
+        return Params(self.lower, self.upper, self.close_radius, self.connectivity, self.min_volume, self.max_volume)
+
+
+@dataclasses.dataclass
+class MarkerStats:
+    label: int
+    count: int
+    sum_idx: tuple
+    sum_mom: tuple
+    volume_mm3: float
+    centroid_index: np.ndarray
+    centroid_lps: np.ndarray
+    centroid_ras: np.ndarray
+    principal_moments: np.ndarray
+    principal_axes: np.ndarray
+
+    @staticmethod
+    def from_c(m: Marker) -> "MarkerStats":
+        return MarkerStats(label=int(m.label), count=int(m.count), sum_idx=tuple(int(v) for v in m.sum_idx),
+                           sum_mom=tuple(int(v) for v in m.sum_mom), volume_mm3=float(m.volume_mm3),
+                           centroid_index=np.array(m.centroid_index[:]), centroid_lps=np.array(m.centroid_lps[:]),
+                           centroid_ras=np.array(m.centroid_ras[:]), principal_moments=np.array(m.principal_moments[:]),
+                           principal_axes=np.array(m.principal_axes[:]).reshape(3, 3))
+
+
+@dataclasses.dataclass
+class DetectionResult:
+    n_labels: int
+    n_runs: int
+    n_foreground: int
+    markers: List[MarkerStats]                   # ascending label = "DetectedFiducials" control-point order
+    body_label: int
+    body_count: int
+    body: Optional[MarkerStats]
+    mask: Optional[torch.Tensor] = None          # uint8 [nz,ny,nx] closed mask (device)
+    labels: Optional[torch.Tensor] = None        # uint32-valued int32 tensor [nz,ny,nx] (device)
+    body_mask: Optional[object] = None           # uint8 [nz,ny,nx] (device tensor, or host array for detect_host)
+
+    @property
+    def fiducials_data(self) -> List[dict]:
+        """The list the reference builds at Mamri.py:1310."""
+        return [{"vol": m.volume_mm3, "centroid": tuple(float(c) for c in m.centroid_lps), "id": m.label}
+                for m in self.markers]
+
+    @property
+    def ras_points(self) -> np.ndarray:
+        return np.array([m.centroid_ras for m in self.markers], dtype=np.float64).reshape(-1, 3)
+
+    @property
+    def marker_labels(self) -> List[str]:
+        return [f"M_{m.label}_{m.volume_mm3:.0f}mm³" for m in self.markers]   # Mamri.py:1317
+
+
+def _desc(shape_zyx, dtype_name, spacing, origin, direction) -> VolumeDesc:
+    nz, ny, nx = (int(v) for v in shape_zyx)
+    d = VolumeDesc()
+    d.nx, d.ny, d.nz = nx, ny, nz
+    d.dtype = _capi.DTYPE_CODES[dtype_name]
+    d.spacing[:] = [float(v) for v in spacing]
+    d.origin[:] = [float(v) for v in origin]
+    d.direction[:] = [float(v) for v in direction]
+    return d
+
+
+class FiducialDetector:
+    """One detection context on one GPU.  Not thread-safe; one scan in flight."""
+
+    def __init__(self, max_dims_xyz: Sequence[int], device: int = 0, max_runs: int = 0, max_markers: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mamri_pose_estimation_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self._lib = _capi.load()
+        self.device = int(device)
+        self.max_dims = tuple(int(v) for v in max_dims_xyz)
+        self._ctx = C.c_void_p()
+        rc = self._lib.mamri_create(C.byref(self._ctx), self.device, *self.max_dims, int(max_runs), int(max_markers))
+        check(rc, None)
+        self.max_markers = int(max_markers) if max_markers else 4096
+        self._markers = (Marker * self.max_markers)()
+        self._pending = None
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.mamri_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    __del__ = close
+
+    # ------------------------------------------------------------------ device-resident path
+    def detect_async(self, volume: torch.Tensor, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), direction=IDENTITY,
+                     params: Optional[DetectParams] = None, want_mask=False, want_labels=False, want_body=False,
+                     out_mask: Optional[torch.Tensor] = None, out_labels: Optional[torch.Tensor] = None,
+                     out_body: Optional[torch.Tensor] = None, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Enqueues one scan.  `volume`: contiguous CUDA tensor [nz, ny, nx] (x fastest)."""
+        if not (volume.is_cuda and volume.is_contiguous() and volume.dim() == 3):
+            raise ValueError("volume must be a contiguous CUDA tensor [nz, ny, nx]")
+        if volume.dtype not in _TORCH_DTYPES:
+            raise ValueError(f"unsupported voxel type {volume.dtype}")
+        params = params or DetectParams()
+        dev = volume.device
+        shape = tuple(volume.shape)
+        if want_mask and out_mask is None:
+            out_mask = torch.empty(shape, dtype=torch.uint8, device=dev)
+        if want_labels and out_labels is None:
+            out_labels = torch.empty(shape, dtype=torch.int32, device=dev)
+        if want_body and out_body is None:
+            out_body = torch.empty(shape, dtype=torch.uint8, device=dev)
+        s = stream or torch.cuda.current_stream(dev)
+        d = _desc(shape, _TORCH_DTYPES[volume.dtype], spacing, origin, direction)
+        p = params.to_c()
+        rc = self._lib.mamri_detect_async(self._ctx, C.byref(d), volume.data_ptr(), C.byref(p),
+                                          out_mask.data_ptr() if out_mask is not None else None,
+                                          out_labels.data_ptr() if out_labels is not None else None,
+                                          out_body.data_ptr() if out_body is not None else None, s.cuda_stream)
+        check(rc, self._ctx)
+        self._pending = (out_mask, out_labels, out_body, volume)   # keep the buffers alive until collect
+
+    def collect(self) -> DetectionResult:
+        summ = Summary()
+        rc = self._lib.mamri_detect_collect(self._ctx, C.byref(summ), self._markers, self.max_markers)
+        pend, self._pending = self._pending, None
+        check(rc, self._ctx)
+        markers = [MarkerStats.from_c(self._markers[i]) for i in range(summ.n_markers)]
+        body = MarkerStats.from_c(summ.body) if summ.body_label else None
+        out_mask, out_labels, out_body = (pend[0], pend[1], pend[2]) if pend else (None, None, None)
+        return DetectionResult(n_labels=int(summ.n_labels), n_runs=int(summ.n_runs), n_foreground=int(summ.n_foreground),
+                               markers=markers, body_label=int(summ.body_label), body_count=int(summ.body_count),
+                               body=body, mask=out_mask, labels=out_labels, body_mask=out_body)
+
+    def detect(self, volume: torch.Tensor, **kw) -> DetectionResult:
+        self.detect_async(volume, **kw)
+        return self.collect()
+
+    # ------------------------------------------------------------------ host-buffer path (the drop-in call)
+    def detect_host_async(self, volume, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), direction=IDENTITY,
+                          params: Optional[DetectParams] = None, body_out=None,
+                          stream: Optional[torch.cuda.Stream] = None) -> None:
+        """`volume`: C-contiguous host array [nz, ny, nx] (numpy, or a pinned CPU torch tensor for full PCIe
+        speed).  `body_out`: optional host uint8 buffer of the same shape receiving the body mask."""
+        arr, keep = _host_view(volume)
+        params = params or DetectParams()
+        d = _desc(arr["shape"], arr["dtype"], spacing, origin, direction)
+        p = params.to_c()
+        body_ptr, keep_b = (None, None)
+        if body_out is not None:
+            b, keep_b = _host_view(body_out)
+            if b["dtype"] != "uint8" or tuple(b["shape"]) != tuple(arr["shape"]):
+                raise ValueError("body_out must be uint8 with the volume's shape")
+            body_ptr = b["ptr"]
+        s = stream or torch.cuda.current_stream(self.device)
+        rc = self._lib.mamri_detect_host_async(self._ctx, C.byref(d), arr["ptr"], C.byref(p), body_ptr, s.cuda_stream)
+        check(rc, self._ctx)
+        self._pending = (None, None, body_out, (keep, keep_b))
+
+    def detect_host(self, volume, **kw) -> DetectionResult:
+        self.detect_host_async(volume, **kw)
+        return self.collect()
+
+    def label_counts(self, n_labels: int) -> np.ndarray:
+        out = np.zeros(max(int(n_labels), 1), dtype=np.uint32)
+        rc = self._lib.mamri_label_counts(self._ctx, out.ctypes.data, out.size)
+        check(rc, self._ctx)
+        return out[:n_labels]
+
+    # ------------------------------------------------------------------ entry-point search
+    def entry_search(self, points: torch.Tensor, normals: torch.Tensor, target, radius=80.0, wx=1.0, wy=-2.0,
+                     cutoff=-0.5, n_path_samples=0, path_mask: Optional[torch.Tensor] = None, ras_to_index=None,
+                     path_free_value=1, stream: Optional[torch.cuda.Stream] = None) -> dict:
+        """Closest suitable entry point among float32 CUDA `points`/`normals` [n,3] (RAS).  Constants default to
+        the reference's (Mamri.py:1009, :1015-1016)."""
+        for t in (points, normals):
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] == 3):
+                raise ValueError("points/normals must be contiguous float32 CUDA tensors [n, 3]")
+        n = int(points.shape[0])
+        tgt = (C.c_double * 3)(*[float(v) for v in target])
+        res = EntryResult()
+        md, m2i, mptr = None, None, None
+        if n_path_samples and path_mask is not None:
+            if not (path_mask.is_cuda and path_mask.is_contiguous() and path_mask.dtype == torch.uint8):
+                raise ValueError("path_mask must be a contiguous uint8 CUDA tensor [nz, ny, nx]")
+            md = C.byref(_desc(tuple(path_mask.shape), "uint8", (1, 1, 1), (0, 0, 0), IDENTITY))
+            m2i = (C.c_double * 12)(*[float(v) for v in np.asarray(ras_to_index, dtype=np.float64).reshape(12)])
+            mptr = path_mask.data_ptr()
+        s = stream or torch.cuda.current_stream(points.device)
+        rc = self._lib.mamri_entry_search(self._ctx, points.data_ptr(), normals.data_ptr(), n, tgt, float(radius),
+                                          float(wx), float(wy), float(cutoff), int(n_path_samples), mptr, md, m2i,
+                                          int(path_free_value), C.byref(res), s.cuda_stream)
+        check(rc, self._ctx)
+        return {"index": int(res.index), "distance": float(res.distance), "point": np.array(res.point[:]),
+                "n_in_radius": int(res.n_in_radius), "n_suitable": int(res.n_suitable)}
+
+
+def _host_view(a):
+    """(ptr, shape, dtype-name) of a C-contiguous host numpy array or CPU torch tensor, plus a keep-alive ref."""
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda or not a.is_contiguous() or a.dim() != 3:
+            raise ValueError("host volume must be a contiguous CPU tensor [nz, ny, nx]")
+        if a.dtype not in _TORCH_DTYPES:
+            raise ValueError(f"unsupported voxel type {a.dtype}")
+        return {"ptr": a.data_ptr(), "shape": tuple(a.shape), "dtype": _TORCH_DTYPES[a.dtype]}, a
+    arr = np.asarray(a)
+    if arr.ndim != 3 or not arr.flags["C_CONTIGUOUS"]:
+        raise ValueError("host volume must be a C-contiguous array [nz, ny, nx]")
+    if arr.dtype.name not in _capi.DTYPE_CODES:
+        raise ValueError(f"unsupported voxel type {arr.dtype}")
+    return {"ptr": arr.ctypes.data, "shape": arr.shape, "dtype": arr.dtype.name}, arr
+
+
+def generate_phantom_cuda(ph, device: int = 0, out: Optional[torch.Tensor] = None,
+                          stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """Creates the phantom described by `ph` (phantom.Phantom) directly in HBM; uint16 [nz, ny, nx]."""
+    lib = _capi.load()
+    nx, ny, nz = ph.dims
+    if out is None:
+        out = torch.empty((nz, ny, nx), dtype=torch.uint16, device=f"cuda:{device}")
+    ell = np.ascontiguousarray(ph.ellipsoids, dtype=np.float32)
+    s = stream or torch.cuda.current_stream(out.device)
+    with torch.cuda.device(out.device):
+        rc = lib.mamri_phantom_generate(out.data_ptr(), nx, ny, nz, ell.ctypes.data_as(C.POINTER(C.c_float)),
+                                        int(ell.shape[0]), float(ph.sigma), int(ph.seed), int(ph.scan_index), s.cuda_stream)
+    check(rc, None)
+    return out

@@ -295,7 +295,8 @@ def small_phantom(dims=(64, 48, 40), n_fiducials=5, n_blobs=6, sigma=12.0, seed=
         ells.append([rng.uniform(0, nx - 1), rng.uniform(0, ny - 1), rng.uniform(0, nz - 1), r, r, r, BLOB])
     for i in range(n_fiducials):
         a = rng.uniform(1.2, 3.2, size=3)
-        c = [rng.uniform(4, nx - 5), rng.uniform(4, ny - 5), rng.uniform(3, nz - 4)]
+        c = [rng.uniform(min(4, nx / 2), max(nx - 5, nx / 2)), rng.uniform(min(4, ny / 2), max(ny - 5, ny / 2)),
+             rng.uniform(min(3, nz / 2), max(nz - 4, nz / 2))]
         if touch_border and i == 0:
             c[0] = 0.5
         ells.append([c[0], c[1], c[2], a[0], a[1], a[2], FIDUCIAL])

@@ -1,0 +1,124 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Bit-exact masks and labels; centroids within 1e-4 voxel; principal axes
+within 1e-3 (up to sign); joint angles within 1e-6 rad."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from mamri_pose_estimation_b200 import phantom
+from oracle import segmentation as seg
+
+
+def _detector(dims_xyz, **kw):
+    from mamri_pose_estimation_b200.detector import FiducialDetector
+    return FiducialDetector(dims_xyz, **kw)
+
+
+def _run_gpu(vol_np, geom, params=None, **kw):
+    from mamri_pose_estimation_b200.detector import DetectParams
+    nz, ny, nx = vol_np.shape
+    det = _detector((nx, ny, nz), **kw)
+    t = torch.from_numpy(vol_np).cuda()
+    res = det.detect(t, spacing=geom.spacing, origin=geom.origin, direction=geom.direction,
+                     params=params or DetectParams(), want_mask=True, want_labels=True, want_body=True)
+    counts = det.label_counts(res.n_labels)
+    det.close()
+    return res, counts
+
+
+def _compare(res, counts, ora, geom, check_axes=True):
+    mask = res.mask.cpu().numpy()
+    labels = res.labels.cpu().numpy().view(np.uint32)
+    assert np.array_equal(mask, ora.closed), "closed mask differs"
+    assert res.n_labels == ora.n_labels
+    assert np.array_equal(labels, ora.labels), "label volume differs"
+    assert np.array_equal(counts.astype(np.int64), ora.counts)
+    assert res.n_foreground == int(ora.closed.sum())
+    assert [m.label for m in res.markers] == [f["id"] for f in ora.fiducials]
+    assert res.body_label == ora.body_label
+    if ora.body_label:
+        assert np.array_equal(res.body_mask.cpu().numpy(), ora.body_mask)
+    by = {s.label: s for s in ora.stats}
+    inv = np.linalg.inv(geom.matrix())
+    for m in res.markers + ([res.body] if res.body else []):
+        s = by[m.label]
+        assert m.count == s.count
+        assert m.sum_idx == s.sum_idx and m.sum_mom == s.sum_mom           # exact integers
+        assert m.volume_mm3 == s.physical_size                              # same IEEE product
+        assert np.abs(m.centroid_index - s.centroid_index).max() <= 1e-4    # voxels
+        assert np.abs(inv @ (m.centroid_lps - s.centroid)).max() <= 1e-4    # voxels
+        assert np.allclose(m.centroid_ras, [-s.centroid[0], -s.centroid[1], s.centroid[2]], atol=1e-9)
+        assert np.allclose(m.principal_moments, s.principal_moments, rtol=1e-9, atol=1e-9)
+        if check_axes:
+            gaps = np.diff(s.principal_moments)
+            if gaps.min() > 1e-3 * max(1.0, abs(s.principal_moments).max()):
+                for k in range(3):
+                    d = abs(float(np.dot(m.principal_axes[k], s.principal_axes[k])))
+                    assert abs(d - 1.0) <= 1e-3
+                assert np.linalg.det(m.principal_axes) > 0
+
+
+@pytest.mark.parametrize("dims,seed,conn,flip", [
+    ((64, 48, 40), 1, 6, False),
+    ((64, 48, 40), 2, 26, True),
+    ((37, 29, 23), 3, 6, True),        # ragged: nx not a multiple of 32
+    ((96, 33, 17), 4, 26, False),
+    ((128, 64, 32), 5, 6, False),      # aligned fast path
+    ((31, 9, 5), 6, 6, False),         # tiny, single partial word
+])
+def test_small_phantoms(cuda_lib, dims, seed, conn, flip):
+    from mamri_pose_estimation_b200.detector import DetectParams
+    ph = phantom.small_phantom(dims=dims, seed=seed, flip_lps=flip, touch_border=(seed % 2 == 0))
+    vol = phantom.generate(ph)
+    geom = seg.Geometry(ph.spacing, ph.origin, ph.direction)
+    prm = DetectParams(connectivity=conn, min_volume=20.0, max_volume=600.0)
+    ora = seg.detect_fiducials(vol, geom, connectivity=conn, min_vol=20.0, max_vol=600.0)
+    res, counts = _run_gpu(vol, geom, prm)
+    _compare(res, counts, ora, geom)
+
+
+@pytest.mark.parametrize("radius", [0, 1, 2, 3])
+def test_random_masks_all_radii(cuda_lib, radius):
+    """Dense random masks (uint8 input, threshold 1..255) stress closing borders and CCL merges."""
+    from mamri_pose_estimation_b200.detector import DetectParams
+    rng = np.random.default_rng(100 + radius)
+    for dims, p in (((45, 22, 19), 0.08), ((64, 16, 12), 0.35), ((33, 31, 30), 0.55)):
+        nx, ny, nz = dims
+        vol = (rng.random((nz, ny, nx)) < p).astype(np.uint8) * 200
+        geom = seg.Geometry((0.7, 0.9, 1.3), (1.0, -2.0, 3.0), (1, 0, 0, 0, 1, 0, 0, 0, 1))
+        for conn in (6, 26):
+            prm = DetectParams(lower=1, upper=255, close_radius=radius, connectivity=conn, min_volume=3.0, max_volume=40.0)
+            ora = seg.detect_fiducials(vol, geom, lo=1, hi=255, close_radius=radius, connectivity=conn,
+                                       min_vol=3.0, max_vol=40.0)
+            res, counts = _run_gpu(vol, geom, prm, max_markers=8192)
+            _compare(res, counts, ora, geom, check_axes=False)
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "int16", "uint16", "int32", "float32"])
+def test_voxel_types(cuda_lib, dtype):
+    from mamri_pose_estimation_b200.detector import DetectParams
+    rng = np.random.default_rng(7)
+    base = rng.integers(0, 200, size=(12, 20, 64))
+    if dtype == "float32":
+        vol = base.astype(np.float32) + rng.random(base.shape).astype(np.float32)
+        vol[0, 0, :5] = np.nan
+    else:
+        vol = base.astype(dtype)
+    geom = seg.Geometry()
+    ora = seg.detect_fiducials(vol, geom, lo=64.5, hi=65535, close_radius=1, min_vol=2, max_vol=50)
+    res, counts = _run_gpu(vol, geom, DetectParams(lower=64.5, upper=65535, close_radius=1, min_volume=2, max_volume=50))
+    _compare(res, counts, ora, geom, check_axes=False)
+
+
+def test_empty_and_full(cuda_lib):
+    from mamri_pose_estimation_b200.detector import DetectParams
+    geom = seg.Geometry()
+    for fill in (0, 500):
+        vol = np.full((9, 10, 40), fill, dtype=np.uint16)
+        ora = seg.detect_fiducials(vol, geom)
+        res, counts = _run_gpu(vol, geom, DetectParams())
+        _compare(res, counts, ora, geom, check_axes=False)
+        assert res.n_labels == (1 if fill else 0)
