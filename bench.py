@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the fiducial seg + CCL + stats hot path (BASELINE.json metric: Gvoxel/s and scans/s,
+% of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # CUDA path (one process per GPU)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the CPU arm (C oracle, all host threads)
+
+A step = one pass of the hot path (threshold -> ball closing -> connected components -> label statistics
+-> marker filter, with the closed mask and the label volume materialised) over one batch of
+`--scans-per-gpu` synthetic 512x512x256 uint16 phantoms per GPU (BASELINE config C2; at 8 GPUs x 8 scans this
+is config C3's 64-scan batch).  Scans shard across ranks with no data-path collective; the only exchange
+is one NCCL all-gather of the per-scan marker tables per step.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Gvoxel/s fiducial seg+CCL+stats"
+ALGO_BYTES_PER_VOXEL = {"threshold_pack": 2.0 + 1.0 / 8.0,    # read u16 once, write 1 bit
+                        "materialise": 1.0 + 4.0 + 1.0 / 8.0}   # write u8 mask + u32 label, read 1 bit
+DIMS = (512, 512, 256)
+MAX_TABLE = 32          # marker slots per scan in the gathered table
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def table_from_results(results):
+    """Fixed-size per-scan marker table for the gather: [S, MAX_TABLE, 8] f64 =
+    (label, count, volume, ras x, ras y, ras z, n_labels, body_label)."""
+    t = np.zeros((len(results), MAX_TABLE, 8), dtype=np.float64)
+    for i, r in enumerate(results):
+        for j, m in enumerate(r.markers[:MAX_TABLE]):
+            t[i, j] = (m.label, m.count, m.volume_mm3, *m.centroid_ras, r.n_labels, r.body_label)
+    return t
+
+
+def run_reference(args):
+    """CPU arm: the path restated in C (oracle/c, OpenMP over all host threads) -- SimpleITK, which the
+    reference calls at Mamri.py:1308-1310, is not installable here.  One C2 scan per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mamri_pose_estimation_b200 import phantom
+    from oracle import c_oracle
+    ph = phantom.config_c2()
+    vol = phantom.generate(ph)
+    n = vol.size
+    for _ in range(args.warmup):
+        c_oracle.run_pipeline(vol)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_oracle.run_pipeline(vol)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt / 1e9
+    cores = c_oracle.num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gvoxel/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "scans_per_s": args.steps / dt,
+            "config": {"workload": "C2: 512x512x256 uint16 phantom, 6 fiducials, Rician sigma 10; 1 scan per step"},
+            "cpu_baseline": {"value": val, "unit": "Gvoxel/s", "cores": cores, "kind": "port",
+                             "sample": "one 512x512x256 scan per step through oracle/c (threshold, closing, CCL, "
+                                       "label sums); SimpleITK itself is not installable offline"},
+            "e2e": {"value": val, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from mamri_pose_estimation_b200 import phantom
+    from mamri_pose_estimation_b200.detector import BatchDetector, DetectParams, generate_phantom_cuda
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    S = args.scans_per_gpu
+    nx, ny, nz = DIMS
+    n_vox = nx * ny * nz
+    specs = [phantom.config_c2(scan_index=rank * S + i) for i in range(S)]
+    vols = [generate_phantom_cuda(p, device=local) for p in specs]
+    torch.cuda.synchronize()
+    sp, org, dr = specs[0].spacing, specs[0].origin, specs[0].direction
+    params = DetectParams()
+    bd = BatchDetector(DIMS, device=local, n_contexts=3)
+    gather_in = torch.zeros((S, MAX_TABLE, 8), dtype=torch.float64, device=dev)
+    gather_out = torch.zeros((world * S, MAX_TABLE, 8), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        res = bd.run(vols, sp, org, dr, params)
+        if world > 1:                                   # the single exchange of the path: marker tables
+            gather_in.copy_(torch.from_numpy(table_from_results(res)), non_blocking=True)
+            dist.all_gather_into_tensor(gather_out, gather_in)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * S * n_vox * args.steps / (ms_max * 1e-3) / 1e9
+
+    # ---------------- end to end through the host-buffer call (pinned host in, markers + body mask out)
+    h_vols = [torch.empty((nz, ny, nx), dtype=torch.uint16).pin_memory() for _ in range(S)]
+    for h, v in zip(h_vols, vols):
+        h.copy_(v)
+    h_body = [torch.empty((nz, ny, nx), dtype=torch.uint8).pin_memory() for _ in range(S)]
+    torch.cuda.synchronize()
+
+    def step_host():
+        r = bd.run_host(h_vols, sp, org, dr, params, body_out=h_body)
+        if world > 1:
+            gather_in.copy_(torch.from_numpy(table_from_results(r)), non_blocking=True)
+            dist.all_gather_into_tensor(gather_out, gather_in)
+        return r
+
+    for _ in range(2):
+        res_h = step_host()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        res_h = step_host()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * S * n_vox * args.steps / (float(t.item()) * 1e-3) / 1e9
+    table_bytes = S * (64 * 248 + 400)                      # eager marker records + summary per scan
+    e2e = {"value": e2e_value, "unit": "Gvoxel/s", "scans_per_s": e2e_value * 1e9 / n_vox,
+           "h2d_bytes_per_step": world * S * n_vox * 2, "d2h_bytes_per_step": world * S * (n_vox + table_bytes // S),
+           "api": "BatchDetector.run_host -> mamri_detect_host_async/mamri_detect_collect (pinned host u16 volume in; "
+                  "marker table + uint8 body mask out)"}
+
+    # ---------------- per-stage times (CUDA events on the launching stream) -> roofline of the dominant kernel
+    stages, roof, cpu, parity = None, None, None, None
+    if rank == 0:
+        det = bd.ctxs[0]
+        det.set_profiling(True)
+        acc = {}
+        reps = 10
+        for i in range(reps + 2):
+            det.detect_async(vols[i % S], spacing=sp, origin=org, direction=dr, params=params,
+                             out_mask=bd.masks[0], out_labels=bd.labels[0])
+            det.collect()
+            if i >= 2:
+                for k, v in det.stage_times_ms().items():
+                    acc[k] = acc.get(k, 0.0) + v / reps
+        det.set_profiling(False)
+        stages = {k: round(v, 4) for k, v in acc.items()}
+        peak, peak_src = measured_peak_gbs()
+        dom = max(ALGO_BYTES_PER_VOXEL, key=lambda k: acc[k])
+        achieved = ALGO_BYTES_PER_VOXEL[dom] * n_vox / (acc[dom] * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_voxel": ALGO_BYTES_PER_VOXEL[dom],
+                "pipeline": {"achieved": 7.0 * n_vox / (sum(acc.values()) * 1e-3) / 1e9,
+                             "frac": 7.0 * n_vox / (sum(acc.values()) * 1e-3) / 1e9 / peak,
+                             "algorithmic_bytes_per_voxel": 7.0, "ms_per_scan_serial": sum(acc.values())}}
+
+        # ---------------- CPU baseline (oracle port) on a bounded sample + full-size parity check on that scan
+        if not args.no_cpu_baseline:
+            from oracle import c_oracle
+            from oracle import segmentation as seg
+            host = vols[0].cpu().numpy()
+            closed, labels, k, sums, dt = c_oracle.run_pipeline(host)
+            cpu = {"value": n_vox / dt / 1e9, "unit": "Gvoxel/s", "cores": c_oracle.num_threads(), "kind": "port",
+                   "sample": "1 of the batch's 512x512x256 scans, once, through oracle/c (threshold, closing, CCL, "
+                             "label sums)", "seconds": dt}
+            det.detect_async(vols[0], spacing=sp, origin=org, direction=dr, params=params,
+                             out_mask=bd.masks[0], out_labels=bd.labels[0])
+            r0 = det.collect()
+            geom = seg.Geometry(sp, org, dr)
+            ora = c_oracle.detect_fiducials(host, geom, want_body_mask=False)
+            parity = {"mask_bit_exact": bool(np.array_equal(bd.masks[0].cpu().numpy(), closed)),
+                      "labels_bit_exact": bool(np.array_equal(bd.labels[0].cpu().numpy().view(np.uint32), labels)),
+                      "markers_equal": [m.label for m in r0.markers] == [f["id"] for f in ora.fiducials],
+                      "max_centroid_err_mm": float(max([np.abs(np.array(m.centroid_lps) - np.array(f["centroid"])).max()
+                                                        for m, f in zip(r0.markers, ora.fiducials)] or [0.0])),
+                      "n_markers": len(r0.markers), "n_labels": r0.n_labels}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Gvoxel/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+                "scans_per_s": world * S * args.steps / (ms_max * 1e-3),
+                "config": {"workload": f"C2: {nx}x{ny}x{nz} uint16 phantom (baseplate + end-effector fiducials, Rician "
+                                       f"sigma 10), {S} distinct scans per GPU per step (8 GPUs x 8 = config C3's batch)",
+                           "scans_per_gpu": S, "outputs": "u8 closed mask + u32 label volume materialised per scan; "
+                                                          "marker table to host",
+                           "l2": f"no flush: each step streams {S} x 128 MiB of distinct inputs per GPU (> 126 MB L2)",
+                           "parallelism": f"scan-sharded x{world}, one NCCL all-gather of marker tables per step"},
+                "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "stages_ms": stages,
+                "gpu_launches": args.steps * S * bd.kernel_launches_per_scan, "parity": parity}
+        print(json.dumps(line), flush=True)
+    bd.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--scans-per-gpu", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 5
+        args.warmup = args.warmup if args.warmup is not None else 1
+        run_reference(args)
+    else:
+        args.steps = args.steps if args.steps is not None else 20
+        args.warmup = args.warmup if args.warmup is not None else 3
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

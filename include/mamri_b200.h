@@ -142,6 +142,13 @@ MAMRI_API int mamri_detect_collect(mamri_ctx* ctx, mamri_summary* summary, mamri
 /* Voxel count of every label 1..K of the last collected scan (GetPhysicalSize / voxel volume). */
 MAMRI_API int mamri_label_counts(mamri_ctx* ctx, uint32_t* h_counts, uint32_t max_labels);
 
+/* ---- measurement hooks (no reference counterpart) ----------------------------------------------- */
+/* With profiling on, detect records CUDA events between its stages on the caller's stream;
+ * mamri_stage_times() then returns, for the last collected scan, the milliseconds of
+ * {threshold+pack, closing, connected components, statistics+filter, materialise}. */
+MAMRI_API int mamri_set_profiling(mamri_ctx* ctx, int enable);
+MAMRI_API int mamri_stage_times(mamri_ctx* ctx, float ms[5]);
+
 /* ---- stage 4b: replaces the loop at Mamri.py:1008-1023 ---------------------------------- */
 /* d_points / d_normals: float32 [n][3] (RAS mm / unit normals), as vtkPolyData stores them.
  * Keeps points with |p - target|^2 <= radius^2 and wx*|nx| + wy*|ny| > cutoff (reference:

@@ -70,6 +70,7 @@ extern "C" int mamri_destroy(mamri_ctx* ctx) {
     cudaFree(ctx->d_block_sums); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
     cudaFree(ctx->d_summary); cudaFree(ctx->d_scalars); cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
     cudaFree(ctx->d_entry_dist); cudaFree(ctx->d_entry_idx); cudaFree(ctx->d_entry_cnt); cudaFree(ctx->d_entry_res);
+    for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaFreeHost(ctx->h_markers); cudaFreeHost(ctx->h_summary); cudaFreeHost(ctx->h_entry_res);
     delete ctx;
     return MAMRI_OK;
@@ -143,7 +144,23 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     if ((e = cudaMallocHost((void**)&ctx->h_summary, sizeof(mamri_summary))) != cudaSuccess) return bail(e, "pinned summary");
     if ((e = cudaMallocHost((void**)&ctx->h_entry_res, sizeof(mamri_entry_result))) != cudaSuccess)
         return bail(e, "pinned entry result");
+    for (int i = 0; i < 6; ++i)
+        if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bail(e, "events");
     *out = ctx;
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_set_profiling(mamri_ctx* ctx, int enable) {
+    if (!ctx) return MAMRI_ERR_INVALID_ARG;
+    ctx->profile = enable != 0;
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_stage_times(mamri_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return MAMRI_ERR_INVALID_ARG;
+    if (ctx->pending) return fail(ctx, MAMRI_ERR_STATE, "collect the pending detect first");
+    DeviceGuard g(ctx->device);
+    for (int i = 0; i < 5; ++i) CK(cudaEventElapsedTime(ms + i, ctx->ev[i], ctx->ev[i + 1]));
     return MAMRI_OK;
 }
 
@@ -172,16 +189,23 @@ extern "C" int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc,
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int nx = desc->nx, ny = desc->ny, nz = desc->nz;
+    const bool prof = ctx->profile;
     CK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(DevScalars), s));
+    if (prof) CK(cudaEventRecord(ctx->ev[0], s));
     CK(launch_threshold_pack(d_volume, desc->dtype, nx, ny, nz, params->lower, params->upper, ctx->d_raw, s));
+    if (prof) CK(cudaEventRecord(ctx->ev[1], s));
     const uint32_t* mask = ctx->d_raw;
     if (params->close_radius > 0) {
         CK(launch_closing(ctx, nx, ny, nz, params->close_radius, s));
         mask = ctx->d_closed;
     }
+    if (prof) CK(cudaEventRecord(ctx->ev[2], s));
     CK(launch_ccl(ctx, mask, nx, ny, nz, params->connectivity, s));
+    if (prof) CK(cudaEventRecord(ctx->ev[3], s));
     CK(launch_stats(ctx, mask, desc, params, s));
+    if (prof) CK(cudaEventRecord(ctx->ev[4], s));
     CK(launch_materialise(ctx, mask, nx, ny, nz, d_mask_out, d_labels_out, d_body_out, s));
+    if (prof) CK(cudaEventRecord(ctx->ev[5], s));
     CK(cudaMemcpyAsync(ctx->h_summary, ctx->d_summary, sizeof(mamri_summary), cudaMemcpyDeviceToHost, s));
     const uint32_t eager = ctx->max_markers < EAGER_MARKERS ? ctx->max_markers : EAGER_MARKERS;
     CK(cudaMemcpyAsync(ctx->h_markers, ctx->d_markers, size_t(eager) * sizeof(mamri_marker), cudaMemcpyDeviceToHost, s));

@@ -105,8 +105,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(uint32_t* __rest
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_runs_assign(const uint32_t* __restrict__ mask, int W, size_t n_words,
                                                               const uint32_t* __restrict__ block_sums,
-                                                              uint32_t* __restrict__ word_base,
-                                                              uint32_t* __restrict__ parent, const DevScalars* sc) {
+                                                              uint32_t* __restrict__ word_base, const DevScalars* sc) {
     __shared__ uint32_t ws[33];
     if (sc->status != MAMRI_OK) return;
     size_t begin, end;
@@ -123,7 +122,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_runs_assign(const uint32_t* __
         uint32_t base = running + block_excl_scan(cnt, ws, total);
         if (i < end) {
             word_base[i] = base;
-            for (uint32_t k = 0; k < cnt; ++k) parent[base + k] = base + k;
         }
         running += total;
     }
@@ -132,11 +130,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_runs_assign(const uint32_t* __
 // ------------------------------------------------------------------------------------------------
 // union-find over runs
 // ------------------------------------------------------------------------------------------------
+// `parent` may live in shared memory (per-slice phase) or in global memory (cross-slice phase);
+// volatile generic loads keep every hop coherent (L2 for global) while other threads hook roots.
 __device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
-    uint32_t p = __ldcg(parent + x);   // L2 loads: other CTAs hook roots concurrently
+    volatile uint32_t* vp = parent;
+    uint32_t p = vp[x];
     while (p != x) {
-        uint32_t gp = __ldcg(parent + p);
-        if (gp != p) parent[x] = gp;   // path halving; any smaller same-set node is a valid parent
+        uint32_t gp = vp[p];
+        if (gp != p) vp[x] = gp;       // path halving; any smaller same-set node is a valid parent
         x = p;
         p = gp;
     }
@@ -155,21 +156,13 @@ __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t 
     }
 }
 
-// Run id of the run containing bit `bit` of word `wi` (x-word `xw` of its row).
-__device__ __forceinline__ uint32_t run_id_at(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
-                                              size_t wi, int xw, int bit) {
-    uint32_t m = mask[wi];
-    uint32_t prev = xw > 0 ? mask[wi - 1] : 0u;
-    return run_id_in_word(word_base[wi], run_starts(m, prev), bit);
-}
-
 // Joins the runs of word (xw,y,z) with the runs of one earlier neighbour row.  DIAG adds the
 // x+-1 contacts (26-connectivity).  Every maximal piece of overlapping bits lies in exactly one run
 // on either side, so one union per piece start suffices; pieces continuing from the previous word
-// are skipped (their start was handled there).
+// are skipped (their start was handled there).  Node ids are run ids minus `id_off`.
 template <bool DIAG>
 __device__ __forceinline__ void join_row(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
-                                         uint32_t* parent, int W, int xw, size_t wi, uint32_t m, uint32_t m_prev,
+                                         uint32_t* parent, uint32_t id_off, int W, int xw, uint32_t m, uint32_t m_prev,
                                          uint32_t base_m, uint32_t starts_m, size_t ni) {
     const uint32_t up = mask[ni];
     const uint32_t up_prev = xw > 0 ? mask[ni - 1] : 0u;
@@ -177,7 +170,8 @@ __device__ __forceinline__ void join_row(const uint32_t* __restrict__ mask, cons
     if (!DIAG && !up) return;
     if (DIAG && !(up | (up_prev >> 31) | (up_next & 1u))) return;
     const uint32_t starts_up = run_starts(up, up_prev);
-    const uint32_t base_up = word_base[ni];
+    const uint32_t base_up = word_base[ni] - id_off;
+    base_m -= id_off;
     // direct (same x) contacts
     uint32_t ov = m & up;
     uint32_t ps = ov & ~((ov << 1) | ((m_prev & up_prev) >> 31));
@@ -201,34 +195,81 @@ __device__ __forceinline__ void join_row(const uint32_t* __restrict__ mask, cons
         while (c) {
             int b = __ffs(c) - 1;
             c &= c - 1;
-            uint32_t rid_up = b < 31 ? run_id_in_word(base_up, starts_up, b + 1) : word_base[ni + 1];
+            uint32_t rid_up = b < 31 ? run_id_in_word(base_up, starts_up, b + 1) : word_base[ni + 1] - id_off;
             uf_union(parent, run_id_in_word(base_m, starts_m, b), rid_up);
         }
     }
 }
 
+// Phase 1 -- block-local: one CTA per z-slice.  The runs of a slice are contiguous in id space, so the
+// CTA keeps their parents in shared memory (local index = run id - first run of the slice), joins
+// every row with the row above it at shared-memory latency (simultaneous hooking builds chains as
+// long as the object is tall; in shared memory a hop costs ~30 cycles instead of an L2 round trip),
+// flattens, and publishes parent[run] = slice-local root as a global id.  Slices with more runs than
+// fit fall back to the same code on the global array.
+constexpr int SLICE_THREADS = 512;
+constexpr uint32_t SLICE_SMEM_RUNS = 12000;      // 48 KB static shared memory
+
 template <bool CONN26>
-__global__ void __launch_bounds__(256) k_union(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
-                                               uint32_t* parent, int W, int ny, int nz, size_t n_words,
-                                               const DevScalars* sc) {
+__global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* __restrict__ mask,
+                                                               const uint32_t* __restrict__ word_base, uint32_t* parent,
+                                                               int W, int ny, int nz, const DevScalars* sc) {
+    __shared__ uint32_t sp[SLICE_SMEM_RUNS];
     if (sc->status != MAMRI_OK) return;
-    for (size_t wi = size_t(blockIdx.x) * blockDim.x + threadIdx.x; wi < n_words; wi += size_t(gridDim.x) * blockDim.x) {
+    const int z = blockIdx.x;
+    const size_t slice_words = size_t(W) * ny;
+    const size_t w0 = size_t(z) * slice_words;
+    const uint32_t r0 = word_base[w0];
+    const uint32_t r1 = (z + 1 < nz) ? word_base[w0 + slice_words] : sc->n_runs;
+    const uint32_t n = r1 - r0;
+    if (n == 0) return;
+    uint32_t* P = (n <= SLICE_SMEM_RUNS) ? sp : parent + r0;
+    for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) P[i] = i;
+    __syncthreads();
+    for (size_t i = size_t(W) + threadIdx.x; i < slice_words; i += SLICE_THREADS) {     // rows y >= 1
+        const size_t wi = w0 + i;
+        const uint32_t m = mask[wi];
+        if (!m) continue;
+        const int xw = int(i % W);
+        const uint32_t m_prev = xw > 0 ? mask[wi - 1] : 0u;
+        join_row<CONN26>(mask, word_base, P, r0, W, xw, m, m_prev, word_base[wi], run_starts(m, m_prev), wi - W);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) {
+        uint32_t x = i, p = P[x];
+        while (p != x) { x = p; p = P[x]; }
+        P[i] = x;                                 // roots stay fixed points: concurrent walkers remain correct
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) parent[r0 + i] = r0 + P[i];
+}
+
+// Phase 2 -- global boundary merge between slices, with atomicMin on the roots.  Joining all slice
+// boundaries at once would again chain the roots nz deep (every hop an L2 round trip), so the
+// boundaries are merged in two rounds: first those inside blocks of `radix` slices (chains <= radix),
+// then the boundaries between blocks (again <= radix of them per chain).
+template <bool CONN26>
+__global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
+                                                 uint32_t* parent, int W, int ny, int nz, size_t n_words, int radix,
+                                                 int between_blocks, const DevScalars* sc) {
+    if (sc->status != MAMRI_OK) return;
+    const size_t slice = size_t(W) * ny;
+    for (size_t wi = slice + size_t(blockIdx.x) * blockDim.x + threadIdx.x; wi < n_words;
+         wi += size_t(gridDim.x) * blockDim.x) {
+        const int z = int(wi / slice);
+        if (((z % radix) == 0) != (between_blocks != 0)) continue;
         const uint32_t m = mask[wi];
         if (!m) continue;
         const size_t row = wi / W;
         const int xw = int(wi - row * W);
-        const int y = int(row % ny), z = int(row / ny);
+        const int y = int(row % ny);
         const uint32_t m_prev = xw > 0 ? mask[wi - 1] : 0u;
         const uint32_t starts_m = run_starts(m, m_prev);
         const uint32_t base_m = word_base[wi];
-        const size_t slice = size_t(W) * ny;
-        if (y > 0) join_row<CONN26>(mask, word_base, parent, W, xw, wi, m, m_prev, base_m, starts_m, wi - W);
-        if (z > 0) {
-            join_row<CONN26>(mask, word_base, parent, W, xw, wi, m, m_prev, base_m, starts_m, wi - slice);
-            if (CONN26) {
-                if (y > 0) join_row<true>(mask, word_base, parent, W, xw, wi, m, m_prev, base_m, starts_m, wi - slice - W);
-                if (y + 1 < ny) join_row<true>(mask, word_base, parent, W, xw, wi, m, m_prev, base_m, starts_m, wi - slice + W);
-            }
+        join_row<CONN26>(mask, word_base, parent, 0u, W, xw, m, m_prev, base_m, starts_m, wi - slice);
+        if (CONN26) {
+            if (y > 0) join_row<true>(mask, word_base, parent, 0u, W, xw, m, m_prev, base_m, starts_m, wi - slice - W);
+            if (y + 1 < ny) join_row<true>(mask, word_base, parent, 0u, W, xw, m, m_prev, base_m, starts_m, wi - slice + W);
         }
     }
 }
@@ -289,14 +330,21 @@ cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int
     uint32_t* bs_roots = c->d_block_sums + 1024;
     k_runs_count<<<G, SCAN_THREADS, 0, s>>>(d_mask, W, n_words, bs_runs);
     k_scan_partials<<<1, SCAN_THREADS, 0, s>>>(bs_runs, G, &c->d_scalars->n_runs, c->max_runs, c->d_scalars);
-    k_runs_assign<<<G, SCAN_THREADS, 0, s>>>(d_mask, W, n_words, bs_runs, c->d_word_base, c->d_parent, c->d_scalars);
+    k_runs_assign<<<G, SCAN_THREADS, 0, s>>>(d_mask, W, n_words, bs_runs, c->d_word_base, c->d_scalars);
+    int radix = 1;
+    while (radix * radix < nz) radix <<= 1;
     size_t ub = (n_words + 255) / 256;
     if (ub > 148 * 16) ub = 148 * 16;
     if (ub == 0) ub = 1;
-    if (connectivity == 26)
-        k_union<true><<<unsigned(ub), 256, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, n_words, c->d_scalars);
-    else
-        k_union<false><<<unsigned(ub), 256, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, n_words, c->d_scalars);
+    if (connectivity == 26) {
+        k_union_slices<true><<<nz, SLICE_THREADS, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, c->d_scalars);
+        if (nz > 1) k_union_z<true><<<unsigned(ub), 256, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, n_words, radix, 0, c->d_scalars);
+        if (nz > radix) k_union_z<true><<<unsigned(ub), 256, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, n_words, radix, 1, c->d_scalars);
+    } else {
+        k_union_slices<false><<<nz, SLICE_THREADS, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, c->d_scalars);
+        if (nz > 1) k_union_z<false><<<unsigned(ub), 256, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, n_words, radix, 0, c->d_scalars);
+        if (nz > radix) k_union_z<false><<<unsigned(ub), 256, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, n_words, radix, 1, c->d_scalars);
+    }
     k_flatten_count<<<G, SCAN_THREADS, 0, s>>>(c->d_parent, bs_roots, c->d_scalars);
     k_scan_partials<<<1, SCAN_THREADS, 0, s>>>(bs_roots, G, &c->d_scalars->n_labels, 0xFFFFFFFFu, c->d_scalars);
     k_rank_roots<<<G, SCAN_THREADS, 0, s>>>(c->d_parent, bs_roots, c->d_run_label, c->d_label_count, c->d_scalars);

@@ -64,6 +64,10 @@ struct mamri_ctx {
     mamri_summary* h_summary;
     mamri_entry_result* h_entry_res;
 
+    // optional per-stage timing (mamri_set_profiling): events recorded between the stage launches
+    bool profile;
+    cudaEvent_t ev[6];
+
     // state of the pending scan
     bool pending;
     cudaStream_t pending_stream;

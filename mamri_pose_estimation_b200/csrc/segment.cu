@@ -133,67 +133,89 @@ cudaError_t launch_threshold_pack(const void* d_vol, int dtype, int nx, int ny, 
 // ------------------------------------------------------------------------------------------------
 // ITK's ball of radius R (FlatStructuringElement::Ball, radiusIsParametric = false) is
 // {d : dx^2+dy^2+dz^2 <= R^2+R}.  On bit-packed rows it is, for every (dy,dz) with
-// dy^2+dz^2 <= R^2+R, an x-interval of half-width h = floor(sqrt(R^2+R-dy^2-dz^2)).  So with
-// S_h(row) = the row dilated (eroded) along x by h, the result word is the OR (AND) of S_h over
-// those rows.  A CTA stages a (TZ+2R) x (TY+2R) x (TXW+2) halo tile of source words in shared
-// memory, derives S_1..S_R once per source word, then every output word is <= (2R+1)^2 LDS + ORs.
-constexpr int TY = 8, TZ = 8, TXW_MAX = 32;
-
+// dy^2+dz^2 <= R^2+R, an x-interval of half-width h = floor(sqrt(R^2+R-dy^2-dz^2)).  With
+// S_h(row) = the row dilated (eroded) along x by h (funnel shifts over three neighbouring words),
+//   P_a(y, z') = OP_{dy} S_{h(dy,a)}(y+dy, z')          (the in-slice part for |dz| = a)
+//   out(y, z)  = OP_{dz} P_|dz|(y, z+dz)                 (OP = OR for dilation, AND for erosion).
+// A thread owns one output word column (xw, y) over a chunk of ZC slices and slides a register
+// window of P values along z: every step loads (2R+1) rows x 3 words of ONE new slice (coalesced,
+// L1-shared with the neighbouring threads), so a source word is loaded ~(2R+1)*3 times per output
+// instead of (2R+1)^2*3 -- no shared memory, no barriers.  The bit volumes are L2-resident (1 bit/voxel).
 __host__ __device__ constexpr int isqrt_c(int v) { int r = 0; while ((r + 1) * (r + 1) <= v) ++r; return r; }
 
 template <int R, bool ERODE>
-__global__ void __launch_bounds__(256) k_morph_tile(BitVol src, BitVol dst, int ox, int oy, int oz, uint32_t tail_mask) {
-    // src coordinate = dst coordinate + (ox, oy, oz)  (words, rows, slices)
-    extern __shared__ uint32_t sm[];
-    const int txw = min(dst.w - int(blockIdx.x) * TXW_MAX, TXW_MAX);   // output words along x in this tile
-    constexpr int HY = TY + 2 * R, HZ = TZ + 2 * R;
-    const int rw = txw + 2;                                           // raw tile row length (1-word halo each side)
-    uint32_t* raw = sm;                                               // [HZ][HY][rw]
-    uint32_t* sh = sm + HZ * HY * rw;                                 // [R][HZ][HY][txw]
-    const int x0 = int(blockIdx.x) * TXW_MAX, y0 = int(blockIdx.y) * TY, z0 = int(blockIdx.z) * TZ;
-
-    for (int i = threadIdx.x; i < HZ * HY * rw; i += blockDim.x) {
-        int tx = i % rw, t = i / rw, ty = t % HY, tz = t / HY;
-        int sx = x0 + tx - 1 + ox, sy = y0 + ty - R + oy, sz = z0 + tz - R + oz;
-        uint32_t v = 0;
-        if (sx >= 0 && sx < src.w && sy >= 0 && sy < src.h && sz >= 0 && sz < src.d)
-            v = src.p[(size_t(sz) * src.h + sy) * src.w + sx];
-        raw[i] = v;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < HZ * HY * txw; i += blockDim.x) {
-        int tx = i % txw, row = i / txw;
-        const uint32_t l = raw[row * rw + tx], c = raw[row * rw + tx + 1], r = raw[row * rw + tx + 2];
-        uint32_t acc = c;
+__device__ __forceinline__ void slice_patterns(const BitVol& src, int sx, int sy, int sz, uint32_t (&P)[R + 1]) {
+    constexpr int R2 = R * R + R;
+#pragma unroll
+    for (int a = 0; a <= R; ++a) P[a] = ERODE ? 0xFFFFFFFFu : 0u;
+    const bool z_ok = sz >= 0 && sz < src.d;
+#pragma unroll
+    for (int dy = -R; dy <= R; ++dy) {
+        const int y = sy + dy;
+        uint32_t l = 0, c = 0, r = 0;
+        if (z_ok && y >= 0 && y < src.h) {
+            const uint32_t* row = src.p + (size_t(sz) * src.h + y) * src.w;
+            if (sx >= 0 && sx < src.w) c = row[sx];
+            if (sx - 1 >= 0 && sx - 1 < src.w) l = row[sx - 1];
+            if (sx + 1 >= 0 && sx + 1 < src.w) r = row[sx + 1];
+        }
+        uint32_t S[R + 1];
+        S[0] = c;
 #pragma unroll
         for (int k = 1; k <= R; ++k) {
-            uint32_t a = (c << k) | (l >> (32 - k)), b = (c >> k) | (r << (32 - k));
-            acc = ERODE ? (acc & a & b) : (acc | a | b);
-            sh[(size_t(k - 1) * HZ * HY + row) * txw + tx] = acc;
+            const uint32_t a = (c << k) | (l >> (32 - k)), b = (c >> k) | (r << (32 - k));
+            S[k] = ERODE ? (S[k - 1] & a & b) : (S[k - 1] | a | b);
+        }
+#pragma unroll
+        for (int a = 0; a <= R; ++a) {
+            const int rem = R2 - dy * dy - a * a;
+            if (rem >= 0) P[a] = ERODE ? (P[a] & S[isqrt_c(rem)]) : (P[a] | S[isqrt_c(rem)]);
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < TZ * TY * txw; i += blockDim.x) {
-        int tx = i % txw, t = i / txw, ty = t % TY, tz = t / TY;
-        int x = x0 + tx, y = y0 + ty, z = z0 + tz;
-        if (y >= dst.h || z >= dst.d) continue;
+}
+
+template <int R, bool ERODE>
+__global__ void __launch_bounds__(256) k_morph_sweep(BitVol src, BitVol dst, int ox, int oy, int oz, uint32_t tail_mask,
+                                                     int zc, int n_chunks) {
+    // src coordinate = dst coordinate + (ox, oy, oz)  (words, rows, slices)
+    const size_t per_chunk = size_t(dst.w) * dst.h;
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= per_chunk * n_chunks) return;
+    const int chunk = int(t / per_chunk);
+    const size_t in_slice = t - size_t(chunk) * per_chunk;
+    const int y = int(in_slice / dst.w), x = int(in_slice - size_t(y) * dst.w);
+    const int z0 = chunk * zc, z1 = min(z0 + zc, dst.d);
+    const int sx = x + ox, sy = y + oy;
+    uint32_t win[2 * R + 1][R + 1];                 // win[j] = patterns of source slice (z + oz) - R + j
+#pragma unroll
+    for (int j = 0; j < 2 * R; ++j) slice_patterns<R, ERODE>(src, sx, sy, z0 + oz - R + j, win[j]);
+    const uint32_t tm = (x == dst.w - 1) ? tail_mask : 0xFFFFFFFFu;
+    for (int z = z0; z < z1; ++z) {
+        slice_patterns<R, ERODE>(src, sx, sy, z + oz + R, win[2 * R]);
         uint32_t acc = ERODE ? 0xFFFFFFFFu : 0u;
 #pragma unroll
         for (int dz = -R; dz <= R; ++dz) {
-#pragma unroll
-            for (int dy = -R; dy <= R; ++dy) {
-                constexpr int R2 = R * R + R;
-                const int rem = R2 - dy * dy - dz * dz;
-                if (rem < 0) continue;
-                const int h = isqrt_c(rem);
-                const int row = (tz + R + dz) * HY + (ty + R + dy);
-                uint32_t v = (h == 0) ? raw[row * rw + tx + 1] : sh[(size_t(h - 1) * HZ * HY + row) * txw + tx];
-                acc = ERODE ? (acc & v) : (acc | v);
-            }
+            const uint32_t v = win[dz + R][dz < 0 ? -dz : dz];
+            acc = ERODE ? (acc & v) : (acc | v);
         }
-        if (x == dst.w - 1) acc &= tail_mask;
-        dst.p[(size_t(z) * dst.h + y) * dst.w + x] = acc;
+        dst.p[(size_t(z) * dst.h + y) * dst.w + x] = acc & tm;
+#pragma unroll
+        for (int j = 0; j < 2 * R; ++j)
+#pragma unroll
+            for (int a = 0; a <= R; ++a) win[j][a] = win[j + 1][a];
     }
+}
+
+template <int R, bool ERODE>
+static cudaError_t morph_launch(BitVol src, BitVol dst, int ox, int oy, int oz, uint32_t tail, cudaStream_t s) {
+    // chunk the z sweep so that the grid has a few hundred thousand threads (148 SMs x 2048)
+    const size_t per_chunk = size_t(dst.w) * dst.h;
+    int zc = 16;
+    while (zc > 4 && per_chunk * ((dst.d + zc - 1) / zc) < size_t(148) * 2048) zc >>= 1;
+    const int n_chunks = (dst.d + zc - 1) / zc;
+    const size_t threads = per_chunk * n_chunks;
+    k_morph_sweep<R, ERODE><<<unsigned((threads + 255) / 256), 256, 0, s>>>(src, dst, ox, oy, oz, tail, zc, n_chunks);
+    return cudaGetLastError();
 }
 
 template <int R>
@@ -202,30 +224,13 @@ static cudaError_t closing_r(mamri_ctx* c, int nx, int ny, int nz, cudaStream_t 
     BitVol raw{c->d_raw, W, ny, nz};
     BitVol dil{c->d_dil, W + 2, ny + 2 * R, nz + 2 * R};
     BitVol out{c->d_closed, W, ny, nz};
-    constexpr int HY = TY + 2 * R, HZ = TZ + 2 * R;
-    auto smem_for = [&](int w) {
-        int txw = w < TXW_MAX ? w : TXW_MAX;
-        return size_t(HZ * HY) * (txw + 2 + R * txw) * sizeof(uint32_t);
-    };
-    static bool attr_set = false;
-    if (!attr_set) {
-        size_t mx = smem_for(TXW_MAX);
-        cudaError_t e = cudaFuncSetAttribute(k_morph_tile<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mx));
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_morph_tile<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mx));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    // dilation: padded output coordinate (xw, y, z) reads raw (xw-1, y-R, z-R)
-    dim3 gd((dil.w + TXW_MAX - 1) / TXW_MAX, (dil.h + TY - 1) / TY, (dil.d + TZ - 1) / TZ);
-    k_morph_tile<R, false><<<gd, 256, smem_for(dil.w), s>>>(raw, dil, -1, -R, -R, 0xFFFFFFFFu);
-    cudaError_t e = cudaGetLastError();
+    // dilation: padded output coordinate (xw, y, z) reads raw (xw-1, y-R, z-R); reads outside raw are 0
+    cudaError_t e = morph_launch<R, false>(raw, dil, -1, -R, -R, 0xFFFFFFFFu, s);
     if (e != cudaSuccess) return e;
-    // erosion: image output coordinate (xw, y, z) reads the padded dilation at (xw+1, y+R, z+R)
+    // erosion: image output coordinate (xw, y, z) reads the padded dilation at (xw+1, y+R, z+R); every
+    // read of an image-domain output stays inside the padded volume
     const uint32_t tail = (nx % 32) ? (0xFFFFFFFFu >> (32 - nx % 32)) : 0xFFFFFFFFu;
-    dim3 ge((out.w + TXW_MAX - 1) / TXW_MAX, (out.h + TY - 1) / TY, (out.d + TZ - 1) / TZ);
-    k_morph_tile<R, true><<<ge, 256, smem_for(out.w), s>>>(dil, out, 1, R, R, tail);
-    return cudaGetLastError();
+    return morph_launch<R, true>(dil, out, 1, R, R, tail, s);
 }
 
 cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s) {

@@ -20,31 +20,69 @@ struct GeomArgs {
 };
 
 // ------------------------------------------------------------------------------------------------
-// warp aggregation: lanes with equal keys are summed, one lane per key issues the atomics
+// aggregation: warp shuffles first, then a per-CTA shared-memory cache, then global atomics
 // ------------------------------------------------------------------------------------------------
-template <int NV, typename V>
-__device__ __forceinline__ void warp_agg_add(uint32_t key, V (&v)[NV], V* table) {
+// One huge component (the body) makes every warp hit the same table row; per-warp global atomics on
+// one address serialise in L2.  Each CTA therefore keeps a small direct-mapped cache of accumulators in
+// shared memory (slot = key % SLOTS, claimed by the first key that arrives, never evicted); cached
+// keys cost a shared-memory atomic, the rest go to global memory; the cache is flushed once per CTA.
+template <int NV, typename V, int SLOTS>
+struct CtaCache {
+    uint32_t tag[SLOTS];
+    V val[SLOTS][NV];
+
+    __device__ void init() {
+        for (int i = threadIdx.x; i < SLOTS; i += blockDim.x) tag[i] = MAMRI_NONE;
+        for (int i = threadIdx.x; i < SLOTS * NV; i += blockDim.x) (&val[0][0])[i] = V(0);
+        __syncthreads();
+    }
+    __device__ __forceinline__ void add(uint32_t key, const V (&v)[NV], V* table) {
+        const int s = int(key % SLOTS);
+        uint32_t t = *(volatile uint32_t*)&tag[s];
+        if (t == MAMRI_NONE) {
+            t = atomicCAS(&tag[s], MAMRI_NONE, key);
+            if (t == MAMRI_NONE) t = key;
+        }
+        if (t == key) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) atomicAdd(&val[s][i], v[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) atomicAdd(table + size_t(key) * NV + i, v[i]);
+        }
+    }
+    __device__ void flush(V* table) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SLOTS * NV; i += blockDim.x) {
+            const uint32_t key = tag[i / NV];
+            const V x = (&val[0][0])[i];
+            if (key != MAMRI_NONE && x != V(0)) atomicAdd(table + size_t(key) * NV + (i % NV), x);
+        }
+    }
+};
+
+// Lanes with equal keys are summed by shuffles; one lane per distinct key forwards to the CTA cache.
+template <int NV, typename V, int SLOTS>
+__device__ __forceinline__ void warp_agg_add(uint32_t key, V (&v)[NV], CtaCache<NV, V, SLOTS>& cache, V* table) {
     const unsigned lane = lane_id();
     const bool valid = key != MAMRI_NONE;
     const unsigned peers = __match_any_sync(FULL, key);
     const bool single = valid && peers == (1u << lane);
-    if (single) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) atomicAdd(table + size_t(key) * NV + i, v[i]);
-    }
+    if (single) cache.add(key, v, table);
     __syncwarp();
     unsigned remaining = __ballot_sync(FULL, valid && !single);
     while (remaining) {
         const int leader = __ffs(remaining) - 1;
         const uint32_t k = __shfl_sync(FULL, key, leader);
         const bool mine = valid && key == k;
+        V x[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            V x = mine ? v[i] : V(0);
+            x[i] = mine ? v[i] : V(0);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-            if (int(lane) == leader) atomicAdd(table + size_t(k) * NV + i, x);
+            for (int o = 16; o > 0; o >>= 1) x[i] += __shfl_xor_sync(FULL, x[i], o);
         }
+        if (int(lane) == leader) cache.add(k, x, table);
         remaining &= ~__ballot_sync(FULL, mine);
     }
 }
@@ -65,7 +103,9 @@ __global__ void __launch_bounds__(256) k_count_labels(const uint32_t* __restrict
                                                       const uint32_t* __restrict__ word_base,
                                                       const uint32_t* __restrict__ run_label, int W, size_t n_words,
                                                       uint32_t* label_count, const DevScalars* sc) {
+    __shared__ CtaCache<1, uint32_t, 64> cache;
     if (sc->status != MAMRI_OK) return;
+    cache.init();
     const unsigned lane = lane_id();
     const size_t warp0 = ((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) << 5;
     const size_t stride = size_t(gridDim.x) * blockDim.x;
@@ -87,9 +127,10 @@ __global__ void __launch_bounds__(256) k_count_labels(const uint32_t* __restrict
                 key = run_label[run_id_in_word(base, starts, b)] - 1u;
                 v[0] = uint32_t(len);
             }
-            warp_agg_add<1, uint32_t>(key, v, label_count);
+            warp_agg_add(key, v, cache, label_count);
         }
     }
+    cache.flush(label_count);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -162,7 +203,9 @@ __global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ ma
                                                  const uint32_t* __restrict__ run_label,
                                                  const uint32_t* __restrict__ label_slot, int W, int ny, size_t n_words,
                                                  unsigned long long* sums, const DevScalars* sc) {
+    __shared__ CtaCache<9, unsigned long long, 16> cache;
     if (sc->status != MAMRI_OK) return;
+    cache.init();
     const unsigned lane = lane_id();
     const size_t warp0 = ((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) << 5;
     const size_t stride = size_t(gridDim.x) * blockDim.x;
@@ -203,9 +246,10 @@ __global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ ma
                     v[8] = (unsigned long long)(n * y * z);                 // sum yz
                 }
             }
-            warp_agg_add<9, unsigned long long>(key, v, sums);
+            warp_agg_add(key, v, cache, sums);
         }
     }
+    cache.flush(sums);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -350,7 +394,7 @@ cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volum
     g.min_volume = prm->min_volume;
     g.max_volume = prm->max_volume;
     size_t wb = (n_words + 255) / 256;
-    if (wb > 148 * 16) wb = 148 * 16;
+    if (wb > 148 * 8) wb = 148 * 8;
     if (wb == 0) wb = 1;
     k_count_labels<<<unsigned(wb), 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, W, n_words, c->d_label_count,
                                                 c->d_scalars);

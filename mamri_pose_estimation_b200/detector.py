@@ -191,6 +191,16 @@ class FiducialDetector:
         self.detect_host_async(volume, **kw)
         return self.collect()
 
+    STAGES = ("threshold_pack", "closing", "ccl", "stats_filter", "materialise")
+
+    def set_profiling(self, enable: bool) -> None:
+        check(self._lib.mamri_set_profiling(self._ctx, int(bool(enable))), self._ctx)
+
+    def stage_times_ms(self) -> dict:
+        ms = (C.c_float * 5)()
+        check(self._lib.mamri_stage_times(self._ctx, ms), self._ctx)
+        return dict(zip(self.STAGES, [float(v) for v in ms]))
+
     def label_counts(self, n_labels: int) -> np.ndarray:
         out = np.zeros(max(int(n_labels), 1), dtype=np.uint32)
         rc = self._lib.mamri_label_counts(self._ctx, out.ctypes.data, out.size)
@@ -255,3 +265,82 @@ def generate_phantom_cuda(ph, device: int = 0, out: Optional[torch.Tensor] = Non
                                         int(ell.shape[0]), float(ph.sigma), int(ph.seed), int(ph.scan_index), s.cuda_stream)
     check(rc, None)
     return out
+
+
+class BatchDetector:
+    """Pipelines a batch of independent scans over a small pool of contexts/streams on one GPU so that
+    the launch + collect latency of one scan hides behind the kernels of the next (scans are independent:
+    ``MamriLogic.process`` handles exactly one inputVolume, Mamri.py:850-858).
+
+    Streams fork from and join back into the caller's current stream, so CUDA events recorded on the
+    current stream around `run` / `run_host` bracket all the work."""
+
+    def __init__(self, dims_xyz: Sequence[int], device: int = 0, n_contexts: int = 3, max_runs: int = 0,
+                 max_markers: int = 0, materialise: bool = True):
+        self.device = int(device)
+        self.dims = tuple(int(v) for v in dims_xyz)
+        nx, ny, nz = self.dims
+        dev = torch.device(f"cuda:{self.device}")
+        self.ctxs = [FiducialDetector(self.dims, device, max_runs, max_markers) for _ in range(n_contexts)]
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_contexts)]
+        self.materialise = materialise
+        self.masks = [torch.empty((nz, ny, nx), dtype=torch.uint8, device=dev) if materialise else None
+                      for _ in range(n_contexts)]
+        self.labels = [torch.empty((nz, ny, nx), dtype=torch.int32, device=dev) if materialise else None
+                       for _ in range(n_contexts)]
+        self._fork = torch.cuda.Event()
+        self._join = [torch.cuda.Event() for _ in range(n_contexts)]
+        self.kernel_launches_per_scan = 17          # threshold 1, closing 2, ccl 8, stats 5, materialise 1
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+
+    def _fork_streams(self):
+        cur = torch.cuda.current_stream(self.device)
+        self._fork.record(cur)
+        for s in self.streams:
+            s.wait_event(self._fork)
+        return cur
+
+    def _join_streams(self, cur):
+        for s, e in zip(self.streams, self._join):
+            e.record(s)
+            cur.wait_event(e)
+
+    def run(self, volumes: Sequence[torch.Tensor], spacing, origin, direction=IDENTITY,
+            params: Optional[DetectParams] = None) -> List[DetectionResult]:
+        """Device-resident scans in, marker tables out (mask + label volumes are materialised into the
+        pool's buffers, as the reference's `closed` / `labeled` temporaries are)."""
+        cur = self._fork_streams()
+        n, k = len(volumes), len(self.ctxs)
+        results: List[Optional[DetectionResult]] = [None] * n
+        for i, v in enumerate(volumes):
+            j = i % k
+            if i >= k:
+                results[i - k] = self.ctxs[j].collect()
+            self.ctxs[j].detect_async(v, spacing=spacing, origin=origin, direction=direction, params=params,
+                                      out_mask=self.masks[j], out_labels=self.labels[j], stream=self.streams[j])
+        for i in range(max(0, n - k), n):
+            results[i] = self.ctxs[i % k].collect()
+        self._join_streams(cur)
+        return results
+
+    def run_host(self, volumes: Sequence, spacing, origin, direction=IDENTITY, params: Optional[DetectParams] = None,
+                 body_out: Optional[Sequence] = None) -> List[DetectionResult]:
+        """Host buffers in (pinned CPU tensors / numpy), marker tables + optional host body masks out: the
+        drop-in call, with the H2D copy of scan i+1 overlapping the kernels and D2H of scan i."""
+        cur = self._fork_streams()
+        n, k = len(volumes), len(self.ctxs)
+        results: List[Optional[DetectionResult]] = [None] * n
+        for i, v in enumerate(volumes):
+            j = i % k
+            if i >= k:
+                results[i - k] = self.ctxs[j].collect()
+            self.ctxs[j].detect_host_async(v, spacing=spacing, origin=origin, direction=direction, params=params,
+                                           body_out=body_out[i] if body_out is not None else None,
+                                           stream=self.streams[j])
+        for i in range(max(0, n - k), n):
+            results[i] = self.ctxs[i % k].collect()
+        self._join_streams(cur)
+        return results
