@@ -65,7 +65,7 @@ extern "C" const char* mamri_last_error(const mamri_ctx* ctx) { return ctx ? ctx
 extern "C" int mamri_destroy(mamri_ctx* ctx) {
     if (!ctx) return MAMRI_OK;
     DeviceGuard g(ctx->device);
-    cudaFree(ctx->d_raw); cudaFree(ctx->d_dil); cudaFree(ctx->d_closed); cudaFree(ctx->d_word_base);
+    cudaFree(ctx->d_raw); cudaFree(ctx->d_planes); cudaFree(ctx->d_dil); cudaFree(ctx->d_closed); cudaFree(ctx->d_word_base);
     cudaFree(ctx->d_parent); cudaFree(ctx->d_run_label); cudaFree(ctx->d_label_count); cudaFree(ctx->d_label_slot);
     cudaFree(ctx->d_block_sums); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
     cudaFree(ctx->d_summary); cudaFree(ctx->d_scalars); cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
@@ -111,7 +111,12 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     ctx->max_markers = max_markers;
     const size_t W = (size_t(max_nx) + 31) / 32;
     ctx->cap_words = W * max_ny * max_nz;
-    ctx->cap_pad_words = (W + 2) * (size_t(max_ny) + 2 * MAMRI_RMAX) * (size_t(max_nz) + 2 * MAMRI_RMAX);
+    ctx->cap_pad_words = (W + 2) * (size_t(max_ny) + 4 * MAMRI_RMAX) * (size_t(max_nz) + 4 * MAMRI_RMAX);
+    if (3 * ctx->cap_pad_words >= (1ull << 32)) {
+        snprintf(g_create_err, sizeof(g_create_err), "volume too large for 32-bit word indexing");
+        delete ctx;
+        return MAMRI_ERR_INVALID_ARG;
+    }
     DeviceGuard g(device);
     auto bail = [&](cudaError_t e, const char* what) {
         snprintf(g_create_err, sizeof(g_create_err), "allocating %s failed: %s", what, cudaGetErrorString(e));
@@ -120,7 +125,8 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     };
     cudaError_t e;
 #define ALLOC(ptr, bytes, what) if ((e = cudaMalloc((void**)&(ptr), (bytes))) != cudaSuccess) return bail(e, what)
-    ALLOC(ctx->d_raw, ctx->cap_words * 4, "raw mask");
+    ALLOC(ctx->d_raw, ctx->cap_pad_words * 4, "raw mask");
+    ALLOC(ctx->d_planes, 3 * ctx->cap_pad_words * 4, "morphology planes");
     ALLOC(ctx->d_dil, ctx->cap_pad_words * 4, "dilated mask");
     ALLOC(ctx->d_closed, ctx->cap_words * 4, "closed mask");
     ALLOC(ctx->d_word_base, ctx->cap_words * 4, "run bases");
@@ -192,13 +198,10 @@ extern "C" int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc,
     const bool prof = ctx->profile;
     CK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(DevScalars), s));
     if (prof) CK(cudaEventRecord(ctx->ev[0], s));
-    CK(launch_threshold_pack(d_volume, desc->dtype, nx, ny, nz, params->lower, params->upper, ctx->d_raw, s));
+    CK(launch_threshold_pack(ctx, d_volume, desc->dtype, nx, ny, nz, params->lower, params->upper, params->close_radius, s));
     if (prof) CK(cudaEventRecord(ctx->ev[1], s));
-    const uint32_t* mask = ctx->d_raw;
-    if (params->close_radius > 0) {
-        CK(launch_closing(ctx, nx, ny, nz, params->close_radius, s));
-        mask = ctx->d_closed;
-    }
+    const uint32_t* mask = ctx->d_closed;
+    if (params->close_radius > 0) CK(launch_closing(ctx, nx, ny, nz, params->close_radius, s));
     if (prof) CK(cudaEventRecord(ctx->ev[2], s));
     CK(launch_ccl(ctx, mask, nx, ny, nz, params->connectivity, s));
     if (prof) CK(cudaEventRecord(ctx->ev[3], s));

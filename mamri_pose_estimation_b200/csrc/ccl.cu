@@ -61,9 +61,9 @@ __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* ws) {
     return t;   // valid in warp 0
 }
 
-__device__ __forceinline__ void chunk_of(size_t n, size_t& begin, size_t& end) {
-    size_t chunk = (n + gridDim.x - 1) / gridDim.x;
-    begin = size_t(blockIdx.x) * chunk;
+__device__ __forceinline__ void chunk_of(uint32_t n, uint32_t& begin, uint32_t& end) {
+    uint32_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    begin = uint32_t(blockIdx.x) * chunk;
     end = begin + chunk < n ? begin + chunk : n;
     if (begin > n) begin = n;
 }
@@ -71,13 +71,13 @@ __device__ __forceinline__ void chunk_of(size_t n, size_t& begin, size_t& end) {
 // ------------------------------------------------------------------------------------------------
 // run numbering: exclusive scan of run starts per word (3 small launches)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS) k_runs_count(const uint32_t* __restrict__ mask, int W, size_t n_words,
+__global__ void __launch_bounds__(SCAN_THREADS) k_runs_count(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
                                                              uint32_t* __restrict__ block_sums) {
     __shared__ uint32_t ws[33];
-    size_t begin, end;
+    uint32_t begin, end;
     chunk_of(n_words, begin, end);
     uint32_t sum = 0;
-    for (size_t i = begin + threadIdx.x; i < end; i += SCAN_THREADS) {
+    for (uint32_t i = begin + threadIdx.x; i < end; i += SCAN_THREADS) {
         uint32_t m = mask[i];
         if (m) {
             uint32_t prev = (i % W) ? mask[i - 1] : 0u;
@@ -103,16 +103,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(uint32_t* __rest
     }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_runs_assign(const uint32_t* __restrict__ mask, int W, size_t n_words,
+__global__ void __launch_bounds__(SCAN_THREADS) k_runs_assign(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
                                                               const uint32_t* __restrict__ block_sums,
                                                               uint32_t* __restrict__ word_base, const DevScalars* sc) {
     __shared__ uint32_t ws[33];
     if (sc->status != MAMRI_OK) return;
-    size_t begin, end;
+    uint32_t begin, end;
     chunk_of(n_words, begin, end);
     uint32_t running = block_sums[blockIdx.x];
-    for (size_t i0 = begin; i0 < end; i0 += SCAN_THREADS) {
-        size_t i = i0 + threadIdx.x;
+    for (uint32_t i0 = begin; i0 < end; i0 += SCAN_THREADS) {
+        uint32_t i = i0 + threadIdx.x;
         uint32_t starts = 0;
         if (i < end) {
             uint32_t m = mask[i];
@@ -163,7 +163,7 @@ __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t 
 template <bool DIAG>
 __device__ __forceinline__ void join_row(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
                                          uint32_t* parent, uint32_t id_off, int W, int xw, uint32_t m, uint32_t m_prev,
-                                         uint32_t base_m, uint32_t starts_m, size_t ni) {
+                                         uint32_t base_m, uint32_t starts_m, uint32_t ni) {
     const uint32_t up = mask[ni];
     const uint32_t up_prev = xw > 0 ? mask[ni - 1] : 0u;
     const uint32_t up_next = (DIAG && xw + 1 < W) ? mask[ni + 1] : 0u;
@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
     __shared__ uint32_t sp[SLICE_SMEM_RUNS];
     if (sc->status != MAMRI_OK) return;
     const int z = blockIdx.x;
-    const size_t slice_words = size_t(W) * ny;
-    const size_t w0 = size_t(z) * slice_words;
+    const uint32_t slice_words = uint32_t(W) * ny;
+    const uint32_t w0 = uint32_t(z) * slice_words;
     const uint32_t r0 = word_base[w0];
     const uint32_t r1 = (z + 1 < nz) ? word_base[w0 + slice_words] : sc->n_runs;
     const uint32_t n = r1 - r0;
@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
     uint32_t* P = (n <= SLICE_SMEM_RUNS) ? sp : parent + r0;
     for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) P[i] = i;
     __syncthreads();
-    for (size_t i = size_t(W) + threadIdx.x; i < slice_words; i += SLICE_THREADS) {     // rows y >= 1
-        const size_t wi = w0 + i;
+    for (uint32_t i = uint32_t(W) + threadIdx.x; i < slice_words; i += SLICE_THREADS) {     // rows y >= 1
+        const uint32_t wi = w0 + i;
         const uint32_t m = mask[wi];
         if (!m) continue;
         const int xw = int(i % W);
@@ -250,17 +250,17 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
 // then the boundaries between blocks (again <= radix of them per chain).
 template <bool CONN26>
 __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
-                                                 uint32_t* parent, int W, int ny, int nz, size_t n_words, int radix,
+                                                 uint32_t* parent, int W, int ny, int nz, uint32_t n_words, int radix,
                                                  int between_blocks, const DevScalars* sc) {
     if (sc->status != MAMRI_OK) return;
-    const size_t slice = size_t(W) * ny;
-    for (size_t wi = slice + size_t(blockIdx.x) * blockDim.x + threadIdx.x; wi < n_words;
-         wi += size_t(gridDim.x) * blockDim.x) {
+    const uint32_t slice = uint32_t(W) * ny;
+    for (uint32_t wi = slice + uint32_t(blockIdx.x) * blockDim.x + threadIdx.x; wi < n_words;
+         wi += uint32_t(gridDim.x) * blockDim.x) {
         const int z = int(wi / slice);
         if (((z % radix) == 0) != (between_blocks != 0)) continue;
         const uint32_t m = mask[wi];
         if (!m) continue;
-        const size_t row = wi / W;
+        const uint32_t row = wi / W;
         const int xw = int(wi - row * W);
         const int y = int(row % ny);
         const uint32_t m_prev = xw > 0 ? mask[wi - 1] : 0u;
@@ -280,10 +280,10 @@ __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ ma
 __global__ void __launch_bounds__(SCAN_THREADS) k_flatten_count(uint32_t* parent, uint32_t* __restrict__ block_sums,
                                                                 const DevScalars* sc) {
     __shared__ uint32_t ws[33];
-    size_t begin, end;
+    uint32_t begin, end;
     chunk_of(sc->n_runs, begin, end);
     uint32_t roots = 0;
-    for (size_t r = begin + threadIdx.x; r < end; r += SCAN_THREADS) {
+    for (uint32_t r = begin + threadIdx.x; r < end; r += SCAN_THREADS) {
         uint32_t x = uint32_t(r), p = parent[x];
         while (p != x) { x = p; p = parent[x]; }
         parent[r] = x;
@@ -298,11 +298,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_rank_roots(const uint32_t* __r
                                                              uint32_t* __restrict__ run_label,
                                                              uint32_t* __restrict__ label_count, const DevScalars* sc) {
     __shared__ uint32_t ws[33];
-    size_t begin, end;
+    uint32_t begin, end;
     chunk_of(sc->n_runs, begin, end);
     uint32_t running = block_sums[blockIdx.x];
-    for (size_t i0 = begin; i0 < end; i0 += SCAN_THREADS) {
-        size_t r = i0 + threadIdx.x;
+    for (uint32_t i0 = begin; i0 < end; i0 += SCAN_THREADS) {
+        uint32_t r = i0 + threadIdx.x;
         uint32_t is_root = (r < end && parent[r] == uint32_t(r)) ? 1u : 0u, total;
         uint32_t rank = running + block_excl_scan(is_root, ws, total);
         if (is_root) {
@@ -315,8 +315,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_rank_roots(const uint32_t* __r
 
 __global__ void __launch_bounds__(256) k_propagate_labels(const uint32_t* __restrict__ parent, uint32_t* run_label,
                                                           const DevScalars* sc) {
-    const size_t n = sc->n_runs;
-    for (size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += size_t(gridDim.x) * blockDim.x) {
+    const uint32_t n = sc->n_runs;
+    for (uint32_t r = uint32_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += uint32_t(gridDim.x) * blockDim.x) {
         uint32_t p = parent[r];
         if (p != uint32_t(r)) run_label[r] = run_label[p];   // roots were written by k_rank_roots
     }
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256) k_propagate_labels(const uint32_t* __rest
 
 cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int connectivity, cudaStream_t s) {
     const int W = (nx + 31) / 32;
-    const size_t n_words = size_t(W) * ny * nz;
+    const uint32_t n_words = uint32_t(W) * ny * nz;
     const int G = MAMRI_SCAN_CTAS;
     uint32_t* bs_runs = c->d_block_sums;
     uint32_t* bs_roots = c->d_block_sums + 1024;
@@ -333,7 +333,7 @@ cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int
     k_runs_assign<<<G, SCAN_THREADS, 0, s>>>(d_mask, W, n_words, bs_runs, c->d_word_base, c->d_scalars);
     int radix = 1;
     while (radix * radix < nz) radix <<= 1;
-    size_t ub = (n_words + 255) / 256;
+    uint32_t ub = (n_words + 255) / 256;
     if (ub > 148 * 16) ub = 148 * 16;
     if (ub == 0) ub = 1;
     if (connectivity == 26) {
@@ -362,19 +362,19 @@ template <bool ALIGNED>
 __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict__ mask,
                                                      const uint32_t* __restrict__ word_base,
                                                      const uint32_t* __restrict__ run_label, int nx, int W,
-                                                     size_t n_words, uint8_t* __restrict__ mask_out,
+                                                     uint32_t n_words, uint8_t* __restrict__ mask_out,
                                                      uint32_t* __restrict__ labels_out, uint8_t* __restrict__ body_out,
                                                      const DevScalars* sc) {
     const bool ok = sc->status == MAMRI_OK;
     const uint32_t body = body_out ? (0xFFFFFFFFu - uint32_t(sc->body_packed & 0xFFFFFFFFull)) : 0u;
     const bool has_body = body_out && (sc->body_packed >> 32) != 0;
     const unsigned lane = lane_id();
-    const size_t warp = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    const uint32_t warp = (uint32_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (uint32_t(gridDim.x) * blockDim.x) >> 5;
     const bool need_labels = (labels_out != nullptr) || (body_out != nullptr);
     if (ALIGNED) {
-        for (size_t w0 = warp * 4; w0 < n_words; w0 += n_warps * 4) {
-            const size_t wi = w0 + (lane >> 3);
+        for (uint32_t w0 = warp * 4; w0 < n_words; w0 += n_warps * 4) {
+            const uint32_t wi = w0 + (lane >> 3);
             if (wi >= n_words) continue;
             const int sub = int(lane & 7u) * 4;
             const uint32_t m = mask[wi];
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict_
                     }
                 }
             }
-            const size_t v = wi * 32 + sub;
+            const uint32_t v = wi * 32 + sub;
             if (labels_out) *reinterpret_cast<uint4*>(labels_out + v) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
             if (mask_out) {
                 uint32_t mb = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
@@ -410,8 +410,8 @@ __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict_
             }
         }
     } else {
-        for (size_t wi = warp; wi < n_words; wi += n_warps) {
-            const size_t row = wi / W;
+        for (uint32_t wi = warp; wi < n_words; wi += n_warps) {
+            const uint32_t row = wi / W;
             const int xw = int(wi - row * W);
             const int x = xw * 32 + int(lane);
             if (x >= nx) continue;
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict_
                 const uint32_t prev = xw > 0 ? mask[wi - 1] : 0u;
                 lab = run_label[run_id_in_word(word_base[wi], run_starts(m, prev), int(lane))];
             }
-            const size_t v = row * size_t(nx) + x;
+            const uint32_t v = row * uint32_t(nx) + x;
             if (labels_out) labels_out[v] = lab;
             if (mask_out) mask_out[v] = on ? 1 : 0;
             if (body_out) body_out[v] = (has_body && lab == body) ? 1 : 0;
@@ -434,18 +434,18 @@ cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int
                                uint32_t* d_labels_out, uint8_t* d_body_out, cudaStream_t s) {
     if (!d_mask_out && !d_labels_out && !d_body_out) return cudaSuccess;
     const int W = (nx + 31) / 32;
-    const size_t n_words = size_t(W) * ny * nz;
+    const uint32_t n_words = uint32_t(W) * ny * nz;
     const bool aligned = (nx % 32 == 0) && ((reinterpret_cast<uintptr_t>(d_labels_out) & 15u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_mask_out) & 3u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_body_out) & 3u) == 0);
     if (aligned) {
-        size_t blocks = (n_words / 4 + 7) / 8;
+        uint32_t blocks = (n_words / 4 + 7) / 8;
         if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
         if (blocks == 0) blocks = 1;
         k_materialise<true><<<unsigned(blocks), 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, nx, W, n_words,
                                                              d_mask_out, d_labels_out, d_body_out, c->d_scalars);
     } else {
-        size_t blocks = (n_words + 7) / 8;
+        uint32_t blocks = (n_words + 7) / 8;
         if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
         if (blocks == 0) blocks = 1;
         k_materialise<false><<<unsigned(blocks), 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, nx, W, n_words,

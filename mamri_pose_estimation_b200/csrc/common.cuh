@@ -35,9 +35,11 @@ struct mamri_ctx {
     size_t cap_words, cap_pad_words;
 
     // scratch (device)
-    uint32_t* d_raw;        // thresholded mask, bit-packed            [cap_words]
-    uint32_t* d_dil;        // dilation on the r-grown domain           [cap_pad_words]
-    uint32_t* d_closed;     // closed mask, bit-packed                  [cap_words]
+    uint32_t* d_raw;        // thresholded mask, bit-packed, zero-apron padded layout   [cap_pad_words]
+    uint32_t* d_planes;     // morphology pass-A planes (x-z part of the ball)          [3 * cap_pad_words]
+    uint32_t* d_dil;        // dilation on the r-grown domain, padded layout            [cap_pad_words]
+    uint32_t* d_closed;     // closed mask, bit-packed [nz][ny][W]                      [cap_words]
+    int raw_nx, raw_ny, raw_nz, raw_r;   // geometry d_raw's zero apron was last cleared for
     uint32_t* d_word_base;  // runs that start before each word         [cap_words]
     uint32_t* d_parent;     // union-find over runs                     [max_runs]
     uint32_t* d_run_label;  // final label of each run                  [max_runs]
@@ -78,8 +80,8 @@ struct mamri_ctx {
 };
 
 // ---- stage launchers (each enqueues on `s`; returns cudaError_t) -------------------------------
-cudaError_t launch_threshold_pack(const void* d_vol, int dtype, int nx, int ny, int nz, double lo, double hi,
-                                  uint32_t* d_bits, cudaStream_t s);
+cudaError_t launch_threshold_pack(mamri_ctx* c, const void* d_vol, int dtype, int nx, int ny, int nz, double lo,
+                                  double hi, int radius, cudaStream_t s);
 cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s);
 cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int connectivity, cudaStream_t s);
 cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volume_desc* desc,

@@ -1,15 +1,31 @@
 // Stage 1: intensity threshold -> bit-packed mask, and binary closing with ITK's ball on the
 // bit-packed mask.  Replaces sitk.BinaryThreshold + sitk.BinaryMorphologicalClosing at
 // Mamri/Mamri.py:1308.  HBM-bound: the voxel volume is read exactly once with 128-bit loads; all
-// morphology runs on 1 bit/voxel data (L2-resident) with shared-memory halo tiles.
+// morphology runs on 1 bit/voxel data that stays L2-resident.
 #include "common.cuh"
 
 #include <limits>
 #include <math.h>
+#include <type_traits>
 
 // ------------------------------------------------------------------------------------------------
 // threshold + pack
 // ------------------------------------------------------------------------------------------------
+// Where the packed words go: either the plain [nz][ny][W] mask, or the interior of the zero-apron
+// padded volume the closing reads (row/slice strides and a start offset).
+struct BitDst {
+    uint32_t* p;
+    uint32_t W, ny;
+    uint32_t row_stride, slice_stride, off;
+    bool linear;
+    __device__ __forceinline__ uint32_t index(uint32_t i) const {
+        if (linear) return i;
+        const uint32_t row = i / W, xw = i - row * W;
+        const uint32_t z = row / ny, y = row - z * ny;
+        return off + z * slice_stride + y * row_stride + xw;
+    }
+};
+
 template <typename T>
 __device__ __forceinline__ bool in_range(T v, T lo, T hi) { return v >= lo && v <= hi; }  // NaN -> false
 
@@ -20,23 +36,23 @@ __device__ __forceinline__ uint4 ld_stream_128(const uint4* p) {
     return r;
 }
 
-// Fast path: nx % 32 == 0 and 16-byte aligned base, so the packed mask is one flat bit array.
+// Fast path: nx % 32 == 0 and 16-byte aligned base, so the voxels of one mask word are contiguous.
 // A warp load instruction covers 512 contiguous bytes; each lane turns its 16 bytes into E bits and
 // 32/E neighbouring lanes are merged into one 32-voxel word by shuffles.
 template <typename T, int UNROLL>
-__global__ void __launch_bounds__(256) k_threshold_pack_flat(const uint4* __restrict__ vol, size_t n_vec, T lo, T hi,
-                                                             uint32_t* __restrict__ bits) {
+__global__ void __launch_bounds__(256) k_threshold_pack_flat(const uint4* __restrict__ vol, uint32_t n_vec, T lo, T hi,
+                                                             BitDst dst) {
     constexpr int E = 16 / sizeof(T);   // voxels per 128-bit load
     constexpr int G = 32 / E;           // lanes per output word
     const unsigned lane = lane_id();
-    const size_t warp = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
-    for (size_t base = warp * (UNROLL * 32); base < n_vec; base += n_warps * (UNROLL * 32)) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp * (UNROLL * 32); base < n_vec; base += n_warps * (UNROLL * 32)) {
         uint4 v[UNROLL];
         bool ok[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            size_t i = base + u * 32 + lane;
+            const uint32_t i = base + u * 32 + lane;
             ok[u] = i < n_vec;
             v[u] = ok[u] ? ld_stream_128(vol + i) : make_uint4(0, 0, 0, 0);
         }
@@ -50,25 +66,25 @@ __global__ void __launch_bounds__(256) k_threshold_pack_flat(const uint4* __rest
             if (!ok[u]) b = 0;
 #pragma unroll
             for (int s = 1; s < G; s <<= 1) b |= __shfl_down_sync(0xFFFFFFFFu, b, s) << (E * s);
-            size_t i = base + u * 32 + lane;
-            if (ok[u] && (lane % G) == 0) bits[i / G] = b;
+            const uint32_t i = base + u * 32 + lane;
+            if (ok[u] && (lane % G) == 0) dst.p[dst.index(i / G)] = b;
         }
     }
 }
 
 // General path (ragged nx or unaligned base): one warp per output word, one voxel per lane.
 template <typename T>
-__global__ void __launch_bounds__(256) k_threshold_pack_rows(const T* __restrict__ vol, int nx, int W, size_t n_words,
-                                                             T lo, T hi, uint32_t* __restrict__ bits) {
+__global__ void __launch_bounds__(256) k_threshold_pack_rows(const T* __restrict__ vol, uint32_t nx, uint32_t n_words,
+                                                             T lo, T hi, BitDst dst) {
     const unsigned lane = lane_id();
-    const size_t warp = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
-    for (size_t wi = warp; wi < n_words; wi += n_warps) {
-        size_t row = wi / W;
-        int x = int(wi - row * W) * 32 + int(lane);
-        bool p = x < nx && in_range(vol[row * size_t(nx) + x], lo, hi);
-        uint32_t b = __ballot_sync(0xFFFFFFFFu, p);
-        if (lane == 0) bits[wi] = b;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t wi = warp; wi < n_words; wi += n_warps) {
+        const uint32_t row = wi / dst.W;
+        const uint32_t x = (wi - row * dst.W) * 32 + lane;
+        const bool p = x < nx && in_range(vol[size_t(row) * nx + x], lo, hi);
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, p);
+        if (lane == 0) dst.p[dst.index(wi)] = b;
     }
 }
 
@@ -87,43 +103,72 @@ template <>
 float cast_bound<float>(double v) { return float(v); }
 
 template <typename T>
-static cudaError_t threshold_pack_t(const void* d_vol, int nx, int ny, int nz, double lo, double hi, uint32_t* d_bits,
+static cudaError_t threshold_pack_t(const void* d_vol, int nx, int ny, int nz, double lo, double hi, BitDst dst,
                                     cudaStream_t s) {
-    const size_t rows = size_t(ny) * nz;
-    const int W = (nx + 31) / 32;
-    const size_t n_words = rows * W;
+    const uint32_t rows = uint32_t(ny) * nz;
+    const uint32_t n_words = rows * dst.W;
     const T tlo = cast_bound<T>(lo), thi = cast_bound<T>(hi);
     const bool flat = (nx % 32 == 0) && ((reinterpret_cast<uintptr_t>(d_vol) & 15u) == 0);
     if (flat) {
         constexpr int E = 16 / sizeof(T);
         constexpr int UNROLL = 4;
-        const size_t n_vec = rows * size_t(nx) / E;
-        size_t warps = (n_vec + UNROLL * 32 - 1) / (UNROLL * 32);
-        size_t blocks = (warps + 7) / 8;
-        const size_t cap = 148 * 8 * 4;           // a few waves of 8 resident CTAs per SM
+        const uint32_t n_vec = uint32_t(size_t(rows) * nx / E);
+        uint32_t warps = (n_vec + UNROLL * 32 - 1) / (UNROLL * 32);
+        uint32_t blocks = (warps + 7) / 8;
+        const uint32_t cap = 148 * 8 * 4;           // a few waves of 8 resident CTAs per SM
         if (blocks > cap) blocks = cap;
         if (blocks == 0) blocks = 1;
-        k_threshold_pack_flat<T, UNROLL><<<unsigned(blocks), 256, 0, s>>>(static_cast<const uint4*>(d_vol), n_vec, tlo,
-                                                                         thi, d_bits);
+        k_threshold_pack_flat<T, UNROLL><<<blocks, 256, 0, s>>>(static_cast<const uint4*>(d_vol), n_vec, tlo, thi, dst);
     } else {
-        size_t blocks = (n_words + 7) / 8;
-        const size_t cap = 148 * 8 * 8;
+        uint32_t blocks = (n_words + 7) / 8;
+        const uint32_t cap = 148 * 8 * 8;
         if (blocks > cap) blocks = cap;
         if (blocks == 0) blocks = 1;
-        k_threshold_pack_rows<T><<<unsigned(blocks), 256, 0, s>>>(static_cast<const T*>(d_vol), nx, W, n_words, tlo, thi,
-                                                                  d_bits);
+        k_threshold_pack_rows<T><<<blocks, 256, 0, s>>>(static_cast<const T*>(d_vol), uint32_t(nx), n_words, tlo, thi, dst);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_threshold_pack(const void* d_vol, int dtype, int nx, int ny, int nz, double lo, double hi,
-                                  uint32_t* d_bits, cudaStream_t s) {
+// Geometry of the padded bit volumes of one closing: 1 pad word on each side of a row, 2R pad rows and
+// slices on each side (R for the dilation's apron + R for the reach of the ball from there).
+struct PadGeom {
+    uint32_t W, Wp, Hp, Dp, slice, words;
+    __host__ PadGeom(int nx, int ny, int nz, int R) {
+        W = uint32_t(nx + 31) / 32;
+        Wp = W + 2; Hp = uint32_t(ny + 4 * R); Dp = uint32_t(nz + 4 * R);
+        slice = Wp * Hp;
+        words = slice * Dp;
+    }
+};
+
+cudaError_t launch_threshold_pack(mamri_ctx* c, const void* d_vol, int dtype, int nx, int ny, int nz, double lo,
+                                  double hi, int radius, cudaStream_t s) {
+    BitDst dst;
+    dst.W = uint32_t(nx + 31) / 32;
+    dst.ny = uint32_t(ny);
+    if (radius == 0) {                       // no closing: straight into the mask the labelling reads
+        dst.p = c->d_closed;
+        dst.row_stride = dst.W; dst.slice_stride = dst.W * dst.ny; dst.off = 0; dst.linear = true;
+    } else {
+        const PadGeom g(nx, ny, nz, radius);
+        // the apron of the padded raw mask must be zero; it is never written, so clear it only when the
+        // geometry changes
+        if (c->raw_nx != nx || c->raw_ny != ny || c->raw_nz != nz || c->raw_r != radius) {
+            cudaError_t e = cudaMemsetAsync(c->d_raw, 0, size_t(g.words) * 4, s);
+            if (e != cudaSuccess) return e;
+            c->raw_nx = nx; c->raw_ny = ny; c->raw_nz = nz; c->raw_r = radius;
+        }
+        dst.p = c->d_raw;
+        dst.row_stride = g.Wp; dst.slice_stride = g.slice;
+        dst.off = uint32_t(2 * radius) * g.slice + uint32_t(2 * radius) * g.Wp + 1;
+        dst.linear = false;
+    }
     switch (dtype) {
-        case MAMRI_U8:  return threshold_pack_t<uint8_t>(d_vol, nx, ny, nz, lo, hi, d_bits, s);
-        case MAMRI_I16: return threshold_pack_t<int16_t>(d_vol, nx, ny, nz, lo, hi, d_bits, s);
-        case MAMRI_U16: return threshold_pack_t<uint16_t>(d_vol, nx, ny, nz, lo, hi, d_bits, s);
-        case MAMRI_I32: return threshold_pack_t<int32_t>(d_vol, nx, ny, nz, lo, hi, d_bits, s);
-        case MAMRI_F32: return threshold_pack_t<float>(d_vol, nx, ny, nz, lo, hi, d_bits, s);
+        case MAMRI_U8:  return threshold_pack_t<uint8_t>(d_vol, nx, ny, nz, lo, hi, dst, s);
+        case MAMRI_I16: return threshold_pack_t<int16_t>(d_vol, nx, ny, nz, lo, hi, dst, s);
+        case MAMRI_U16: return threshold_pack_t<uint16_t>(d_vol, nx, ny, nz, lo, hi, dst, s);
+        case MAMRI_I32: return threshold_pack_t<int32_t>(d_vol, nx, ny, nz, lo, hi, dst, s);
+        case MAMRI_F32: return threshold_pack_t<float>(d_vol, nx, ny, nz, lo, hi, dst, s);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -133,104 +178,162 @@ cudaError_t launch_threshold_pack(const void* d_vol, int dtype, int nx, int ny, 
 // ------------------------------------------------------------------------------------------------
 // ITK's ball of radius R (FlatStructuringElement::Ball, radiusIsParametric = false) is
 // {d : dx^2+dy^2+dz^2 <= R^2+R}.  On bit-packed rows it is, for every (dy,dz) with
-// dy^2+dz^2 <= R^2+R, an x-interval of half-width h = floor(sqrt(R^2+R-dy^2-dz^2)).  With
-// S_h(row) = the row dilated (eroded) along x by h (funnel shifts over three neighbouring words),
-//   P_a(y, z') = OP_{dy} S_{h(dy,a)}(y+dy, z')          (the in-slice part for |dz| = a)
-//   out(y, z)  = OP_{dz} P_|dz|(y, z+dz)                 (OP = OR for dilation, AND for erosion).
-// A thread owns one output word column (xw, y) over a chunk of ZC slices and slides a register
-// window of P values along z: every step loads (2R+1) rows x 3 words of ONE new slice (coalesced,
-// L1-shared with the neighbouring threads), so a source word is loaded ~(2R+1)*3 times per output
-// instead of (2R+1)^2*3 -- no shared memory, no barriers.  The bit volumes are L2-resident (1 bit/voxel).
+// dy^2+dz^2 <= R^2+R, an x-interval of half-width h(dy,dz) = floor(sqrt(R^2+R-dy^2-dz^2)).  With
+// S_h(row) = the row dilated (eroded) along x by h (funnel shifts over three neighbouring words):
+//   pass A   P_a(y', z) = OP_{dz} S_{h(a,dz)}(y', z+dz)      the x-z part of the ball at |dy| = a
+//   pass B   out(y, z)  = OP_{dy} P_|dy|(y+dy, z)              (OP = OR for dilation, AND for erosion)
+// Pass A: a thread owns one word column (xw, y') over a chunk of slices and slides a register window
+// of S values along z, so each source word is loaded once (+ chunk halo) and shifted once; all loads
+// and stores are coalesced along the slice.  Values of a with identical h(a, .) share one plane
+// (for R = 2: a = 0 and 1).  Pass B is 2R+1 coalesced loads per output word.  All volumes share one
+// padded layout with a zero apron, so neither pass has bounds checks, shared memory or barriers.
 __host__ __device__ constexpr int isqrt_c(int v) { int r = 0; while ((r + 1) * (r + 1) <= v) ++r; return r; }
 
-template <int R, bool ERODE>
-__device__ __forceinline__ void slice_patterns(const BitVol& src, int sx, int sy, int sz, uint32_t (&P)[R + 1]) {
-    constexpr int R2 = R * R + R;
-#pragma unroll
-    for (int a = 0; a <= R; ++a) P[a] = ERODE ? 0xFFFFFFFFu : 0u;
-    const bool z_ok = sz >= 0 && sz < src.d;
-#pragma unroll
-    for (int dy = -R; dy <= R; ++dy) {
-        const int y = sy + dy;
-        uint32_t l = 0, c = 0, r = 0;
-        if (z_ok && y >= 0 && y < src.h) {
-            const uint32_t* row = src.p + (size_t(sz) * src.h + y) * src.w;
-            if (sx >= 0 && sx < src.w) c = row[sx];
-            if (sx - 1 >= 0 && sx - 1 < src.w) l = row[sx - 1];
-            if (sx + 1 >= 0 && sx + 1 < src.w) r = row[sx + 1];
-        }
-        uint32_t S[R + 1];
-        S[0] = c;
-#pragma unroll
-        for (int k = 1; k <= R; ++k) {
-            const uint32_t a = (c << k) | (l >> (32 - k)), b = (c >> k) | (r << (32 - k));
-            S[k] = ERODE ? (S[k - 1] & a & b) : (S[k - 1] | a | b);
-        }
-#pragma unroll
-        for (int a = 0; a <= R; ++a) {
-            const int rem = R2 - dy * dy - a * a;
-            if (rem >= 0) P[a] = ERODE ? (P[a] & S[isqrt_c(rem)]) : (P[a] | S[isqrt_c(rem)]);
-        }
+template <int R>
+struct Ball {
+    static constexpr int R2 = R * R + R;
+    __host__ __device__ static constexpr int h(int a, int d) {
+        return (R2 - a * a - d * d) < 0 ? -1 : isqrt_c(R2 - a * a - d * d);
+    }
+    __host__ __device__ static constexpr bool same(int a, int b) {
+        for (int d = -R; d <= R; ++d)
+            if (h(a, d) != h(b, d)) return false;
+        return true;
+    }
+    __host__ __device__ static constexpr int canon(int a) {
+        for (int b = 0; b < a; ++b)
+            if (same(a, b)) return b;
+        return a;
+    }
+    __host__ __device__ static constexpr int plane(int a) {      // index of a's plane among the distinct ones
+        int n = 0;
+        for (int b = 0; b < canon(a); ++b) n += (canon(b) == b) ? 1 : 0;
+        return n;
+    }
+    __host__ __device__ static constexpr int n_planes() {
+        int n = 0;
+        for (int b = 0; b <= R; ++b) n += (canon(b) == b) ? 1 : 0;
+        return n;
+    }
+};
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
+template <int B, int E, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
     }
 }
 
 template <int R, bool ERODE>
-__global__ void __launch_bounds__(256) k_morph_sweep(BitVol src, BitVol dst, int ox, int oy, int oz, uint32_t tail_mask,
-                                                     int zc, int n_chunks) {
-    // src coordinate = dst coordinate + (ox, oy, oz)  (words, rows, slices)
-    const size_t per_chunk = size_t(dst.w) * dst.h;
-    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void load_shifted(const uint32_t* __restrict__ p, bool has_l, bool has_r, uint32_t (&S)[R + 1]) {
+    const uint32_t c = p[0];
+    const uint32_t l = has_l ? p[-1] : 0u, r = has_r ? p[1] : 0u;
+    S[0] = c;
+#pragma unroll
+    for (int k = 1; k <= R; ++k) {
+        const uint32_t a = (c << k) | (l >> (32 - k)), b = (c >> k) | (r << (32 - k));
+        S[k] = ERODE ? (S[k - 1] & a & b) : (S[k - 1] | a | b);
+    }
+}
+
+template <int R, bool ERODE>
+__global__ void __launch_bounds__(256) k_morph_planes(const uint32_t* __restrict__ src, uint32_t* __restrict__ planes,
+                                                      uint32_t Wp, uint32_t slice, uint32_t words, uint32_t y_lo,
+                                                      uint32_t y_cnt, uint32_t z_lo, uint32_t z_hi, uint32_t zc,
+                                                      uint32_t n_chunks) {
+    const uint32_t per_chunk = Wp * y_cnt;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= per_chunk * n_chunks) return;
-    const int chunk = int(t / per_chunk);
-    const size_t in_slice = t - size_t(chunk) * per_chunk;
-    const int y = int(in_slice / dst.w), x = int(in_slice - size_t(y) * dst.w);
-    const int z0 = chunk * zc, z1 = min(z0 + zc, dst.d);
-    const int sx = x + ox, sy = y + oy;
-    uint32_t win[2 * R + 1][R + 1];                 // win[j] = patterns of source slice (z + oz) - R + j
+    const uint32_t chunk = t / per_chunk, rem = t - chunk * per_chunk;
+    const uint32_t yy = rem / Wp, xw = rem - yy * Wp;
+    const uint32_t row_off = (y_lo + yy) * Wp + xw;
+    const uint32_t z0 = z_lo + chunk * zc, z1 = min(z0 + zc, z_hi);
+    const bool has_l = xw > 0, has_r = xw + 1 < Wp;
+    uint32_t S[2 * R + 1][R + 1];                   // S[j] = shifted rows of slice z - R + j
 #pragma unroll
-    for (int j = 0; j < 2 * R; ++j) slice_patterns<R, ERODE>(src, sx, sy, z0 + oz - R + j, win[j]);
-    const uint32_t tm = (x == dst.w - 1) ? tail_mask : 0xFFFFFFFFu;
-    for (int z = z0; z < z1; ++z) {
-        slice_patterns<R, ERODE>(src, sx, sy, z + oz + R, win[2 * R]);
-        uint32_t acc = ERODE ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-        for (int dz = -R; dz <= R; ++dz) {
-            const uint32_t v = win[dz + R][dz < 0 ? -dz : dz];
-            acc = ERODE ? (acc & v) : (acc | v);
-        }
-        dst.p[(size_t(z) * dst.h + y) * dst.w + x] = acc & tm;
+    for (int j = 0; j < 2 * R; ++j) load_shifted<R, ERODE>(src + (z0 - R + j) * slice + row_off, has_l, has_r, S[j]);
+    for (uint32_t z = z0; z < z1; ++z) {
+        load_shifted<R, ERODE>(src + (z + R) * slice + row_off, has_l, has_r, S[2 * R]);
+        static_for<0, R + 1>([&](auto ia) {
+            constexpr int a = decltype(ia)::value;
+            if constexpr (Ball<R>::canon(a) == a) {
+                uint32_t acc = ERODE ? 0xFFFFFFFFu : 0u;
+                static_for<0, 2 * R + 1>([&](auto id) {
+                    constexpr int dz = decltype(id)::value - R;
+                    constexpr int hh = Ball<R>::h(a, dz);
+                    if constexpr (hh >= 0) acc = ERODE ? (acc & S[dz + R][hh]) : (acc | S[dz + R][hh]);
+                });
+                constexpr uint32_t pl = uint32_t(Ball<R>::plane(a));
+                planes[pl * words + z * slice + row_off] = acc;
+            }
+        });
 #pragma unroll
         for (int j = 0; j < 2 * R; ++j)
 #pragma unroll
-            for (int a = 0; a <= R; ++a) win[j][a] = win[j + 1][a];
+            for (int k = 0; k <= R; ++k) S[j][k] = S[j + 1][k];
     }
 }
 
-template <int R, bool ERODE>
-static cudaError_t morph_launch(BitVol src, BitVol dst, int ox, int oy, int oz, uint32_t tail, cudaStream_t s) {
-    // chunk the z sweep so that the grid has a few hundred thousand threads (148 SMs x 2048)
-    const size_t per_chunk = size_t(dst.w) * dst.h;
-    int zc = 16;
-    while (zc > 4 && per_chunk * ((dst.d + zc - 1) / zc) < size_t(148) * 2048) zc >>= 1;
-    const int n_chunks = (dst.d + zc - 1) / zc;
-    const size_t threads = per_chunk * n_chunks;
-    k_morph_sweep<R, ERODE><<<unsigned((threads + 255) / 256), 256, 0, s>>>(src, dst, ox, oy, oz, tail, zc, n_chunks);
-    return cudaGetLastError();
+// Pass B.  TO_IMAGE = false: writes the padded dilation.  TO_IMAGE = true: writes the plain [nz][ny][W]
+// closed mask (erosion), masking the bits beyond nx in the last word of a row.
+template <int R, bool ERODE, bool TO_IMAGE>
+__global__ void __launch_bounds__(256) k_morph_combine(const uint32_t* __restrict__ planes, uint32_t* __restrict__ dst,
+                                                       uint32_t Wp, uint32_t slice, uint32_t words, uint32_t x_lo,
+                                                       uint32_t x_cnt, uint32_t y_lo, uint32_t y_cnt, uint32_t z_lo,
+                                                       uint32_t z_cnt, uint32_t tail_mask) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= x_cnt * y_cnt * z_cnt) return;
+    const uint32_t row = t / x_cnt, xx = t - row * x_cnt;
+    const uint32_t zz = row / y_cnt, yy = row - zz * y_cnt;
+    const uint32_t idx = (z_lo + zz) * slice + (y_lo + yy) * Wp + (x_lo + xx);
+    uint32_t acc = ERODE ? 0xFFFFFFFFu : 0u;
+    static_for<0, 2 * R + 1>([&](auto id) {
+        constexpr int dy = decltype(id)::value - R;
+        constexpr uint32_t pl = uint32_t(Ball<R>::plane(dy < 0 ? -dy : dy));
+        const uint32_t v = planes[pl * words + idx + uint32_t(dy * int(Wp))];
+        acc = ERODE ? (acc & v) : (acc | v);
+    });
+    if (TO_IMAGE) {
+        if (xx == x_cnt - 1) acc &= tail_mask;
+        dst[t] = acc;                               // (zz * ny + yy) * W + xx == t
+    } else {
+        dst[idx] = acc;
+    }
 }
 
 template <int R>
 static cudaError_t closing_r(mamri_ctx* c, int nx, int ny, int nz, cudaStream_t s) {
-    const int W = (nx + 31) / 32;
-    BitVol raw{c->d_raw, W, ny, nz};
-    BitVol dil{c->d_dil, W + 2, ny + 2 * R, nz + 2 * R};
-    BitVol out{c->d_closed, W, ny, nz};
-    // dilation: padded output coordinate (xw, y, z) reads raw (xw-1, y-R, z-R); reads outside raw are 0
-    cudaError_t e = morph_launch<R, false>(raw, dil, -1, -R, -R, 0xFFFFFFFFu, s);
-    if (e != cudaSuccess) return e;
-    // erosion: image output coordinate (xw, y, z) reads the padded dilation at (xw+1, y+R, z+R); every
-    // read of an image-domain output stays inside the padded volume
+    const PadGeom g(nx, ny, nz, R);
+    auto chunks = [&](uint32_t per_chunk, uint32_t depth, uint32_t& zc, uint32_t& n_chunks) {
+        zc = 16;                                    // keep >= one full wave of threads (148 SMs x 2048)
+        while (zc > 4 && size_t(per_chunk) * ((depth + zc - 1) / zc) < size_t(148) * 2048) zc >>= 1;
+        n_chunks = (depth + zc - 1) / zc;
+    };
+    uint32_t zc, nch;
+    // ---- dilation: P_a on every padded row, slices [R, nz+3R); D on rows [R, ny+3R), same slices
+    const uint32_t dz_lo = R, dz_hi = uint32_t(nz) + 3 * R;
+    chunks(g.Wp * g.Hp, dz_hi - dz_lo, zc, nch);
+    uint32_t threads = g.Wp * g.Hp * nch;
+    k_morph_planes<R, false><<<(threads + 255) / 256, 256, 0, s>>>(c->d_raw, c->d_planes, g.Wp, g.slice, g.words, 0, g.Hp,
+                                                                  dz_lo, dz_hi, zc, nch);
+    const uint32_t dy_cnt = uint32_t(ny) + 2 * R;
+    threads = g.Wp * dy_cnt * (dz_hi - dz_lo);
+    k_morph_combine<R, false, false><<<(threads + 255) / 256, 256, 0, s>>>(c->d_planes, c->d_dil, g.Wp, g.slice, g.words, 0,
+                                                                           g.Wp, R, dy_cnt, dz_lo, dz_hi - dz_lo,
+                                                                           0xFFFFFFFFu);
+    // ---- erosion: P_a on rows [R, ny+3R), image slices [2R, nz+2R); E on the image domain
+    const uint32_t ez_lo = 2 * R, ez_hi = uint32_t(nz) + 2 * R;
+    chunks(g.Wp * dy_cnt, ez_hi - ez_lo, zc, nch);
+    threads = g.Wp * dy_cnt * nch;
+    k_morph_planes<R, true><<<(threads + 255) / 256, 256, 0, s>>>(c->d_dil, c->d_planes, g.Wp, g.slice, g.words, R, dy_cnt,
+                                                                 ez_lo, ez_hi, zc, nch);
     const uint32_t tail = (nx % 32) ? (0xFFFFFFFFu >> (32 - nx % 32)) : 0xFFFFFFFFu;
-    return morph_launch<R, true>(dil, out, 1, R, R, tail, s);
+    threads = g.W * uint32_t(ny) * uint32_t(nz);
+    k_morph_combine<R, true, true><<<(threads + 255) / 256, 256, 0, s>>>(c->d_planes, c->d_closed, g.Wp, g.slice, g.words, 1,
+                                                                         g.W, 2 * R, uint32_t(ny), 2 * R, uint32_t(nz), tail);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s) {

@@ -48,7 +48,7 @@ struct CtaCache {
             for (int i = 0; i < NV; ++i) atomicAdd(&val[s][i], v[i]);
         } else {
 #pragma unroll
-            for (int i = 0; i < NV; ++i) atomicAdd(table + size_t(key) * NV + i, v[i]);
+            for (int i = 0; i < NV; ++i) atomicAdd(table + uint32_t(key) * NV + i, v[i]);
         }
     }
     __device__ void flush(V* table) {
@@ -56,7 +56,7 @@ struct CtaCache {
         for (int i = threadIdx.x; i < SLOTS * NV; i += blockDim.x) {
             const uint32_t key = tag[i / NV];
             const V x = (&val[0][0])[i];
-            if (key != MAMRI_NONE && x != V(0)) atomicAdd(table + size_t(key) * NV + (i % NV), x);
+            if (key != MAMRI_NONE && x != V(0)) atomicAdd(table + uint32_t(key) * NV + (i % NV), x);
         }
     }
 };
@@ -101,16 +101,16 @@ __device__ __forceinline__ void pop_piece(uint32_t& pm, int& b, int& len) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_count_labels(const uint32_t* __restrict__ mask,
                                                       const uint32_t* __restrict__ word_base,
-                                                      const uint32_t* __restrict__ run_label, int W, size_t n_words,
+                                                      const uint32_t* __restrict__ run_label, int W, uint32_t n_words,
                                                       uint32_t* label_count, const DevScalars* sc) {
     __shared__ CtaCache<1, uint32_t, 64> cache;
     if (sc->status != MAMRI_OK) return;
     cache.init();
     const unsigned lane = lane_id();
-    const size_t warp0 = ((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) << 5;
-    const size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t w0 = warp0; w0 < n_words; w0 += stride) {
-        const size_t wi = w0 + lane;
+    const uint32_t warp0 = ((uint32_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) << 5;
+    const uint32_t stride = uint32_t(gridDim.x) * blockDim.x;
+    for (uint32_t w0 = warp0; w0 < n_words; w0 += stride) {
+        const uint32_t wi = w0 + lane;
         uint32_t pm = wi < n_words ? mask[wi] : 0u;
         if (!__any_sync(FULL, pm != 0u)) continue;
         uint32_t starts = 0, base = 0;
@@ -140,11 +140,11 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ lab
                                                 uint32_t* __restrict__ cand_label, uint32_t max_markers, GeomArgs g,
                                                 DevScalars* sc) {
     const unsigned lane = lane_id();
-    const size_t n = sc->n_labels;
-    const size_t warp0 = ((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) << 5;
-    const size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t l0 = warp0; l0 < n; l0 += stride) {
-        const size_t l = l0 + lane;
+    const uint32_t n = sc->n_labels;
+    const uint32_t warp0 = ((uint32_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) << 5;
+    const uint32_t stride = uint32_t(gridDim.x) * blockDim.x;
+    for (uint32_t l0 = warp0; l0 < n; l0 += stride) {
+        const uint32_t l = l0 + lane;
         unsigned long long packed = 0ull, cnt64 = 0ull;
         if (l < n) {
             const uint32_t cnt = label_count[l];
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) k_prepare_moments(uint32_t* __restrict__ 
         cand_label[max_markers] = body;
     }
     for (uint32_t i = threadIdx.x; i < n * 9u; i += blockDim.x) sums[i] = 0ull;
-    for (uint32_t i = threadIdx.x; i < 9u; i += blockDim.x) sums[size_t(max_markers) * 9u + i] = 0ull;
+    for (uint32_t i = threadIdx.x; i < 9u; i += blockDim.x) sums[uint32_t(max_markers) * 9u + i] = 0ull;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -201,22 +201,22 @@ __device__ __forceinline__ unsigned long long sum_sq_upto(long long k) {   // su
 
 __global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
                                                  const uint32_t* __restrict__ run_label,
-                                                 const uint32_t* __restrict__ label_slot, int W, int ny, size_t n_words,
+                                                 const uint32_t* __restrict__ label_slot, int W, int ny, uint32_t n_words,
                                                  unsigned long long* sums, const DevScalars* sc) {
     __shared__ CtaCache<9, unsigned long long, 16> cache;
     if (sc->status != MAMRI_OK) return;
     cache.init();
     const unsigned lane = lane_id();
-    const size_t warp0 = ((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) << 5;
-    const size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t w0 = warp0; w0 < n_words; w0 += stride) {
-        const size_t wi = w0 + lane;
+    const uint32_t warp0 = ((uint32_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) << 5;
+    const uint32_t stride = uint32_t(gridDim.x) * blockDim.x;
+    for (uint32_t w0 = warp0; w0 < n_words; w0 += stride) {
+        const uint32_t wi = w0 + lane;
         uint32_t pm = wi < n_words ? mask[wi] : 0u;
         if (!__any_sync(FULL, pm != 0u)) continue;
         uint32_t starts = 0, base = 0;
         long long x0 = 0, y = 0, z = 0;
         if (pm) {
-            const size_t row = wi / W;
+            const uint32_t row = wi / W;
             const int xw = int(wi - row * W);
             starts = run_starts(pm, xw > 0 ? mask[wi - 1] : 0u);
             base = word_base[wi];
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256) k_finalize(const uint32_t* __restrict__ c
         const uint32_t lab = cand_label[i];
         uint32_t rank = 0;
         for (uint32_t j = 0; j < n; ++j) rank += cand_label[j] < lab;
-        make_marker(markers + rank, lab, label_count[lab - 1u], sums + size_t(i) * 9u, g);
+        make_marker(markers + rank, lab, label_count[lab - 1u], sums + uint32_t(i) * 9u, g);
     }
     if (threadIdx.x == 0) {
         summary->n_labels = sc->n_labels;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256) k_finalize(const uint32_t* __restrict__ c
             const uint32_t body = 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull);
             summary->body_label = body;
             summary->body_count = bp >> 32;
-            make_marker(&summary->body, body, bp >> 32, sums + size_t(max_markers) * 9u, g);
+            make_marker(&summary->body, body, bp >> 32, sums + uint32_t(max_markers) * 9u, g);
         } else {
             summary->body_label = 0;
             summary->body_count = 0;
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256) k_finalize(const uint32_t* __restrict__ c
 cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volume_desc* desc, const mamri_params* prm,
                          cudaStream_t s) {
     const int W = (desc->nx + 31) / 32;
-    const size_t n_words = size_t(W) * desc->ny * desc->nz;
+    const uint32_t n_words = uint32_t(W) * desc->ny * desc->nz;
     GeomArgs g;
     for (int i = 0; i < 3; ++i) { g.spacing[i] = desc->spacing[i]; g.origin[i] = desc->origin[i]; }
     for (int i = 0; i < 9; ++i) g.dir[i] = desc->direction[i];
@@ -393,7 +393,7 @@ cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volum
     g.voxel_volume = vv;
     g.min_volume = prm->min_volume;
     g.max_volume = prm->max_volume;
-    size_t wb = (n_words + 255) / 256;
+    uint32_t wb = (n_words + 255) / 256;
     if (wb > 148 * 8) wb = 148 * 8;
     if (wb == 0) wb = 1;
     k_count_labels<<<unsigned(wb), 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, W, n_words, c->d_label_count,
