@@ -149,7 +149,7 @@ def run_native(args):
     torch.cuda.synchronize()
     sp, org, dr = specs[0].spacing, specs[0].origin, specs[0].direction
     params = DetectParams()
-    bd = BatchDetector(DIMS, device=local, n_contexts=3)
+    bd = BatchDetector(DIMS, device=local, n_contexts=int(os.environ.get("MAMRI_BENCH_CONTEXTS", "3")))
     gather_in = torch.zeros((S, MAX_TABLE, 8), dtype=torch.float64, device=dev)
     gather_out = torch.zeros((world * S, MAX_TABLE, 8), dtype=torch.float64, device=dev) if world > 1 else None
 

@@ -373,40 +373,64 @@ __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict_
     const uint32_t n_warps = (uint32_t(gridDim.x) * blockDim.x) >> 5;
     const bool need_labels = (labels_out != nullptr) || (body_out != nullptr);
     if (ALIGNED) {
-        for (uint32_t w0 = warp * 4; w0 < n_words; w0 += n_warps * 4) {
-            const uint32_t wi = w0 + (lane >> 3);
-            if (wi >= n_words) continue;
+        // 32 mask words per trip: one coalesced load, then 8 rounds in which lane l serves word
+        // 4k + l/8 (fetched by shuffle), voxels 4*(l%8)..+3.  The next trip's words are loaded first.
+        uint32_t w0 = warp * 32;
+        uint32_t m_next = (w0 + lane < n_words) ? mask[w0 + lane] : 0u;
+        for (; w0 < n_words; w0 += n_warps * 32) {
+            const uint32_t m_l = m_next;
+            const uint32_t wn = w0 + n_warps * 32 + lane;
+            m_next = (wn < n_words) ? mask[wn] : 0u;
+            const bool resolve = need_labels && ok && __any_sync(0xFFFFFFFFu, m_l != 0u);
+            uint32_t starts_l = 0, base_l = 0;
+            if (resolve) {
+                uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, m_l, 1);
+                if (lane == 0) prev = w0 > 0 ? mask[w0 - 1] : 0u;
+                if (m_l) {
+                    if ((w0 + lane) % W == 0) prev = 0u;
+                    starts_l = run_starts(m_l, prev);
+                    base_l = word_base[w0 + lane];
+                }
+            }
             const int sub = int(lane & 7u) * 4;
-            const uint32_t m = mask[wi];
-            const uint32_t nib = (m >> sub) & 0xFu;
-            uint32_t lab[4] = {0u, 0u, 0u, 0u};
-            if (nib && need_labels && ok) {
-                const uint32_t prev = (wi % W) ? mask[wi - 1] : 0u;
-                const uint32_t starts = run_starts(m, prev);
-                const uint32_t base = word_base[wi];
-                uint32_t last_rid = MAMRI_NONE, last_lab = 0u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (nib & (1u << k)) {
-                        uint32_t rid = run_id_in_word(base, starts, sub + k);
-                        if (rid != last_rid) { last_rid = rid; last_lab = run_label[rid]; }
-                        lab[k] = last_lab;
+            for (int k = 0; k < 8; ++k) {
+                const int src = k * 4 + int(lane >> 3);
+                const uint32_t m = __shfl_sync(0xFFFFFFFFu, m_l, src);
+                uint32_t starts = 0, base = 0;
+                if (resolve) {
+                    starts = __shfl_sync(0xFFFFFFFFu, starts_l, src);
+                    base = __shfl_sync(0xFFFFFFFFu, base_l, src);
+                }
+                const uint32_t wi = w0 + src;
+                if (wi >= n_words) continue;
+                const uint32_t nib = (m >> sub) & 0xFu;
+                uint32_t lab[4] = {0u, 0u, 0u, 0u};
+                if (nib && resolve) {
+                    uint32_t last_rid = MAMRI_NONE, last_lab = 0u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (nib & (1u << q)) {
+                            uint32_t rid = run_id_in_word(base, starts, sub + q);
+                            if (rid != last_rid) { last_rid = rid; last_lab = run_label[rid]; }
+                            lab[q] = last_lab;
+                        }
                     }
                 }
-            }
-            const uint32_t v = wi * 32 + sub;
-            if (labels_out) *reinterpret_cast<uint4*>(labels_out + v) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
-            if (mask_out) {
-                uint32_t mb = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-                *reinterpret_cast<uint32_t*>(mask_out + v) = mb;
-            }
-            if (body_out) {
-                uint32_t bb = 0;
-                if (has_body) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) bb |= (lab[k] == body ? 1u : 0u) << (8 * k);
+                const uint32_t v = wi * 32 + sub;
+                if (labels_out) *reinterpret_cast<uint4*>(labels_out + v) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+                if (mask_out) {
+                    uint32_t mb = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+                    *reinterpret_cast<uint32_t*>(mask_out + v) = mb;
                 }
-                *reinterpret_cast<uint32_t*>(body_out + v) = bb;
+                if (body_out) {
+                    uint32_t bb = 0;
+                    if (has_body) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) bb |= (lab[q] == body ? 1u : 0u) << (8 * q);
+                    }
+                    *reinterpret_cast<uint32_t*>(body_out + v) = bb;
+                }
             }
         }
     } else {
@@ -439,8 +463,8 @@ cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int
                          ((reinterpret_cast<uintptr_t>(d_mask_out) & 3u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(d_body_out) & 3u) == 0);
     if (aligned) {
-        uint32_t blocks = (n_words / 4 + 7) / 8;
-        if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
+        uint32_t blocks = (n_words / 32 + 7) / 8;
+        if (blocks > 148 * 8 * 2) blocks = 148 * 8 * 2;
         if (blocks == 0) blocks = 1;
         k_materialise<true><<<unsigned(blocks), 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, nx, W, n_words,
                                                              d_mask_out, d_labels_out, d_body_out, c->d_scalars);

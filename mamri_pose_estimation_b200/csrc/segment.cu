@@ -36,38 +36,86 @@ __device__ __forceinline__ uint4 ld_stream_128(const uint4* p) {
     return r;
 }
 
-// Fast path: nx % 32 == 0 and 16-byte aligned base, so the voxels of one mask word are contiguous.
-// A warp load instruction covers 512 contiguous bytes; each lane turns its 16 bytes into E bits and
-// 32/E neighbouring lanes are merged into one 32-voxel word by shuffles.
-template <typename T, int UNROLL>
-__global__ void __launch_bounds__(256) k_threshold_pack_flat(const uint4* __restrict__ vol, uint32_t n_vec, T lo, T hi,
-                                                             BitDst dst) {
-    constexpr int E = 16 / sizeof(T);   // voxels per 128-bit load
-    constexpr int G = 32 / E;           // lanes per output word
-    const unsigned lane = lane_id();
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t base = warp * (UNROLL * 32); base < n_vec; base += n_warps * (UNROLL * 32)) {
-        uint4 v[UNROLL];
-        bool ok[UNROLL];
+// Fast path: nx % 32 == 0 and 16-byte aligned base, so every row is a whole number of 128-bit vectors
+// and of mask words.  blockIdx.y = slice, warps stride over the rows of the slice two at a time (no
+// index divisions anywhere).  A warp load instruction covers 512 contiguous bytes; each lane turns its
+// 16 bytes into E bits and 32/E neighbouring lanes are merged into one 32-voxel word by shuffles.
+// Generic: one compare pair per voxel.
+template <typename T>
+struct RangeTest {
+    T lo, hi;
+    __device__ __forceinline__ uint32_t pack(uint4 q) const {
+        constexpr int E = 16 / sizeof(T);
+        union { uint4 q; T e[E]; } cvt;
+        cvt.q = q;
+        uint32_t b = 0;
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const uint32_t i = base + u * 32 + lane;
-            ok[u] = i < n_vec;
-            v[u] = ok[u] ? ld_stream_128(vol + i) : make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < E; ++k) b |= (in_range(cvt.e[k], lo, hi) ? 1u : 0u) << k;
+        return b;
+    }
+};
+
+// 16-bit voxels (the MR case): two voxels per 32-bit register, compared without unpacking.  For
+// 16-bit lanes a, l:  d = (a | 0x8000) - (l & 0x7FFF) never borrows across lanes and its top bit is
+// (a & 0x7FFF) >= (l & 0x7FFF); the lanes' own top bits settle the rest:  a >= l  <=>
+// msb(l) ? msb(a & d) : msb(a | d).  a <= h is h >= a.  Signed voxels are biased by 0x8000 first
+// (flips the order of the top bit only).  ~2.6 instructions per voxel when the upper bound is the
+// type's maximum (the reference's 65535), ~4.6 otherwise, against ~10 for compare-and-select.
+template <bool LO_MSB, bool HI_MSB, bool CHECK_HI, bool SIGNED>
+struct RangeTest16 {
+    uint32_t lo_c;      // (lo & 0x7FFF) in both lanes
+    uint32_t hi_c;      // (hi | 0x8000) in both lanes
+    __device__ __forceinline__ uint32_t lanes(uint32_t w) const {
+        const uint32_t H = 0x80008000u;
+        if (SIGNED) w ^= H;
+        const uint32_t d = (w | H) - lo_c;
+        uint32_t r = LO_MSB ? (w & d) : (w | d);
+        if (CHECK_HI) {
+            const uint32_t d2 = hi_c - (w & ~H);
+            r &= HI_MSB ? (~w | d2) : (~w & d2);
         }
+        return r & H;                       // bit 15 / bit 31 = low / high voxel in range
+    }
+    __device__ __forceinline__ uint32_t pack(uint4 q) const {
+        const uint32_t s = (lanes(q.x) >> 15) | (lanes(q.y) >> 13) | (lanes(q.z) >> 11) | (lanes(q.w) >> 9);
+        return (s | (s >> 15)) & 0xFFu;     // low voxels sit on even bits, high voxels 16 above: interleave
+    }
+};
+
+template <int VOXEL_BYTES, typename Test>
+__global__ void __launch_bounds__(256) k_threshold_pack_vec(const uint4* __restrict__ vol, uint32_t vec_per_row,
+                                                            uint32_t ny, Test test, uint32_t* __restrict__ dst,
+                                                            uint32_t row_stride, uint32_t slice_stride, uint32_t off) {
+    constexpr int E = 16 / VOXEL_BYTES; // voxels per 128-bit load
+    constexpr int G = 32 / E;           // lanes per output word
+    constexpr int U = 2;                // vectors per lane per row in flight (x 2 rows)
+    const unsigned lane = lane_id();
+    const uint32_t z = blockIdx.y;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    const uint4* slice_src = vol + size_t(z) * ny * vec_per_row;
+    uint32_t* slice_dst = dst + off + z * slice_stride;
+    for (uint32_t y0 = warp * 2; y0 < ny; y0 += n_warps * 2) {
+        for (uint32_t u0 = 0; u0 < vec_per_row; u0 += 32 * U) {
+            uint4 v[2][U];
+            bool ok[2][U];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            union { uint4 q; T e[E]; } cvt;
-            cvt.q = v[u];
-            uint32_t b = 0;
+            for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int k = 0; k < E; ++k) b |= (in_range(cvt.e[k], lo, hi) ? 1u : 0u) << k;
-            if (!ok[u]) b = 0;
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t i = u0 + u * 32 + lane;
+                    ok[r][u] = (y0 + r < ny) && i < vec_per_row;
+                    v[r][u] = ok[r][u] ? ld_stream_128(slice_src + size_t(y0 + r) * vec_per_row + i) : make_uint4(0, 0, 0, 0);
+                }
 #pragma unroll
-            for (int s = 1; s < G; s <<= 1) b |= __shfl_down_sync(0xFFFFFFFFu, b, s) << (E * s);
-            const uint32_t i = base + u * 32 + lane;
-            if (ok[u] && (lane % G) == 0) dst.p[dst.index(i / G)] = b;
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    uint32_t b = ok[r][u] ? test.pack(v[r][u]) : 0u;
+#pragma unroll
+                    for (int s = 1; s < G; s <<= 1) b |= __shfl_down_sync(0xFFFFFFFFu, b, s) << (E * s);
+                    if (ok[r][u] && (lane % G) == 0) slice_dst[(y0 + r) * row_stride + (u0 + u * 32 + lane) / G] = b;
+                }
         }
     }
 }
@@ -111,14 +159,33 @@ static cudaError_t threshold_pack_t(const void* d_vol, int nx, int ny, int nz, d
     const bool flat = (nx % 32 == 0) && ((reinterpret_cast<uintptr_t>(d_vol) & 15u) == 0);
     if (flat) {
         constexpr int E = 16 / sizeof(T);
-        constexpr int UNROLL = 4;
-        const uint32_t n_vec = uint32_t(size_t(rows) * nx / E);
-        uint32_t warps = (n_vec + UNROLL * 32 - 1) / (UNROLL * 32);
-        uint32_t blocks = (warps + 7) / 8;
-        const uint32_t cap = 148 * 8 * 4;           // a few waves of 8 resident CTAs per SM
-        if (blocks > cap) blocks = cap;
-        if (blocks == 0) blocks = 1;
-        k_threshold_pack_flat<T, UNROLL><<<blocks, 256, 0, s>>>(static_cast<const uint4*>(d_vol), n_vec, tlo, thi, dst);
+        // ~4 waves of 8 resident CTAs per SM; 8 warps per CTA, each warp takes two rows per trip
+        uint32_t gx = (uint32_t(ny) + 15) / 16;
+        const uint32_t want = (148 * 8 * 4 + uint32_t(nz) - 1) / uint32_t(nz);
+        if (gx > want) gx = want;
+        if (gx == 0) gx = 1;
+        const dim3 grid(gx, uint32_t(nz));
+        const uint4* src = static_cast<const uint4*>(d_vol);
+        if constexpr (sizeof(T) == 2) {
+            constexpr bool SG = std::is_signed<T>::value;
+            const uint32_t bias = SG ? 0x8000u : 0u;
+            uint32_t l = (uint32_t(uint16_t(tlo)) ^ bias), h = (uint32_t(uint16_t(thi)) ^ bias);
+            if (l > h) { l = 0xFFFFu; h = 0u; }                 // empty range: a >= 0xFFFF && a <= 0
+            const uint32_t lo_c = (l & 0x7FFFu) * 0x10001u, hi_c = (h | 0x8000u) * 0x10001u;
+            const bool lm = (l & 0x8000u) != 0, hm = (h & 0x8000u) != 0, ch = h != 0xFFFFu;
+            const uint32_t vpr = uint32_t(nx) / E;
+#define MAMRI_T16(LM, HM, CH)                                                                                         \
+    k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>><<<grid, 256, 0, s>>>(src, vpr, uint32_t(ny),                   \
+        RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off)
+            if (!ch) { if (lm) MAMRI_T16(true, true, false); else MAMRI_T16(false, true, false); }
+            else if (lm) { if (hm) MAMRI_T16(true, true, true); else MAMRI_T16(true, false, true); }
+            else { if (hm) MAMRI_T16(false, true, true); else MAMRI_T16(false, false, true); }
+#undef MAMRI_T16
+        } else {
+            RangeTest<T> t{tlo, thi};
+            k_threshold_pack_vec<int(sizeof(T)), RangeTest<T>><<<grid, 256, 0, s>>>(src, uint32_t(nx) / E, uint32_t(ny), t, dst.p,
+                                                                                 dst.row_stride, dst.slice_stride, dst.off);
+        }
     } else {
         uint32_t blocks = (n_words + 7) / 8;
         const uint32_t cap = 148 * 8 * 8;
