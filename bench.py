@@ -83,16 +83,6 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def table_from_results(results):
-    """Fixed-size per-scan marker table for the gather: [S, MAX_TABLE, 8] f64 =
-    (label, count, volume, ras x, ras y, ras z, n_labels, body_label)."""
-    t = np.zeros((len(results), MAX_TABLE, 8), dtype=np.float64)
-    for i, r in enumerate(results):
-        for j, m in enumerate(r.markers[:MAX_TABLE]):
-            t[i, j] = (m.label, m.count, m.volume_mm3, *m.centroid_ras, r.n_labels, r.body_label)
-    return t
-
-
 def run_reference(args):
     """CPU arm: the path restated in C (oracle/c, OpenMP over all host threads) -- SimpleITK, which the
     reference calls at Mamri.py:1308-1310, is not installable here.  One C2 scan per step."""
@@ -129,6 +119,7 @@ def run_native(args):
     import torch.distributed as dist
     from mamri_pose_estimation_b200 import phantom
     from mamri_pose_estimation_b200.detector import BatchDetector, DetectParams, generate_phantom_cuda
+    from mamri_pose_estimation_b200.distributed import gather_tables, pack_table
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -151,13 +142,12 @@ def run_native(args):
     params = DetectParams()
     bd = BatchDetector(DIMS, device=local, n_contexts=int(os.environ.get("MAMRI_BENCH_CONTEXTS", "3")))
     gather_in = torch.zeros((S, MAX_TABLE, 8), dtype=torch.float64, device=dev)
-    gather_out = torch.zeros((world * S, MAX_TABLE, 8), dtype=torch.float64, device=dev) if world > 1 else None
 
     def step():
         res = bd.run(vols, sp, org, dr, params)
         if world > 1:                                   # the single exchange of the path: marker tables
-            gather_in.copy_(torch.from_numpy(table_from_results(res)), non_blocking=True)
-            dist.all_gather_into_tensor(gather_out, gather_in)
+            gather_in.copy_(torch.from_numpy(pack_table(res)), non_blocking=True)
+            gather_tables(gather_in)
         return res
 
     def barrier():
@@ -194,8 +184,8 @@ def run_native(args):
     def step_host():
         r = bd.run_host(h_vols, sp, org, dr, params, body_out=h_body)
         if world > 1:
-            gather_in.copy_(torch.from_numpy(table_from_results(r)), non_blocking=True)
-            dist.all_gather_into_tensor(gather_out, gather_in)
+            gather_in.copy_(torch.from_numpy(pack_table(r)), non_blocking=True)
+            gather_tables(gather_in)
         return r
 
     for _ in range(2):

@@ -1,0 +1,194 @@
+"""Slicer-free mirror of the two `MamriLogic` methods this package replaces, with the reference's
+names, arguments and error behaviour, delegating to the CUDA path through the C ABI:
+
+  * ``MamriLogic.volume_threshold_segmentation(pNode)``   Mamri/Mamri.py:1304-1341
+  * ``MamriLogic.findAndSetEntryPoint(pNode)``            Mamri/Mamri.py:987-1033
+
+The reference stores its results in the MRML scene (markups node "DetectedFiducials", segmentation
+node "AutoBodySegmentation", markups node "ClosestSuitableEntryPoint").  Here the scene is a plain
+dict of tiny node objects with the accessor names the reference's downstream code uses
+(`GetNumberOfControlPoints`, `GetNthControlPointPositionWorld`, ...), so `joint_detection`-style
+consumers read them the same way.  There is no CPU fallback: without the CUDA library / a GPU the
+constructor raises.
+"""
+from __future__ import annotations
+
+import dataclasses
+import logging
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .detector import IDENTITY, DetectParams, DetectionResult, FiducialDetector
+
+
+# ----------------------------------------------------------------------------- scene stand-ins
+@dataclasses.dataclass
+class ScalarVolumeNode:
+    """What `sitkUtils.PullVolumeFromSlicer(pNode.inputVolume)` yields (Mamri.py:1306): voxels [nz,ny,nx]
+    (numpy array, CPU tensor or CUDA tensor) plus the image geometry in LPS."""
+    array: object
+    spacing: Sequence[float] = (1.0, 1.0, 1.0)
+    origin: Sequence[float] = (0.0, 0.0, 0.0)
+    direction: Sequence[float] = IDENTITY
+    name: str = "inputVolume"
+
+
+class MarkupsFiducialNode:
+    """vtkMRMLMarkupsFiducialNode subset used by the reference (Mamri.py:1313-1317, 1345-1347)."""
+
+    def __init__(self, name: str):
+        self.name = name
+        self._points: List[List[float]] = []
+        self._labels: List[str] = []
+
+    def AddControlPoint(self, ras) -> int:
+        self._points.append([float(v) for v in ras])
+        self._labels.append("")
+        return len(self._points) - 1
+
+    AddControlPointWorld = AddControlPoint
+
+    def SetNthControlPointLabel(self, idx: int, label: str) -> None:
+        self._labels[idx] = label
+
+    def GetNthControlPointLabel(self, idx: int) -> str:
+        return self._labels[idx]
+
+    def GetNumberOfControlPoints(self) -> int:
+        return len(self._points)
+
+    def GetNthControlPointPositionWorld(self, idx: int):
+        return tuple(self._points[idx])
+
+    def points(self) -> np.ndarray:
+        return np.asarray(self._points, dtype=np.float64).reshape(-1, 3)
+
+
+@dataclasses.dataclass
+class SegmentationNode:
+    """Stand-in for the "AutoBodySegmentation" node (Mamri.py:1328-1341): the uint8 body labelmap the
+    reference imports, plus -- optionally -- the closed-surface points/normals Slicer would derive from
+    it (supplied by the host application; the voxel-to-surface conversion is Slicer's)."""
+    name: str
+    body_mask: object                       # uint8 [nz,ny,nx] (host array or CUDA tensor)
+    body_label: int
+    spacing: Sequence[float]
+    origin: Sequence[float]
+    direction: Sequence[float]
+    surface_points: Optional[object] = None     # float32 [n,3] RAS
+    surface_normals: Optional[object] = None    # float32 [n,3]
+
+
+@dataclasses.dataclass
+class MamriParameterNode:
+    """Fields of the reference's parameter node that the two methods read or write (Mamri.py:50-61)."""
+    inputVolume: Optional[ScalarVolumeNode] = None
+    segmentationNode: Optional[SegmentationNode] = None
+    targetFiducialNode: Optional[MarkupsFiducialNode] = None
+    entryPointFiducialNode: Optional[MarkupsFiducialNode] = None
+    safetyDistance: float = 5.0
+
+
+class MamriLogic:
+    """The fiducial-detection and entry-point parts of the reference's MamriLogic."""
+
+    def __init__(self, device: int = 0) -> None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("MamriLogic (B200 path) needs a CUDA device; there is no CPU fallback")
+        # constants of MamriLogic.__init__ (Mamri.py:810-813) and of findAndSetEntryPoint (:1009, :1015-1016)
+        self.INTENSITY_THRESHOLD = 65.0
+        self.MIN_VOLUME_THRESHOLD = 50.0
+        self.MAX_VOLUME_THRESHOLD = 1500.0
+        self.DISTANCE_TOLERANCE = 5.0
+        self.SEARCH_RADIUS = 80.0
+        self.device = int(device)
+        self.scene: Dict[str, object] = {}
+        self._detector: Optional[FiducialDetector] = None
+        self.last_detection: Optional[DetectionResult] = None
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _clear_node_by_name(self, name: str) -> None:
+        self.scene.pop(name, None)
+
+    def _detector_for(self, dims_xyz) -> FiducialDetector:
+        d = self._detector
+        if d is None or any(a > b for a, b in zip(dims_xyz, d.max_dims)):
+            if d is not None:
+                d.close()
+            self._detector = d = FiducialDetector(dims_xyz, device=self.device)
+        return d
+
+    # -- Mamri.py:1304-1341 ------------------------------------------------------------------------
+    def volume_threshold_segmentation(self, pNode: MamriParameterNode) -> None:
+        '''Segments the input MRI volume to isolate fiducials and the main anatomical structure.'''
+        try:
+            vol = pNode.inputVolume
+            arr = vol.array
+            shape = tuple(arr.shape)
+            if len(shape) != 3:
+                raise ValueError(f"volume must be 3-D, got shape {shape}")
+        except Exception as e:                       # the reference's guarded pull (Mamri.py:1306-1307)
+            logging.error(f"Failed to pull volume: {e}")
+            return
+        nz, ny, nx = shape
+        det = self._detector_for((nx, ny, nz))
+        params = DetectParams(lower=self.INTENSITY_THRESHOLD, upper=65535.0, close_radius=2, connectivity=6,
+                              min_volume=self.MIN_VOLUME_THRESHOLD, max_volume=self.MAX_VOLUME_THRESHOLD)
+        if isinstance(arr, torch.Tensor) and arr.is_cuda:
+            res = det.detect(arr, spacing=vol.spacing, origin=vol.origin, direction=vol.direction, params=params,
+                             want_body=True)
+            body_mask = res.body_mask
+        else:
+            body_host = np.empty(shape, dtype=np.uint8)
+            res = det.detect_host(arr, spacing=vol.spacing, origin=vol.origin, direction=vol.direction, params=params,
+                                  body_out=body_host)
+            body_mask = body_host
+        self.last_detection = res
+        fiducials_data = res.fiducials_data
+        self._clear_node_by_name("DetectedFiducials")
+        if fiducials_data:
+            node = MarkupsFiducialNode("DetectedFiducials")
+            self.scene["DetectedFiducials"] = node
+            for fd in fiducials_data:
+                lps = fd["centroid"]
+                idx = node.AddControlPoint([-lps[0], -lps[1], lps[2]])
+                node.SetNthControlPointLabel(idx, f"M_{fd['id']}_{fd['vol']:.0f}mm³")
+        if res.n_labels == 0:
+            return                                   # `if not all_labels: return`        (Mamri.py:1319)
+        if not res.body_label:
+            return                                   # `if not non_fiducial_labels: return` (Mamri.py:1321)
+        self._clear_node_by_name("AutoBodySegmentation")
+        seg = SegmentationNode(name="AutoBodySegmentation", body_mask=body_mask, body_label=res.body_label,
+                               spacing=tuple(vol.spacing), origin=tuple(vol.origin), direction=tuple(vol.direction))
+        self.scene["AutoBodySegmentation"] = seg
+        pNode.segmentationNode = seg
+
+    # -- Mamri.py:987-1033 -------------------------------------------------------------------------
+    def findAndSetEntryPoint(self, pNode: MamriParameterNode) -> None:
+        '''Finds and marks the closest suitable entry point on the body surface for the biopsy needle.'''
+        targetNode = pNode.targetFiducialNode
+        segmentationNode = self.scene.get("AutoBodySegmentation")
+        if not (targetNode and targetNode.GetNumberOfControlPoints() > 0 and segmentationNode):
+            logging.error("Please place a target marker and ensure 'AutoBodySegmentation' exists.")
+            return
+        pts, nrm = segmentationNode.surface_points, segmentationNode.surface_normals
+        if pts is None or nrm is None or len(pts) == 0:
+            return                                   # `if not body_poly: return` (Mamri.py:995-996)
+        dev = torch.device(f"cuda:{self.device}")
+        pts_t = torch.as_tensor(pts, dtype=torch.float32).to(dev).contiguous()
+        nrm_t = torch.as_tensor(nrm, dtype=torch.float32).to(dev).contiguous()
+        target_pos = np.array(targetNode.GetNthControlPointPositionWorld(0), dtype=np.float64)
+        det = self._detector or self._detector_for((32, 32, 32))
+        best = det.entry_search(pts_t, nrm_t, target_pos, radius=self.SEARCH_RADIUS, wx=1.0, wy=-2.0, cutoff=-0.5)
+        if best["index"] < 0:
+            logging.warning(f"Could not find a suitable side-entry point within {self.SEARCH_RADIUS}mm of the target.")
+            return
+        newNodeName = "ClosestSuitableEntryPoint"
+        self._clear_node_by_name(newNodeName)
+        entryNode = MarkupsFiducialNode(newNodeName)
+        self.scene[newNodeName] = entryNode
+        entryNode.AddControlPointWorld(best["point"])
+        entryNode.SetNthControlPointLabel(0, "Suitable Entry")
+        pNode.entryPointFiducialNode = entryNode

@@ -1,0 +1,75 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/mamri_b200.h declares;
+argument validation that needs no device works; there is no CPU fallback."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mamri_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"MAMRI_API\s+[\w\s\*]+?\b(mamri_\w+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = declared_symbols()
+    for must in ("mamri_create", "mamri_destroy", "mamri_detect_async", "mamri_detect_host_async",
+                 "mamri_detect_collect", "mamri_entry_search", "mamri_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(cuda_lib):
+    from mamri_pose_estimation_b200 import _capi
+    for name in declared_symbols():
+        assert hasattr(cuda_lib, name), f"{name} declared in the header but not exported"
+        assert name in _capi.SIGNATURES, f"{name} has no ctypes signature"
+    assert cuda_lib.mamri_version().decode().startswith("mamri_b200")
+
+
+def test_ctypes_structs_match_header_sizes(cuda_lib, tmp_path):
+    """sizeof of every struct as gcc sees the header == sizeof of the ctypes mirror."""
+    import subprocess
+    from mamri_pose_estimation_b200 import _capi
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "mamri_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n",'
+                   'sizeof(mamri_volume_desc),sizeof(mamri_params),sizeof(mamri_marker),sizeof(mamri_summary),'
+                   'sizeof(mamri_entry_result));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    mirrors = [_capi.VolumeDesc, _capi.Params, _capi.Marker, _capi.Summary, _capi.EntryResult]
+    assert sizes == [C.sizeof(m) for m in mirrors]
+    p = _capi.Params()
+    cuda_lib.mamri_default_params(C.byref(p))
+    assert (p.lower, p.upper, p.close_radius, p.connectivity, p.min_volume, p.max_volume) == (65.0, 65535.0, 2, 6, 50.0, 1500.0)
+
+
+def test_no_cpu_fallback_without_gpu(cuda_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mamri_pose_estimation_b200 import _capi
+    ctx = C.c_void_p()
+    rc = cuda_lib.mamri_create(C.byref(ctx), 0, 64, 64, 64, 0, 0)
+    assert rc == _capi.MAMRI_ERR_NO_DEVICE and not ctx.value
+    assert b"no CPU fallback" in cuda_lib.mamri_last_error(None)
+    from mamri_pose_estimation_b200.detector import FiducialDetector
+    with pytest.raises(RuntimeError):
+        FiducialDetector((64, 64, 64))
+    from mamri_pose_estimation_b200.logic import MamriLogic
+    with pytest.raises(RuntimeError):
+        MamriLogic()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "mamri_pose_estimation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{f} imports the oracle"
+                assert "libmamri_oracle" not in text, f"{f} links the oracle"

@@ -1,0 +1,242 @@
+"""GPU tests beyond the per-stage parity: BASELINE configs at full size against the C oracle, the
+joint-angle criterion, the host-buffer (drop-in) call, the MamriLogic mirror, batching, entry search,
+capacity errors and size-independent properties."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from mamri_pose_estimation_b200 import phantom
+from oracle import c_oracle
+from oracle import kinematics as kin
+from oracle import segmentation as seg
+
+
+def _geom(ph):
+    return seg.Geometry(ph.spacing, ph.origin, ph.direction)
+
+
+def _assert_equal_detection(res, ora, mask=None, labels=None):
+    if mask is not None:
+        assert np.array_equal(mask, ora.closed)
+    if labels is not None:
+        assert np.array_equal(labels, ora.labels)
+    assert res.n_labels == ora.n_labels
+    assert [m.label for m in res.markers] == [f["id"] for f in ora.fiducials]
+    assert res.body_label == ora.body_label
+    for m, f in zip(res.markers, ora.fiducials):
+        assert m.volume_mm3 == f["vol"]
+        assert np.abs(np.array(m.centroid_lps) - np.array(f["centroid"])).max() <= 1e-9
+
+
+def test_c1_end_to_end_joint_angles(cuda_lib):
+    """Config C1: 256x256x128, 9 fiducials.  Masks/labels bit-exact, centroids <= 1e-4 voxel, and the
+    reference's matching + registration + IK chain gives the same joint angles (<= 1e-6 rad) from the CUDA
+    markers as from the oracle markers."""
+    from mamri_pose_estimation_b200.detector import FiducialDetector
+    ph = phantom.config_c1()
+    vol = phantom.generate(ph)
+    geom = _geom(ph)
+    ora = c_oracle.detect_fiducials(vol, geom)
+    det = FiducialDetector(ph.dims)
+    res = det.detect(torch.from_numpy(vol).cuda(), spacing=ph.spacing, origin=ph.origin, direction=ph.direction,
+                     want_mask=True, want_labels=True, want_body=True)
+    _assert_equal_detection(res, ora, res.mask.cpu().numpy(), res.labels.cpu().numpy().view(np.uint32))
+    assert np.array_equal(res.body_mask.cpu().numpy(), ora.body_mask)
+    assert len(res.markers) == 9
+    inv = np.linalg.inv(geom.matrix())
+    for m, f in zip(res.markers, ora.fiducials):
+        assert np.abs(inv @ (np.array(m.centroid_lps) - np.array(f["centroid"]))).max() <= 1e-4
+    ang_gpu, ident_gpu, _ = kin.pose_from_markers(res.ras_points)
+    ang_ora, ident_ora, _ = kin.pose_from_markers(ora.ras_points)
+    assert ang_gpu is not None and ang_ora is not None
+    assert {k: [m["id"] for m in v] for k, v in ident_gpu.items()} == {k: [m["id"] for m in v] for k, v in ident_ora.items()}
+    assert np.abs(ang_gpu - ang_ora).max() <= 1e-6
+    # and the oracle chain recovers the phantom's pose (voxel quantisation limits it to ~1-2 degrees)
+    assert np.abs(np.degrees(ang_ora) - np.array(phantom.ROBOT_POSE_DEG)).max() < 2.0
+    det.close()
+
+
+def test_c2_full_size_device_phantom(cuda_lib):
+    """Config C2 at full size, phantom generated on the device: bit-exact against the C oracle."""
+    from mamri_pose_estimation_b200.detector import FiducialDetector, generate_phantom_cuda
+    ph = phantom.config_c2()
+    d_vol = generate_phantom_cuda(ph)
+    det = FiducialDetector(ph.dims)
+    res = det.detect(d_vol, spacing=ph.spacing, origin=ph.origin, direction=ph.direction, want_mask=True, want_labels=True)
+    host = d_vol.cpu().numpy()
+    ora = c_oracle.detect_fiducials(host, _geom(ph), want_body_mask=False)
+    _assert_equal_detection(res, ora, res.mask.cpu().numpy(), res.labels.cpu().numpy().view(np.uint32))
+    assert len(res.markers) == 6
+    det.close()
+
+
+@pytest.mark.parametrize("conn", [6, 26])
+def test_c4_merge_stress_reduced(cuda_lib, conn):
+    """Config C4's ingredients (sigma 20 specks, 2000 blobs incl. tile-straddling ones and 26-only diagonal
+    chains, 32 fiducials) at 512x512x256 so the C oracle finishes in seconds."""
+    from mamri_pose_estimation_b200.detector import DetectParams, FiducialDetector, generate_phantom_cuda
+    ph = phantom.config_c4(dims=(512, 512, 256), n_blobs=2000)
+    d_vol = generate_phantom_cuda(ph)
+    det = FiducialDetector(ph.dims, max_runs=ph.n_voxels // 4, max_markers=16384)
+    res = det.detect(d_vol, spacing=ph.spacing, origin=ph.origin, direction=ph.direction,
+                     params=DetectParams(connectivity=conn), want_mask=True, want_labels=True)
+    ora = c_oracle.detect_fiducials(d_vol.cpu().numpy(), _geom(ph), connectivity=conn, want_body_mask=False)
+    _assert_equal_detection(res, ora, res.mask.cpu().numpy(), res.labels.cpu().numpy().view(np.uint32))
+    assert np.array_equal(det.label_counts(res.n_labels).astype(np.int64), ora.counts)
+    assert res.n_labels > 1000
+    det.close()
+
+
+def test_device_phantom_matches_numpy_twin(cuda_lib):
+    from mamri_pose_estimation_b200.detector import generate_phantom_cuda
+    ph = phantom.small_phantom(dims=(96, 64, 40), seed=8, sigma=15.0)
+    host = phantom.generate(ph)
+    dev = generate_phantom_cuda(ph).cpu().numpy()
+    clean = dataclass_replace(ph, sigma=0.0)
+    assert np.array_equal(generate_phantom_cuda(clean).cpu().numpy(), phantom.paint_signal(ph)), "noise-free signal is bit-identical"
+    mism = (host != dev).mean()
+    assert mism < 1e-3, f"noisy voxels differ on {mism:.2e} of the volume (libm vs CUDA rounding)"
+    assert np.abs(host.astype(int) - dev.astype(int)).max() <= 1
+
+
+def dataclass_replace(ph, **kw):
+    import dataclasses
+    return dataclasses.replace(ph, **kw)
+
+
+def test_host_buffer_call_and_logic_mirror(cuda_lib):
+    """The drop-in call: host volume in, markers + host body mask out, through MamriLogic's method names."""
+    from mamri_pose_estimation_b200.logic import MamriLogic, MamriParameterNode, MarkupsFiducialNode, ScalarVolumeNode
+    ph = phantom.small_phantom(dims=(96, 80, 48), n_fiducials=6, seed=12, spacing=(1.2, 1.2, 2.4))
+    vol = phantom.generate(ph)
+    ora = seg.detect_fiducials(vol, _geom(ph))
+    logic = MamriLogic()
+    pNode = MamriParameterNode(inputVolume=ScalarVolumeNode(vol, ph.spacing, ph.origin, ph.direction))
+    logic.volume_threshold_segmentation(pNode)
+    node = logic.scene.get("DetectedFiducials")
+    if ora.fiducials:
+        assert node.GetNumberOfControlPoints() == len(ora.fiducials)
+        assert np.allclose(node.points(), ora.ras_points, atol=1e-9)
+        assert [node.GetNthControlPointLabel(i) for i in range(len(ora.fiducials))] == ora.marker_labels
+    else:
+        assert node is None
+    assert pNode.segmentationNode is not None and pNode.segmentationNode.body_label == ora.body_label
+    assert np.array_equal(pNode.segmentationNode.body_mask, ora.body_mask)
+    # a broken input volume is logged and ignored, like the reference's guarded pull (Mamri.py:1306-1307)
+    logic.volume_threshold_segmentation(MamriParameterNode(inputVolume=None))
+    # entry point through the mirror
+    pts, nrm, tgt = phantom.surface_candidates(20000, seed=3)
+    pNode.segmentationNode.surface_points, pNode.segmentationNode.surface_normals = pts, nrm
+    t = MarkupsFiducialNode("target")
+    t.AddControlPoint(tgt)
+    pNode.targetFiducialNode = t
+    logic.findAndSetEntryPoint(pNode)
+    wi, wd = kin.find_entry_point(pts, nrm, tgt)
+    assert wi >= 0
+    assert np.allclose(pNode.entryPointFiducialNode.GetNthControlPointPositionWorld(0), pts[wi].astype(np.float64))
+
+
+def test_entry_search_parity_and_path_sampling(cuda_lib):
+    from mamri_pose_estimation_b200.detector import FiducialDetector
+    det = FiducialDetector((64, 64, 64))
+    for n, seed in ((1, 1), (1000, 2), (262144, 3)):
+        pts, nrm, tgt = phantom.surface_candidates(n, seed=seed)
+        r = det.entry_search(torch.from_numpy(pts).cuda(), torch.from_numpy(nrm).cuda(), tgt)
+        wi, wd = kin.find_entry_point(pts, nrm, tgt)
+        assert r["index"] == wi
+        if wi >= 0:
+            assert r["distance"] == wd, "float64 distance is bit-identical"
+            assert np.array_equal(r["point"], pts[wi].astype(np.float64))
+    # nothing suitable: all normals along y
+    pts, nrm, tgt = phantom.surface_candidates(512, seed=4)
+    bad = np.zeros_like(nrm); bad[:, 1] = 1.0
+    r = det.entry_search(torch.from_numpy(pts).cuda(), torch.from_numpy(bad).cuda(), tgt)
+    assert r["index"] == -1 and r["n_suitable"] == 0
+    # needle-path sampling against a voxel mask (extension; numpy restatement of the same rule)
+    pts, nrm, tgt = phantom.surface_candidates(4096, seed=5)
+    dims = (64, 64, 64)
+    mask = np.ones(dims[::-1], dtype=np.uint8)
+    mask[20:44, 10:30, 30:64] = 0                               # an obstacle the needle may not cross
+    m = np.array([[0.2, 0, 0, 32], [0, 0.2, 0, 32], [0, 0, 0.2, 32]], dtype=np.float64)   # RAS mm -> index
+    S = 16
+    r = det.entry_search(torch.from_numpy(pts).cuda(), torch.from_numpy(nrm).cuda(), tgt, n_path_samples=S,
+                         path_mask=torch.from_numpy(mask).cuda(), ras_to_index=m, path_free_value=1)
+    p64 = pts.astype(np.float64)
+    d = p64 - tgt
+    d2 = d[:, 0] ** 2 + d[:, 1] ** 2 + d[:, 2] ** 2
+    ok = (d2 <= 80.0 ** 2) & ((np.abs(nrm[:, 0].astype(np.float64)) - 2 * np.abs(nrm[:, 1].astype(np.float64))) > -0.5)
+    for k in range(1, S + 1):
+        q = p64 + (k / (S + 1)) * (tgt - p64)
+        idx = np.rint(q @ m[:, :3].T + m[:, 3]).astype(np.int64)
+        inside = ((idx >= 0) & (idx < np.array(dims))).all(axis=1)
+        val = np.zeros(len(pts), dtype=np.int64)
+        ii = idx[inside]
+        val[inside] = mask[ii[:, 2], ii[:, 1], ii[:, 0]]
+        ok &= val == 1
+    want = int(np.flatnonzero(ok)[np.argmin(np.sqrt(d2)[ok])]) if ok.any() else -1
+    assert r["index"] == want and r["n_suitable"] == int(ok.sum())
+    det.close()
+
+
+def test_batch_detector_matches_single(cuda_lib):
+    from mamri_pose_estimation_b200.detector import BatchDetector, FiducialDetector, generate_phantom_cuda
+    specs = [phantom.small_phantom(dims=(128, 96, 64), seed=40, scan_index=i) for i in range(7)]
+    vols = [generate_phantom_cuda(p) for p in specs]
+    bd = BatchDetector(specs[0].dims, n_contexts=3)
+    batch = bd.run(vols, specs[0].spacing, specs[0].origin, specs[0].direction)
+    hosts = [v.cpu().pin_memory() for v in vols]
+    bodies = [torch.empty(v.shape, dtype=torch.uint8).pin_memory() for v in vols]
+    batch_h = bd.run_host(hosts, specs[0].spacing, specs[0].origin, specs[0].direction, body_out=bodies)
+    one = FiducialDetector(specs[0].dims)
+    for v, rb, rh, body in zip(vols, batch, batch_h, bodies):
+        r1 = one.detect(v, spacing=specs[0].spacing, origin=specs[0].origin, direction=specs[0].direction, want_body=True)
+        for r in (rb, rh):
+            assert r.n_labels == r1.n_labels and r.body_label == r1.body_label
+            assert [(m.label, m.count, m.sum_idx, m.sum_mom) for m in r.markers] == \
+                   [(m.label, m.count, m.sum_idx, m.sum_mom) for m in r1.markers]
+        assert np.array_equal(body.numpy(), r1.body_mask.cpu().numpy())
+    bd.close(); one.close()
+
+
+def test_capacity_errors_are_reported_not_fatal(cuda_lib):
+    from mamri_pose_estimation_b200 import _capi
+    from mamri_pose_estimation_b200.detector import DetectParams, FiducialDetector
+    rng = np.random.default_rng(0)
+    vol = torch.from_numpy((rng.random((16, 64, 64)) < 0.3).astype(np.uint8) * 200).cuda()
+    small = FiducialDetector((64, 64, 16), max_runs=1 << 20, max_markers=4)
+    with pytest.raises(_capi.MamriError) as e:
+        small.detect(vol, params=DetectParams(lower=1, upper=255, close_radius=0, min_volume=1, max_volume=5))
+    assert e.value.code == _capi.MAMRI_ERR_CAPACITY
+    # the context stays usable
+    r = small.detect(vol, params=DetectParams(lower=1, upper=255, close_radius=0, min_volume=1e9, max_volume=2e9))
+    assert r.n_labels > 0 and not r.markers
+    with pytest.raises(_capi.MamriError):
+        small.detect(torch.zeros((17, 64, 64), dtype=torch.uint8, device="cuda"))   # larger than the context
+    with pytest.raises(_capi.MamriError):
+        small.detect(vol, params=DetectParams(connectivity=18))
+    small.close()
+
+
+def test_size_independent_properties(cuda_lib):
+    """Closing is extensive and idempotent; 26-components are unions of 6-components; counts sum to the mask."""
+    from mamri_pose_estimation_b200.detector import DetectParams, FiducialDetector, generate_phantom_cuda
+    ph = phantom.config_c4(dims=(256, 256, 128), n_blobs=400)
+    d_vol = generate_phantom_cuda(ph)
+    det = FiducialDetector(ph.dims, max_runs=ph.n_voxels // 4, max_markers=16384)
+    r6 = det.detect(d_vol, spacing=ph.spacing, params=DetectParams(connectivity=6), want_mask=True, want_labels=True)
+    raw = det.detect(d_vol, spacing=ph.spacing, params=DetectParams(close_radius=0), want_mask=True).mask
+    assert bool((r6.mask >= raw).all()), "closing is extensive"
+    again = det.detect(r6.mask * 200, spacing=ph.spacing, params=DetectParams(lower=1, upper=255), want_mask=True).mask
+    assert torch.equal(again, r6.mask), "closing is idempotent"
+    l6 = r6.labels.clone()
+    r26 = det.detect(d_vol, spacing=ph.spacing, params=DetectParams(connectivity=26), want_labels=True)
+    assert r26.n_labels <= r6.n_labels
+    pair = torch.unique(torch.stack([l6.flatten().long(), r26.labels.flatten().long()]), dim=1)
+    assert pair.shape[1] == r6.n_labels + 1, "every 6-component lies in exactly one 26-component"
+    assert int(det.label_counts(r26.n_labels).astype(np.int64).sum()) == r26.n_foreground == int(r6.mask.sum())
+    det.close()

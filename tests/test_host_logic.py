@@ -1,0 +1,60 @@
+"""Host-side logic that needs no GPU: phantom generator, Philox, sharding, table packing."""
+import types
+
+import numpy as np
+import pytest
+
+from mamri_pose_estimation_b200 import distributed as mdist
+from mamri_pose_estimation_b200 import phantom
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors for philox4x32-10
+    def h(c, k):
+        return [int(x[0]) for x in phantom.philox4x32_10([c[0]], [c[1]], [c[2]], [c[3]], k[0], k[1])]
+    assert h((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert h((0xffffffff,) * 4, (0xffffffff,) * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert h((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_phantom_is_deterministic_and_chunk_independent():
+    ph = phantom.small_phantom(dims=(33, 21, 9), seed=4)
+    a = phantom.generate(ph)
+    b = phantom.add_rician_noise(phantom.paint_signal(ph), ph.sigma, ph.seed, ph.scan_index, chunk=1001)
+    assert np.array_equal(a, b)
+    c = phantom.generate(phantom.small_phantom(dims=(33, 21, 9), seed=4, scan_index=1))
+    assert not np.array_equal(a, c), "scan_index selects a different noise stream"
+
+
+def test_noise_statistics():
+    sig = np.zeros((16, 64, 64), dtype=np.uint16)
+    v = phantom.add_rician_noise(sig, 20.0, 7).astype(np.float64)
+    # Rayleigh: mean sigma*sqrt(pi/2), P(v > 65) = exp(-65^2 / (2*400)) ~ 5.1e-3
+    assert abs(v.mean() - 20.0 * np.sqrt(np.pi / 2)) < 0.3
+    assert abs((v > 65).mean() - np.exp(-65 ** 2 / 800.0)) < 1.5e-3
+
+
+def test_baseline_configs_have_the_documented_content():
+    c1, c2 = phantom.config_c1(), phantom.config_c2()
+    assert c1.dims == (256, 256, 128) and c1.truth["n_fiducials"] == 9 and c1.sigma == 10.0
+    assert c2.dims == (512, 512, 256) and c2.truth["n_fiducials"] == 6
+    assert phantom.config_c3(5).scan_index == 5 and phantom.config_c3(5).sigma == 15.0
+    c4 = phantom.config_c4()
+    assert c4.dims == (1024, 1024, 512) and c4.truth["n_fiducials"] == 32 and c4.sigma == 20.0
+    pts, nrm, tgt = phantom.surface_candidates(1000)
+    assert pts.shape == (1000, 3) and pts.dtype == np.float32 and np.allclose(np.linalg.norm(nrm, axis=1), 1, atol=1e-5)
+
+
+def test_sharding_is_a_partition():
+    for n, w in ((64, 8), (10, 4), (3, 8)):
+        seen = sorted(i for r in range(w) for i in mdist.shard_indices(n, r, w))
+        assert seen == list(range(n))
+
+
+def test_pack_table_layout():
+    m = types.SimpleNamespace(label=3, count=100, volume_mm3=51.2, centroid_ras=np.array([1.0, 2.0, 3.0]))
+    r = types.SimpleNamespace(markers=[m], n_labels=7, body_label=1)
+    t = mdist.pack_table([r, r])
+    assert t.shape == (2, mdist.TABLE_SLOTS, mdist.TABLE_FIELDS)
+    assert t[1, 0].tolist() == [3, 100, 51.2, 1.0, 2.0, 3.0, 7, 1] and not t[:, 1:].any()
