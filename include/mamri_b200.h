@@ -148,6 +148,9 @@ MAMRI_API int mamri_label_counts(mamri_ctx* ctx, uint32_t* h_counts, uint32_t ma
  * {threshold+pack, closing, connected components, statistics+filter, materialise}. */
 MAMRI_API int mamri_set_profiling(mamri_ctx* ctx, int enable);
 MAMRI_API int mamri_stage_times(mamri_ctx* ctx, float ms[5]);
+/* Per-kernel milliseconds of the last profiled scan, in launch order; returns the number of entries
+ * written (<= max_n) or a negative status. */
+MAMRI_API int mamri_kernel_times(mamri_ctx* ctx, float* ms, const char** names, int max_n);
 
 /* ---- stage 4b: replaces the loop at Mamri.py:1008-1023 ---------------------------------- */
 /* d_points / d_normals: float32 [n][3] (RAS mm / unit normals), as vtkPolyData stores them.

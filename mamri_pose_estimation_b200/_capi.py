@@ -62,6 +62,7 @@ SIGNATURES = {
     "mamri_label_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "mamri_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mamri_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "mamri_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.c_int]),
     "mamri_entry_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_double,
                                      C.c_double, C.c_double, C.c_double, C.c_int32, C.c_void_p, C.POINTER(VolumeDesc),
                                      C.POINTER(C.c_double), C.c_int32, C.POINTER(EntryResult), C.c_void_p]),

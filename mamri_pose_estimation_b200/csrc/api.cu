@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 #include <new>
+#include <stdlib.h>
 
 static char g_create_err[512] = "";
 
@@ -66,11 +67,15 @@ extern "C" int mamri_destroy(mamri_ctx* ctx) {
     if (!ctx) return MAMRI_OK;
     DeviceGuard g(ctx->device);
     cudaFree(ctx->d_raw); cudaFree(ctx->d_planes); cudaFree(ctx->d_dil); cudaFree(ctx->d_closed); cudaFree(ctx->d_word_base);
-    cudaFree(ctx->d_parent); cudaFree(ctx->d_run_label); cudaFree(ctx->d_label_count); cudaFree(ctx->d_label_slot);
+    cudaFree(ctx->d_run_pos); cudaFree(ctx->d_run_len); cudaFree(ctx->d_parent); cudaFree(ctx->d_run_label); cudaFree(ctx->d_label_count); cudaFree(ctx->d_label_slot);
     cudaFree(ctx->d_block_sums); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
     cudaFree(ctx->d_summary); cudaFree(ctx->d_scalars); cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
     cudaFree(ctx->d_entry_dist); cudaFree(ctx->d_entry_idx); cudaFree(ctx->d_entry_cnt); cudaFree(ctx->d_entry_res);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 48; ++i) if (ctx->ev_fine[i]) cudaEventDestroy(ctx->ev_fine[i]);
+    if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
+    if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
+    cudaFree(ctx->d_dyn); cudaFreeHost(ctx->h_dyn);
     cudaFreeHost(ctx->h_markers); cudaFreeHost(ctx->h_summary); cudaFreeHost(ctx->h_entry_res);
     delete ctx;
     return MAMRI_OK;
@@ -130,6 +135,8 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     ALLOC(ctx->d_dil, ctx->cap_pad_words * 4, "dilated mask");
     ALLOC(ctx->d_closed, ctx->cap_words * 4, "closed mask");
     ALLOC(ctx->d_word_base, ctx->cap_words * 4, "run bases");
+    ALLOC(ctx->d_run_pos, size_t(max_runs) * 4, "run positions");
+    ALLOC(ctx->d_run_len, size_t(max_runs) * 4, "run lengths");
     ALLOC(ctx->d_parent, size_t(max_runs) * 4, "union-find parents");
     ALLOC(ctx->d_run_label, size_t(max_runs) * 4, "run labels");
     ALLOC(ctx->d_label_count, size_t(max_runs) * 4, "label counts");
@@ -152,6 +159,13 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
         return bail(e, "pinned entry result");
     for (int i = 0; i < 6; ++i)
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bail(e, "events");
+    if ((e = cudaMalloc((void**)&ctx->d_dyn, sizeof(DynArgs))) != cudaSuccess) return bail(e, "dynamic args");
+    if ((e = cudaMallocHost((void**)&ctx->h_dyn, sizeof(DynArgs))) != cudaSuccess) return bail(e, "pinned dynamic args");
+    if ((e = cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "capture stream");
+    {
+        const char* ng = getenv("MAMRI_NO_GRAPH");
+        ctx->use_graph = !(ng && ng[0] == '1');
+    }
     *out = ctx;
     return MAMRI_OK;
 }
@@ -170,6 +184,18 @@ extern "C" int mamri_stage_times(mamri_ctx* ctx, float* ms) {
     return MAMRI_OK;
 }
 
+extern "C" int mamri_kernel_times(mamri_ctx* ctx, float* ms, const char** names, int max_n) {
+    if (!ctx || !ms || !names) return MAMRI_ERR_INVALID_ARG;
+    if (ctx->pending) return fail(ctx, MAMRI_ERR_STATE, "collect the pending detect first");
+    DeviceGuard g(ctx->device);
+    int n = ctx->n_fine < max_n ? ctx->n_fine : max_n;
+    for (int i = 0; i < n; ++i) {
+        CK(cudaEventElapsedTime(ms + i, i == 0 ? ctx->ev[0] : ctx->ev_fine[i - 1], ctx->ev_fine[i]));
+        names[i] = ctx->fine_name[i];
+    }
+    return n;
+}
+
 static int validate(mamri_ctx* ctx, const mamri_volume_desc* d, const mamri_params* p) {
     if (!d || !p) return fail(ctx, MAMRI_ERR_INVALID_ARG, "desc/params is NULL");
     if (d->nx <= 0 || d->ny <= 0 || d->nz <= 0) return fail(ctx, MAMRI_ERR_INVALID_ARG, "volume dimensions must be positive");
@@ -184,6 +210,31 @@ static int validate(mamri_ctx* ctx, const mamri_volume_desc* d, const mamri_para
     return MAMRI_OK;
 }
 
+// Enqueues the stage kernels and the result copies on `s` (a real stream or one in capture mode).
+static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, cudaStream_t s) {
+    const mamri_volume_desc* desc = &k.desc;
+    const mamri_params* params = &k.prm;
+    const int nx = desc->nx, ny = desc->ny, nz = desc->nz;
+    CK(cudaMemcpyAsync(ctx->d_dyn, ctx->h_dyn, sizeof(DynArgs), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(DevScalars), s));
+    if (prof) { ctx->n_fine = 0; CK(cudaEventRecord(ctx->ev[0], s)); }
+    CK(launch_threshold_pack(ctx, k.vol_aligned, desc->dtype, nx, ny, nz, params->lower, params->upper, params->close_radius, s));
+    if (prof) CK(cudaEventRecord(ctx->ev[1], s));
+    const uint32_t* mask = ctx->d_closed;
+    if (params->close_radius > 0) CK(launch_closing(ctx, nx, ny, nz, params->close_radius, s));
+    if (prof) CK(cudaEventRecord(ctx->ev[2], s));
+    CK(launch_ccl(ctx, mask, nx, ny, nz, params->connectivity, s));
+    if (prof) CK(cudaEventRecord(ctx->ev[3], s));
+    CK(launch_stats(ctx, mask, desc, params, s));
+    if (prof) CK(cudaEventRecord(ctx->ev[4], s));
+    if (k.has_mask || k.has_labels || k.has_body) CK(launch_materialise(ctx, mask, nx, ny, nz, k.outs_aligned, s));
+    if (prof) CK(cudaEventRecord(ctx->ev[5], s));
+    CK(cudaMemcpyAsync(ctx->h_summary, ctx->d_summary, sizeof(mamri_summary), cudaMemcpyDeviceToHost, s));
+    const uint32_t eager = ctx->max_markers < EAGER_MARKERS ? ctx->max_markers : EAGER_MARKERS;
+    CK(cudaMemcpyAsync(ctx->h_markers, ctx->d_markers, size_t(eager) * sizeof(mamri_marker), cudaMemcpyDeviceToHost, s));
+    return MAMRI_OK;
+}
+
 extern "C" int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* d_volume,
                                   const mamri_params* params, uint8_t* d_mask_out, uint32_t* d_labels_out,
                                   uint8_t* d_body_out, void* stream) {
@@ -194,24 +245,47 @@ extern "C" int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc,
     if (ctx->pending) return fail(ctx, MAMRI_ERR_STATE, "a detect is already pending on this context; collect it first");
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int nx = desc->nx, ny = desc->ny, nz = desc->nz;
-    const bool prof = ctx->profile;
-    CK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(DevScalars), s));
-    if (prof) CK(cudaEventRecord(ctx->ev[0], s));
-    CK(launch_threshold_pack(ctx, d_volume, desc->dtype, nx, ny, nz, params->lower, params->upper, params->close_radius, s));
-    if (prof) CK(cudaEventRecord(ctx->ev[1], s));
-    const uint32_t* mask = ctx->d_closed;
-    if (params->close_radius > 0) CK(launch_closing(ctx, nx, ny, nz, params->close_radius, s));
-    if (prof) CK(cudaEventRecord(ctx->ev[2], s));
-    CK(launch_ccl(ctx, mask, nx, ny, nz, params->connectivity, s));
-    if (prof) CK(cudaEventRecord(ctx->ev[3], s));
-    CK(launch_stats(ctx, mask, desc, params, s));
-    if (prof) CK(cudaEventRecord(ctx->ev[4], s));
-    CK(launch_materialise(ctx, mask, nx, ny, nz, d_mask_out, d_labels_out, d_body_out, s));
-    if (prof) CK(cudaEventRecord(ctx->ev[5], s));
-    CK(cudaMemcpyAsync(ctx->h_summary, ctx->d_summary, sizeof(mamri_summary), cudaMemcpyDeviceToHost, s));
-    const uint32_t eager = ctx->max_markers < EAGER_MARKERS ? ctx->max_markers : EAGER_MARKERS;
-    CK(cudaMemcpyAsync(ctx->h_markers, ctx->d_markers, size_t(eager) * sizeof(mamri_marker), cudaMemcpyDeviceToHost, s));
+    GraphKey k;
+    memset(&k, 0, sizeof(k));
+    k.desc = *desc;
+    k.prm = *params;
+    k.vol_aligned = (reinterpret_cast<uintptr_t>(d_volume) & 15u) == 0;
+    k.outs_aligned = ((reinterpret_cast<uintptr_t>(d_labels_out) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(d_mask_out) & 3u) == 0) && ((reinterpret_cast<uintptr_t>(d_body_out) & 3u) == 0);
+    k.has_mask = d_mask_out != nullptr; k.has_labels = d_labels_out != nullptr; k.has_body = d_body_out != nullptr;
+    ctx->h_dyn->vol = d_volume;
+    ctx->h_dyn->mask_out = d_mask_out;
+    ctx->h_dyn->labels_out = d_labels_out;
+    ctx->h_dyn->body_out = d_body_out;
+    CK(prepare_raw_apron(ctx, desc->nx, desc->ny, desc->nz, params->close_radius, s));
+    if (ctx->profile || !ctx->use_graph) {
+        rc = enqueue_pipeline(ctx, k, ctx->profile, s);
+        if (rc != MAMRI_OK) return rc;
+    } else {
+        if (!ctx->gvalid || memcmp(&k, &ctx->gkey, sizeof(k)) != 0) {
+            // (re)capture: the pipeline is a fixed kernel sequence for a given geometry and parameter set
+            if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
+            ctx->gvalid = false;
+            CK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_pipeline(ctx, k, false, ctx->cap_stream);
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamEndCapture(ctx->cap_stream, &graph);
+            if (rc != MAMRI_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) {
+                snprintf(ctx->err, sizeof(ctx->err), "graph capture failed: %s", cudaGetErrorString(e));
+                return MAMRI_ERR_CUDA;
+            }
+            e = cudaGraphInstantiate(&ctx->gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) {
+                snprintf(ctx->err, sizeof(ctx->err), "graph instantiation failed: %s", cudaGetErrorString(e));
+                return MAMRI_ERR_CUDA;
+            }
+            ctx->gkey = k;
+            ctx->gvalid = true;
+        }
+        CK(cudaGraphLaunch(ctx->gexec, s));
+    }
     ctx->pending = true;
     ctx->pending_stream = s;
     ctx->last_desc = *desc;

@@ -11,6 +11,8 @@
 // of the stage is the final label write (materialise.cu side of this file).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 constexpr int SCAN_THREADS = 1024;
 
 // ------------------------------------------------------------------------------------------------
@@ -69,7 +71,7 @@ __device__ __forceinline__ void chunk_of(uint32_t n, uint32_t& begin, uint32_t& 
 }
 
 // ------------------------------------------------------------------------------------------------
-// run numbering: exclusive scan of run starts per word (3 small launches)
+// run numbering: exclusive scan of run starts per word, and the run table
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SCAN_THREADS) k_runs_count(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
                                                              uint32_t* __restrict__ block_sums) {
@@ -88,40 +90,69 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_runs_count(const uint32_t* __r
     if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
 }
 
-// One CTA: exclusive scan of the per-CTA partials in place; total -> *out_total (capacity-checked).
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(uint32_t* __restrict__ block_sums, int n_blocks,
-                                                                unsigned int* out_total, unsigned int limit,
-                                                                DevScalars* sc) {
-    __shared__ uint32_t ws[33];
-    uint32_t v = int(threadIdx.x) < n_blocks ? block_sums[threadIdx.x] : 0u;
-    uint32_t total;
-    uint32_t ex = block_excl_scan(v, ws, total);
-    if (int(threadIdx.x) < n_blocks) block_sums[threadIdx.x] = ex;
-    if (threadIdx.x == 0) {
-        if (total > limit) { sc->status = MAMRI_ERR_CAPACITY; total = 0; }
-        *out_total = total;
-    }
+// Exclusive prefix of this CTA over the per-CTA partials (every CTA rescans the <= 1024 partials
+// itself: cheaper than a separate one-CTA launch); `total` = grand total.
+__device__ __forceinline__ uint32_t scan_partials(const uint32_t* __restrict__ block_sums, uint32_t* ws, uint32_t& total) {
+    __shared__ uint32_t mine;
+    const uint32_t v = threadIdx.x < gridDim.x ? block_sums[threadIdx.x] : 0u;
+    const uint32_t ex = block_excl_scan(v, ws, total);
+    if (threadIdx.x == blockIdx.x) mine = ex;
+    __syncthreads();
+    return mine;
 }
 
+// word_base[w] = number of runs that start before word w; run table: position (word*32 + bit of the
+// first voxel) and length of every run, in raster order.
 __global__ void __launch_bounds__(SCAN_THREADS) k_runs_assign(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
                                                               const uint32_t* __restrict__ block_sums,
-                                                              uint32_t* __restrict__ word_base, const DevScalars* sc) {
+                                                              uint32_t* __restrict__ word_base,
+                                                              uint32_t* __restrict__ run_pos, uint32_t* __restrict__ run_len,
+                                                              uint32_t max_runs, DevScalars* sc) {
     __shared__ uint32_t ws[33];
-    if (sc->status != MAMRI_OK) return;
+    uint32_t total_runs;
+    uint32_t running = scan_partials(block_sums, ws, total_runs);
+    if (total_runs > max_runs) {                      // every CTA sees the same total
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sc->status = MAMRI_ERR_CAPACITY; sc->n_runs = 0; }
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc->n_runs = total_runs;
     uint32_t begin, end;
     chunk_of(n_words, begin, end);
-    uint32_t running = block_sums[blockIdx.x];
     for (uint32_t i0 = begin; i0 < end; i0 += SCAN_THREADS) {
-        uint32_t i = i0 + threadIdx.x;
-        uint32_t starts = 0;
+        const uint32_t i = i0 + threadIdx.x;
+        uint32_t m = 0, starts = 0, xw = 0;
         if (i < end) {
-            uint32_t m = mask[i];
-            if (m) starts = run_starts(m, (i % W) ? mask[i - 1] : 0u);
+            m = mask[i];
+            if (m) {
+                xw = i % W;
+                starts = run_starts(m, xw ? mask[i - 1] : 0u);
+            }
         }
         uint32_t cnt = __popc(starts), total;
         uint32_t base = running + block_excl_scan(cnt, ws, total);
         if (i < end) {
             word_base[i] = base;
+            uint32_t st = starts, r = base;
+            while (st) {
+                const int b = __ffs(st) - 1;
+                st &= st - 1;
+                const uint32_t t = m >> b;                       // run bits from its start
+                uint32_t len;
+                if (t != (0xFFFFFFFFu >> b)) {
+                    len = __ffs(~t) - 1;                         // ends inside this word
+                } else {
+                    len = 32 - b;                                // reaches bit 31: follow it through the next words
+                    for (uint32_t k = 1; xw + k < uint32_t(W); ++k) {
+                        const uint32_t nm = mask[i + k];
+                        if (nm == 0xFFFFFFFFu) { len += 32; continue; }
+                        len += __ffs(~nm) - 1;
+                        break;
+                    }
+                }
+                run_pos[r] = i * 32u + uint32_t(b);
+                run_len[r] = len;
+                ++r;
+            }
         }
         running += total;
     }
@@ -156,83 +187,74 @@ __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t 
     }
 }
 
-// Joins the runs of word (xw,y,z) with the runs of one earlier neighbour row.  DIAG adds the
-// x+-1 contacts (26-connectivity).  Every maximal piece of overlapping bits lies in exactly one run
-// on either side, so one union per piece start suffices; pieces continuing from the previous word
-// are skipped (their start was handled there).  Node ids are run ids minus `id_off`.
+// Joins run `node` (x range [gx0, gx0+len) of its row) with every run of one earlier neighbour row
+// that touches it: same x for face connectivity; DIAG widens the range by one voxel each side
+// (26-connectivity).  Every maximal piece of neighbour bits inside the range lies in exactly one
+// neighbour run, so one union per piece start suffices (a piece continuing from the previous word
+// belongs to the run already joined).  Node ids are run ids minus `id_off`.
 template <bool DIAG>
-__device__ __forceinline__ void join_row(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
-                                         uint32_t* parent, uint32_t id_off, int W, int xw, uint32_t m, uint32_t m_prev,
-                                         uint32_t base_m, uint32_t starts_m, uint32_t ni) {
-    const uint32_t up = mask[ni];
-    const uint32_t up_prev = xw > 0 ? mask[ni - 1] : 0u;
-    const uint32_t up_next = (DIAG && xw + 1 < W) ? mask[ni + 1] : 0u;
-    if (!DIAG && !up) return;
-    if (DIAG && !(up | (up_prev >> 31) | (up_next & 1u))) return;
-    const uint32_t starts_up = run_starts(up, up_prev);
-    const uint32_t base_up = word_base[ni] - id_off;
-    base_m -= id_off;
-    // direct (same x) contacts
-    uint32_t ov = m & up;
-    uint32_t ps = ov & ~((ov << 1) | ((m_prev & up_prev) >> 31));
-    while (ps) {
-        int b = __ffs(ps) - 1;
-        ps &= ps - 1;
-        uf_union(parent, run_id_in_word(base_m, starts_m, b), run_id_in_word(base_up, starts_up, b));
-    }
-    if (DIAG) {
-        // bit b of m touching up(b-1) where up(b) is clear: the run of `up` ending at b-1
-        // (skipped when m(b-1) is set too: the direct contact at b-1 already joined the same two runs)
-        uint32_t a = m & ~up & ((up << 1) | (up_prev >> 31)) & ~((m << 1) | (m_prev >> 31));
-        while (a) {
-            int b = __ffs(a) - 1;
-            a &= a - 1;
-            uint32_t rid_up = b > 0 ? run_id_in_word(base_up, starts_up, b - 1) : base_up - 1u;
-            uf_union(parent, run_id_in_word(base_m, starts_m, b), rid_up);
+__device__ __forceinline__ void join_run(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
+                                         uint32_t* parent, uint32_t id_off, int W, uint32_t node, int gx0, int len,
+                                         uint32_t nbr_row) {
+    int lo = gx0 - (DIAG ? 1 : 0), hi = gx0 + len - 1 + (DIAG ? 1 : 0);
+    if (lo < 0) lo = 0;
+    if (hi > W * 32 - 1) hi = W * 32 - 1;
+    const int w_lo = lo >> 5, w_hi = hi >> 5;
+    uint32_t carry = 0;
+    for (int w = w_lo; w <= w_hi; ++w) {
+        const uint32_t up = mask[nbr_row + w];
+        uint32_t seg = 0xFFFFFFFFu;
+        if (w == w_lo) seg &= 0xFFFFFFFFu << (lo & 31);
+        if (w == w_hi) seg &= 0xFFFFFFFFu >> (31 - (hi & 31));
+        const uint32_t t = up & seg;
+        uint32_t ps = t & ~((t << 1) | carry);
+        if (ps) {
+            const uint32_t up_prev = w > 0 ? mask[nbr_row + w - 1] : 0u;
+            const uint32_t starts_up = run_starts(up, up_prev);
+            const uint32_t base_up = word_base[nbr_row + w] - id_off;
+            while (ps) {
+                const int bit = __ffs(ps) - 1;
+                ps &= ps - 1;
+                uf_union(parent, node, run_id_in_word(base_up, starts_up, bit));
+            }
         }
-        // bit b of m touching up(b+1) where up(b) is clear: the run of `up` starting at b+1
-        uint32_t c = m & ~up & ((up >> 1) | (up_next << 31)) & ~(m >> 1);
-        while (c) {
-            int b = __ffs(c) - 1;
-            c &= c - 1;
-            uint32_t rid_up = b < 31 ? run_id_in_word(base_up, starts_up, b + 1) : word_base[ni + 1] - id_off;
-            uf_union(parent, run_id_in_word(base_m, starts_m, b), rid_up);
-        }
+        carry = t >> 31;
     }
 }
 
 // Phase 1 -- block-local: one CTA per z-slice.  The runs of a slice are contiguous in id space, so the
 // CTA keeps their parents in shared memory (local index = run id - first run of the slice), joins
-// every row with the row above it at shared-memory latency (simultaneous hooking builds chains as
-// long as the object is tall; in shared memory a hop costs ~30 cycles instead of an L2 round trip),
-// flattens, and publishes parent[run] = slice-local root as a global id.  Slices with more runs than
-// fit fall back to the same code on the global array.
+// every run with the runs of the row above at shared-memory latency (simultaneous hooking builds
+// chains as long as the object is tall; in shared memory a hop costs ~30 cycles instead of an L2 round
+// trip), flattens, and publishes parent[run] = slice-local root as a global id.  Slices with more runs
+// than fit fall back to the same code on the global array.
 constexpr int SLICE_THREADS = 512;
 constexpr uint32_t SLICE_SMEM_RUNS = 12000;      // 48 KB static shared memory
 
 template <bool CONN26>
 __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* __restrict__ mask,
-                                                               const uint32_t* __restrict__ word_base, uint32_t* parent,
+                                                               const uint32_t* __restrict__ word_base,
+                                                               const uint32_t* __restrict__ run_pos,
+                                                               const uint32_t* __restrict__ run_len, uint32_t* parent,
                                                                int W, int ny, int nz, const DevScalars* sc) {
     __shared__ uint32_t sp[SLICE_SMEM_RUNS];
     if (sc->status != MAMRI_OK) return;
-    const int z = blockIdx.x;
+    const uint32_t z = blockIdx.x;
     const uint32_t slice_words = uint32_t(W) * ny;
-    const uint32_t w0 = uint32_t(z) * slice_words;
+    const uint32_t w0 = z * slice_words;
     const uint32_t r0 = word_base[w0];
-    const uint32_t r1 = (z + 1 < nz) ? word_base[w0 + slice_words] : sc->n_runs;
+    const uint32_t r1 = (z + 1 < uint32_t(nz)) ? word_base[w0 + slice_words] : sc->n_runs;
     const uint32_t n = r1 - r0;
     if (n == 0) return;
     uint32_t* P = (n <= SLICE_SMEM_RUNS) ? sp : parent + r0;
     for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) P[i] = i;
     __syncthreads();
-    for (uint32_t i = uint32_t(W) + threadIdx.x; i < slice_words; i += SLICE_THREADS) {     // rows y >= 1
-        const uint32_t wi = w0 + i;
-        const uint32_t m = mask[wi];
-        if (!m) continue;
-        const int xw = int(i % W);
-        const uint32_t m_prev = xw > 0 ? mask[wi - 1] : 0u;
-        join_row<CONN26>(mask, word_base, P, r0, W, xw, m, m_prev, word_base[wi], run_starts(m, m_prev), wi - W);
+    for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) {
+        const uint32_t pos = run_pos[r0 + i];
+        const uint32_t wi = pos >> 5, row = wi / W;
+        if (row == z * ny) continue;                                        // y == 0: no row above in this slice
+        const int gx0 = int((wi - row * W) * 32 + (pos & 31u));
+        join_run<CONN26>(mask, word_base, P, r0, W, i, gx0, int(run_len[r0 + i]), (row - 1) * W);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) {
@@ -250,32 +272,30 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
 // then the boundaries between blocks (again <= radix of them per chain).
 template <bool CONN26>
 __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
-                                                 uint32_t* parent, int W, int ny, int nz, uint32_t n_words, int radix,
-                                                 int between_blocks, const DevScalars* sc) {
+                                                 const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_len,
+                                                 uint32_t* parent, int W, int ny, int radix, int between_blocks,
+                                                 const DevScalars* sc) {
     if (sc->status != MAMRI_OK) return;
-    const uint32_t slice = uint32_t(W) * ny;
-    for (uint32_t wi = slice + uint32_t(blockIdx.x) * blockDim.x + threadIdx.x; wi < n_words;
-         wi += uint32_t(gridDim.x) * blockDim.x) {
-        const int z = int(wi / slice);
-        if (((z % radix) == 0) != (between_blocks != 0)) continue;
-        const uint32_t m = mask[wi];
-        if (!m) continue;
-        const uint32_t row = wi / W;
-        const int xw = int(wi - row * W);
-        const int y = int(row % ny);
-        const uint32_t m_prev = xw > 0 ? mask[wi - 1] : 0u;
-        const uint32_t starts_m = run_starts(m, m_prev);
-        const uint32_t base_m = word_base[wi];
-        join_row<CONN26>(mask, word_base, parent, 0u, W, xw, m, m_prev, base_m, starts_m, wi - slice);
+    const uint32_t n = sc->n_runs;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const uint32_t pos = run_pos[r];
+        const uint32_t wi = pos >> 5, row = wi / W;
+        const uint32_t z = row / ny;
+        if (z == 0 || ((z % radix) == 0) != (between_blocks != 0)) continue;
+        const uint32_t y = row - z * ny;
+        const int gx0 = int((wi - row * W) * 32 + (pos & 31u));
+        const int len = int(run_len[r]);
+        const uint32_t below = (row - ny) * W;                              // row (y, z-1)
+        join_run<CONN26>(mask, word_base, parent, 0u, W, r, gx0, len, below);
         if (CONN26) {
-            if (y > 0) join_row<true>(mask, word_base, parent, 0u, W, xw, m, m_prev, base_m, starts_m, wi - slice - W);
-            if (y + 1 < ny) join_row<true>(mask, word_base, parent, 0u, W, xw, m, m_prev, base_m, starts_m, wi - slice + W);
+            if (y > 0) join_run<true>(mask, word_base, parent, 0u, W, r, gx0, len, below - W);
+            if (y + 1 < uint32_t(ny)) join_run<true>(mask, word_base, parent, 0u, W, r, gx0, len, below + W);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// flatten, rank the roots (ITK-consecutive labels), propagate to every run
+// flatten, rank the roots (ITK-consecutive labels)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SCAN_THREADS) k_flatten_count(uint32_t* parent, uint32_t* __restrict__ block_sums,
                                                                 const DevScalars* sc) {
@@ -293,14 +313,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_flatten_count(uint32_t* parent
     if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
 }
 
+// run_label[root] = 1 + number of roots before it (roots are ordered by minimum linear index, so this
+// is ITK's consecutive numbering); non-root runs get their label from their root in the next kernel.
 __global__ void __launch_bounds__(SCAN_THREADS) k_rank_roots(const uint32_t* __restrict__ parent,
                                                              const uint32_t* __restrict__ block_sums,
                                                              uint32_t* __restrict__ run_label,
-                                                             uint32_t* __restrict__ label_count, const DevScalars* sc) {
+                                                             uint32_t* __restrict__ label_count, DevScalars* sc) {
     __shared__ uint32_t ws[33];
+    uint32_t total_roots;
+    uint32_t running = scan_partials(block_sums, ws, total_roots);
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc->n_labels = total_roots;
     uint32_t begin, end;
     chunk_of(sc->n_runs, begin, end);
-    uint32_t running = block_sums[blockIdx.x];
     for (uint32_t i0 = begin; i0 < end; i0 += SCAN_THREADS) {
         uint32_t r = i0 + threadIdx.x;
         uint32_t is_root = (r < end && parent[r] == uint32_t(r)) ? 1u : 0u, total;
@@ -313,15 +337,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_rank_roots(const uint32_t* __r
     }
 }
 
-__global__ void __launch_bounds__(256) k_propagate_labels(const uint32_t* __restrict__ parent, uint32_t* run_label,
-                                                          const DevScalars* sc) {
-    const uint32_t n = sc->n_runs;
-    for (uint32_t r = uint32_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += uint32_t(gridDim.x) * blockDim.x) {
-        uint32_t p = parent[r];
-        if (p != uint32_t(r)) run_label[r] = run_label[p];   // roots were written by k_rank_roots
-    }
-}
-
 cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int connectivity, cudaStream_t s) {
     const int W = (nx + 31) / 32;
     const uint32_t n_words = uint32_t(W) * ny * nz;
@@ -329,26 +344,46 @@ cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int
     uint32_t* bs_runs = c->d_block_sums;
     uint32_t* bs_roots = c->d_block_sums + 1024;
     k_runs_count<<<G, SCAN_THREADS, 0, s>>>(d_mask, W, n_words, bs_runs);
-    k_scan_partials<<<1, SCAN_THREADS, 0, s>>>(bs_runs, G, &c->d_scalars->n_runs, c->max_runs, c->d_scalars);
-    k_runs_assign<<<G, SCAN_THREADS, 0, s>>>(d_mask, W, n_words, bs_runs, c->d_word_base, c->d_scalars);
+    prof_mark(c, s, "runs_count");
+    k_runs_assign<<<G, SCAN_THREADS, 0, s>>>(d_mask, W, n_words, bs_runs, c->d_word_base, c->d_run_pos, c->d_run_len,
+                                            c->max_runs, c->d_scalars);
+    prof_mark(c, s, "runs_assign");
     int radix = 1;
     while (radix * radix < nz) radix <<= 1;
-    uint32_t ub = (n_words + 255) / 256;
-    if (ub > 148 * 16) ub = 148 * 16;
-    if (ub == 0) ub = 1;
+    const int RG = MAMRI_RUN_CTAS;
     if (connectivity == 26) {
-        k_union_slices<true><<<nz, SLICE_THREADS, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, c->d_scalars);
-        if (nz > 1) k_union_z<true><<<unsigned(ub), 256, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, n_words, radix, 0, c->d_scalars);
-        if (nz > radix) k_union_z<true><<<unsigned(ub), 256, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, n_words, radix, 1, c->d_scalars);
+        k_union_slices<true><<<nz, SLICE_THREADS, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W,
+                                                          ny, nz, c->d_scalars);
+        prof_mark(c, s, "union_slices");
+        if (nz > 1) {
+            k_union_z<true><<<RG, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 0,
+                                               c->d_scalars);
+            prof_mark(c, s, "union_z_within_blocks");
+        }
+        if (nz > radix) {
+            k_union_z<true><<<RG, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 1,
+                                               c->d_scalars);
+            prof_mark(c, s, "union_z_between_blocks");
+        }
     } else {
-        k_union_slices<false><<<nz, SLICE_THREADS, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, c->d_scalars);
-        if (nz > 1) k_union_z<false><<<unsigned(ub), 256, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, n_words, radix, 0, c->d_scalars);
-        if (nz > radix) k_union_z<false><<<unsigned(ub), 256, 0, s>>>(d_mask, c->d_word_base, c->d_parent, W, ny, nz, n_words, radix, 1, c->d_scalars);
+        k_union_slices<false><<<nz, SLICE_THREADS, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W,
+                                                           ny, nz, c->d_scalars);
+        prof_mark(c, s, "union_slices");
+        if (nz > 1) {
+            k_union_z<false><<<RG, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 0,
+                                                c->d_scalars);
+            prof_mark(c, s, "union_z_within_blocks");
+        }
+        if (nz > radix) {
+            k_union_z<false><<<RG, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 1,
+                                                c->d_scalars);
+            prof_mark(c, s, "union_z_between_blocks");
+        }
     }
     k_flatten_count<<<G, SCAN_THREADS, 0, s>>>(c->d_parent, bs_roots, c->d_scalars);
-    k_scan_partials<<<1, SCAN_THREADS, 0, s>>>(bs_roots, G, &c->d_scalars->n_labels, 0xFFFFFFFFu, c->d_scalars);
+    prof_mark(c, s, "flatten_count");
     k_rank_roots<<<G, SCAN_THREADS, 0, s>>>(c->d_parent, bs_roots, c->d_run_label, c->d_label_count, c->d_scalars);
-    k_propagate_labels<<<148 * 4, 256, 0, s>>>(c->d_parent, c->d_run_label, c->d_scalars);
+    prof_mark(c, s, "rank_roots");
     return cudaGetLastError();
 }
 
@@ -362,9 +397,11 @@ template <bool ALIGNED>
 __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict__ mask,
                                                      const uint32_t* __restrict__ word_base,
                                                      const uint32_t* __restrict__ run_label, int nx, int W,
-                                                     uint32_t n_words, uint8_t* __restrict__ mask_out,
-                                                     uint32_t* __restrict__ labels_out, uint8_t* __restrict__ body_out,
+                                                     uint32_t n_words, const DynArgs* __restrict__ dyn,
                                                      const DevScalars* sc) {
+    uint8_t* __restrict__ mask_out = dyn->mask_out;
+    uint32_t* __restrict__ labels_out = dyn->labels_out;
+    uint8_t* __restrict__ body_out = dyn->body_out;
     const bool ok = sc->status == MAMRI_OK;
     const uint32_t body = body_out ? (0xFFFFFFFFu - uint32_t(sc->body_packed & 0xFFFFFFFFull)) : 0u;
     const bool has_body = body_out && (sc->body_packed >> 32) != 0;
@@ -454,26 +491,25 @@ __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict_
     }
 }
 
-cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, uint8_t* d_mask_out,
-                               uint32_t* d_labels_out, uint8_t* d_body_out, cudaStream_t s) {
-    if (!d_mask_out && !d_labels_out && !d_body_out) return cudaSuccess;
+cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int outs_aligned,
+                               cudaStream_t s) {
     const int W = (nx + 31) / 32;
     const uint32_t n_words = uint32_t(W) * ny * nz;
-    const bool aligned = (nx % 32 == 0) && ((reinterpret_cast<uintptr_t>(d_labels_out) & 15u) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(d_mask_out) & 3u) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(d_body_out) & 3u) == 0);
+    const bool aligned = (nx % 32 == 0) && outs_aligned;
     if (aligned) {
         uint32_t blocks = (n_words / 32 + 7) / 8;
-        if (blocks > 148 * 8 * 2) blocks = 148 * 8 * 2;
+        static const int per_sm = [] { const char* e = getenv("MAMRI_MAT_CTAS_PER_SM"); return e ? atoi(e) : 16; }();
+        if (blocks > uint32_t(148 * per_sm)) blocks = uint32_t(148 * per_sm);
         if (blocks == 0) blocks = 1;
-        k_materialise<true><<<unsigned(blocks), 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, nx, W, n_words,
-                                                             d_mask_out, d_labels_out, d_body_out, c->d_scalars);
+        k_materialise<true><<<blocks, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, nx, W, n_words, c->d_dyn,
+                                                   c->d_scalars);
     } else {
         uint32_t blocks = (n_words + 7) / 8;
         if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
         if (blocks == 0) blocks = 1;
-        k_materialise<false><<<unsigned(blocks), 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, nx, W, n_words,
-                                                              d_mask_out, d_labels_out, d_body_out, c->d_scalars);
+        k_materialise<false><<<blocks, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, nx, W, n_words, c->d_dyn,
+                                                    c->d_scalars);
     }
+    prof_mark(c, s, "materialise");
     return cudaGetLastError();
 }

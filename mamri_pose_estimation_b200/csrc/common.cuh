@@ -10,6 +10,7 @@
 
 #define MAMRI_RMAX 3                 // largest closing radius the scratch layout is sized for
 #define MAMRI_SCAN_CTAS 592          // 148 SMs x 4: CTA count of the chunked scans
+#define MAMRI_RUN_CTAS (148 * 4)     // CTA count of the per-run kernels (grid-stride over the run table)
 #define MAMRI_NONE 0xFFFFFFFFu
 
 // Device-side scalars of one scan (one cudaMemsetAsync clears them).
@@ -20,6 +21,24 @@ struct DevScalars {
     int          status;             // MAMRI_OK / MAMRI_ERR_CAPACITY
     unsigned long long body_packed;  // (count << 32) | (0xFFFFFFFF - label): atomicMax picks largest, lowest label
     unsigned long long n_foreground;
+    unsigned int done_select;        // CTAs of k_select that have finished (last one prepares the moment table)
+    unsigned int done_moments;       // CTAs of k_moments that have finished (last one finalises)
+};
+
+// Per-call pointers, read by the kernels from device memory so that the captured CUDA graph of the
+// pipeline stays valid when only the caller's buffers change.
+struct DynArgs {
+    const void* vol;
+    uint8_t* mask_out;
+    uint32_t* labels_out;
+    uint8_t* body_out;
+};
+
+// Everything else a captured pipeline depends on.
+struct GraphKey {
+    mamri_volume_desc desc;
+    mamri_params prm;
+    int vol_aligned, outs_aligned, has_mask, has_labels, has_body;
 };
 
 // Bit-packed volume: `w` 32-voxel words per row, `h` rows per slice, `d` slices.
@@ -41,6 +60,8 @@ struct mamri_ctx {
     uint32_t* d_closed;     // closed mask, bit-packed [nz][ny][W]                      [cap_words]
     int raw_nx, raw_ny, raw_nz, raw_r;   // geometry d_raw's zero apron was last cleared for
     uint32_t* d_word_base;  // runs that start before each word         [cap_words]
+    uint32_t* d_run_pos;    // word*32 + bit of each run's first voxel   [max_runs]
+    uint32_t* d_run_len;    // voxels in each run                        [max_runs]
     uint32_t* d_parent;     // union-find over runs                     [max_runs]
     uint32_t* d_run_label;  // final label of each run                  [max_runs]
     uint32_t* d_label_count;// voxels per label                         [max_runs]
@@ -66,9 +87,21 @@ struct mamri_ctx {
     mamri_summary* h_summary;
     mamri_entry_result* h_entry_res;
 
+    // CUDA graph of the whole pipeline (captured on first use of a configuration, relaunched afterwards)
+    DynArgs* d_dyn;
+    DynArgs* h_dyn;                  // pinned; copied to d_dyn by the graph's first node
+    cudaStream_t cap_stream;
+    cudaGraphExec_t gexec;
+    GraphKey gkey;
+    bool gvalid;
+    bool use_graph;
+
     // optional per-stage timing (mamri_set_profiling): events recorded between the stage launches
     bool profile;
     cudaEvent_t ev[6];
+    cudaEvent_t ev_fine[48];          // one event after every kernel launch (profile mode only)
+    const char* fine_name[48];
+    int n_fine;
 
     // state of the pending scan
     bool pending;
@@ -79,15 +112,24 @@ struct mamri_ctx {
     char err[512];
 };
 
+// Profile mode: mark the end of the kernel just launched.
+inline void prof_mark(mamri_ctx* c, cudaStream_t s, const char* name) {
+    if (!c->profile || c->n_fine >= 48) return;
+    if (!c->ev_fine[c->n_fine] && cudaEventCreate(&c->ev_fine[c->n_fine]) != cudaSuccess) return;
+    cudaEventRecord(c->ev_fine[c->n_fine], s);
+    c->fine_name[c->n_fine++] = name;
+}
+
 // ---- stage launchers (each enqueues on `s`; returns cudaError_t) -------------------------------
-cudaError_t launch_threshold_pack(mamri_ctx* c, const void* d_vol, int dtype, int nx, int ny, int nz, double lo,
+cudaError_t prepare_raw_apron(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s);
+cudaError_t launch_threshold_pack(mamri_ctx* c, int vol_aligned16, int dtype, int nx, int ny, int nz, double lo,
                                   double hi, int radius, cudaStream_t s);
 cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s);
 cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int connectivity, cudaStream_t s);
 cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volume_desc* desc,
                          const mamri_params* prm, cudaStream_t s);
-cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, uint8_t* d_mask_out,
-                               uint32_t* d_labels_out, uint8_t* d_body_out, cudaStream_t s);
+cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int outs_aligned,
+                               cudaStream_t s);
 cudaError_t launch_entry_search(mamri_ctx* c, const float* d_points, const float* d_normals, long long n,
                                 const double target[3], double radius, double wx, double wy, double cutoff,
                                 int n_path_samples, const uint8_t* d_path_mask, int mnx, int mny, int mnz,

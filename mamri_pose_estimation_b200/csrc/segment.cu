@@ -6,6 +6,7 @@
 
 #include <limits>
 #include <math.h>
+#include <stdlib.h>
 #include <type_traits>
 
 // ------------------------------------------------------------------------------------------------
@@ -83,9 +84,10 @@ struct RangeTest16 {
 };
 
 template <int VOXEL_BYTES, typename Test>
-__global__ void __launch_bounds__(256) k_threshold_pack_vec(const uint4* __restrict__ vol, uint32_t vec_per_row,
+__global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __restrict__ dyn, uint32_t vec_per_row,
                                                             uint32_t ny, Test test, uint32_t* __restrict__ dst,
                                                             uint32_t row_stride, uint32_t slice_stride, uint32_t off) {
+    const uint4* __restrict__ vol = static_cast<const uint4*>(dyn->vol);
     constexpr int E = 16 / VOXEL_BYTES; // voxels per 128-bit load
     constexpr int G = 32 / E;           // lanes per output word
     constexpr int U = 2;                // vectors per lane per row in flight (x 2 rows)
@@ -122,8 +124,9 @@ __global__ void __launch_bounds__(256) k_threshold_pack_vec(const uint4* __restr
 
 // General path (ragged nx or unaligned base): one warp per output word, one voxel per lane.
 template <typename T>
-__global__ void __launch_bounds__(256) k_threshold_pack_rows(const T* __restrict__ vol, uint32_t nx, uint32_t n_words,
+__global__ void __launch_bounds__(256) k_threshold_pack_rows(const DynArgs* __restrict__ dyn, uint32_t nx, uint32_t n_words,
                                                              T lo, T hi, BitDst dst) {
+    const T* __restrict__ vol = static_cast<const T*>(dyn->vol);
     const unsigned lane = lane_id();
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -151,21 +154,23 @@ template <>
 float cast_bound<float>(double v) { return float(v); }
 
 template <typename T>
-static cudaError_t threshold_pack_t(const void* d_vol, int nx, int ny, int nz, double lo, double hi, BitDst dst,
-                                    cudaStream_t s) {
+static cudaError_t threshold_pack_t(mamri_ctx* c, int vol_aligned16, int nx, int ny, int nz, double lo, double hi,
+                                    BitDst dst, cudaStream_t s) {
+    const DynArgs* dyn = c->d_dyn;
     const uint32_t rows = uint32_t(ny) * nz;
     const uint32_t n_words = rows * dst.W;
     const T tlo = cast_bound<T>(lo), thi = cast_bound<T>(hi);
-    const bool flat = (nx % 32 == 0) && ((reinterpret_cast<uintptr_t>(d_vol) & 15u) == 0);
+    const bool flat = (nx % 32 == 0) && vol_aligned16;
     if (flat) {
         constexpr int E = 16 / sizeof(T);
         // ~4 waves of 8 resident CTAs per SM; 8 warps per CTA, each warp takes two rows per trip
         uint32_t gx = (uint32_t(ny) + 15) / 16;
-        const uint32_t want = (148 * 8 * 4 + uint32_t(nz) - 1) / uint32_t(nz);
+        static const int per_sm = [] { const char* e = getenv("MAMRI_THR_CTAS_PER_SM"); return e ? atoi(e) : 32; }();
+        const uint32_t want = (uint32_t(148 * per_sm) + uint32_t(nz) - 1) / uint32_t(nz);
         if (gx > want) gx = want;
         if (gx == 0) gx = 1;
         const dim3 grid(gx, uint32_t(nz));
-        const uint4* src = static_cast<const uint4*>(d_vol);
+        const DynArgs* src = dyn;
         if constexpr (sizeof(T) == 2) {
             constexpr bool SG = std::is_signed<T>::value;
             const uint32_t bias = SG ? 0x8000u : 0u;
@@ -191,8 +196,9 @@ static cudaError_t threshold_pack_t(const void* d_vol, int nx, int ny, int nz, d
         const uint32_t cap = 148 * 8 * 8;
         if (blocks > cap) blocks = cap;
         if (blocks == 0) blocks = 1;
-        k_threshold_pack_rows<T><<<blocks, 256, 0, s>>>(static_cast<const T*>(d_vol), uint32_t(nx), n_words, tlo, thi, dst);
+        k_threshold_pack_rows<T><<<blocks, 256, 0, s>>>(dyn, uint32_t(nx), n_words, tlo, thi, dst);
     }
+    prof_mark(c, s, "threshold_pack");
     return cudaGetLastError();
 }
 
@@ -208,7 +214,19 @@ struct PadGeom {
     }
 };
 
-cudaError_t launch_threshold_pack(mamri_ctx* c, const void* d_vol, int dtype, int nx, int ny, int nz, double lo,
+// The apron of the padded raw mask must be zero; it is never written, so it is cleared only when the
+// geometry changes (outside the captured graph).
+cudaError_t prepare_raw_apron(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s) {
+    if (radius == 0) return cudaSuccess;
+    if (c->raw_nx == nx && c->raw_ny == ny && c->raw_nz == nz && c->raw_r == radius) return cudaSuccess;
+    const PadGeom g(nx, ny, nz, radius);
+    cudaError_t e = cudaMemsetAsync(c->d_raw, 0, size_t(g.words) * 4, s);
+    if (e != cudaSuccess) return e;
+    c->raw_nx = nx; c->raw_ny = ny; c->raw_nz = nz; c->raw_r = radius;
+    return cudaSuccess;
+}
+
+cudaError_t launch_threshold_pack(mamri_ctx* c, int vol_aligned16, int dtype, int nx, int ny, int nz, double lo,
                                   double hi, int radius, cudaStream_t s) {
     BitDst dst;
     dst.W = uint32_t(nx + 31) / 32;
@@ -218,24 +236,17 @@ cudaError_t launch_threshold_pack(mamri_ctx* c, const void* d_vol, int dtype, in
         dst.row_stride = dst.W; dst.slice_stride = dst.W * dst.ny; dst.off = 0; dst.linear = true;
     } else {
         const PadGeom g(nx, ny, nz, radius);
-        // the apron of the padded raw mask must be zero; it is never written, so clear it only when the
-        // geometry changes
-        if (c->raw_nx != nx || c->raw_ny != ny || c->raw_nz != nz || c->raw_r != radius) {
-            cudaError_t e = cudaMemsetAsync(c->d_raw, 0, size_t(g.words) * 4, s);
-            if (e != cudaSuccess) return e;
-            c->raw_nx = nx; c->raw_ny = ny; c->raw_nz = nz; c->raw_r = radius;
-        }
         dst.p = c->d_raw;
         dst.row_stride = g.Wp; dst.slice_stride = g.slice;
         dst.off = uint32_t(2 * radius) * g.slice + uint32_t(2 * radius) * g.Wp + 1;
         dst.linear = false;
     }
     switch (dtype) {
-        case MAMRI_U8:  return threshold_pack_t<uint8_t>(d_vol, nx, ny, nz, lo, hi, dst, s);
-        case MAMRI_I16: return threshold_pack_t<int16_t>(d_vol, nx, ny, nz, lo, hi, dst, s);
-        case MAMRI_U16: return threshold_pack_t<uint16_t>(d_vol, nx, ny, nz, lo, hi, dst, s);
-        case MAMRI_I32: return threshold_pack_t<int32_t>(d_vol, nx, ny, nz, lo, hi, dst, s);
-        case MAMRI_F32: return threshold_pack_t<float>(d_vol, nx, ny, nz, lo, hi, dst, s);
+        case MAMRI_U8:  return threshold_pack_t<uint8_t>(c, vol_aligned16, nx, ny, nz, lo, hi, dst, s);
+        case MAMRI_I16: return threshold_pack_t<int16_t>(c, vol_aligned16, nx, ny, nz, lo, hi, dst, s);
+        case MAMRI_U16: return threshold_pack_t<uint16_t>(c, vol_aligned16, nx, ny, nz, lo, hi, dst, s);
+        case MAMRI_I32: return threshold_pack_t<int32_t>(c, vol_aligned16, nx, ny, nz, lo, hi, dst, s);
+        case MAMRI_F32: return threshold_pack_t<float>(c, vol_aligned16, nx, ny, nz, lo, hi, dst, s);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -385,21 +396,25 @@ static cudaError_t closing_r(mamri_ctx* c, int nx, int ny, int nz, cudaStream_t 
     uint32_t threads = g.Wp * g.Hp * nch;
     k_morph_planes<R, false><<<(threads + 255) / 256, 256, 0, s>>>(c->d_raw, c->d_planes, g.Wp, g.slice, g.words, 0, g.Hp,
                                                                   dz_lo, dz_hi, zc, nch);
+    prof_mark(c, s, "morph_planes_dilate");
     const uint32_t dy_cnt = uint32_t(ny) + 2 * R;
     threads = g.Wp * dy_cnt * (dz_hi - dz_lo);
     k_morph_combine<R, false, false><<<(threads + 255) / 256, 256, 0, s>>>(c->d_planes, c->d_dil, g.Wp, g.slice, g.words, 0,
                                                                            g.Wp, R, dy_cnt, dz_lo, dz_hi - dz_lo,
                                                                            0xFFFFFFFFu);
+    prof_mark(c, s, "morph_combine_dilate");
     // ---- erosion: P_a on rows [R, ny+3R), image slices [2R, nz+2R); E on the image domain
     const uint32_t ez_lo = 2 * R, ez_hi = uint32_t(nz) + 2 * R;
     chunks(g.Wp * dy_cnt, ez_hi - ez_lo, zc, nch);
     threads = g.Wp * dy_cnt * nch;
     k_morph_planes<R, true><<<(threads + 255) / 256, 256, 0, s>>>(c->d_dil, c->d_planes, g.Wp, g.slice, g.words, R, dy_cnt,
                                                                  ez_lo, ez_hi, zc, nch);
+    prof_mark(c, s, "morph_planes_erode");
     const uint32_t tail = (nx % 32) ? (0xFFFFFFFFu >> (32 - nx % 32)) : 0xFFFFFFFFu;
     threads = g.W * uint32_t(ny) * uint32_t(nz);
     k_morph_combine<R, true, true><<<(threads + 255) / 256, 256, 0, s>>>(c->d_planes, c->d_closed, g.Wp, g.slice, g.words, 1,
                                                                          g.W, 2 * R, uint32_t(ny), 2 * R, uint32_t(nz), tail);
+    prof_mark(c, s, "morph_combine_erode");
     return cudaGetLastError();
 }
 

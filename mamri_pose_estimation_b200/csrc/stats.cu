@@ -2,10 +2,10 @@
 // Replaces sitk.LabelShapeStatisticsImageFilter().Execute + GetLabels/GetPhysicalSize/GetCentroid and
 // the list comprehension / max() at Mamri/Mamri.py:1309-1310, 1316-1322.
 //
-// Statistics are accumulated as exact integers per x-run PIECE (the part of a run inside one 32-voxel
-// word), using closed forms for sum x and sum x^2 over the piece, so the work is O(#runs) instead of
-// O(#voxels).  Lanes of a warp that hit the same label are combined with warp shuffles before one
-// atomic per (warp, label): integer sums are order-independent -> bit-reproducible.  Two phases bound
+// Statistics are accumulated as exact integers per x-RUN (one thread per entry of the run table), using
+// closed forms for sum x and sum x^2 over the run, so the work is O(#runs) instead of O(#voxels).
+// Lanes of a warp that hit the same label are combined with warp shuffles before one atomic per
+// (warp, label): integer sums are order-independent -> bit-reproducible.  Two phases bound
 // the table on noisy scans: voxel counts for every label first, then second moments only for the
 // labels that pass the volume filter (plus the body).  Finalisation (centroid, physical size,
 // principal moments/axes) is float64 on the device.
@@ -87,48 +87,29 @@ __device__ __forceinline__ void warp_agg_add(uint32_t key, V (&v)[NV], CtaCache<
     }
 }
 
-// First maximal piece of set bits of `pm`: start bit and length; clears it from pm.
-__device__ __forceinline__ void pop_piece(uint32_t& pm, int& b, int& len) {
-    b = __ffs(pm) - 1;
-    uint32_t t = pm >> b;
-    len = (t == 0xFFFFFFFFu) ? 32 : (__ffs(~t) - 1);
-    uint32_t bits = (len == 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
-    pm &= ~(bits << b);
-}
-
 // ------------------------------------------------------------------------------------------------
-// phase 1: voxel count of every label
+// phase 1: voxel count of every label (also gives every non-root run its final label)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_count_labels(const uint32_t* __restrict__ mask,
-                                                      const uint32_t* __restrict__ word_base,
-                                                      const uint32_t* __restrict__ run_label, int W, uint32_t n_words,
+__global__ void __launch_bounds__(256) k_count_labels(const uint32_t* __restrict__ parent,
+                                                      const uint32_t* __restrict__ run_len, uint32_t* run_label,
                                                       uint32_t* label_count, const DevScalars* sc) {
     __shared__ CtaCache<1, uint32_t, 64> cache;
     if (sc->status != MAMRI_OK) return;
     cache.init();
-    const unsigned lane = lane_id();
-    const uint32_t warp0 = ((uint32_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) << 5;
-    const uint32_t stride = uint32_t(gridDim.x) * blockDim.x;
-    for (uint32_t w0 = warp0; w0 < n_words; w0 += stride) {
-        const uint32_t wi = w0 + lane;
-        uint32_t pm = wi < n_words ? mask[wi] : 0u;
-        if (!__any_sync(FULL, pm != 0u)) continue;
-        uint32_t starts = 0, base = 0;
-        if (pm) {
-            starts = run_starts(pm, (wi % W) ? mask[wi - 1] : 0u);
-            base = word_base[wi];
+    const uint32_t n = sc->n_runs;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t r0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < n; r0 += stride) {
+        const uint32_t r = r0 + lane_id();
+        uint32_t key = MAMRI_NONE;
+        uint32_t v[1] = {0u};
+        if (r < n) {
+            const uint32_t root = parent[r];
+            const uint32_t label = run_label[root];          // roots were ranked by k_rank_roots
+            if (root != r) run_label[r] = label;
+            key = label - 1u;
+            v[0] = run_len[r];
         }
-        while (__any_sync(FULL, pm != 0u)) {
-            uint32_t key = MAMRI_NONE;
-            uint32_t v[1] = {0u};
-            if (pm) {
-                int b, len;
-                pop_piece(pm, b, len);
-                key = run_label[run_id_in_word(base, starts, b)] - 1u;
-                v[0] = uint32_t(len);
-            }
-            warp_agg_add(key, v, cache, label_count);
-        }
+        warp_agg_add(key, v, cache, label_count);
     }
     cache.flush(label_count);
 }
@@ -137,12 +118,12 @@ __global__ void __launch_bounds__(256) k_count_labels(const uint32_t* __restrict
 // stage 4a: volume filter (Mamri.py:1310) and body label (Mamri.py:1320-1322)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ label_count, uint32_t* __restrict__ label_slot,
-                                                uint32_t* __restrict__ cand_label, uint32_t max_markers, GeomArgs g,
-                                                DevScalars* sc) {
+                                                uint32_t* __restrict__ cand_label, unsigned long long* __restrict__ sums,
+                                                uint32_t max_markers, GeomArgs g, DevScalars* sc) {
     const unsigned lane = lane_id();
     const uint32_t n = sc->n_labels;
-    const uint32_t warp0 = ((uint32_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) << 5;
-    const uint32_t stride = uint32_t(gridDim.x) * blockDim.x;
+    const uint32_t warp0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;
+    const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t l0 = warp0; l0 < n; l0 += stride) {
         const uint32_t l = l0 + lane;
         unsigned long long packed = 0ull, cnt64 = 0ull;
@@ -152,12 +133,12 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ lab
             const double vol = double(cnt) * g.voxel_volume;        // GetPhysicalSize
             if (vol >= g.min_volume && vol <= g.max_volume) {         // inclusive bounds
                 uint32_t slot = atomicAdd(&sc->n_cand, 1u);
-                if (slot < max_markers) { cand_label[slot] = uint32_t(l) + 1u; label_slot[l] = slot; }
+                if (slot < max_markers) { cand_label[slot] = l + 1u; label_slot[l] = slot; }
                 else label_slot[l] = MAMRI_NONE;
             } else {
                 label_slot[l] = MAMRI_NONE;
                 // max(..., key=GetPhysicalSize) returns the FIRST maximum -> lowest label on ties
-                packed = (cnt64 << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t(l) + 1u));
+                packed = (cnt64 << 32) | (unsigned long long)(0xFFFFFFFFu - (l + 1u));
             }
         }
 #pragma unroll
@@ -171,24 +152,27 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ lab
             if (cnt64) atomicAdd(&sc->n_foreground, cnt64);
         }
     }
-}
-
-// One CTA: clamps the candidate count, gives the body the extra slot `max_markers`, zeroes the sums.
-__global__ void __launch_bounds__(256) k_prepare_moments(uint32_t* __restrict__ label_slot, uint32_t* __restrict__ cand_label,
-                                                         unsigned long long* __restrict__ sums, uint32_t max_markers,
-                                                         DevScalars* sc) {
-    uint32_t n = sc->n_cand;
-    if (n > max_markers) {
-        n = max_markers;
+    // The last CTA to finish clamps the candidate count, gives the body the extra slot `max_markers`
+    // and zeroes the moment sums of the slots in use.
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&sc->done_select, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    uint32_t nc = *(volatile unsigned int*)&sc->n_cand;
+    if (nc > max_markers) {
+        nc = max_markers;
         if (threadIdx.x == 0) sc->status = MAMRI_ERR_CAPACITY;
     }
-    const unsigned long long bp = sc->body_packed;
-    if (threadIdx.x == 0 && (bp >> 32) != 0ull && sc->n_labels > 0) {
-        uint32_t body = 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull);
+    const unsigned long long bp = *(volatile unsigned long long*)&sc->body_packed;
+    if (threadIdx.x == 0 && (bp >> 32) != 0ull) {
+        const uint32_t body = 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull);
         label_slot[body - 1u] = max_markers;
         cand_label[max_markers] = body;
     }
-    for (uint32_t i = threadIdx.x; i < n * 9u; i += blockDim.x) sums[i] = 0ull;
+    for (uint32_t i = threadIdx.x; i < nc * 9u; i += blockDim.x) sums[i] = 0ull;
     for (uint32_t i = threadIdx.x; i < 9u; i += blockDim.x) sums[uint32_t(max_markers) * 9u + i] = 0ull;
 }
 
@@ -199,57 +183,57 @@ __device__ __forceinline__ unsigned long long sum_sq_upto(long long k) {   // su
     return (unsigned long long)(k * (k + 1) * (2 * k + 1) / 6);
 }
 
-__global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
+__device__ void finalize_block(const uint32_t* cand_label, const uint32_t* label_count, const unsigned long long* sums,
+                               uint32_t max_markers, const GeomArgs& g, mamri_marker* markers, mamri_summary* summary,
+                               const DevScalars* sc);
+
+__global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_len,
                                                  const uint32_t* __restrict__ run_label,
-                                                 const uint32_t* __restrict__ label_slot, int W, int ny, uint32_t n_words,
-                                                 unsigned long long* sums, const DevScalars* sc) {
+                                                 const uint32_t* __restrict__ label_slot, int W, int ny,
+                                                 unsigned long long* sums, const uint32_t* __restrict__ cand_label,
+                                                 const uint32_t* __restrict__ label_count, uint32_t max_markers, GeomArgs g,
+                                                 mamri_marker* __restrict__ markers, mamri_summary* summary, DevScalars* sc) {
     __shared__ CtaCache<9, unsigned long long, 16> cache;
-    if (sc->status != MAMRI_OK) return;
     cache.init();
-    const unsigned lane = lane_id();
-    const uint32_t warp0 = ((uint32_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) << 5;
-    const uint32_t stride = uint32_t(gridDim.x) * blockDim.x;
-    for (uint32_t w0 = warp0; w0 < n_words; w0 += stride) {
-        const uint32_t wi = w0 + lane;
-        uint32_t pm = wi < n_words ? mask[wi] : 0u;
-        if (!__any_sync(FULL, pm != 0u)) continue;
-        uint32_t starts = 0, base = 0;
-        long long x0 = 0, y = 0, z = 0;
-        if (pm) {
-            const uint32_t row = wi / W;
-            const int xw = int(wi - row * W);
-            starts = run_starts(pm, xw > 0 ? mask[wi - 1] : 0u);
-            base = word_base[wi];
-            x0 = 32ll * xw;
-            y = (long long)(row % ny);
-            z = (long long)(row / ny);
-        }
-        while (__any_sync(FULL, pm != 0u)) {
-            uint32_t key = MAMRI_NONE;
-            unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            if (pm) {
-                int b, len;
-                pop_piece(pm, b, len);
-                const uint32_t label = run_label[run_id_in_word(base, starts, b)];
-                key = label_slot[label - 1u];
-                if (key != MAMRI_NONE) {
-                    const long long xs = x0 + b, xe = xs + len - 1, n = len;
-                    const unsigned long long sx = (unsigned long long)((xs + xe) * n / 2);
-                    v[0] = sx;                                              // sum x
-                    v[1] = (unsigned long long)(n * y);                     // sum y
-                    v[2] = (unsigned long long)(n * z);                     // sum z
-                    v[3] = sum_sq_upto(xe) - sum_sq_upto(xs - 1);           // sum xx
-                    v[4] = (unsigned long long)(n * y * y);                 // sum yy
-                    v[5] = (unsigned long long)(n * z * z);                 // sum zz
-                    v[6] = sx * (unsigned long long)y;                      // sum xy
-                    v[7] = sx * (unsigned long long)z;                      // sum xz
-                    v[8] = (unsigned long long)(n * y * z);                 // sum yz
-                }
+    const bool ok = sc->status == MAMRI_OK;
+    const uint32_t n = ok ? sc->n_runs : 0u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t r0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < n; r0 += stride) {
+        const uint32_t r = r0 + lane_id();
+        uint32_t key = MAMRI_NONE;
+        unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (r < n) {
+            key = label_slot[run_label[r] - 1u];
+            if (key != MAMRI_NONE) {
+                const uint32_t pos = run_pos[r];
+                const uint32_t wi = pos >> 5, row = wi / W;
+                const long long z = row / ny, y = row - uint32_t(z) * ny;
+                const long long xs = (long long)(wi - row * W) * 32 + (pos & 31u);
+                const long long len = run_len[r], xe = xs + len - 1;
+                const unsigned long long sx = (unsigned long long)((xs + xe) * len / 2);
+                v[0] = sx;                                              // sum x
+                v[1] = (unsigned long long)(len * y);                   // sum y
+                v[2] = (unsigned long long)(len * z);                   // sum z
+                v[3] = sum_sq_upto(xe) - sum_sq_upto(xs - 1);           // sum xx
+                v[4] = (unsigned long long)(len * y * y);               // sum yy
+                v[5] = (unsigned long long)(len * z * z);               // sum zz
+                v[6] = sx * (unsigned long long)y;                      // sum xy
+                v[7] = sx * (unsigned long long)z;                      // sum xz
+                v[8] = (unsigned long long)(len * y * z);               // sum yz
             }
-            warp_agg_add(key, v, cache, sums);
         }
+        warp_agg_add(key, v, cache, sums);
     }
     cache.flush(sums);
+    // The last CTA to finish turns the sums into the marker table and the summary.
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&sc->done_moments, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    finalize_block(cand_label, label_count, sums, max_markers, g, markers, summary, sc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -345,12 +329,11 @@ __device__ void make_marker(mamri_marker* out, uint32_t label, unsigned long lon
     *out = m;
 }
 
-// One CTA: orders the kept labels ascending (= GetLabels order), emits their records and the summary.
-__global__ void __launch_bounds__(256) k_finalize(const uint32_t* __restrict__ cand_label,
-                                                  const uint32_t* __restrict__ label_count,
-                                                  const unsigned long long* __restrict__ sums, uint32_t max_markers,
-                                                  GeomArgs g, mamri_marker* __restrict__ markers, mamri_summary* summary,
-                                                  const DevScalars* sc) {
+// One CTA (the last of k_moments): orders the kept labels ascending (= GetLabels order), emits their
+// records and the summary.  Sums were accumulated with L2 atomics; read them past L1.
+__device__ void finalize_block(const uint32_t* cand_label, const uint32_t* label_count, const unsigned long long* sums,
+                               uint32_t max_markers, const GeomArgs& g, mamri_marker* markers, mamri_summary* summary,
+                               const DevScalars* sc) {
     const bool ok = sc->status == MAMRI_OK;
     const uint32_t n_all = sc->n_cand;
     const uint32_t n = ok ? (n_all < max_markers ? n_all : max_markers) : 0u;
@@ -358,7 +341,9 @@ __global__ void __launch_bounds__(256) k_finalize(const uint32_t* __restrict__ c
         const uint32_t lab = cand_label[i];
         uint32_t rank = 0;
         for (uint32_t j = 0; j < n; ++j) rank += cand_label[j] < lab;
-        make_marker(markers + rank, lab, label_count[lab - 1u], sums + uint32_t(i) * 9u, g);
+        unsigned long long s9[9];
+        for (int k = 0; k < 9; ++k) s9[k] = __ldcg(sums + i * 9u + k);
+        make_marker(markers + rank, lab, __ldcg(label_count + lab - 1u), s9, g);
     }
     if (threadIdx.x == 0) {
         summary->n_labels = sc->n_labels;
@@ -372,7 +357,9 @@ __global__ void __launch_bounds__(256) k_finalize(const uint32_t* __restrict__ c
             const uint32_t body = 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull);
             summary->body_label = body;
             summary->body_count = bp >> 32;
-            make_marker(&summary->body, body, bp >> 32, sums + uint32_t(max_markers) * 9u, g);
+            unsigned long long s9[9];
+            for (int k = 0; k < 9; ++k) s9[k] = __ldcg(sums + max_markers * 9u + k);
+            make_marker(&summary->body, body, bp >> 32, s9, g);
         } else {
             summary->body_label = 0;
             summary->body_count = 0;
@@ -384,7 +371,6 @@ __global__ void __launch_bounds__(256) k_finalize(const uint32_t* __restrict__ c
 cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volume_desc* desc, const mamri_params* prm,
                          cudaStream_t s) {
     const int W = (desc->nx + 31) / 32;
-    const uint32_t n_words = uint32_t(W) * desc->ny * desc->nz;
     GeomArgs g;
     for (int i = 0; i < 3; ++i) { g.spacing[i] = desc->spacing[i]; g.origin[i] = desc->origin[i]; }
     for (int i = 0; i < 9; ++i) g.dir[i] = desc->direction[i];
@@ -393,16 +379,15 @@ cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volum
     g.voxel_volume = vv;
     g.min_volume = prm->min_volume;
     g.max_volume = prm->max_volume;
-    uint32_t wb = (n_words + 255) / 256;
-    if (wb > 148 * 8) wb = 148 * 8;
-    if (wb == 0) wb = 1;
-    k_count_labels<<<unsigned(wb), 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, W, n_words, c->d_label_count,
-                                                c->d_scalars);
-    k_select<<<148 * 2, 256, 0, s>>>(c->d_label_count, c->d_label_slot, c->d_cand_label, c->max_markers, g, c->d_scalars);
-    k_prepare_moments<<<1, 256, 0, s>>>(c->d_label_slot, c->d_cand_label, c->d_cand_sums, c->max_markers, c->d_scalars);
-    k_moments<<<unsigned(wb), 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, c->d_label_slot, W, desc->ny, n_words,
-                                           c->d_cand_sums, c->d_scalars);
-    k_finalize<<<1, 256, 0, s>>>(c->d_cand_label, c->d_label_count, c->d_cand_sums, c->max_markers, g, c->d_markers,
-                                 c->d_summary, c->d_scalars);
+    const int RG = MAMRI_RUN_CTAS;
+    k_count_labels<<<RG, 256, 0, s>>>(c->d_parent, c->d_run_len, c->d_run_label, c->d_label_count, c->d_scalars);
+    prof_mark(c, s, "count_labels");
+    k_select<<<148 * 2, 256, 0, s>>>(c->d_label_count, c->d_label_slot, c->d_cand_label, c->d_cand_sums, c->max_markers, g,
+                                     c->d_scalars);
+    prof_mark(c, s, "select");
+    k_moments<<<RG, 256, 0, s>>>(c->d_run_pos, c->d_run_len, c->d_run_label, c->d_label_slot, W, desc->ny, c->d_cand_sums,
+                                 c->d_cand_label, c->d_label_count, c->max_markers, g, c->d_markers, c->d_summary,
+                                 c->d_scalars);
+    prof_mark(c, s, "moments_finalize");
     return cudaGetLastError();
 }

@@ -201,6 +201,15 @@ class FiducialDetector:
         check(self._lib.mamri_stage_times(self._ctx, ms), self._ctx)
         return dict(zip(self.STAGES, [float(v) for v in ms]))
 
+    def kernel_times_ms(self) -> list:
+        """[(kernel, ms)] of the last profiled scan, in launch order."""
+        ms = (C.c_float * 48)()
+        names = (C.c_char_p * 48)()
+        n = self._lib.mamri_kernel_times(self._ctx, ms, names, 48)
+        if n < 0:
+            check(n, self._ctx)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
     def label_counts(self, n_labels: int) -> np.ndarray:
         out = np.zeros(max(int(n_labels), 1), dtype=np.uint32)
         rc = self._lib.mamri_label_counts(self._ctx, out.ctypes.data, out.size)

@@ -23,4 +23,8 @@ for i in range(a.scans):
     r = det.detect(vol, spacing=ph.spacing, origin=ph.origin, direction=ph.direction,
                    params=DetectParams(connectivity=a.conn), out_mask=mask, out_labels=lab)
     print(i, r.n_labels, r.n_runs, len(r.markers), r.body_label, det.stage_times_ms())
+kt = det.kernel_times_ms()
+for n, ms in kt:
+    print(f'{ms*1e3:9.2f} us  {n}')
+print(f'sum {sum(m for _, m in kt)*1e3:.1f} us')
 det.close()
