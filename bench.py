@@ -17,7 +17,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import time
 
@@ -43,44 +42,52 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region, sampled every 5 ms through NVML on a
+    background thread (nvidia-smi -lms needs longer to start than a short run lasts)."""
 
     def __init__(self, gpu_index: int):
-        self.proc = None
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception as e:          # no NVML: report that instead of inventing numbers
+            self._err = str(e)
+
+    def _run(self):
+        nv = self._nv
+        flags = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for name, bit in flags.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self._thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable: " + getattr(self, "_err", "?")]}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": sorted(self.reasons)}
 
 
 def run_reference(args):
@@ -91,6 +98,7 @@ def run_reference(args):
         return
     from mamri_pose_estimation_b200 import phantom
     from oracle import c_oracle
+    c_oracle.use_all_cores()
     ph = phantom.config_c2()
     vol = phantom.generate(ph)
     n = vol.size
@@ -140,7 +148,7 @@ def run_native(args):
     torch.cuda.synchronize()
     sp, org, dr = specs[0].spacing, specs[0].origin, specs[0].direction
     params = DetectParams()
-    bd = BatchDetector(DIMS, device=local, n_contexts=int(os.environ.get("MAMRI_BENCH_CONTEXTS", "3")))
+    bd = BatchDetector(DIMS, device=local, n_contexts=int(os.environ.get("MAMRI_BENCH_CONTEXTS", "4")))
     gather_in = torch.zeros((S, MAX_TABLE, 8), dtype=torch.float64, device=dev)
 
     def step():
@@ -159,7 +167,7 @@ def run_native(args):
     for _ in range(max(args.warmup, 3)):
         res = step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 else None       # NVML thread, 5 ms period, timed region only
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -200,7 +208,9 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * S * n_vox * args.steps / (float(t.item()) * 1e-3) / 1e9
-    table_bytes = S * (64 * 248 + 400)                      # eager marker records + summary per scan
+    import ctypes
+    from mamri_pose_estimation_b200 import _capi
+    table_bytes = S * (64 * ctypes.sizeof(_capi.Marker) + ctypes.sizeof(_capi.Summary))   # eager marker records + summary
     e2e = {"value": e2e_value, "unit": "Gvoxel/s", "scans_per_s": e2e_value * 1e9 / n_vox,
            "h2d_bytes_per_step": world * S * n_vox * 2, "d2h_bytes_per_step": world * S * (n_vox + table_bytes // S),
            "api": "BatchDetector.run_host -> mamri_detect_host_async/mamri_detect_collect (pinned host u16 volume in; "
@@ -242,6 +252,7 @@ def run_native(args):
         if not args.no_cpu_baseline:
             from oracle import c_oracle
             from oracle import segmentation as seg
+            c_oracle.use_all_cores()
             host = vols[0].cpu().numpy()
             closed, labels, k, sums, dt = c_oracle.run_pipeline(host)
             cpu = {"value": n_vox / dt / 1e9, "unit": "Gvoxel/s", "cores": c_oracle.num_threads(), "kind": "port",

@@ -28,6 +28,14 @@ API int oracle_num_threads(void) {
 #endif
 }
 
+API void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ---- sitk.BinaryThreshold(img, lo, hi)                     Mamri.py:1308 ------------------------------ */
 /* bounds are static_cast to the pixel type (truncation; clamped when out of range), both ends inclusive */
 static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }

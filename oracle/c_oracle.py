@@ -30,12 +30,22 @@ def load():
         lib.oracle_label_sums.restype = C.c_int
         lib.oracle_label_sums.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
         lib.oracle_num_threads.restype = C.c_int
+        lib.oracle_set_num_threads.restype = None
+        lib.oracle_set_num_threads.argtypes = [C.c_int]
         _lib = lib
     return _lib
 
 
 def num_threads() -> int:
     return int(load().oracle_num_threads())
+
+
+def use_all_cores() -> int:
+    """Sets the OpenMP team to every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    load().oracle_set_num_threads(n)
+    return num_threads()
 
 
 def run_pipeline(vol: np.ndarray, lo=seg.INTENSITY_THRESHOLD, hi=seg.UPPER_THRESHOLD, close_radius=seg.CLOSE_RADIUS,
