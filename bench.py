@@ -213,13 +213,13 @@ def run_native(args):
     table_bytes = S * (64 * ctypes.sizeof(_capi.Marker) + ctypes.sizeof(_capi.Summary))   # eager marker records + summary
     e2e = {"value": e2e_value, "unit": "Gvoxel/s", "scans_per_s": e2e_value * 1e9 / n_vox,
            "h2d_bytes_per_step": world * S * n_vox * 2, "d2h_bytes_per_step": world * S * (n_vox + table_bytes // S),
-           "api": "BatchDetector.run_host -> mamri_detect_host_async/mamri_detect_collect (pinned host u16 volume in; "
+           "api": "BatchDetector.run_host -> mamri_pool_detect_host (pinned host u16 volumes in; "
                   "marker table + uint8 body mask out)"}
 
     # ---------------- per-stage times (CUDA events on the launching stream) -> roofline of the dominant kernel
     stages, roof, cpu, parity = None, None, None, None
     if rank == 0:
-        det = bd.ctxs[0]
+        det = bd.context(0)
         det.set_profiling(True)
         acc = {}
         reps = 10

@@ -142,6 +142,37 @@ MAMRI_API int mamri_detect_collect(mamri_ctx* ctx, mamri_summary* summary, mamri
 /* Voxel count of every label 1..K of the last collected scan (GetPhysicalSize / voxel volume). */
 MAMRI_API int mamri_label_counts(mamri_ctx* ctx, uint32_t* h_counts, uint32_t max_labels);
 
+/* ---- batches of independent scans ------------------------------------------------------- */
+/* MamriLogic.process handles one inputVolume per call (Mamri.py:850-858), so scans are independent.
+ * A pool owns n_contexts contexts and as many streams on one device and pipelines a batch over
+ * them: scan i runs on context i % n_contexts, and its enqueue + collect overlap the kernels of the
+ * scans in flight on the other contexts.  The host loop lives in the library (no per-scan call
+ * overhead in the caller's language). */
+typedef struct mamri_pool mamri_pool;
+MAMRI_API int mamri_pool_create(mamri_pool** pool, int device, int32_t n_contexts, int32_t max_nx, int32_t max_ny,
+                      int32_t max_nz, uint32_t max_runs, uint32_t max_markers);
+MAMRI_API int mamri_pool_destroy(mamri_pool* pool);
+MAMRI_API const char* mamri_pool_last_error(const mamri_pool* pool);
+/* Context k of the pool (0 <= k < n_contexts), e.g. for mamri_set_profiling; NULL if out of range. */
+MAMRI_API mamri_ctx* mamri_pool_context(mamri_pool* pool, int32_t k);
+/* n device-resident scans of one geometry.  d_volumes[i] is scan i; d_mask_out / d_labels_out /
+ * d_body_out are NULL or arrays of n device pointers (entries may repeat when the caller only wants
+ * them as temporaries, provided entries i and i + n_contexts are the only ones that alias).
+ * summaries[n] and markers[n * max_markers_per_scan] (host) receive what mamri_detect_collect
+ * returns per scan.  The pool's streams fork from and join back into `stream`; the call returns
+ * when every scan has been collected.  Returns MAMRI_OK or the first failing scan's status (the
+ * other scans are still processed; per-scan status is in summaries[i].device_status). */
+MAMRI_API int mamri_pool_detect(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* d_volumes, int32_t n,
+                      const mamri_params* params, uint8_t* const* d_mask_out, uint32_t* const* d_labels_out,
+                      uint8_t* const* d_body_out, mamri_summary* summaries, mamri_marker* markers,
+                      uint32_t max_markers_per_scan, void* stream);
+/* Same from/to HOST buffers (pinned for full PCIe speed): the H2D copy of scan i+1 overlaps the
+ * kernels and the body-mask D2H of scan i.  h_body_out is NULL or an array of n host pointers. */
+MAMRI_API int mamri_pool_detect_host(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes,
+                           int32_t n, const mamri_params* params, uint8_t* const* h_body_out,
+                           mamri_summary* summaries, mamri_marker* markers, uint32_t max_markers_per_scan,
+                           void* stream);
+
 /* ---- measurement hooks (no reference counterpart) ----------------------------------------------- */
 /* With profiling on, detect records CUDA events between its stages on the caller's stream;
  * mamri_stage_times() then returns, for the last collected scan, the milliseconds of

@@ -59,6 +59,17 @@ SIGNATURES = {
     "mamri_detect_host_async": (C.c_int, [C.c_void_p, C.POINTER(VolumeDesc), C.c_void_p, C.POINTER(Params),
                                           C.c_void_p, C.c_void_p]),
     "mamri_detect_collect": (C.c_int, [C.c_void_p, C.POINTER(Summary), C.POINTER(Marker), C.c_uint32]),
+    "mamri_pool_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
+                                    C.c_uint32]),
+    "mamri_pool_destroy": (C.c_int, [C.c_void_p]),
+    "mamri_pool_last_error": (C.c_char_p, [C.c_void_p]),
+    "mamri_pool_context": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "mamri_pool_detect": (C.c_int, [C.c_void_p, C.POINTER(VolumeDesc), C.POINTER(C.c_void_p), C.c_int32, C.POINTER(Params),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                    C.POINTER(Summary), C.POINTER(Marker), C.c_uint32, C.c_void_p]),
+    "mamri_pool_detect_host": (C.c_int, [C.c_void_p, C.POINTER(VolumeDesc), C.POINTER(C.c_void_p), C.c_int32,
+                                         C.POINTER(Params), C.POINTER(C.c_void_p), C.POINTER(Summary), C.POINTER(Marker),
+                                         C.c_uint32, C.c_void_p]),
     "mamri_label_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "mamri_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mamri_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
@@ -99,4 +110,10 @@ class MamriError(RuntimeError):
 def check(rc: int, ctx=None) -> None:
     if rc != MAMRI_OK:
         msg = load().mamri_last_error(ctx)
+        raise MamriError(rc, msg.decode() if msg else "unknown error")
+
+
+def check_pool(rc: int, pool=None) -> None:
+    if rc != MAMRI_OK:
+        msg = load().mamri_pool_last_error(pool)
         raise MamriError(rc, msg.decode() if msg else "unknown error")

@@ -18,6 +18,23 @@ static char g_create_err[512] = "";
         }                                                                                              \
     } while (0)
 
+// Launch priorities and programmatic dependent launch (common.cuh: launch_k).
+const LaunchTuning& launch_tuning() {
+    static const LaunchTuning t = [] {
+        LaunchTuning v;
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { least = greatest = 0; cudaGetLastError(); }
+        v.prio_small = greatest;     // numerically lowest = scheduled first
+        v.prio_big = least;
+        v.pdl = 1;
+        if (const char* e = getenv("MAMRI_PRIO_SMALL")) v.prio_small = atoi(e);
+        if (const char* e = getenv("MAMRI_PRIO_BIG")) v.prio_big = atoi(e);
+        if (const char* e = getenv("MAMRI_PDL")) v.pdl = atoi(e);
+        return v;
+    }();
+    return t;
+}
+
 namespace {
 struct DeviceGuard {
     int prev = -1;
@@ -116,7 +133,7 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     ctx->max_markers = max_markers;
     const size_t W = (size_t(max_nx) + 31) / 32;
     ctx->cap_words = W * max_ny * max_nz;
-    ctx->cap_pad_words = (W + 2) * (size_t(max_ny) + 4 * MAMRI_RMAX) * (size_t(max_nz) + 4 * MAMRI_RMAX);
+    ctx->cap_pad_words = ((W + 2 + 3) & ~size_t(3)) * (size_t(max_ny) + 4 * MAMRI_RMAX) * (size_t(max_nz) + 4 * MAMRI_RMAX);
     if (3 * ctx->cap_pad_words >= (1ull << 32)) {
         snprintf(g_create_err, sizeof(g_create_err), "volume too large for 32-bit word indexing");
         delete ctx;
@@ -354,6 +371,148 @@ extern "C" int mamri_detect_collect(mamri_ctx* ctx, mamri_summary* summary, mamr
     }
     if (n) memcpy(h_markers, ctx->h_markers, size_t(n) * sizeof(mamri_marker));
     return MAMRI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pool: a batch of independent scans pipelined over a few contexts/streams (host loop in C++)
+// ------------------------------------------------------------------------------------------------
+struct mamri_pool {
+    int device, k;
+    mamri_ctx** ctx;
+    cudaStream_t* streams;
+    cudaEvent_t fork;
+    cudaEvent_t* join;
+    char err[512];
+};
+
+static char g_pool_err[512] = "";
+
+extern "C" const char* mamri_pool_last_error(const mamri_pool* pool) { return pool ? pool->err : g_pool_err; }
+
+extern "C" int mamri_pool_destroy(mamri_pool* pool) {
+    if (!pool) return MAMRI_OK;
+    DeviceGuard g(pool->device);
+    for (int i = 0; i < pool->k; ++i) {
+        if (pool->ctx && pool->ctx[i]) mamri_destroy(pool->ctx[i]);
+        if (pool->streams && pool->streams[i]) cudaStreamDestroy(pool->streams[i]);
+        if (pool->join && pool->join[i]) cudaEventDestroy(pool->join[i]);
+    }
+    if (pool->fork) cudaEventDestroy(pool->fork);
+    delete[] pool->ctx; delete[] pool->streams; delete[] pool->join;
+    delete pool;
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_pool_create(mamri_pool** out, int device, int32_t n_contexts, int32_t max_nx, int32_t max_ny,
+                                 int32_t max_nz, uint32_t max_runs, uint32_t max_markers) {
+    if (!out) { snprintf(g_pool_err, sizeof(g_pool_err), "pool output pointer is NULL"); return MAMRI_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (n_contexts < 1 || n_contexts > 64) {
+        snprintf(g_pool_err, sizeof(g_pool_err), "n_contexts must be 1..64");
+        return MAMRI_ERR_INVALID_ARG;
+    }
+    mamri_pool* p = new (std::nothrow) mamri_pool();
+    if (!p) { snprintf(g_pool_err, sizeof(g_pool_err), "out of host memory"); return MAMRI_ERR_CUDA; }
+    memset(p, 0, sizeof(*p));
+    p->device = device; p->k = n_contexts;
+    p->ctx = new (std::nothrow) mamri_ctx*[n_contexts]();
+    p->streams = new (std::nothrow) cudaStream_t[n_contexts]();
+    p->join = new (std::nothrow) cudaEvent_t[n_contexts]();
+    if (!p->ctx || !p->streams || !p->join) {
+        snprintf(g_pool_err, sizeof(g_pool_err), "out of host memory");
+        mamri_pool_destroy(p);
+        return MAMRI_ERR_CUDA;
+    }
+    for (int i = 0; i < n_contexts; ++i) {
+        int rc = mamri_create(&p->ctx[i], device, max_nx, max_ny, max_nz, max_runs, max_markers);
+        if (rc != MAMRI_OK) {
+            snprintf(g_pool_err, sizeof(g_pool_err), "context %d: %s", i, mamri_last_error(nullptr));
+            mamri_pool_destroy(p);
+            return rc;
+        }
+    }
+    DeviceGuard g(device);
+    cudaError_t e = cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming);
+    for (int i = 0; i < n_contexts && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        snprintf(g_pool_err, sizeof(g_pool_err), "creating the pool's streams failed: %s", cudaGetErrorString(e));
+        mamri_pool_destroy(p);
+        return MAMRI_ERR_CUDA;
+    }
+    *out = p;
+    return MAMRI_OK;
+}
+
+extern "C" mamri_ctx* mamri_pool_context(mamri_pool* pool, int32_t k) {
+    return (pool && k >= 0 && k < pool->k) ? pool->ctx[k] : nullptr;
+}
+
+static int pool_run(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* volumes, bool host, int32_t n,
+                    const mamri_params* params, uint8_t* const* mask_out, uint32_t* const* labels_out,
+                    uint8_t* const* body_out, mamri_summary* summaries, mamri_marker* markers, uint32_t max_m,
+                    void* stream) {
+    if (!pool) return MAMRI_ERR_INVALID_ARG;
+    auto pfail = [&](int code, const char* msg) { snprintf(pool->err, sizeof(pool->err), "%s", msg); return code; };
+    if (n < 0 || (n > 0 && (!volumes || !summaries))) return pfail(MAMRI_ERR_INVALID_ARG, "bad batch arguments");
+    if (max_m > 0 && !markers) return pfail(MAMRI_ERR_INVALID_ARG, "markers array is NULL");
+    if (n == 0) return MAMRI_OK;
+    DeviceGuard g(pool->device);
+    cudaStream_t cur = static_cast<cudaStream_t>(stream);
+    const int K = pool->k;
+    cudaError_t e = cudaEventRecord(pool->fork, cur);
+    for (int j = 0; j < K && j < n && e == cudaSuccess; ++j) e = cudaStreamWaitEvent(pool->streams[j], pool->fork, 0);
+    if (e != cudaSuccess) return pfail(MAMRI_ERR_CUDA, cudaGetErrorString(e));
+    int first_err = MAMRI_OK;
+    auto note = [&](int rc, int scan, mamri_ctx* c) {
+        if (rc != MAMRI_OK && first_err == MAMRI_OK) {
+            first_err = rc;
+            snprintf(pool->err, sizeof(pool->err), "scan %d: %s", scan, mamri_last_error(c));
+        }
+    };
+    auto collect = [&](int i) {
+        mamri_ctx* c = pool->ctx[i % K];
+        if (!c->pending) { memset(&summaries[i], 0, sizeof(mamri_summary)); summaries[i].device_status = MAMRI_ERR_STATE; return; }
+        int rc = mamri_detect_collect(c, &summaries[i], markers ? markers + size_t(i) * max_m : nullptr, max_m);
+        note(rc, i, c);
+    };
+    for (int i = 0; i < n; ++i) {
+        const int j = i % K;
+        if (i >= K) collect(i - K);
+        mamri_ctx* c = pool->ctx[j];
+        int rc;
+        if (host)
+            rc = mamri_detect_host_async(c, desc, volumes[i], params, body_out ? body_out[i] : nullptr, pool->streams[j]);
+        else
+            rc = mamri_detect_async(c, desc, volumes[i], params, mask_out ? mask_out[i] : nullptr,
+                                    labels_out ? labels_out[i] : nullptr, body_out ? body_out[i] : nullptr, pool->streams[j]);
+        note(rc, i, c);
+    }
+    for (int i = (n > K ? n - K : 0); i < n; ++i) collect(i);
+    for (int j = 0; j < K && j < n; ++j) {
+        if (cudaEventRecord(pool->join[j], pool->streams[j]) != cudaSuccess ||
+            cudaStreamWaitEvent(cur, pool->join[j], 0) != cudaSuccess)
+            return pfail(MAMRI_ERR_CUDA, "joining the pool's streams failed");
+    }
+    return first_err;
+}
+
+extern "C" int mamri_pool_detect(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* d_volumes, int32_t n,
+                                 const mamri_params* params, uint8_t* const* d_mask_out, uint32_t* const* d_labels_out,
+                                 uint8_t* const* d_body_out, mamri_summary* summaries, mamri_marker* markers,
+                                 uint32_t max_markers_per_scan, void* stream) {
+    return pool_run(pool, desc, d_volumes, false, n, params, d_mask_out, d_labels_out, d_body_out, summaries, markers,
+                    max_markers_per_scan, stream);
+}
+
+extern "C" int mamri_pool_detect_host(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes,
+                                      int32_t n, const mamri_params* params, uint8_t* const* h_body_out,
+                                      mamri_summary* summaries, mamri_marker* markers, uint32_t max_markers_per_scan,
+                                      void* stream) {
+    return pool_run(pool, desc, h_volumes, true, n, params, nullptr, nullptr, h_body_out, summaries, markers,
+                    max_markers_per_scan, stream);
 }
 
 extern "C" int mamri_label_counts(mamri_ctx* ctx, uint32_t* h_counts, uint32_t max_labels) {

@@ -75,6 +75,7 @@ __device__ __forceinline__ void chunk_of(uint32_t n, uint32_t& begin, uint32_t& 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SCAN_THREADS) k_runs_count(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
                                                              uint32_t* __restrict__ block_sums) {
+    pdl_wait();
     __shared__ uint32_t ws[33];
     uint32_t begin, end;
     chunk_of(n_words, begin, end);
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_runs_assign(const uint32_t* __
                                                               uint32_t* __restrict__ word_base,
                                                               uint32_t* __restrict__ run_pos, uint32_t* __restrict__ run_len,
                                                               uint32_t max_runs, DevScalars* sc) {
+    pdl_wait();
     __shared__ uint32_t ws[33];
     uint32_t total_runs;
     uint32_t running = scan_partials(block_sums, ws, total_runs);
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
                                                                const uint32_t* __restrict__ run_pos,
                                                                const uint32_t* __restrict__ run_len, uint32_t* parent,
                                                                int W, int ny, int nz, const DevScalars* sc) {
+    pdl_wait();
     __shared__ uint32_t sp[SLICE_SMEM_RUNS];
     if (sc->status != MAMRI_OK) return;
     const uint32_t z = blockIdx.x;
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ ma
                                                  const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_len,
                                                  uint32_t* parent, int W, int ny, int radix, int between_blocks,
                                                  const DevScalars* sc) {
+    pdl_wait();
     if (sc->status != MAMRI_OK) return;
     const uint32_t n = sc->n_runs;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
@@ -299,6 +303,7 @@ __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ ma
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SCAN_THREADS) k_flatten_count(uint32_t* parent, uint32_t* __restrict__ block_sums,
                                                                 const DevScalars* sc) {
+    pdl_wait();
     __shared__ uint32_t ws[33];
     uint32_t begin, end;
     chunk_of(sc->n_runs, begin, end);
@@ -319,6 +324,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_rank_roots(const uint32_t* __r
                                                              const uint32_t* __restrict__ block_sums,
                                                              uint32_t* __restrict__ run_label,
                                                              uint32_t* __restrict__ label_count, DevScalars* sc) {
+    pdl_wait();
     __shared__ uint32_t ws[33];
     uint32_t total_roots;
     uint32_t running = scan_partials(block_sums, ws, total_roots);
@@ -343,46 +349,39 @@ cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int
     const int G = MAMRI_SCAN_CTAS;
     uint32_t* bs_runs = c->d_block_sums;
     uint32_t* bs_roots = c->d_block_sums + 1024;
-    k_runs_count<<<G, SCAN_THREADS, 0, s>>>(d_mask, W, n_words, bs_runs);
+    LK(k_runs_count, G, SCAN_THREADS, s, false, d_mask, W, n_words, bs_runs);
     prof_mark(c, s, "runs_count");
-    k_runs_assign<<<G, SCAN_THREADS, 0, s>>>(d_mask, W, n_words, bs_runs, c->d_word_base, c->d_run_pos, c->d_run_len,
-                                            c->max_runs, c->d_scalars);
+    LK(k_runs_assign, G, SCAN_THREADS, s, false, d_mask, W, n_words, bs_runs, c->d_word_base, c->d_run_pos, c->d_run_len, c->max_runs, c->d_scalars);
     prof_mark(c, s, "runs_assign");
     int radix = 1;
     while (radix * radix < nz) radix <<= 1;
     const int RG = MAMRI_RUN_CTAS;
     if (connectivity == 26) {
-        k_union_slices<true><<<nz, SLICE_THREADS, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W,
-                                                          ny, nz, c->d_scalars);
+        LK(k_union_slices<true>, nz, SLICE_THREADS, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, nz, c->d_scalars);
         prof_mark(c, s, "union_slices");
         if (nz > 1) {
-            k_union_z<true><<<RG, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 0,
-                                               c->d_scalars);
+            LK(k_union_z<true>, RG, 256, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 0, c->d_scalars);
             prof_mark(c, s, "union_z_within_blocks");
         }
         if (nz > radix) {
-            k_union_z<true><<<RG, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 1,
-                                               c->d_scalars);
+            LK(k_union_z<true>, RG, 256, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 1, c->d_scalars);
             prof_mark(c, s, "union_z_between_blocks");
         }
     } else {
-        k_union_slices<false><<<nz, SLICE_THREADS, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W,
-                                                           ny, nz, c->d_scalars);
+        LK(k_union_slices<false>, nz, SLICE_THREADS, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, nz, c->d_scalars);
         prof_mark(c, s, "union_slices");
         if (nz > 1) {
-            k_union_z<false><<<RG, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 0,
-                                                c->d_scalars);
+            LK(k_union_z<false>, RG, 256, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 0, c->d_scalars);
             prof_mark(c, s, "union_z_within_blocks");
         }
         if (nz > radix) {
-            k_union_z<false><<<RG, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 1,
-                                                c->d_scalars);
+            LK(k_union_z<false>, RG, 256, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 1, c->d_scalars);
             prof_mark(c, s, "union_z_between_blocks");
         }
     }
-    k_flatten_count<<<G, SCAN_THREADS, 0, s>>>(c->d_parent, bs_roots, c->d_scalars);
+    LK(k_flatten_count, G, SCAN_THREADS, s, false, c->d_parent, bs_roots, c->d_scalars);
     prof_mark(c, s, "flatten_count");
-    k_rank_roots<<<G, SCAN_THREADS, 0, s>>>(c->d_parent, bs_roots, c->d_run_label, c->d_label_count, c->d_scalars);
+    LK(k_rank_roots, G, SCAN_THREADS, s, false, c->d_parent, bs_roots, c->d_run_label, c->d_label_count, c->d_scalars);
     prof_mark(c, s, "rank_roots");
     return cudaGetLastError();
 }
@@ -399,6 +398,7 @@ __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict_
                                                      const uint32_t* __restrict__ run_label, int nx, int W,
                                                      uint32_t n_words, const DynArgs* __restrict__ dyn,
                                                      const DevScalars* sc) {
+    pdl_wait();
     uint8_t* __restrict__ mask_out = dyn->mask_out;
     uint32_t* __restrict__ labels_out = dyn->labels_out;
     uint8_t* __restrict__ body_out = dyn->body_out;
@@ -501,14 +501,12 @@ cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int
         static const int per_sm = [] { const char* e = getenv("MAMRI_MAT_CTAS_PER_SM"); return e ? atoi(e) : 16; }();
         if (blocks > uint32_t(148 * per_sm)) blocks = uint32_t(148 * per_sm);
         if (blocks == 0) blocks = 1;
-        k_materialise<true><<<blocks, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, nx, W, n_words, c->d_dyn,
-                                                   c->d_scalars);
+        LK(k_materialise<true>, blocks, 256, s, true, d_mask, c->d_word_base, c->d_run_label, nx, W, n_words, c->d_dyn, c->d_scalars);
     } else {
         uint32_t blocks = (n_words + 7) / 8;
         if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
         if (blocks == 0) blocks = 1;
-        k_materialise<false><<<blocks, 256, 0, s>>>(d_mask, c->d_word_base, c->d_run_label, nx, W, n_words, c->d_dyn,
-                                                    c->d_scalars);
+        LK(k_materialise<false>, blocks, 256, s, true, d_mask, c->d_word_base, c->d_run_label, nx, W, n_words, c->d_dyn, c->d_scalars);
     }
     prof_mark(c, s, "materialise");
     return cudaGetLastError();

@@ -137,9 +137,64 @@ cudaError_t launch_entry_search(mamri_ctx* c, const float* d_points, const float
 cudaError_t launch_phantom(uint16_t* d_volume, int nx, int ny, int nz, const float* h_ell, int n_ell, float sigma,
                            unsigned long long seed, unsigned int scan_index, cudaStream_t s);
 
+// ---- kernel launches ---------------------------------------------------------------------------
+// Every pipeline kernel goes through launch_k: it attaches (a) a launch priority -- the two DRAM-bound
+// kernels (threshold+pack, materialise) run at the lowest priority and the short latency-bound kernels
+// between them at the highest, so that in a pipelined batch the short kernels of one scan are
+// scheduled ahead of the queued CTAs of another scan's streaming kernel -- and (b) programmatic
+// dependent launch: the next kernel's CTAs are set up while the current kernel drains; every kernel
+// therefore starts with pdl_wait() (griddepcontrol.wait) before it touches memory.
+// MAMRI_PRIO_SMALL / MAMRI_PRIO_BIG / MAMRI_PDL override the defaults (experiments only).
+struct LaunchTuning { int prio_small, prio_big, pdl; };
+const LaunchTuning& launch_tuning();
+
+template <typename... KA, typename... A>
+inline cudaError_t launch_ks(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool big, A&&... args) {
+    const LaunchTuning& t = launch_tuning();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    unsigned n = 0;
+    at[n].id = cudaLaunchAttributePriority;
+    at[n].val.priority = big ? t.prio_big : t.prio_small;
+    ++n;
+    if (t.pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at; cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
+
+template <typename... KA, typename... A>
+inline cudaError_t launch_k(void (*kern)(KA...), dim3 grid, dim3 block, cudaStream_t s, bool big, A&&... args) {
+    return launch_ks(kern, grid, block, 0, s, big, static_cast<A&&>(args)...);
+}
+
+#define LKS(...)                                                   \
+    do {                                                           \
+        cudaError_t _lk_e = launch_ks(__VA_ARGS__);                \
+        if (_lk_e != cudaSuccess) return _lk_e;                    \
+    } while (0)
+
+#define LK(...)                                                    \
+    do {                                                           \
+        cudaError_t _lk_e = launch_k(__VA_ARGS__);                 \
+        if (_lk_e != cudaSuccess) return _lk_e;                    \
+    } while (0)
+
 // ---- small device helpers ---------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// Programmatic dependent launch: wait for the preceding kernel's memory to be visible, then let the
+// following kernel's CTAs be scheduled as soon as every CTA of this one has got this far.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 // Run-start bits of word `m` given the previous word of the same row (0 at the row start).
 __device__ __forceinline__ uint32_t run_starts(uint32_t m, uint32_t prev) { return m & ~((m << 1) | (prev >> 31)); }

@@ -87,6 +87,7 @@ template <int VOXEL_BYTES, typename Test>
 __global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __restrict__ dyn, uint32_t vec_per_row,
                                                             uint32_t ny, Test test, uint32_t* __restrict__ dst,
                                                             uint32_t row_stride, uint32_t slice_stride, uint32_t off) {
+    pdl_wait();
     const uint4* __restrict__ vol = static_cast<const uint4*>(dyn->vol);
     constexpr int E = 16 / VOXEL_BYTES; // voxels per 128-bit load
     constexpr int G = 32 / E;           // lanes per output word
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __res
 template <typename T>
 __global__ void __launch_bounds__(256) k_threshold_pack_rows(const DynArgs* __restrict__ dyn, uint32_t nx, uint32_t n_words,
                                                              T lo, T hi, BitDst dst) {
+    pdl_wait();
     const T* __restrict__ vol = static_cast<const T*>(dyn->vol);
     const unsigned lane = lane_id();
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -180,35 +182,34 @@ static cudaError_t threshold_pack_t(mamri_ctx* c, int vol_aligned16, int nx, int
             const bool lm = (l & 0x8000u) != 0, hm = (h & 0x8000u) != 0, ch = h != 0xFFFFu;
             const uint32_t vpr = uint32_t(nx) / E;
 #define MAMRI_T16(LM, HM, CH)                                                                                         \
-    k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>><<<grid, 256, 0, s>>>(src, vpr, uint32_t(ny),                   \
-        RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off)
+    LK(k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>>, grid, 256, s, true, src, vpr, uint32_t(ny), RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off)
             if (!ch) { if (lm) MAMRI_T16(true, true, false); else MAMRI_T16(false, true, false); }
             else if (lm) { if (hm) MAMRI_T16(true, true, true); else MAMRI_T16(true, false, true); }
             else { if (hm) MAMRI_T16(false, true, true); else MAMRI_T16(false, false, true); }
 #undef MAMRI_T16
         } else {
             RangeTest<T> t{tlo, thi};
-            k_threshold_pack_vec<int(sizeof(T)), RangeTest<T>><<<grid, 256, 0, s>>>(src, uint32_t(nx) / E, uint32_t(ny), t, dst.p,
-                                                                                 dst.row_stride, dst.slice_stride, dst.off);
+            LK(k_threshold_pack_vec<int(sizeof(T)), RangeTest<T>>, grid, 256, s, true, src, uint32_t(nx) / E, uint32_t(ny), t, dst.p, dst.row_stride, dst.slice_stride, dst.off);
         }
     } else {
         uint32_t blocks = (n_words + 7) / 8;
         const uint32_t cap = 148 * 8 * 8;
         if (blocks > cap) blocks = cap;
         if (blocks == 0) blocks = 1;
-        k_threshold_pack_rows<T><<<blocks, 256, 0, s>>>(dyn, uint32_t(nx), n_words, tlo, thi, dst);
+        LK(k_threshold_pack_rows<T>, blocks, 256, s, true, dyn, uint32_t(nx), n_words, tlo, thi, dst);
     }
     prof_mark(c, s, "threshold_pack");
     return cudaGetLastError();
 }
 
-// Geometry of the padded bit volumes of one closing: 1 pad word on each side of a row, 2R pad rows and
+// Geometry of the padded bit volumes of one closing: 1 pad word left and >= 1 right of a row (row stride a
+// multiple of 16 bytes, so whole rows can be moved with bulk copies), 2R pad rows and
 // slices on each side (R for the dilation's apron + R for the reach of the ball from there).
 struct PadGeom {
     uint32_t W, Wp, Hp, Dp, slice, words;
     __host__ PadGeom(int nx, int ny, int nz, int R) {
         W = uint32_t(nx + 31) / 32;
-        Wp = W + 2; Hp = uint32_t(ny + 4 * R); Dp = uint32_t(nz + 4 * R);
+        Wp = (W + 2 + 3) & ~3u; Hp = uint32_t(ny + 4 * R); Dp = uint32_t(nz + 4 * R);
         slice = Wp * Hp;
         words = slice * Dp;
     }
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(256) k_morph_planes(const uint32_t* __restrict
                                                       uint32_t Wp, uint32_t slice, uint32_t words, uint32_t y_lo,
                                                       uint32_t y_cnt, uint32_t z_lo, uint32_t z_hi, uint32_t zc,
                                                       uint32_t n_chunks) {
+    pdl_wait();
     const uint32_t per_chunk = Wp * y_cnt;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= per_chunk * n_chunks) return;
@@ -361,6 +363,7 @@ __global__ void __launch_bounds__(256) k_morph_combine(const uint32_t* __restric
                                                        uint32_t Wp, uint32_t slice, uint32_t words, uint32_t x_lo,
                                                        uint32_t x_cnt, uint32_t y_lo, uint32_t y_cnt, uint32_t z_lo,
                                                        uint32_t z_cnt, uint32_t tail_mask) {
+    pdl_wait();
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= x_cnt * y_cnt * z_cnt) return;
     const uint32_t row = t / x_cnt, xx = t - row * x_cnt;
@@ -381,6 +384,45 @@ __global__ void __launch_bounds__(256) k_morph_combine(const uint32_t* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One-kernel-per-operation variant: no intermediate planes in memory.
+// ------------------------------------------------------------------------------------------------
+// A thread owns one word column xw for a strip of SY output rows and walks a chunk of slices.  Every
+// step it reads the SY + 2R source rows of the incoming slice z' (three words each for the x shifts,
+// all hits in L1/L2), folds them over y into one value per output row and per |dz| class
+//   Q_c(y, z') = OP_{dy} S_{h(dy, c)}(y + dy, z')
+// and scatters those into a ring of 2R+1 pending output slices, acc[z' - dz] OP= Q_|dz|; the slice
+// z' - R is then complete and is stored.  The ring lives in registers (SY x (2R+1) words); source
+// words are read (SY + 2R) / SY x (zc + 2R) / zc times, the result is written once.
+template <int R>
+struct BallZ {          // classes of dz with identical y-profiles h(., dz)
+    __host__ __device__ static constexpr bool same(int a, int b) {
+        for (int d = -R; d <= R; ++d)
+            if (Ball<R>::h(d < 0 ? -d : d, a) != Ball<R>::h(d < 0 ? -d : d, b)) return false;
+        return true;
+    }
+    __host__ __device__ static constexpr int canon(int a) {
+        for (int b = 0; b < a; ++b)
+            if (same(a, b)) return b;
+        return a;
+    }
+    __host__ __device__ static constexpr int cls(int a) {
+        int n = 0;
+        for (int b = 0; b < canon(a); ++b) n += (canon(b) == b) ? 1 : 0;
+        return n;
+    }
+    __host__ __device__ static constexpr int n_cls() {
+        int n = 0;
+        for (int b = 0; b <= R; ++b) n += (canon(b) == b) ? 1 : 0;
+        return n;
+    }
+    __host__ __device__ static constexpr int rep(int c) {        // a |dz| of class c
+        for (int b = 0; b <= R; ++b)
+            if (cls(b) == c) return b;
+        return 0;
+    }
+};
+
 template <int R>
 static cudaError_t closing_r(mamri_ctx* c, int nx, int ny, int nz, cudaStream_t s) {
     const PadGeom g(nx, ny, nz, R);
@@ -394,35 +436,213 @@ static cudaError_t closing_r(mamri_ctx* c, int nx, int ny, int nz, cudaStream_t 
     const uint32_t dz_lo = R, dz_hi = uint32_t(nz) + 3 * R;
     chunks(g.Wp * g.Hp, dz_hi - dz_lo, zc, nch);
     uint32_t threads = g.Wp * g.Hp * nch;
-    k_morph_planes<R, false><<<(threads + 255) / 256, 256, 0, s>>>(c->d_raw, c->d_planes, g.Wp, g.slice, g.words, 0, g.Hp,
-                                                                  dz_lo, dz_hi, zc, nch);
+    LK(k_morph_planes<R, false>, (threads + 255) / 256, 256, s, false, c->d_raw, c->d_planes, g.Wp, g.slice, g.words, 0, g.Hp, dz_lo, dz_hi, zc, nch);
     prof_mark(c, s, "morph_planes_dilate");
     const uint32_t dy_cnt = uint32_t(ny) + 2 * R;
     threads = g.Wp * dy_cnt * (dz_hi - dz_lo);
-    k_morph_combine<R, false, false><<<(threads + 255) / 256, 256, 0, s>>>(c->d_planes, c->d_dil, g.Wp, g.slice, g.words, 0,
-                                                                           g.Wp, R, dy_cnt, dz_lo, dz_hi - dz_lo,
-                                                                           0xFFFFFFFFu);
+    LK(k_morph_combine<R, false, false>, (threads + 255) / 256, 256, s, false, c->d_planes, c->d_dil, g.Wp, g.slice, g.words, 0, g.Wp, R, dy_cnt, dz_lo, dz_hi - dz_lo, 0xFFFFFFFFu);
     prof_mark(c, s, "morph_combine_dilate");
     // ---- erosion: P_a on rows [R, ny+3R), image slices [2R, nz+2R); E on the image domain
     const uint32_t ez_lo = 2 * R, ez_hi = uint32_t(nz) + 2 * R;
     chunks(g.Wp * dy_cnt, ez_hi - ez_lo, zc, nch);
     threads = g.Wp * dy_cnt * nch;
-    k_morph_planes<R, true><<<(threads + 255) / 256, 256, 0, s>>>(c->d_dil, c->d_planes, g.Wp, g.slice, g.words, R, dy_cnt,
-                                                                 ez_lo, ez_hi, zc, nch);
+    LK(k_morph_planes<R, true>, (threads + 255) / 256, 256, s, false, c->d_dil, c->d_planes, g.Wp, g.slice, g.words, R, dy_cnt, ez_lo, ez_hi, zc, nch);
     prof_mark(c, s, "morph_planes_erode");
     const uint32_t tail = (nx % 32) ? (0xFFFFFFFFu >> (32 - nx % 32)) : 0xFFFFFFFFu;
     threads = g.W * uint32_t(ny) * uint32_t(nz);
-    k_morph_combine<R, true, true><<<(threads + 255) / 256, 256, 0, s>>>(c->d_planes, c->d_closed, g.Wp, g.slice, g.words, 1,
-                                                                         g.W, 2 * R, uint32_t(ny), 2 * R, uint32_t(nz), tail);
+    LK(k_morph_combine<R, true, true>, (threads + 255) / 256, 256, s, false, c->d_planes, c->d_closed, g.Wp, g.slice, g.words, 1, g.W, 2 * R, uint32_t(ny), 2 * R, uint32_t(nz), tail);
     prof_mark(c, s, "morph_combine_erode");
     return cudaGetLastError();
 }
 
+// One CTA produces a tile of TY rows x TZ slices x all word columns.  Thread 0 fetches the source tile
+// with its halo of R rows / slices -- the rows of one slice are contiguous in the padded layout, so it is
+// one bulk copy (cp.async.bulk, completion on an mbarrier) per slice, no address arithmetic in the other
+// threads and no registers staging the data.  Then each thread owns one word column for a strip of SY
+// output rows and walks the slices of the tile in shared memory as described above.
+struct TileArgs {
+    uint32_t Wp, slice;                 // padded row / slice strides (words); Wp % 4 == 0
+    uint32_t x_lo, x_cnt;               // output word columns
+    uint32_t y_lo, y_cnt;               // output rows (padded coordinates)
+    uint32_t z_lo, z_hi;                // output slices (padded coordinates)
+    uint32_t TY, TZ;                    // tile: output rows / slices per CTA (TY % SY == 0)
+    uint32_t out_w, out_ny;             // TO_IMAGE: row length / rows per slice of the plain mask
+    uint32_t tail_mask;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+template <int R, bool ERODE, bool TO_IMAGE, int SY>
+__global__ void __launch_bounds__(1024) k_morph_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, TileArgs a) {
+    extern __shared__ __align__(128) uint32_t tile[];              // [TZ+2R][TY+2R][Wp], then the mbarrier
+    constexpr int RING = 2 * R + 1, NC = BallZ<R>::n_cls();
+    constexpr uint32_t NEUTRAL = ERODE ? 0xFFFFFFFFu : 0u;
+    const uint32_t rows_alloc = a.TY + 2 * R;
+    const uint32_t y0t = a.y_lo + blockIdx.x * a.TY, z0 = a.z_lo + blockIdx.y * a.TZ;
+    const uint32_t y_end = a.y_lo + a.y_cnt, z1 = min(z0 + a.TZ, a.z_hi);
+    const uint32_t ys0 = y0t - R, zs0 = z0 - R;                    // first source row / slice of the tile
+    const uint32_t rows_src = min(rows_alloc, y_end + R - ys0);    // rows past y_end - 1 + R feed no output
+    const uint32_t n_slices = z1 + R - zs0;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tile + (a.TZ + 2 * R) * rows_alloc * a.Wp);
+    const uint32_t bar_s = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();                                                    // the source is the previous kernel's output
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = rows_src * a.Wp * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes * n_slices) : "memory");
+        for (uint32_t k = 0; k < n_slices; ++k) {
+            const uint32_t* g = src + size_t(zs0 + k) * a.slice + ys0 * a.Wp;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(tile + k * rows_alloc * a.Wp)), "l"(g), "r"(bytes), "r"(bar_s) : "memory");
+        }
+    }
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar_s) : "memory");
+    }
+    const uint32_t n_strips = a.TY / SY;
+    if (threadIdx.x >= a.x_cnt * n_strips) return;
+    const uint32_t strip = threadIdx.x / a.x_cnt, xx = threadIdx.x - strip * a.x_cnt;
+    const uint32_t xw = a.x_lo + xx;
+    const uint32_t y0 = y0t + strip * SY;                          // first output row of the strip
+    if (y0 >= y_end) return;
+    const bool has_l = xw > 0, has_r = xw + 1 < a.Wp;
+    const uint32_t* col = tile + (strip * SY) * a.Wp + xw;         // local row strip*SY = source row y0 - R
+
+    uint32_t acc[SY][RING];
+#pragma unroll
+    for (int y = 0; y < SY; ++y)
+#pragma unroll
+        for (int j = 0; j < RING; ++j) acc[y][j] = NEUTRAL;
+
+    for (uint32_t k = 0; k < n_slices; ++k) {                      // incoming source slice zs0 + k
+        uint32_t Q[NC][SY];
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int y = 0; y < SY; ++y) Q[c][y] = NEUTRAL;
+        const uint32_t* p = col + k * rows_alloc * a.Wp;
+        static_for<0, SY + 2 * R>([&](auto ir) {
+            constexpr int r = decltype(ir)::value;                 // source row y0 - R + r
+            uint32_t S[R + 1];
+            load_shifted<R, ERODE>(p + r * a.Wp, has_l, has_r, S); // rows past rows_src: unloaded, feed discarded outputs only
+            static_for<0, SY>([&](auto iy) {
+                constexpr int y = decltype(iy)::value;
+                constexpr int dy = r - R - y;
+                if constexpr (dy >= -R && dy <= R) {
+                    static_for<0, NC>([&](auto ic) {
+                        constexpr int c = decltype(ic)::value;
+                        constexpr int hh = Ball<R>::h(dy < 0 ? -dy : dy, BallZ<R>::rep(c));
+                        if constexpr (hh >= 0) Q[c][y] = ERODE ? (Q[c][y] & S[hh]) : (Q[c][y] | S[hh]);
+                    });
+                }
+            });
+        });
+        // acc[y][j] is the output slice zs0 + k - R + j; it sees the incoming slice at dz = R - j
+#pragma unroll
+        for (int y = 0; y < SY; ++y)
+            static_for<0, RING>([&](auto ij) {
+                constexpr int j = decltype(ij)::value;
+                constexpr int adz = (R - j) < 0 ? (j - R) : (R - j);
+                constexpr int c = BallZ<R>::cls(adz);
+                acc[y][j] = ERODE ? (acc[y][j] & Q[c][y]) : (acc[y][j] | Q[c][y]);
+            });
+        if (k >= 2 * R) {                                           // output slice zs0 + k - R = z0 + (k - 2R) is complete
+            const uint32_t zo = z0 + k - 2 * R;
+#pragma unroll
+            for (int y = 0; y < SY; ++y) {
+                if (y0 + y < y_end) {
+                    uint32_t v = acc[y][0];
+                    if (TO_IMAGE) {
+                        if (xx == a.x_cnt - 1) v &= a.tail_mask;
+                        dst[((zo - a.z_lo) * a.out_ny + (y0 + y - a.y_lo)) * a.out_w + xx] = v;
+                    } else {
+                        dst[zo * a.slice + (y0 + y) * a.Wp + xw] = v;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int y = 0; y < SY; ++y) {
+#pragma unroll
+            for (int j = 0; j + 1 < RING; ++j) acc[y][j] = acc[y][j + 1];
+            acc[y][RING - 1] = NEUTRAL;
+        }
+    }
+}
+
+// Tile shape for a padded row of Wp words: the largest of a few candidates whose tile + halo fits the
+// shared-memory budget (two CTAs per SM) with at most 1024 threads; false = row too wide, use the planes kernels.
+template <int R, int SY>
+static bool tile_plan(uint32_t Wp, uint32_t& TY, uint32_t& TZ, uint32_t& smem) {
+    static const uint32_t cand[][2] = {{32, 16}, {32, 8}, {16, 8}, {16, 4}, {8, 4}};
+    for (auto& c : cand) {
+        const uint32_t bytes = Wp * (c[0] + 2 * R) * (c[1] + 2 * R) * 4u + 16u;
+        if (bytes <= 100u * 1024u && Wp * (c[0] / SY) <= 1024u && c[0] % SY == 0) {
+            TY = c[0]; TZ = c[1]; smem = bytes;
+            return true;
+        }
+    }
+    return false;
+}
+
+template <int R, int SY>
+static cudaError_t closing_tile_r(mamri_ctx* c, int nx, int ny, int nz, uint32_t TY, uint32_t TZ, uint32_t smem,
+                                  cudaStream_t s) {
+    const PadGeom g(nx, ny, nz, R);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_morph_tile<R, false, false, SY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 + 16);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_morph_tile<R, true, true, SY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 + 16);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    TileArgs a;
+    a.Wp = g.Wp; a.slice = g.slice; a.TY = TY; a.TZ = TZ;
+    // dilation on the r-grown domain: rows [R, ny+3R), slices [R, nz+3R), every padded word column
+    a.x_lo = 0; a.x_cnt = g.Wp; a.y_lo = R; a.y_cnt = uint32_t(ny) + 2 * R; a.z_lo = R; a.z_hi = uint32_t(nz) + 3 * R;
+    a.out_w = 0; a.out_ny = 0; a.tail_mask = 0xFFFFFFFFu;
+    uint32_t threads = ((a.x_cnt * (TY / SY) + 31) / 32) * 32;
+    dim3 grid((a.y_cnt + TY - 1) / TY, (a.z_hi - a.z_lo + TZ - 1) / TZ);
+    LKS(k_morph_tile<R, false, false, SY>, grid, threads, smem, s, false, c->d_raw, c->d_dil, a);
+    prof_mark(c, s, "dilate");
+    // erosion back on the image domain, straight into the plain [nz][ny][W] mask
+    a.x_lo = 1; a.x_cnt = g.W; a.y_lo = 2 * R; a.y_cnt = uint32_t(ny); a.z_lo = 2 * R; a.z_hi = uint32_t(nz) + 2 * R;
+    a.out_w = g.W; a.out_ny = uint32_t(ny);
+    a.tail_mask = (nx % 32) ? (0xFFFFFFFFu >> (32 - nx % 32)) : 0xFFFFFFFFu;
+    threads = ((a.x_cnt * (TY / SY) + 31) / 32) * 32;
+    grid = dim3((a.y_cnt + TY - 1) / TY, (a.z_hi - a.z_lo + TZ - 1) / TZ);
+    LKS(k_morph_tile<R, true, true, SY>, grid, threads, smem, s, false, c->d_dil, c->d_closed, a);
+    prof_mark(c, s, "erode");
+    return cudaGetLastError();
+}
+
+template <int R, int SY>
+static cudaError_t closing_dispatch(mamri_ctx* c, int nx, int ny, int nz, cudaStream_t s) {
+    static const int use_planes = [] { const char* e = getenv("MAMRI_MORPH_PLANES"); return e ? atoi(e) : 0; }();
+    uint32_t TY, TZ, smem;
+    if (!use_planes && tile_plan<R, SY>(PadGeom(nx, ny, nz, R).Wp, TY, TZ, smem)) {
+        if (const char* e = getenv("MAMRI_TILE_TZ")) {              // experiments only
+            TZ = uint32_t(atoi(e));
+            smem = PadGeom(nx, ny, nz, R).Wp * (TY + 2 * R) * (TZ + 2 * R) * 4u + 16u;
+        }
+        return closing_tile_r<R, SY>(c, nx, ny, nz, TY, TZ, smem, s);
+    }
+    return closing_r<R>(c, nx, ny, nz, s);
+}
+
 cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s) {
     switch (radius) {
-        case 1: return closing_r<1>(c, nx, ny, nz, s);
-        case 2: return closing_r<2>(c, nx, ny, nz, s);
-        case 3: return closing_r<3>(c, nx, ny, nz, s);
+        case 1: return closing_dispatch<1, 4>(c, nx, ny, nz, s);
+        case 2: return closing_dispatch<2, 4>(c, nx, ny, nz, s);
+        case 3: return closing_dispatch<3, 4>(c, nx, ny, nz, s);
         default: return cudaErrorInvalidValue;
     }
 }

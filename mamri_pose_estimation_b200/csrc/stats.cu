@@ -93,6 +93,7 @@ __device__ __forceinline__ void warp_agg_add(uint32_t key, V (&v)[NV], CtaCache<
 __global__ void __launch_bounds__(256) k_count_labels(const uint32_t* __restrict__ parent,
                                                       const uint32_t* __restrict__ run_len, uint32_t* run_label,
                                                       uint32_t* label_count, const DevScalars* sc) {
+    pdl_wait();
     __shared__ CtaCache<1, uint32_t, 64> cache;
     if (sc->status != MAMRI_OK) return;
     cache.init();
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256) k_count_labels(const uint32_t* __restrict
 __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ label_count, uint32_t* __restrict__ label_slot,
                                                 uint32_t* __restrict__ cand_label, unsigned long long* __restrict__ sums,
                                                 uint32_t max_markers, GeomArgs g, DevScalars* sc) {
+    pdl_wait();
     const unsigned lane = lane_id();
     const uint32_t n = sc->n_labels;
     const uint32_t warp0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ ru
                                                  unsigned long long* sums, const uint32_t* __restrict__ cand_label,
                                                  const uint32_t* __restrict__ label_count, uint32_t max_markers, GeomArgs g,
                                                  mamri_marker* __restrict__ markers, mamri_summary* summary, DevScalars* sc) {
+    pdl_wait();
     __shared__ CtaCache<9, unsigned long long, 16> cache;
     cache.init();
     const bool ok = sc->status == MAMRI_OK;
@@ -380,14 +383,11 @@ cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volum
     g.min_volume = prm->min_volume;
     g.max_volume = prm->max_volume;
     const int RG = MAMRI_RUN_CTAS;
-    k_count_labels<<<RG, 256, 0, s>>>(c->d_parent, c->d_run_len, c->d_run_label, c->d_label_count, c->d_scalars);
+    LK(k_count_labels, RG, 256, s, false, c->d_parent, c->d_run_len, c->d_run_label, c->d_label_count, c->d_scalars);
     prof_mark(c, s, "count_labels");
-    k_select<<<148 * 2, 256, 0, s>>>(c->d_label_count, c->d_label_slot, c->d_cand_label, c->d_cand_sums, c->max_markers, g,
-                                     c->d_scalars);
+    LK(k_select, 148 * 2, 256, s, false, c->d_label_count, c->d_label_slot, c->d_cand_label, c->d_cand_sums, c->max_markers, g, c->d_scalars);
     prof_mark(c, s, "select");
-    k_moments<<<RG, 256, 0, s>>>(c->d_run_pos, c->d_run_len, c->d_run_label, c->d_label_slot, W, desc->ny, c->d_cand_sums,
-                                 c->d_cand_label, c->d_label_count, c->max_markers, g, c->d_markers, c->d_summary,
-                                 c->d_scalars);
+    LK(k_moments, RG, 256, s, false, c->d_run_pos, c->d_run_len, c->d_run_label, c->d_label_slot, W, desc->ny, c->d_cand_sums, c->d_cand_label, c->d_label_count, c->max_markers, g, c->d_markers, c->d_summary, c->d_scalars);
     prof_mark(c, s, "moments_finalize");
     return cudaGetLastError();
 }

@@ -116,7 +116,8 @@ class FiducialDetector:
 
     def close(self) -> None:
         if getattr(self, "_ctx", None) and self._ctx.value:
-            self._lib.mamri_destroy(self._ctx)
+            if getattr(self, "_owned", True):            # views of a pool's contexts are destroyed by the pool
+                self._lib.mamri_destroy(self._ctx)
             self._ctx = C.c_void_p()
 
     __del__ = close
@@ -276,80 +277,161 @@ def generate_phantom_cuda(ph, device: int = 0, out: Optional[torch.Tensor] = Non
     return out
 
 
-class BatchDetector:
-    """Pipelines a batch of independent scans over a small pool of contexts/streams on one GPU so that
-    the launch + collect latency of one scan hides behind the kernels of the next (scans are independent:
-    ``MamriLogic.process`` handles exactly one inputVolume, Mamri.py:850-858).
+class BatchResult:
+    """Results of one batch, held as the C arrays `mamri_pool_detect` filled; a sequence of
+    `DetectionResult` built on demand (so the per-scan Python objects cost nothing unless they are read)."""
 
-    Streams fork from and join back into the caller's current stream, so CUDA events recorded on the
+    def __init__(self, n, summaries, markers, max_m, outs):
+        self.n, self._summ, self._mk, self._max_m, self._outs = n, summaries, markers, max_m, outs
+        self._cache = {}
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i) -> DetectionResult:
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self.n))]
+        if i < 0:
+            i += self.n
+        if not 0 <= i < self.n:
+            raise IndexError(i)
+        if i not in self._cache:
+            summ = self._summ[i]
+            k = min(int(summ.n_markers), self._max_m)
+            markers = [MarkerStats.from_c(self._mk[i * self._max_m + j]) for j in range(k)]
+            body = MarkerStats.from_c(summ.body) if summ.body_label else None
+            m, l, b = self._outs(i)
+            self._cache[i] = DetectionResult(n_labels=int(summ.n_labels), n_runs=int(summ.n_runs),
+                                             n_foreground=int(summ.n_foreground), markers=markers,
+                                             body_label=int(summ.body_label), body_count=int(summ.body_count), body=body,
+                                             mask=m, labels=l, body_mask=b)
+        return self._cache[i]
+
+    def __iter__(self):
+        return (self[i] for i in range(self.n))
+
+    def table(self, slots: int = 32) -> np.ndarray:
+        """[n, slots, 8] float64: label, count, volume_mm3, RAS x y z, n_labels, body_label (distributed.pack_table)."""
+        mk = np.frombuffer(self._mk, dtype=np.dtype(Marker)).reshape(self.n, self._max_m)[:, :slots]
+        sm = np.frombuffer(self._summ, dtype=np.dtype(Summary))
+        t = np.zeros((self.n, slots, 8), dtype=np.float64)
+        k = min(slots, self._max_m)
+        valid = np.arange(k)[None, :] < np.minimum(sm["n_markers"], k)[:, None]
+        t[:, :k, 0] = mk["label"]
+        t[:, :k, 1] = mk["count"]
+        t[:, :k, 2] = mk["volume_mm3"]
+        t[:, :k, 3:6] = mk["centroid_ras"]
+        t[:, :k, 6] = sm["n_labels"][:, None]
+        t[:, :k, 7] = sm["body_label"][:, None]
+        t[:, :k][~valid] = 0.0
+        return t
+
+
+class BatchDetector:
+    """A batch of independent scans pipelined over a pool of contexts/streams on one GPU (`mamri_pool_*`): the
+    enqueue + collect latency of one scan hides behind the kernels of the others (scans are independent:
+    ``MamriLogic.process`` handles exactly one inputVolume, Mamri.py:850-858).  The per-scan loop runs inside the
+    library; one call per batch crosses the ctypes boundary.
+
+    The pool's streams fork from and join back into the caller's current stream, so CUDA events recorded on the
     current stream around `run` / `run_host` bracket all the work."""
 
-    def __init__(self, dims_xyz: Sequence[int], device: int = 0, n_contexts: int = 3, max_runs: int = 0,
-                 max_markers: int = 0, materialise: bool = True):
+    def __init__(self, dims_xyz: Sequence[int], device: int = 0, n_contexts: int = 4, max_runs: int = 0,
+                 max_markers: int = 64, materialise: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mamri_pose_estimation_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self._lib = _capi.load()
         self.device = int(device)
         self.dims = tuple(int(v) for v in dims_xyz)
+        self.n_contexts = int(n_contexts)
+        self.max_markers = int(max_markers)
         nx, ny, nz = self.dims
         dev = torch.device(f"cuda:{self.device}")
-        self.ctxs = [FiducialDetector(self.dims, device, max_runs, max_markers) for _ in range(n_contexts)]
-        self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_contexts)]
+        self._pool = C.c_void_p()
+        _capi.check_pool(self._lib.mamri_pool_create(C.byref(self._pool), self.device, self.n_contexts, nx, ny, nz,
+                                                     int(max_runs), self.max_markers), None)
         self.materialise = materialise
         self.masks = [torch.empty((nz, ny, nx), dtype=torch.uint8, device=dev) if materialise else None
-                      for _ in range(n_contexts)]
+                      for _ in range(self.n_contexts)]
         self.labels = [torch.empty((nz, ny, nx), dtype=torch.int32, device=dev) if materialise else None
-                       for _ in range(n_contexts)]
-        self._fork = torch.cuda.Event()
-        self._join = [torch.cuda.Event() for _ in range(n_contexts)]
-        self.kernel_launches_per_scan = 17          # threshold 1, closing 2, ccl 8, stats 5, materialise 1
+                       for _ in range(self.n_contexts)]
+        self.kernel_launches_per_scan = 16          # threshold 1, closing 4, ccl 7, stats 3, materialise 1
 
     def close(self):
-        for c in self.ctxs:
-            c.close()
+        if getattr(self, "_pool", None) and self._pool.value:
+            self._lib.mamri_pool_destroy(self._pool)
+            self._pool = C.c_void_p()
 
-    def _fork_streams(self):
-        cur = torch.cuda.current_stream(self.device)
-        self._fork.record(cur)
-        for s in self.streams:
-            s.wait_event(self._fork)
-        return cur
+    __del__ = close
 
-    def _join_streams(self, cur):
-        for s, e in zip(self.streams, self._join):
-            e.record(s)
-            cur.wait_event(e)
+    def context(self, k: int = 0) -> "FiducialDetector":
+        """Context k of the pool as a FiducialDetector view (profiling hooks, single scans); owned by the pool."""
+        view = FiducialDetector.__new__(FiducialDetector)
+        view._lib, view.device, view.max_dims = self._lib, self.device, self.dims
+        view._ctx = C.c_void_p(self._lib.mamri_pool_context(self._pool, int(k)))
+        if not view._ctx.value:
+            raise IndexError(k)
+        view.max_markers = self.max_markers
+        view._markers = (Marker * self.max_markers)()
+        view._pending = None
+        view._owned = False                  # the pool destroys its contexts
+        return view
+
+    @staticmethod
+    def _ptrs(items, n):
+        arr = (C.c_void_p * n)()
+        for i in range(n):
+            arr[i] = items[i]
+        return arr
 
     def run(self, volumes: Sequence[torch.Tensor], spacing, origin, direction=IDENTITY,
-            params: Optional[DetectParams] = None) -> List[DetectionResult]:
-        """Device-resident scans in, marker tables out (mask + label volumes are materialised into the
-        pool's buffers, as the reference's `closed` / `labeled` temporaries are)."""
-        cur = self._fork_streams()
-        n, k = len(volumes), len(self.ctxs)
-        results: List[Optional[DetectionResult]] = [None] * n
-        for i, v in enumerate(volumes):
-            j = i % k
-            if i >= k:
-                results[i - k] = self.ctxs[j].collect()
-            self.ctxs[j].detect_async(v, spacing=spacing, origin=origin, direction=direction, params=params,
-                                      out_mask=self.masks[j], out_labels=self.labels[j], stream=self.streams[j])
-        for i in range(max(0, n - k), n):
-            results[i] = self.ctxs[i % k].collect()
-        self._join_streams(cur)
-        return results
+            params: Optional[DetectParams] = None) -> BatchResult:
+        """Device-resident scans in, marker tables out (mask + label volumes are materialised into the pool's
+        ring of buffers, as the reference's `closed` / `labeled` temporaries are)."""
+        n, k = len(volumes), self.n_contexts
+        v0 = volumes[0]
+        for v in volumes:
+            if not (v.is_cuda and v.is_contiguous() and v.dim() == 3 and v.dtype == v0.dtype and v.shape == v0.shape):
+                raise ValueError("volumes must be contiguous CUDA tensors [nz, ny, nx] of one shape and type")
+        d = _desc(tuple(v0.shape), _TORCH_DTYPES[v0.dtype], spacing, origin, direction)
+        p = (params or DetectParams()).to_c()
+        summ = (Summary * n)()
+        mk = (Marker * (n * self.max_markers))()
+        vp = self._ptrs([v.data_ptr() for v in volumes], n)
+        mp = self._ptrs([self.masks[i % k].data_ptr() for i in range(n)], n) if self.materialise else None
+        lp = self._ptrs([self.labels[i % k].data_ptr() for i in range(n)], n) if self.materialise else None
+        s = torch.cuda.current_stream(self.device)
+        rc = self._lib.mamri_pool_detect(self._pool, C.byref(d), vp, n, C.byref(p), mp, lp, None, summ, mk,
+                                         self.max_markers, s.cuda_stream)
+        _capi.check_pool(rc, self._pool)
+        masks, labels = self.masks, self.labels
+        return BatchResult(n, summ, mk, self.max_markers, lambda i: (masks[i % k], labels[i % k], None))
 
     def run_host(self, volumes: Sequence, spacing, origin, direction=IDENTITY, params: Optional[DetectParams] = None,
-                 body_out: Optional[Sequence] = None) -> List[DetectionResult]:
+                 body_out: Optional[Sequence] = None) -> BatchResult:
         """Host buffers in (pinned CPU tensors / numpy), marker tables + optional host body masks out: the
-        drop-in call, with the H2D copy of scan i+1 overlapping the kernels and D2H of scan i."""
-        cur = self._fork_streams()
-        n, k = len(volumes), len(self.ctxs)
-        results: List[Optional[DetectionResult]] = [None] * n
-        for i, v in enumerate(volumes):
-            j = i % k
-            if i >= k:
-                results[i - k] = self.ctxs[j].collect()
-            self.ctxs[j].detect_host_async(v, spacing=spacing, origin=origin, direction=direction, params=params,
-                                           body_out=body_out[i] if body_out is not None else None,
-                                           stream=self.streams[j])
-        for i in range(max(0, n - k), n):
-            results[i] = self.ctxs[i % k].collect()
-        self._join_streams(cur)
-        return results
+        drop-in call for a batch, with the H2D copy of scan i+1 overlapping the kernels and D2H of scan i."""
+        n = len(volumes)
+        views = [_host_view(v) for v in volumes]
+        a0 = views[0][0]
+        for a, _ in views:
+            if a["dtype"] != a0["dtype"] or tuple(a["shape"]) != tuple(a0["shape"]):
+                raise ValueError("host volumes must share one shape and type")
+        d = _desc(a0["shape"], a0["dtype"], spacing, origin, direction)
+        p = (params or DetectParams()).to_c()
+        summ = (Summary * n)()
+        mk = (Marker * (n * self.max_markers))()
+        vp = self._ptrs([a["ptr"] for a, _ in views], n)
+        bp = None
+        if body_out is not None:
+            bviews = [_host_view(b) for b in body_out]
+            for b, _ in bviews:
+                if b["dtype"] != "uint8" or tuple(b["shape"]) != tuple(a0["shape"]):
+                    raise ValueError("body_out must be uint8 with the volume's shape")
+            bp = self._ptrs([b["ptr"] for b, _ in bviews], n)
+        s = torch.cuda.current_stream(self.device)
+        rc = self._lib.mamri_pool_detect_host(self._pool, C.byref(d), vp, n, C.byref(p), bp, summ, mk, self.max_markers,
+                                              s.cuda_stream)
+        _capi.check_pool(rc, self._pool)
+        return BatchResult(n, summ, mk, self.max_markers,
+                           lambda i: (None, None, body_out[i] if body_out is not None else None))

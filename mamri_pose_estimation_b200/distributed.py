@@ -22,6 +22,8 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
 def pack_table(results: Sequence) -> np.ndarray:
     """Fixed-size table [S, TABLE_SLOTS, TABLE_FIELDS] float64 from DetectionResult-like objects
     (attributes: markers[label,count,volume_mm3,centroid_ras], n_labels, body_label)."""
+    if hasattr(results, "table"):                     # detector.BatchResult: vectorised from the C arrays
+        return results.table(TABLE_SLOTS)
     t = np.zeros((len(results), TABLE_SLOTS, TABLE_FIELDS), dtype=np.float64)
     for i, r in enumerate(results):
         for j, m in enumerate(r.markers[:TABLE_SLOTS]):
