@@ -85,13 +85,16 @@ extern "C" int mamri_destroy(mamri_ctx* ctx) {
     DeviceGuard g(ctx->device);
     cudaFree(ctx->d_raw); cudaFree(ctx->d_planes); cudaFree(ctx->d_dil); cudaFree(ctx->d_closed); cudaFree(ctx->d_word_base);
     cudaFree(ctx->d_run_pos); cudaFree(ctx->d_run_len); cudaFree(ctx->d_parent); cudaFree(ctx->d_run_label); cudaFree(ctx->d_label_count); cudaFree(ctx->d_label_slot);
-    cudaFree(ctx->d_block_sums); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
+    cudaFree(ctx->d_root_count); cudaFree(ctx->d_scan_runs); cudaFree(ctx->d_scan_rank); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
     cudaFree(ctx->d_summary); cudaFree(ctx->d_scalars); cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
     cudaFree(ctx->d_entry_dist); cudaFree(ctx->d_entry_idx); cudaFree(ctx->d_entry_cnt); cudaFree(ctx->d_entry_res);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 48; ++i) if (ctx->ev_fine[i]) cudaEventDestroy(ctx->ev_fine[i]);
     if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
     if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
+    if (ctx->cap_stream2) cudaStreamDestroy(ctx->cap_stream2);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     cudaFree(ctx->d_dyn); cudaFreeHost(ctx->h_dyn);
     cudaFreeHost(ctx->h_markers); cudaFreeHost(ctx->h_summary); cudaFreeHost(ctx->h_entry_res);
     delete ctx;
@@ -158,7 +161,14 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     ALLOC(ctx->d_run_label, size_t(max_runs) * 4, "run labels");
     ALLOC(ctx->d_label_count, size_t(max_runs) * 4, "label counts");
     ALLOC(ctx->d_label_slot, size_t(max_runs) * 4, "label slots");
-    ALLOC(ctx->d_block_sums, 2048 * 4, "scan partials");
+    ALLOC(ctx->d_root_count, size_t(max_runs) * 4, "root counts");
+    {   // look-back states of the two single-pass scans (tile sizes: ccl.cu RS_TILE = 2048 words, FR_TILE = 1024 runs)
+        const size_t t_runs = ctx->cap_words / 2048 + 2, t_rank = size_t(max_runs) / 1024 + 2;
+        ALLOC(ctx->d_scan_runs, t_runs * 8, "scan states");
+        ALLOC(ctx->d_scan_rank, t_rank * 8, "scan states");
+        if ((e = cudaMemset(ctx->d_scan_runs, 0, t_runs * 8)) != cudaSuccess) return bail(e, "scan states");
+        if ((e = cudaMemset(ctx->d_scan_rank, 0, t_rank * 8)) != cudaSuccess) return bail(e, "scan states");
+    }
     ALLOC(ctx->d_cand_label, (size_t(max_markers) + 1) * 4, "candidate labels");
     ALLOC(ctx->d_cand_sums, (size_t(max_markers) + 1) * 9 * 8, "candidate sums");
     ALLOC(ctx->d_markers, size_t(max_markers) * sizeof(mamri_marker), "marker table");
@@ -179,6 +189,9 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     if ((e = cudaMalloc((void**)&ctx->d_dyn, sizeof(DynArgs))) != cudaSuccess) return bail(e, "dynamic args");
     if ((e = cudaMallocHost((void**)&ctx->h_dyn, sizeof(DynArgs))) != cudaSuccess) return bail(e, "pinned dynamic args");
     if ((e = cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "capture stream");
+    if ((e = cudaStreamCreateWithFlags(&ctx->cap_stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "capture stream");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "events");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "events");
     {
         const char* ng = getenv("MAMRI_NO_GRAPH");
         ctx->use_graph = !(ng && ng[0] == '1');
@@ -228,7 +241,9 @@ static int validate(mamri_ctx* ctx, const mamri_volume_desc* d, const mamri_para
 }
 
 // Enqueues the stage kernels and the result copies on `s` (a real stream or one in capture mode).
-static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, cudaStream_t s) {
+// `fork` (capture only): once the labels are final, the per-voxel outputs are written on a second
+// branch while the first computes the moments and copies the tables -- the two do not depend on each other.
+static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool fork, cudaStream_t s) {
     const mamri_volume_desc* desc = &k.desc;
     const mamri_params* params = &k.prm;
     const int nx = desc->nx, ny = desc->ny, nz = desc->nz;
@@ -242,13 +257,23 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, cudaSt
     if (prof) CK(cudaEventRecord(ctx->ev[2], s));
     CK(launch_ccl(ctx, mask, nx, ny, nz, params->connectivity, s));
     if (prof) CK(cudaEventRecord(ctx->ev[3], s));
-    CK(launch_stats(ctx, mask, desc, params, s));
+    CK(launch_select(ctx, desc, params, s));
+    const bool outputs = k.has_mask || k.has_labels || k.has_body;
+    const bool forked = fork && outputs;
+    if (forked) {
+        CK(cudaEventRecord(ctx->ev_fork, s));
+        CK(cudaStreamWaitEvent(ctx->cap_stream2, ctx->ev_fork, 0));
+        CK(launch_materialise(ctx, mask, nx, ny, nz, k.outs_aligned, ctx->cap_stream2));
+        CK(cudaEventRecord(ctx->ev_join, ctx->cap_stream2));
+    }
+    CK(launch_moments(ctx, desc, params, s));
     if (prof) CK(cudaEventRecord(ctx->ev[4], s));
-    if (k.has_mask || k.has_labels || k.has_body) CK(launch_materialise(ctx, mask, nx, ny, nz, k.outs_aligned, s));
+    if (outputs && !forked) CK(launch_materialise(ctx, mask, nx, ny, nz, k.outs_aligned, s));
     if (prof) CK(cudaEventRecord(ctx->ev[5], s));
     CK(cudaMemcpyAsync(ctx->h_summary, ctx->d_summary, sizeof(mamri_summary), cudaMemcpyDeviceToHost, s));
     const uint32_t eager = ctx->max_markers < EAGER_MARKERS ? ctx->max_markers : EAGER_MARKERS;
     CK(cudaMemcpyAsync(ctx->h_markers, ctx->d_markers, size_t(eager) * sizeof(mamri_marker), cudaMemcpyDeviceToHost, s));
+    if (forked) CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     return MAMRI_OK;
 }
 
@@ -274,9 +299,11 @@ extern "C" int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc,
     ctx->h_dyn->mask_out = d_mask_out;
     ctx->h_dyn->labels_out = d_labels_out;
     ctx->h_dyn->body_out = d_body_out;
+    ctx->h_dyn->gen = ++ctx->gen;            // generation 0 is the cleared state: never used
+    if ((ctx->gen & 0x3FFFFFFFu) == 0) ctx->h_dyn->gen = ++ctx->gen;
     CK(prepare_raw_apron(ctx, desc->nx, desc->ny, desc->nz, params->close_radius, s));
     if (ctx->profile || !ctx->use_graph) {
-        rc = enqueue_pipeline(ctx, k, ctx->profile, s);
+        rc = enqueue_pipeline(ctx, k, ctx->profile, false, s);
         if (rc != MAMRI_OK) return rc;
     } else {
         if (!ctx->gvalid || memcmp(&k, &ctx->gkey, sizeof(k)) != 0) {
@@ -284,7 +311,7 @@ extern "C" int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc,
             if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
             ctx->gvalid = false;
             CK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
-            rc = enqueue_pipeline(ctx, k, false, ctx->cap_stream);
+            rc = enqueue_pipeline(ctx, k, false, true, ctx->cap_stream);
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamEndCapture(ctx->cap_stream, &graph);
             if (rc != MAMRI_OK) { if (graph) cudaGraphDestroy(graph); return rc; }

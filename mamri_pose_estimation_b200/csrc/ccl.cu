@@ -13,10 +13,8 @@
 
 #include <stdlib.h>
 
-constexpr int SCAN_THREADS = 1024;
-
 // ------------------------------------------------------------------------------------------------
-// block-wide primitives (blockDim.x == SCAN_THREADS)
+// warp scan
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     const unsigned lane = lane_id();
@@ -28,135 +26,120 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     return v;
 }
 
-// Exclusive prefix of `v` over the block; `total` = block sum.  `ws` is 33 words of shared memory.
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* ws, uint32_t& total) {
+// ------------------------------------------------------------------------------------------------
+// run numbering: single-pass exclusive scan of run starts per word, and the run table
+// ------------------------------------------------------------------------------------------------
+// word_base[w] = number of runs that start before word w; run table: position (word*32 + bit of the
+// first voxel) and length of every run, in raster order.  One pass over the mask: a CTA takes a tile of
+// RS_TILE words (8 consecutive words per thread, two 128-bit loads), scans its run-start counts, gets
+// the count of all earlier tiles by decoupled look-back and writes its part of both tables.
+constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS;
+
+__device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t* ws /*[9]*/, uint32_t& total) {
     const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
-    uint32_t inc = warp_incl_scan(v);
+    const uint32_t inc = warp_incl_scan(v);
     if (lane == 31) ws[wid] = inc;
     __syncthreads();
-    if (wid == 0) {
-        uint32_t t = ws[lane];
-        uint32_t ti = warp_incl_scan(t);
-        ws[lane] = ti - t;
-        if (lane == 31) ws[32] = ti;
-    }
-    __syncthreads();
-    uint32_t r = ws[wid] + inc - v;
-    total = ws[32];
-    __syncthreads();
-    return r;
-}
-
-__device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* ws) {
-    const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
+    uint32_t off = 0, tot = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    if (lane == 0) ws[wid] = v;
-    __syncthreads();
-    uint32_t t = 0;
-    if (wid == 0) {
-        t = ws[lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t t = ws[w];
+        if (w < int(wid)) off += t;
+        tot += t;
     }
+    total = tot;
     __syncthreads();
-    return t;   // valid in warp 0
+    return off + inc - v;
 }
 
-__device__ __forceinline__ void chunk_of(uint32_t n, uint32_t& begin, uint32_t& end) {
-    uint32_t chunk = (n + gridDim.x - 1) / gridDim.x;
-    begin = uint32_t(blockIdx.x) * chunk;
-    end = begin + chunk < n ? begin + chunk : n;
-    if (begin > n) begin = n;
-}
-
-// ------------------------------------------------------------------------------------------------
-// run numbering: exclusive scan of run starts per word, and the run table
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS) k_runs_count(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
-                                                             uint32_t* __restrict__ block_sums) {
+__global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
+                                                          volatile unsigned long long* state, const DynArgs* __restrict__ dyn,
+                                                          uint32_t* __restrict__ word_base, uint32_t* __restrict__ run_pos,
+                                                          uint32_t* __restrict__ run_len, uint32_t* __restrict__ root_count,
+                                                          uint32_t max_runs, DevScalars* sc) {
     pdl_wait();
-    __shared__ uint32_t ws[33];
-    uint32_t begin, end;
-    chunk_of(n_words, begin, end);
-    uint32_t sum = 0;
-    for (uint32_t i = begin + threadIdx.x; i < end; i += SCAN_THREADS) {
-        uint32_t m = mask[i];
-        if (m) {
-            uint32_t prev = (i % W) ? mask[i - 1] : 0u;
-            sum += __popc(run_starts(m, prev));
+    __shared__ uint32_t ws[9];
+    __shared__ uint32_t s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&sc->ticket_runs, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile, n_tiles = gridDim.x;
+    const uint32_t i0 = tile * RS_TILE + threadIdx.x * RS_ITEMS;
+    uint32_t m[RS_ITEMS], starts[RS_ITEMS];
+    uint32_t cnt = 0;
+    if (i0 + RS_ITEMS <= n_words) {
+        const uint4 q0 = *reinterpret_cast<const uint4*>(mask + i0), q1 = *reinterpret_cast<const uint4*>(mask + i0 + 4);
+        m[0] = q0.x; m[1] = q0.y; m[2] = q0.z; m[3] = q0.w; m[4] = q1.x; m[5] = q1.y; m[6] = q1.z; m[7] = q1.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k) m[k] = (i0 + k < n_words) ? mask[i0 + k] : 0u;
+    }
+    {
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k) any |= m[k];
+        uint32_t prev = (any && i0 > 0) ? mask[i0 - 1] : 0u;
+        uint32_t xw = i0 % uint32_t(W);
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k) {
+            starts[k] = run_starts(m[k], xw ? prev : 0u);
+            cnt += __popc(starts[k]);
+            prev = m[k];
+            if (++xw == uint32_t(W)) xw = 0;
         }
     }
-    uint32_t t = block_sum(sum, ws);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
-}
-
-// Exclusive prefix of this CTA over the per-CTA partials (every CTA rescans the <= 1024 partials
-// itself: cheaper than a separate one-CTA launch); `total` = grand total.
-__device__ __forceinline__ uint32_t scan_partials(const uint32_t* __restrict__ block_sums, uint32_t* ws, uint32_t& total) {
-    __shared__ uint32_t mine;
-    const uint32_t v = threadIdx.x < gridDim.x ? block_sums[threadIdx.x] : 0u;
-    const uint32_t ex = block_excl_scan(v, ws, total);
-    if (threadIdx.x == blockIdx.x) mine = ex;
-    __syncthreads();
-    return mine;
-}
-
-// word_base[w] = number of runs that start before word w; run table: position (word*32 + bit of the
-// first voxel) and length of every run, in raster order.
-__global__ void __launch_bounds__(SCAN_THREADS) k_runs_assign(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
-                                                              const uint32_t* __restrict__ block_sums,
-                                                              uint32_t* __restrict__ word_base,
-                                                              uint32_t* __restrict__ run_pos, uint32_t* __restrict__ run_len,
-                                                              uint32_t max_runs, DevScalars* sc) {
-    pdl_wait();
-    __shared__ uint32_t ws[33];
-    uint32_t total_runs;
-    uint32_t running = scan_partials(block_sums, ws, total_runs);
-    if (total_runs > max_runs) {                      // every CTA sees the same total
-        if (blockIdx.x == 0 && threadIdx.x == 0) { sc->status = MAMRI_ERR_CAPACITY; sc->n_runs = 0; }
-        return;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) sc->n_runs = total_runs;
-    uint32_t begin, end;
-    chunk_of(n_words, begin, end);
-    for (uint32_t i0 = begin; i0 < end; i0 += SCAN_THREADS) {
-        const uint32_t i = i0 + threadIdx.x;
-        uint32_t m = 0, starts = 0, xw = 0;
-        if (i < end) {
-            m = mask[i];
-            if (m) {
-                xw = i % W;
-                starts = run_starts(m, xw ? mask[i - 1] : 0u);
+    uint32_t total;
+    const uint32_t ex = block_excl_scan256(cnt, ws, total);
+    if (threadIdx.x < 32) {
+        const uint32_t before = scan_lookback(state, tile, total, dyn->gen);
+        if (threadIdx.x == 0) {
+            s_prefix = before;
+            if (tile == n_tiles - 1) {                   // grand total: every later stage keys off n_runs / status
+                if (before + total > max_runs) { sc->status = MAMRI_ERR_CAPACITY; sc->n_runs = 0; }
+                else sc->n_runs = before + total;
             }
         }
-        uint32_t cnt = __popc(starts), total;
-        uint32_t base = running + block_excl_scan(cnt, ws, total);
-        if (i < end) {
-            word_base[i] = base;
-            uint32_t st = starts, r = base;
-            while (st) {
-                const int b = __ffs(st) - 1;
-                st &= st - 1;
-                const uint32_t t = m >> b;                       // run bits from its start
-                uint32_t len;
-                if (t != (0xFFFFFFFFu >> b)) {
-                    len = __ffs(~t) - 1;                         // ends inside this word
-                } else {
-                    len = 32 - b;                                // reaches bit 31: follow it through the next words
-                    for (uint32_t k = 1; xw + k < uint32_t(W); ++k) {
-                        const uint32_t nm = mask[i + k];
-                        if (nm == 0xFFFFFFFFu) { len += 32; continue; }
-                        len += __ffs(~nm) - 1;
-                        break;
-                    }
+    }
+    __syncthreads();
+    uint32_t base = s_prefix + ex;
+    uint32_t wb[RS_ITEMS];
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        wb[k] = base;
+        const uint32_t i = i0 + k;
+        uint32_t st = starts[k], r = base;
+        while (st) {
+            const int b = __ffs(st) - 1;
+            st &= st - 1;
+            const uint32_t t = m[k] >> b;                        // run bits from its start
+            uint32_t len;
+            if (t != (0xFFFFFFFFu >> b)) {
+                len = __ffs(~t) - 1;                             // ends inside this word
+            } else {
+                len = 32 - b;                                    // reaches bit 31: follow it through the next words
+                const uint32_t xw = i % uint32_t(W);
+                for (uint32_t j = 1; xw + j < uint32_t(W); ++j) {
+                    const uint32_t nm = mask[i + j];
+                    if (nm == 0xFFFFFFFFu) { len += 32; continue; }
+                    len += __ffs(~nm) - 1;
+                    break;
                 }
+            }
+            if (r < max_runs) {
                 run_pos[r] = i * 32u + uint32_t(b);
                 run_len[r] = len;
-                ++r;
+                root_count[r] = 0u;                              // accumulated by k_flatten_rank on the roots
             }
+            ++r;
         }
-        running += total;
+        base += __popc(starts[k]);
+    }
+    if (i0 + RS_ITEMS <= n_words) {
+        *reinterpret_cast<uint4*>(word_base + i0) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+        *reinterpret_cast<uint4*>(word_base + i0 + 4) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k)
+            if (i0 + k < n_words) word_base[i0 + k] = wb[k];
     }
 }
 
@@ -299,60 +282,103 @@ __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ ma
 }
 
 // ------------------------------------------------------------------------------------------------
-// flatten, rank the roots (ITK-consecutive labels)
+// flatten, count, rank the roots (ITK-consecutive labels) -- one pass over the run table
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS) k_flatten_count(uint32_t* parent, uint32_t* __restrict__ block_sums,
-                                                                const DevScalars* sc) {
-    pdl_wait();
-    __shared__ uint32_t ws[33];
-    uint32_t begin, end;
-    chunk_of(sc->n_runs, begin, end);
-    uint32_t roots = 0;
-    for (uint32_t r = begin + threadIdx.x; r < end; r += SCAN_THREADS) {
-        uint32_t x = uint32_t(r), p = parent[x];
-        while (p != x) { x = p; p = parent[x]; }
-        parent[r] = x;
-        roots += (x == uint32_t(r));
-    }
-    uint32_t t = block_sum(roots, ws);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
-}
+// Per run: parent[r] = root; the run's voxels are added to root_count[root] (lanes of a warp that share
+// a root are combined by shuffles, then a per-CTA shared-memory cache, then global atomics -- one huge
+// component would otherwise serialise every warp on one address).  Roots are ranked by a single-pass
+// scan with decoupled look-back: run_label[root] = 1 + number of roots before it; roots are ordered by
+// minimum linear index, so this is ITK's consecutive numbering.
+constexpr int FR_THREADS = 256, FR_ITEMS = 4, FR_TILE = FR_THREADS * FR_ITEMS;
 
-// run_label[root] = 1 + number of roots before it (roots are ordered by minimum linear index, so this
-// is ITK's consecutive numbering); non-root runs get their label from their root in the next kernel.
-__global__ void __launch_bounds__(SCAN_THREADS) k_rank_roots(const uint32_t* __restrict__ parent,
-                                                             const uint32_t* __restrict__ block_sums,
-                                                             uint32_t* __restrict__ run_label,
-                                                             uint32_t* __restrict__ label_count, DevScalars* sc) {
+__global__ void __launch_bounds__(FR_THREADS) k_flatten_rank(uint32_t* parent, const uint32_t* __restrict__ run_len,
+                                                             volatile unsigned long long* state,
+                                                             const DynArgs* __restrict__ dyn, uint32_t* __restrict__ run_label,
+                                                             uint32_t* root_count, DevScalars* sc) {
     pdl_wait();
-    __shared__ uint32_t ws[33];
-    uint32_t total_roots;
-    uint32_t running = scan_partials(block_sums, ws, total_roots);
-    if (blockIdx.x == 0 && threadIdx.x == 0) sc->n_labels = total_roots;
-    uint32_t begin, end;
-    chunk_of(sc->n_runs, begin, end);
-    for (uint32_t i0 = begin; i0 < end; i0 += SCAN_THREADS) {
-        uint32_t r = i0 + threadIdx.x;
-        uint32_t is_root = (r < end && parent[r] == uint32_t(r)) ? 1u : 0u, total;
-        uint32_t rank = running + block_excl_scan(is_root, ws, total);
-        if (is_root) {
-            run_label[r] = rank + 1u;
-            label_count[rank] = 0u;
-        }
-        running += total;
+    __shared__ CtaCache<1, uint32_t, 64> cache;
+    __shared__ uint32_t ws[9];
+    __shared__ uint32_t s_tile, s_prefix;
+    if (sc->status != MAMRI_OK) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->n_labels = 0;
+        return;
     }
+    const uint32_t n = sc->n_runs;
+    const uint32_t n_tiles = (n + FR_TILE - 1) / FR_TILE;
+    if (n_tiles == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->n_labels = 0;
+        return;
+    }
+    cache.init();
+    // the grid is sized for the run-table capacity; CTAs draw tiles until the table is exhausted
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&sc->ticket_rank, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= n_tiles) break;
+        const uint32_t r0 = tile * FR_TILE + (threadIdx.x >> 5) * (32 * FR_ITEMS) + lane_id();
+        uint32_t roots = 0, is_root[FR_ITEMS];
+#pragma unroll
+        for (int k = 0; k < FR_ITEMS; ++k) {
+            const uint32_t r = r0 + k * 32;                          // warp-contiguous: coalesced, one key per lane
+            uint32_t key = MAMRI_NONE, v[1] = {0u};
+            is_root[k] = 0;
+            if (r < n) {
+                uint32_t x = r, p = parent[x];
+                while (p != x) { x = p; p = parent[x]; }
+                parent[r] = x;                                       // roots stay fixed points: concurrent walkers stay correct
+                is_root[k] = (x == r);
+                key = x;
+                v[0] = run_len[r];
+            }
+            roots += is_root[k];
+            warp_agg_add(key, v, cache, root_count);
+        }
+        // rank: items are ordered (warp, k, lane) inside the tile, so scan per k-row
+        uint32_t row_tot[FR_ITEMS], row_ex[FR_ITEMS];
+#pragma unroll
+        for (int k = 0; k < FR_ITEMS; ++k) {
+            const uint32_t inc = warp_incl_scan(is_root[k]);
+            row_ex[k] = inc - is_root[k];
+            row_tot[k] = __shfl_sync(FULL, inc, 31);
+        }
+        uint32_t warp_total = 0;
+#pragma unroll
+        for (int k = 0; k < FR_ITEMS; ++k) { const uint32_t t = row_tot[k]; row_tot[k] = warp_total; warp_total += t; }
+        const unsigned wid = threadIdx.x >> 5;
+        if (lane_id() == 0) ws[wid] = warp_total;
+        __syncthreads();
+        uint32_t off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t t = ws[w];
+            if (w < int(wid)) off += t;
+            total += t;
+        }
+        if (threadIdx.x < 32) {
+            const uint32_t before = scan_lookback(state, tile, total, dyn->gen);
+            if (threadIdx.x == 0) {
+                s_prefix = before;
+                if (tile == n_tiles - 1) sc->n_labels = before + total;
+            }
+        }
+        __syncthreads();
+        const uint32_t base = s_prefix + off;
+#pragma unroll
+        for (int k = 0; k < FR_ITEMS; ++k)
+            if (is_root[k]) run_label[r0 + k * 32] = base + row_tot[k] + row_ex[k] + 1u;
+    }
+    cache.flush(root_count);
 }
 
 cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int connectivity, cudaStream_t s) {
     const int W = (nx + 31) / 32;
     const uint32_t n_words = uint32_t(W) * ny * nz;
-    const int G = MAMRI_SCAN_CTAS;
-    uint32_t* bs_runs = c->d_block_sums;
-    uint32_t* bs_roots = c->d_block_sums + 1024;
-    LK(k_runs_count, G, SCAN_THREADS, s, false, d_mask, W, n_words, bs_runs);
-    prof_mark(c, s, "runs_count");
-    LK(k_runs_assign, G, SCAN_THREADS, s, false, d_mask, W, n_words, bs_runs, c->d_word_base, c->d_run_pos, c->d_run_len, c->max_runs, c->d_scalars);
-    prof_mark(c, s, "runs_assign");
+    const uint32_t scan_tiles = (n_words + RS_TILE - 1) / RS_TILE;
+    LK(k_runs_scan, scan_tiles, RS_THREADS, s, false, d_mask, W, n_words, c->d_scan_runs, c->d_dyn, c->d_word_base,
+       c->d_run_pos, c->d_run_len, c->d_root_count, c->max_runs, c->d_scalars);
+    prof_mark(c, s, "runs_scan");
     int radix = 1;
     while (radix * radix < nz) radix <<= 1;
     const int RG = MAMRI_RUN_CTAS;
@@ -379,10 +405,9 @@ cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int
             prof_mark(c, s, "union_z_between_blocks");
         }
     }
-    LK(k_flatten_count, G, SCAN_THREADS, s, false, c->d_parent, bs_roots, c->d_scalars);
-    prof_mark(c, s, "flatten_count");
-    LK(k_rank_roots, G, SCAN_THREADS, s, false, c->d_parent, bs_roots, c->d_run_label, c->d_label_count, c->d_scalars);
-    prof_mark(c, s, "rank_roots");
+    LK(k_flatten_rank, RG, FR_THREADS, s, false, c->d_parent, c->d_run_len, c->d_scan_rank, c->d_dyn, c->d_run_label,
+       c->d_root_count, c->d_scalars);
+    prof_mark(c, s, "flatten_rank");
     return cudaGetLastError();
 }
 

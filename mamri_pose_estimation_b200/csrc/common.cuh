@@ -21,6 +21,8 @@ struct DevScalars {
     int          status;             // MAMRI_OK / MAMRI_ERR_CAPACITY
     unsigned long long body_packed;  // (count << 32) | (0xFFFFFFFF - label): atomicMax picks largest, lowest label
     unsigned long long n_foreground;
+    unsigned int ticket_runs;        // tile tickets of k_runs_scan / k_flatten_rank
+    unsigned int ticket_rank;
     unsigned int done_select;        // CTAs of k_select that have finished (last one prepares the moment table)
     unsigned int done_moments;       // CTAs of k_moments that have finished (last one finalises)
 };
@@ -32,6 +34,7 @@ struct DynArgs {
     uint8_t* mask_out;
     uint32_t* labels_out;
     uint8_t* body_out;
+    uint32_t gen;                    // launch generation (tags the look-back states of the single-pass scans)
 };
 
 // Everything else a captured pipeline depends on.
@@ -64,9 +67,12 @@ struct mamri_ctx {
     uint32_t* d_run_len;    // voxels in each run                        [max_runs]
     uint32_t* d_parent;     // union-find over runs                     [max_runs]
     uint32_t* d_run_label;  // final label of each run                  [max_runs]
+    uint32_t* d_root_count; // voxels of the component rooted at each run (roots only) [max_runs]
     uint32_t* d_label_count;// voxels per label                         [max_runs]
-    uint32_t* d_label_slot; // marker-table slot of each label / NONE   [max_runs]
-    uint32_t* d_block_sums; // scan partials                            [2 * 1024]
+    uint32_t* d_label_slot; // marker-table slot of each ROOT run / NONE [max_runs]
+    unsigned long long* d_scan_runs;  // look-back states of k_runs_scan     [tiles of cap_words]
+    unsigned long long* d_scan_rank;  // look-back states of k_flatten_rank  [tiles of max_runs]
+    uint32_t gen;
     uint32_t* d_cand_label; // label of each slot                       [max_markers + 1]
     unsigned long long* d_cand_sums; // 9 sums per slot (sx sy sz xx yy zz xy xz yz) [(max_markers+1)*9]
     mamri_marker* d_markers;         // sorted marker table              [max_markers]
@@ -91,6 +97,8 @@ struct mamri_ctx {
     DynArgs* d_dyn;
     DynArgs* h_dyn;                  // pinned; copied to d_dyn by the graph's first node
     cudaStream_t cap_stream;
+    cudaStream_t cap_stream2;        // second branch of the captured graph (materialise || moments + table copies)
+    cudaEvent_t ev_fork, ev_join;
     cudaGraphExec_t gexec;
     GraphKey gkey;
     bool gvalid;
@@ -126,8 +134,8 @@ cudaError_t launch_threshold_pack(mamri_ctx* c, int vol_aligned16, int dtype, in
                                   double hi, int radius, cudaStream_t s);
 cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s);
 cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int connectivity, cudaStream_t s);
-cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volume_desc* desc,
-                         const mamri_params* prm, cudaStream_t s);
+cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
+cudaError_t launch_moments(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
 cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int outs_aligned,
                                cudaStream_t s);
 cudaError_t launch_entry_search(mamri_ctx* c, const float* d_points, const float* d_normals, long long n,
@@ -194,6 +202,123 @@ __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ void pdl_wait() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+
+#define FULL 0xFFFFFFFFu
+
+// ---- single-pass prefix sums over tiles (decoupled look-back) ------------------------------------
+// One 64-bit word per tile: [63:34] generation of the launch that wrote it, [33:2] value, [1:0] flag
+// (1 = the tile's own total, 2 = inclusive prefix).  Words of older generations read as "empty", so the
+// array never needs clearing; tiles are handed out by an atomic ticket, hence a tile only ever waits
+// for tiles whose CTAs are already running.
+__device__ __forceinline__ unsigned long long scan_pack(uint32_t gen, uint32_t value, uint32_t flag) {
+    return ((unsigned long long)(gen & 0x3FFFFFFFu) << 34) | ((unsigned long long)value << 2) | flag;
+}
+
+// Called by the whole first warp of the CTA that owns `tile`: publishes `total`, returns the sum of the
+// totals of all earlier tiles.
+__device__ __forceinline__ uint32_t scan_lookback(volatile unsigned long long* state, uint32_t tile, uint32_t total,
+                                                  uint32_t gen) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (tile == 0) {
+        if (lane == 0) state[0] = scan_pack(gen, total, 2u);
+        return 0u;
+    }
+    if (lane == 0) state[tile] = scan_pack(gen, total, 1u);
+    const unsigned long long g30 = gen & 0x3FFFFFFFu;
+    uint32_t excl = 0;
+    int pos = int(tile);
+    while (true) {
+        const int idx = pos - 1 - int(lane);
+        uint32_t flag = 2u, val = 0u;                    // before the first tile: inclusive prefix 0
+        if (idx >= 0) {
+            unsigned long long v;
+            do {
+                v = state[idx];
+                flag = ((v >> 34) == g30) ? uint32_t(v & 3u) : 0u;
+            } while (flag == 0u);
+            val = uint32_t(v >> 2);
+        }
+        const unsigned incl = __ballot_sync(FULL, flag == 2u);
+        const int first = incl ? (__ffs(incl) - 1) : 31; // nearest earlier tile with an inclusive prefix
+        uint32_t c = int(lane) <= first ? val : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+        excl += c;
+        if (incl) break;
+        pos -= 32;
+    }
+    if (lane == 0) state[tile] = scan_pack(gen, excl + total, 2u);
+    return excl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// aggregation: warp shuffles first, then a per-CTA shared-memory cache, then global atomics
+// ------------------------------------------------------------------------------------------------
+// One huge component (the body) makes every warp hit the same table row; per-warp global atomics on
+// one address serialise in L2.  Each CTA therefore keeps a small direct-mapped cache of accumulators in
+// shared memory (slot = key % SLOTS, claimed by the first key that arrives, never evicted); cached
+// keys cost a shared-memory atomic, the rest go to global memory; the cache is flushed once per CTA.
+template <int NV, typename V, int SLOTS>
+struct CtaCache {
+    uint32_t tag[SLOTS];
+    V val[SLOTS][NV];
+
+    __device__ void init() {
+        for (int i = threadIdx.x; i < SLOTS; i += blockDim.x) tag[i] = MAMRI_NONE;
+        for (int i = threadIdx.x; i < SLOTS * NV; i += blockDim.x) (&val[0][0])[i] = V(0);
+        __syncthreads();
+    }
+    __device__ __forceinline__ void add(uint32_t key, const V (&v)[NV], V* table) {
+        const int s = int(key % SLOTS);
+        uint32_t t = *(volatile uint32_t*)&tag[s];
+        if (t == MAMRI_NONE) {
+            t = atomicCAS(&tag[s], MAMRI_NONE, key);
+            if (t == MAMRI_NONE) t = key;
+        }
+        if (t == key) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) atomicAdd(&val[s][i], v[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) atomicAdd(table + uint32_t(key) * NV + i, v[i]);
+        }
+    }
+    __device__ void flush(V* table) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SLOTS * NV; i += blockDim.x) {
+            const uint32_t key = tag[i / NV];
+            const V x = (&val[0][0])[i];
+            if (key != MAMRI_NONE && x != V(0)) atomicAdd(table + uint32_t(key) * NV + (i % NV), x);
+        }
+    }
+};
+
+// Lanes with equal keys are summed by shuffles; one lane per distinct key forwards to the CTA cache.
+template <int NV, typename V, int SLOTS>
+__device__ __forceinline__ void warp_agg_add(uint32_t key, V (&v)[NV], CtaCache<NV, V, SLOTS>& cache, V* table) {
+    const unsigned lane = lane_id();
+    const bool valid = key != MAMRI_NONE;
+    const unsigned peers = __match_any_sync(FULL, key);
+    const bool single = valid && peers == (1u << lane);
+    if (single) cache.add(key, v, table);
+    __syncwarp();
+    unsigned remaining = __ballot_sync(FULL, valid && !single);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const uint32_t k = __shfl_sync(FULL, key, leader);
+        const bool mine = valid && key == k;
+        V x[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            x[i] = mine ? v[i] : V(0);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x[i] += __shfl_xor_sync(FULL, x[i], o);
+        }
+        if (int(lane) == leader) cache.add(k, x, table);
+        remaining &= ~__ballot_sync(FULL, mine);
+    }
 }
 
 // Run-start bits of word `m` given the previous word of the same row (0 at the row start).

@@ -11,8 +11,6 @@
 // principal moments/axes) is float64 on the device.
 #include "common.cuh"
 
-#define FULL 0xFFFFFFFFu
-
 struct GeomArgs {
     double spacing[3], origin[3], dir[9];
     double voxel_volume;     // spacing[0]*spacing[1]*spacing[2], multiplied in that order on the host
@@ -20,127 +18,41 @@ struct GeomArgs {
 };
 
 // ------------------------------------------------------------------------------------------------
-// aggregation: warp shuffles first, then a per-CTA shared-memory cache, then global atomics
-// ------------------------------------------------------------------------------------------------
-// One huge component (the body) makes every warp hit the same table row; per-warp global atomics on
-// one address serialise in L2.  Each CTA therefore keeps a small direct-mapped cache of accumulators in
-// shared memory (slot = key % SLOTS, claimed by the first key that arrives, never evicted); cached
-// keys cost a shared-memory atomic, the rest go to global memory; the cache is flushed once per CTA.
-template <int NV, typename V, int SLOTS>
-struct CtaCache {
-    uint32_t tag[SLOTS];
-    V val[SLOTS][NV];
-
-    __device__ void init() {
-        for (int i = threadIdx.x; i < SLOTS; i += blockDim.x) tag[i] = MAMRI_NONE;
-        for (int i = threadIdx.x; i < SLOTS * NV; i += blockDim.x) (&val[0][0])[i] = V(0);
-        __syncthreads();
-    }
-    __device__ __forceinline__ void add(uint32_t key, const V (&v)[NV], V* table) {
-        const int s = int(key % SLOTS);
-        uint32_t t = *(volatile uint32_t*)&tag[s];
-        if (t == MAMRI_NONE) {
-            t = atomicCAS(&tag[s], MAMRI_NONE, key);
-            if (t == MAMRI_NONE) t = key;
-        }
-        if (t == key) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) atomicAdd(&val[s][i], v[i]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) atomicAdd(table + uint32_t(key) * NV + i, v[i]);
-        }
-    }
-    __device__ void flush(V* table) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < SLOTS * NV; i += blockDim.x) {
-            const uint32_t key = tag[i / NV];
-            const V x = (&val[0][0])[i];
-            if (key != MAMRI_NONE && x != V(0)) atomicAdd(table + uint32_t(key) * NV + (i % NV), x);
-        }
-    }
-};
-
-// Lanes with equal keys are summed by shuffles; one lane per distinct key forwards to the CTA cache.
-template <int NV, typename V, int SLOTS>
-__device__ __forceinline__ void warp_agg_add(uint32_t key, V (&v)[NV], CtaCache<NV, V, SLOTS>& cache, V* table) {
-    const unsigned lane = lane_id();
-    const bool valid = key != MAMRI_NONE;
-    const unsigned peers = __match_any_sync(FULL, key);
-    const bool single = valid && peers == (1u << lane);
-    if (single) cache.add(key, v, table);
-    __syncwarp();
-    unsigned remaining = __ballot_sync(FULL, valid && !single);
-    while (remaining) {
-        const int leader = __ffs(remaining) - 1;
-        const uint32_t k = __shfl_sync(FULL, key, leader);
-        const bool mine = valid && key == k;
-        V x[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            x[i] = mine ? v[i] : V(0);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x[i] += __shfl_xor_sync(FULL, x[i], o);
-        }
-        if (int(lane) == leader) cache.add(k, x, table);
-        remaining &= ~__ballot_sync(FULL, mine);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// phase 1: voxel count of every label (also gives every non-root run its final label)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_count_labels(const uint32_t* __restrict__ parent,
-                                                      const uint32_t* __restrict__ run_len, uint32_t* run_label,
-                                                      uint32_t* label_count, const DevScalars* sc) {
-    pdl_wait();
-    __shared__ CtaCache<1, uint32_t, 64> cache;
-    if (sc->status != MAMRI_OK) return;
-    cache.init();
-    const uint32_t n = sc->n_runs;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t r0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < n; r0 += stride) {
-        const uint32_t r = r0 + lane_id();
-        uint32_t key = MAMRI_NONE;
-        uint32_t v[1] = {0u};
-        if (r < n) {
-            const uint32_t root = parent[r];
-            const uint32_t label = run_label[root];          // roots were ranked by k_rank_roots
-            if (root != r) run_label[r] = label;
-            key = label - 1u;
-            v[0] = run_len[r];
-        }
-        warp_agg_add(key, v, cache, label_count);
-    }
-    cache.flush(label_count);
-}
-
-// ------------------------------------------------------------------------------------------------
 // stage 4a: volume filter (Mamri.py:1310) and body label (Mamri.py:1320-1322)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ label_count, uint32_t* __restrict__ label_slot,
-                                                uint32_t* __restrict__ cand_label, unsigned long long* __restrict__ sums,
-                                                uint32_t max_markers, GeomArgs g, DevScalars* sc) {
+// One thread per run.  Roots carry their component's voxel count (k_flatten_rank) and label: they apply
+// the volume filter, claim a marker slot and bid for the body; every other run copies its root's label.
+__global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ root_count,
+                                                uint32_t* run_label, uint32_t* __restrict__ label_count,
+                                                uint32_t* __restrict__ label_slot, uint32_t* __restrict__ cand_label,
+                                                unsigned long long* __restrict__ sums, uint32_t max_markers, GeomArgs g,
+                                                DevScalars* sc) {
     pdl_wait();
     const unsigned lane = lane_id();
-    const uint32_t n = sc->n_labels;
+    const uint32_t n = sc->status == MAMRI_OK ? sc->n_runs : 0u;
     const uint32_t warp0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t l0 = warp0; l0 < n; l0 += stride) {
-        const uint32_t l = l0 + lane;
+    for (uint32_t r0 = warp0; r0 < n; r0 += stride) {
+        const uint32_t r = r0 + lane;
         unsigned long long packed = 0ull, cnt64 = 0ull;
-        if (l < n) {
-            const uint32_t cnt = label_count[l];
-            cnt64 = cnt;
-            const double vol = double(cnt) * g.voxel_volume;        // GetPhysicalSize
-            if (vol >= g.min_volume && vol <= g.max_volume) {         // inclusive bounds
-                uint32_t slot = atomicAdd(&sc->n_cand, 1u);
-                if (slot < max_markers) { cand_label[slot] = l + 1u; label_slot[l] = slot; }
-                else label_slot[l] = MAMRI_NONE;
+        if (r < n) {
+            const uint32_t root = parent[r];
+            if (root != r) {
+                run_label[r] = run_label[root];                   // roots were ranked by k_flatten_rank
             } else {
-                label_slot[l] = MAMRI_NONE;
-                // max(..., key=GetPhysicalSize) returns the FIRST maximum -> lowest label on ties
-                packed = (cnt64 << 32) | (unsigned long long)(0xFFFFFFFFu - (l + 1u));
+                const uint32_t cnt = root_count[r], label = run_label[r];
+                label_count[label - 1u] = cnt;
+                cnt64 = cnt;
+                const double vol = double(cnt) * g.voxel_volume;        // GetPhysicalSize
+                uint32_t slot = MAMRI_NONE;
+                if (vol >= g.min_volume && vol <= g.max_volume) {         // inclusive bounds
+                    slot = atomicAdd(&sc->n_cand, 1u);
+                    if (slot < max_markers) cand_label[slot] = label; else slot = MAMRI_NONE;
+                } else {
+                    // max(..., key=GetPhysicalSize) returns the FIRST maximum -> lowest label on ties
+                    packed = (cnt64 << 32) | (unsigned long long)(0xFFFFFFFFu - label);
+                }
+                label_slot[r] = slot;
             }
         }
 #pragma unroll
@@ -154,7 +66,7 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ lab
             if (cnt64) atomicAdd(&sc->n_foreground, cnt64);
         }
     }
-    // The last CTA to finish clamps the candidate count, gives the body the extra slot `max_markers`
+    // The last CTA to finish clamps the candidate count, names the body's label in slot `max_markers`
     // and zeroes the moment sums of the slots in use.
     __shared__ bool last;
     __threadfence();
@@ -169,11 +81,7 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ lab
         if (threadIdx.x == 0) sc->status = MAMRI_ERR_CAPACITY;
     }
     const unsigned long long bp = *(volatile unsigned long long*)&sc->body_packed;
-    if (threadIdx.x == 0 && (bp >> 32) != 0ull) {
-        const uint32_t body = 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull);
-        label_slot[body - 1u] = max_markers;
-        cand_label[max_markers] = body;
-    }
+    if (threadIdx.x == 0 && (bp >> 32) != 0ull) cand_label[max_markers] = 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull);
     for (uint32_t i = threadIdx.x; i < nc * 9u; i += blockDim.x) sums[i] = 0ull;
     for (uint32_t i = threadIdx.x; i < 9u; i += blockDim.x) sums[uint32_t(max_markers) * 9u + i] = 0ull;
 }
@@ -190,23 +98,26 @@ __device__ void finalize_block(const uint32_t* cand_label, const uint32_t* label
                                const DevScalars* sc);
 
 __global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_len,
-                                                 const uint32_t* __restrict__ run_label,
+                                                 const uint32_t* __restrict__ parent, const uint32_t* __restrict__ run_label,
                                                  const uint32_t* __restrict__ label_slot, int W, int ny,
                                                  unsigned long long* sums, const uint32_t* __restrict__ cand_label,
                                                  const uint32_t* __restrict__ label_count, uint32_t max_markers, GeomArgs g,
                                                  mamri_marker* __restrict__ markers, mamri_summary* summary, DevScalars* sc) {
-    pdl_wait();
     __shared__ CtaCache<9, unsigned long long, 16> cache;
+    pdl_wait();
     cache.init();
     const bool ok = sc->status == MAMRI_OK;
     const uint32_t n = ok ? sc->n_runs : 0u;
+    const unsigned long long bp = sc->body_packed;
+    const uint32_t body = (bp >> 32) != 0ull ? 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull) : 0u;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t r0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < n; r0 += stride) {
         const uint32_t r = r0 + lane_id();
         uint32_t key = MAMRI_NONE;
         unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (r < n) {
-            key = label_slot[run_label[r] - 1u];
+            key = label_slot[parent[r]];
+            if (key == MAMRI_NONE && run_label[r] == body) key = max_markers;   // the body has the extra slot
             if (key != MAMRI_NONE) {
                 const uint32_t pos = run_pos[r];
                 const uint32_t wi = pos >> 5, row = wi / W;
@@ -371,9 +282,7 @@ __device__ void finalize_block(const uint32_t* cand_label, const uint32_t* label
     }
 }
 
-cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volume_desc* desc, const mamri_params* prm,
-                         cudaStream_t s) {
-    const int W = (desc->nx + 31) / 32;
+static GeomArgs geom_args(const mamri_volume_desc* desc, const mamri_params* prm) {
     GeomArgs g;
     for (int i = 0; i < 3; ++i) { g.spacing[i] = desc->spacing[i]; g.origin[i] = desc->origin[i]; }
     for (int i = 0; i < 9; ++i) g.dir[i] = desc->direction[i];
@@ -382,12 +291,24 @@ cudaError_t launch_stats(mamri_ctx* c, const uint32_t* d_mask, const mamri_volum
     g.voxel_volume = vv;
     g.min_volume = prm->min_volume;
     g.max_volume = prm->max_volume;
-    const int RG = MAMRI_RUN_CTAS;
-    LK(k_count_labels, RG, 256, s, false, c->d_parent, c->d_run_len, c->d_run_label, c->d_label_count, c->d_scalars);
-    prof_mark(c, s, "count_labels");
-    LK(k_select, 148 * 2, 256, s, false, c->d_label_count, c->d_label_slot, c->d_cand_label, c->d_cand_sums, c->max_markers, g, c->d_scalars);
+    return g;
+}
+
+// Volume filter + body label + final label of every run: everything `materialise` needs.
+cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
+    const GeomArgs g = geom_args(desc, prm);
+    LK(k_select, MAMRI_RUN_CTAS, 256, s, false, c->d_parent, c->d_root_count, c->d_run_label, c->d_label_count, c->d_label_slot,
+       c->d_cand_label, c->d_cand_sums, c->max_markers, g, c->d_scalars);
     prof_mark(c, s, "select");
-    LK(k_moments, RG, 256, s, false, c->d_run_pos, c->d_run_len, c->d_run_label, c->d_label_slot, W, desc->ny, c->d_cand_sums, c->d_cand_label, c->d_label_count, c->max_markers, g, c->d_markers, c->d_summary, c->d_scalars);
+    return cudaGetLastError();
+}
+
+// Moments of the kept labels + body, and the marker table / summary (independent of `materialise`).
+cudaError_t launch_moments(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
+    const GeomArgs g = geom_args(desc, prm);
+    const int W = (desc->nx + 31) / 32;
+    LK(k_moments, MAMRI_RUN_CTAS, 256, s, false, c->d_run_pos, c->d_run_len, c->d_parent, c->d_run_label, c->d_label_slot, W, desc->ny,
+       c->d_cand_sums, c->d_cand_label, c->d_label_count, c->max_markers, g, c->d_markers, c->d_summary, c->d_scalars);
     prof_mark(c, s, "moments_finalize");
     return cudaGetLastError();
 }
