@@ -86,7 +86,7 @@ extern "C" int mamri_destroy(mamri_ctx* ctx) {
     cudaFree(ctx->d_raw); cudaFree(ctx->d_planes); cudaFree(ctx->d_dil); cudaFree(ctx->d_closed); cudaFree(ctx->d_word_base);
     cudaFree(ctx->d_run_pos); cudaFree(ctx->d_run_len); cudaFree(ctx->d_parent); cudaFree(ctx->d_run_label); cudaFree(ctx->d_label_count); cudaFree(ctx->d_label_slot);
     cudaFree(ctx->d_root_count); cudaFree(ctx->d_scan_runs); cudaFree(ctx->d_scan_rank); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
-    cudaFree(ctx->d_summary); cudaFree(ctx->d_scalars); cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
+    cudaFree(ctx->d_summary); if (!ctx->shared_args) cudaFree(ctx->d_scalars); cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
     cudaFree(ctx->d_entry_dist); cudaFree(ctx->d_entry_idx); cudaFree(ctx->d_entry_cnt); cudaFree(ctx->d_entry_res);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 48; ++i) if (ctx->ev_fine[i]) cudaEventDestroy(ctx->ev_fine[i]);
@@ -95,7 +95,7 @@ extern "C" int mamri_destroy(mamri_ctx* ctx) {
     if (ctx->cap_stream2) cudaStreamDestroy(ctx->cap_stream2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    cudaFree(ctx->d_dyn); cudaFreeHost(ctx->h_dyn);
+    if (!ctx->shared_args) { cudaFree(ctx->d_dyn); cudaFreeHost(ctx->h_dyn); }
     cudaFreeHost(ctx->h_markers); cudaFreeHost(ctx->h_summary); cudaFreeHost(ctx->h_entry_res);
     delete ctx;
     return MAMRI_OK;
@@ -162,8 +162,8 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     ALLOC(ctx->d_label_count, size_t(max_runs) * 4, "label counts");
     ALLOC(ctx->d_label_slot, size_t(max_runs) * 4, "label slots");
     ALLOC(ctx->d_root_count, size_t(max_runs) * 4, "root counts");
-    {   // look-back states of the two single-pass scans (tile sizes: ccl.cu RS_TILE = 2048 words, FR_TILE = 1024 runs)
-        const size_t t_runs = ctx->cap_words / 2048 + 2, t_rank = size_t(max_runs) / 1024 + 2;
+    {   // look-back states of the two single-pass scans (tile sizes: ccl.cu RS_TILE = 8192 words, FR_TILE = 1024 runs)
+        const size_t t_runs = ctx->cap_words / 8192 + 2, t_rank = size_t(max_runs) / 1024 + 2;
         ALLOC(ctx->d_scan_runs, t_runs * 8, "scan states");
         ALLOC(ctx->d_scan_rank, t_rank * 8, "scan states");
         if ((e = cudaMemset(ctx->d_scan_runs, 0, t_runs * 8)) != cudaSuccess) return bail(e, "scan states");
@@ -293,7 +293,7 @@ extern "C" int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc,
     k.prm = *params;
     k.vol_aligned = (reinterpret_cast<uintptr_t>(d_volume) & 15u) == 0;
     k.outs_aligned = ((reinterpret_cast<uintptr_t>(d_labels_out) & 15u) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(d_mask_out) & 3u) == 0) && ((reinterpret_cast<uintptr_t>(d_body_out) & 3u) == 0);
+                     ((reinterpret_cast<uintptr_t>(d_mask_out) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_body_out) & 15u) == 0);
     k.has_mask = d_mask_out != nullptr; k.has_labels = d_labels_out != nullptr; k.has_body = d_body_out != nullptr;
     ctx->h_dyn->vol = d_volume;
     ctx->h_dyn->mask_out = d_mask_out;
@@ -403,12 +403,30 @@ extern "C" int mamri_detect_collect(mamri_ctx* ctx, mamri_summary* summary, mamr
 // ------------------------------------------------------------------------------------------------
 // pool: a batch of independent scans pipelined over a few contexts/streams (host loop in C++)
 // ------------------------------------------------------------------------------------------------
+struct WaveGraph {
+    cudaGraphExec_t exec;
+    GraphKey key;
+    bool valid;
+};
+
 struct mamri_pool {
     int device, k;
     mamri_ctx** ctx;
     cudaStream_t* streams;
     cudaEvent_t fork;
     cudaEvent_t* join;
+    // device-resident batches run as ONE captured graph per wave of up to k scans (see enqueue_wave)
+    DynArgs* d_dyn_all;              // [k], contexts' d_dyn point into it -> one copy per wave
+    DynArgs* h_dyn_all;              // [k] pinned
+    DevScalars* d_scalars_all;       // [k] -> one memset per wave
+    cudaStream_t hbm;                // capture origin: carries the streaming kernels of all scans, one after another
+    cudaEvent_t* ev_thr;             // [k] threshold of scan i done
+    cudaEvent_t* ev_sel;             // [k] labels of scan i final
+    cudaEvent_t* ev_done;            // [k] tables of scan i copied
+    WaveGraph* waves;                // [k + 1], indexed by the number of scans in the wave
+    bool use_wave_graph;
+    bool trace;                      // MAMRI_WAVE_TRACE=1: timing events inside the wave graph, timeline on stderr
+    cudaEvent_t* ev_trace;           // [k * 8]
     char err[512];
 };
 
@@ -424,8 +442,18 @@ extern "C" int mamri_pool_destroy(mamri_pool* pool) {
         if (pool->streams && pool->streams[i]) cudaStreamDestroy(pool->streams[i]);
         if (pool->join && pool->join[i]) cudaEventDestroy(pool->join[i]);
     }
+    for (int i = 0; i < pool->k; ++i) {
+        if (pool->ev_thr && pool->ev_thr[i]) cudaEventDestroy(pool->ev_thr[i]);
+        if (pool->ev_sel && pool->ev_sel[i]) cudaEventDestroy(pool->ev_sel[i]);
+        if (pool->ev_done && pool->ev_done[i]) cudaEventDestroy(pool->ev_done[i]);
+    }
+    for (int i = 0; pool->waves && i <= pool->k; ++i)
+        if (pool->waves[i].exec) cudaGraphExecDestroy(pool->waves[i].exec);
+    if (pool->hbm) cudaStreamDestroy(pool->hbm);
+    cudaFree(pool->d_dyn_all); cudaFreeHost(pool->h_dyn_all); cudaFree(pool->d_scalars_all);
     if (pool->fork) cudaEventDestroy(pool->fork);
     delete[] pool->ctx; delete[] pool->streams; delete[] pool->join;
+    delete[] pool->ev_thr; delete[] pool->ev_sel; delete[] pool->ev_done; delete[] pool->waves;
     delete pool;
     return MAMRI_OK;
 }
@@ -445,7 +473,11 @@ extern "C" int mamri_pool_create(mamri_pool** out, int device, int32_t n_context
     p->ctx = new (std::nothrow) mamri_ctx*[n_contexts]();
     p->streams = new (std::nothrow) cudaStream_t[n_contexts]();
     p->join = new (std::nothrow) cudaEvent_t[n_contexts]();
-    if (!p->ctx || !p->streams || !p->join) {
+    p->ev_thr = new (std::nothrow) cudaEvent_t[n_contexts]();
+    p->ev_sel = new (std::nothrow) cudaEvent_t[n_contexts]();
+    p->ev_done = new (std::nothrow) cudaEvent_t[n_contexts]();
+    p->waves = new (std::nothrow) WaveGraph[n_contexts + 1]();
+    if (!p->ctx || !p->streams || !p->join || !p->ev_thr || !p->ev_sel || !p->ev_done || !p->waves) {
         snprintf(g_pool_err, sizeof(g_pool_err), "out of host memory");
         mamri_pool_destroy(p);
         return MAMRI_ERR_CUDA;
@@ -463,6 +495,30 @@ extern "C" int mamri_pool_create(mamri_pool** out, int device, int32_t n_context
     for (int i = 0; i < n_contexts && e == cudaSuccess; ++i) {
         e = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_thr[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_sel[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->hbm, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_dyn_all, sizeof(DynArgs) * n_contexts);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_dyn_all, sizeof(DynArgs) * n_contexts);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_scalars_all, sizeof(DevScalars) * n_contexts);
+    if (e == cudaSuccess) {
+        // the contexts' per-call arguments and scalars become slices of the pool's arrays
+        for (int i = 0; i < n_contexts; ++i) {
+            mamri_ctx* c = p->ctx[i];
+            cudaFree(c->d_dyn); cudaFreeHost(c->h_dyn); cudaFree(c->d_scalars);
+            c->d_dyn = p->d_dyn_all + i; c->h_dyn = p->h_dyn_all + i; c->d_scalars = p->d_scalars_all + i;
+            c->shared_args = true;
+        }
+        const char* tr = getenv("MAMRI_WAVE_TRACE");
+        p->trace = tr && tr[0] == '1';
+        if (p->trace) {
+            p->ev_trace = new (std::nothrow) cudaEvent_t[n_contexts * 8]();
+            for (int i = 0; p->ev_trace && i < n_contexts * 8; ++i) cudaEventCreate(&p->ev_trace[i]);
+        }
+        const char* ng = getenv("MAMRI_NO_WAVE_GRAPH");
+        p->use_wave_graph = !(ng && ng[0] == '1') && p->ctx[0]->use_graph;
     }
     if (e != cudaSuccess) {
         snprintf(g_pool_err, sizeof(g_pool_err), "creating the pool's streams failed: %s", cudaGetErrorString(e));
@@ -477,6 +533,140 @@ extern "C" mamri_ctx* mamri_pool_context(mamri_pool* pool, int32_t k) {
     return (pool && k >= 0 && k < pool->k) ? pool->ctx[k] : nullptr;
 }
 
+#define CKP(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t _e = (call);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            snprintf(pool->err, sizeof(pool->err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                              \
+            return MAMRI_ERR_CUDA;                                                                     \
+        }                                                                                              \
+    } while (0)
+
+// One wave = up to k device-resident scans, scan i on context i, as ONE graph.  The two DRAM-bound
+// kernels of every scan sit on a single chain (threshold 0..m-1, then materialise 0..m-1): run one at a
+// time they reach their stand-alone bandwidth, whereas several of them sharing HBM slow each other down.
+// The latency-bound middle of scan i (closing, labelling, filter) branches off after its threshold and
+// runs beside the chain; the chain reaches materialise(0) only after the thresholds of the other scans,
+// by which time labels(0) are final, so the chain never waits.  Moments + table copies of scan i form a
+// third branch off its labels.
+static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
+#define TRACE(i, j, st) do { if (pool->trace && pool->ev_trace) CKP(cudaEventRecordWithFlags(pool->ev_trace[(i) * 8 + (j)], st, cudaEventRecordExternal)); } while (0)
+    const mamri_volume_desc* desc = &k.desc;
+    const mamri_params* prm = &k.prm;
+    const int nx = desc->nx, ny = desc->ny, nz = desc->nz;
+    cudaStream_t H = pool->hbm;
+    CKP(cudaMemcpyAsync(pool->d_dyn_all, pool->h_dyn_all, sizeof(DynArgs) * m, cudaMemcpyHostToDevice, H));
+    CKP(cudaMemsetAsync(pool->d_scalars_all, 0, sizeof(DevScalars) * m, H));
+    for (int i = 0; i < m; ++i) {
+        TRACE(i, 0, H);
+        CKP(launch_threshold_pack(pool->ctx[i], k.vol_aligned, desc->dtype, nx, ny, nz, prm->lower, prm->upper, prm->close_radius, H));
+        TRACE(i, 1, H);
+        CKP(cudaEventRecord(pool->ev_thr[i], H));
+    }
+    const bool outputs = k.has_mask || k.has_labels || k.has_body;
+    for (int i = 0; i < m; ++i) {
+        mamri_ctx* c = pool->ctx[i];
+        cudaStream_t s = pool->streams[i];
+        CKP(cudaStreamWaitEvent(s, pool->ev_thr[i], 0));
+        if (prm->close_radius > 0) CKP(launch_closing(c, nx, ny, nz, prm->close_radius, s));
+        TRACE(i, 2, s);
+        CKP(launch_ccl(c, c->d_closed, nx, ny, nz, prm->connectivity, s));
+        TRACE(i, 3, s);
+        CKP(launch_select(c, desc, prm, s));
+        TRACE(i, 4, s);
+        CKP(cudaEventRecord(pool->ev_sel[i], s));
+    }
+    if (outputs)
+        for (int i = 0; i < m; ++i) {
+            CKP(cudaStreamWaitEvent(H, pool->ev_sel[i], 0));
+            TRACE(i, 5, H);
+            CKP(launch_materialise(pool->ctx[i], pool->ctx[i]->d_closed, nx, ny, nz, k.outs_aligned, H));
+            TRACE(i, 6, H);
+        }
+    for (int i = 0; i < m; ++i) {
+        mamri_ctx* c = pool->ctx[i];
+        cudaStream_t s = pool->streams[i];
+        CKP(launch_moments(c, desc, prm, s));
+        CKP(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(mamri_summary), cudaMemcpyDeviceToHost, s));
+        const uint32_t eager = c->max_markers < EAGER_MARKERS ? c->max_markers : EAGER_MARKERS;
+        CKP(cudaMemcpyAsync(c->h_markers, c->d_markers, size_t(eager) * sizeof(mamri_marker), cudaMemcpyDeviceToHost, s));
+        TRACE(i, 7, s);
+        CKP(cudaEventRecord(pool->ev_done[i], s));
+        CKP(cudaStreamWaitEvent(H, pool->ev_done[i], 0));
+    }
+#undef TRACE
+    return MAMRI_OK;
+}
+
+// Runs scans [first, first + m) as one wave on `cur` and collects them.
+static int pool_wave(mamri_pool* pool, const GraphKey& k, const void* const* volumes, int first, int m,
+                     uint8_t* const* mask_out, uint32_t* const* labels_out, uint8_t* const* body_out,
+                     mamri_summary* summaries, mamri_marker* markers, uint32_t max_m, cudaStream_t cur, int* first_err) {
+    for (int i = 0; i < m; ++i) {
+        mamri_ctx* c = pool->ctx[i];
+        DynArgs* d = c->h_dyn;
+        d->vol = volumes[first + i];
+        d->mask_out = mask_out ? mask_out[first + i] : nullptr;
+        d->labels_out = labels_out ? labels_out[first + i] : nullptr;
+        d->body_out = body_out ? body_out[first + i] : nullptr;
+        d->gen = ++c->gen;
+        if ((c->gen & 0x3FFFFFFFu) == 0) d->gen = ++c->gen;
+        CKP(prepare_raw_apron(c, k.desc.nx, k.desc.ny, k.desc.nz, k.prm.close_radius, cur));
+    }
+    WaveGraph& w = pool->waves[m];
+    if (!w.valid || memcmp(&w.key, &k, sizeof(k)) != 0) {
+        if (w.exec) { cudaGraphExecDestroy(w.exec); w.exec = nullptr; }
+        w.valid = false;
+        CKP(cudaStreamBeginCapture(pool->hbm, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_wave(pool, k, m);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(pool->hbm, &graph);
+        if (rc != MAMRI_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+        if (e != cudaSuccess) {
+            snprintf(pool->err, sizeof(pool->err), "wave graph capture failed: %s", cudaGetErrorString(e));
+            return MAMRI_ERR_CUDA;
+        }
+        const cudaError_t e2 = cudaGraphInstantiate(&w.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e2 != cudaSuccess) {
+            snprintf(pool->err, sizeof(pool->err), "wave graph instantiation failed: %s", cudaGetErrorString(e2));
+            return MAMRI_ERR_CUDA;
+        }
+        w.key = k;
+        w.valid = true;
+    }
+    CKP(cudaGraphLaunch(w.exec, cur));
+    if (pool->trace && pool->ev_trace) {
+        static int dumps = 0;
+        CKP(cudaStreamSynchronize(cur));
+        if (++dumps == 12) {                         // one steady-state wave
+            static const char* names[8] = {"thr>", "thr<", "clo<", "ccl<", "sel<", "mat>", "mat<", "mom<"};
+            for (int i = 0; i < m; ++i) {
+                fprintf(stderr, "scan %d:", i);
+                for (int j = 0; j < 8; ++j) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, pool->ev_trace[0], pool->ev_trace[i * 8 + j]);
+                    fprintf(stderr, " %s%7.1f", names[j], ms * 1e3f);
+                }
+                fprintf(stderr, "  us\n");
+            }
+        }
+    }
+    for (int i = 0; i < m; ++i) {
+        mamri_ctx* c = pool->ctx[i];
+        c->pending = true;
+        c->pending_stream = cur;
+        c->last_desc = k.desc;
+        const int rc = mamri_detect_collect(c, &summaries[first + i], markers ? markers + size_t(first + i) * max_m : nullptr, max_m);
+        if (rc != MAMRI_OK && *first_err == MAMRI_OK) {
+            *first_err = rc;
+            snprintf(pool->err, sizeof(pool->err), "scan %d: %s", first + i, mamri_last_error(c));
+        }
+    }
+    return MAMRI_OK;
+}
+
 static int pool_run(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* volumes, bool host, int32_t n,
                     const mamri_params* params, uint8_t* const* mask_out, uint32_t* const* labels_out,
                     uint8_t* const* body_out, mamri_summary* summaries, mamri_marker* markers, uint32_t max_m,
@@ -489,10 +679,36 @@ static int pool_run(mamri_pool* pool, const mamri_volume_desc* desc, const void*
     DeviceGuard g(pool->device);
     cudaStream_t cur = static_cast<cudaStream_t>(stream);
     const int K = pool->k;
+    int first_err = MAMRI_OK;
+    bool profiling = false;
+    for (int j = 0; j < K; ++j) profiling = profiling || pool->ctx[j]->profile || pool->ctx[j]->pending;
+    if (!host && pool->use_wave_graph && !profiling) {
+        int rc = validate(pool->ctx[0], desc, params);
+        if (rc != MAMRI_OK) return pfail(rc, mamri_last_error(pool->ctx[0]));
+        GraphKey k;
+        memset(&k, 0, sizeof(k));
+        k.desc = *desc;
+        k.prm = *params;
+        k.has_mask = mask_out != nullptr; k.has_labels = labels_out != nullptr; k.has_body = body_out != nullptr;
+        k.vol_aligned = 1; k.outs_aligned = 1;
+        for (int i = 0; i < n; ++i) {
+            if (!volumes[i]) return pfail(MAMRI_ERR_INVALID_ARG, "volume pointer is NULL");
+            if (reinterpret_cast<uintptr_t>(volumes[i]) & 15u) k.vol_aligned = 0;
+            if ((mask_out && (reinterpret_cast<uintptr_t>(mask_out[i]) & 15u)) ||
+                (labels_out && (reinterpret_cast<uintptr_t>(labels_out[i]) & 15u)) ||
+                (body_out && (reinterpret_cast<uintptr_t>(body_out[i]) & 15u)))
+                k.outs_aligned = 0;
+        }
+        for (int first = 0; first < n; first += K) {
+            const int m = n - first < K ? n - first : K;
+            rc = pool_wave(pool, k, volumes, first, m, mask_out, labels_out, body_out, summaries, markers, max_m, cur, &first_err);
+            if (rc != MAMRI_OK) return rc;
+        }
+        return first_err;
+    }
     cudaError_t e = cudaEventRecord(pool->fork, cur);
     for (int j = 0; j < K && j < n && e == cudaSuccess; ++j) e = cudaStreamWaitEvent(pool->streams[j], pool->fork, 0);
     if (e != cudaSuccess) return pfail(MAMRI_ERR_CUDA, cudaGetErrorString(e));
-    int first_err = MAMRI_OK;
     auto note = [&](int rc, int scan, mamri_ctx* c) {
         if (rc != MAMRI_OK && first_err == MAMRI_OK) {
             first_err = rc;

@@ -31,18 +31,19 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 // ------------------------------------------------------------------------------------------------
 // word_base[w] = number of runs that start before word w; run table: position (word*32 + bit of the
 // first voxel) and length of every run, in raster order.  One pass over the mask: a CTA takes a tile of
-// RS_TILE words (8 consecutive words per thread, two 128-bit loads), scans its run-start counts, gets
+// RS_TILE words (16 consecutive words per thread, 128-bit loads), scans its run-start counts, gets
 // the count of all earlier tiles by decoupled look-back and writes its part of both tables.
-constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_THREADS = 512, RS_ITEMS = 16, RS_TILE = RS_THREADS * RS_ITEMS;   // few, large tiles: short look-back chains
 
-__device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t* ws /*[9]*/, uint32_t& total) {
+template <int WARPS>
+__device__ __forceinline__ uint32_t block_excl_scan_w(uint32_t v, uint32_t* ws /*[WARPS]*/, uint32_t& total) {
     const unsigned lane = lane_id(), wid = threadIdx.x >> 5;
     const uint32_t inc = warp_incl_scan(v);
     if (lane == 31) ws[wid] = inc;
     __syncthreads();
     uint32_t off = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < WARPS; ++w) {
         const uint32_t t = ws[w];
         if (w < int(wid)) off += t;
         tot += t;
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
                                                           uint32_t* __restrict__ run_len, uint32_t* __restrict__ root_count,
                                                           uint32_t max_runs, DevScalars* sc) {
     pdl_wait();
-    __shared__ uint32_t ws[9];
+    __shared__ uint32_t ws[RS_THREADS / 32];
     __shared__ uint32_t s_tile, s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(&sc->ticket_runs, 1u);
     __syncthreads();
@@ -67,8 +68,11 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
     uint32_t m[RS_ITEMS], starts[RS_ITEMS];
     uint32_t cnt = 0;
     if (i0 + RS_ITEMS <= n_words) {
-        const uint4 q0 = *reinterpret_cast<const uint4*>(mask + i0), q1 = *reinterpret_cast<const uint4*>(mask + i0 + 4);
-        m[0] = q0.x; m[1] = q0.y; m[2] = q0.z; m[3] = q0.w; m[4] = q1.x; m[5] = q1.y; m[6] = q1.z; m[7] = q1.w;
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; k += 4) {
+            const uint4 q = *reinterpret_cast<const uint4*>(mask + i0 + k);
+            m[k] = q.x; m[k + 1] = q.y; m[k + 2] = q.z; m[k + 3] = q.w;
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < RS_ITEMS; ++k) m[k] = (i0 + k < n_words) ? mask[i0 + k] : 0u;
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
         }
     }
     uint32_t total;
-    const uint32_t ex = block_excl_scan256(cnt, ws, total);
+    const uint32_t ex = block_excl_scan_w<RS_THREADS / 32>(cnt, ws, total);
     if (threadIdx.x < 32) {
         const uint32_t before = scan_lookback(state, tile, total, dyn->gen);
         if (threadIdx.x == 0) {
@@ -134,8 +138,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
         base += __popc(starts[k]);
     }
     if (i0 + RS_ITEMS <= n_words) {
-        *reinterpret_cast<uint4*>(word_base + i0) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
-        *reinterpret_cast<uint4*>(word_base + i0 + 4) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; k += 4)
+            *reinterpret_cast<uint4*>(word_base + i0 + k) = make_uint4(wb[k], wb[k + 1], wb[k + 2], wb[k + 3]);
     } else {
 #pragma unroll
         for (int k = 0; k < RS_ITEMS; ++k)
@@ -242,13 +247,18 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
         const int gx0 = int((wi - row * W) * 32 + (pos & 31u));
         join_run<CONN26>(mask, word_base, P, r0, W, i, gx0, int(run_len[r0 + i]), (row - 1) * W);
     }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) {
-        uint32_t x = i, p = P[x];
-        while (p != x) { x = p; p = P[x]; }
-        P[i] = x;                                 // roots stay fixed points: concurrent walkers remain correct
+    // flatten by pointer jumping: a convex object leaves a chain as long as it is tall, which a per-run
+    // walk would follow hop by hop; doubling reaches the root in log2(height) rounds
+    bool again = true;
+    while (again) {
+        __syncthreads();
+        bool changed = false;
+        for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) {
+            const uint32_t p = P[i], pp = P[p];   // a concurrent update of P[p] still yields an ancestor
+            if (pp != p) { P[i] = pp; changed = true; }
+        }
+        again = __syncthreads_or(changed);
     }
-    __syncthreads();
     for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) parent[r0 + i] = r0 + P[i];
 }
 
@@ -417,13 +427,23 @@ cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int
 // Aligned path (nx % 32 == 0): a warp writes 4 words = 128 voxels per iteration; lane l owns word
 // l/8, voxels 4*(l%8)..+3 -> one 16-byte label store and one 4-byte mask store per lane, i.e.
 // 512 B / 128 B contiguous per warp instruction.
+__device__ __forceinline__ void st_stream(uint4* p, uint4 v, bool hint) {
+    if (hint) asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else *p = v;
+}
+__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v, bool hint) {
+    if (hint) asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else *p = v;
+}
+
 template <bool ALIGNED>
 __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict__ mask,
                                                      const uint32_t* __restrict__ word_base,
                                                      const uint32_t* __restrict__ run_label, int nx, int W,
                                                      uint32_t n_words, const DynArgs* __restrict__ dyn,
-                                                     const DevScalars* sc) {
+                                                     const DevScalars* sc, int stream_hint) {
     pdl_wait();
+    const bool hint = stream_hint != 0;
     uint8_t* __restrict__ mask_out = dyn->mask_out;
     uint32_t* __restrict__ labels_out = dyn->labels_out;
     uint8_t* __restrict__ body_out = dyn->body_out;
@@ -480,10 +500,12 @@ __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict_
                     }
                 }
                 const uint32_t v = wi * 32 + sub;
-                if (labels_out) *reinterpret_cast<uint4*>(labels_out + v) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+                // streaming stores: the volumes are written once and not read back by this pipeline, so they
+                // should not push the bit-packed intermediates of the scans in flight out of L2
+                if (labels_out) st_stream(reinterpret_cast<uint4*>(labels_out + v), make_uint4(lab[0], lab[1], lab[2], lab[3]), hint);
                 if (mask_out) {
                     uint32_t mb = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-                    *reinterpret_cast<uint32_t*>(mask_out + v) = mb;
+                    st_stream(reinterpret_cast<uint32_t*>(mask_out + v), mb, hint);
                 }
                 if (body_out) {
                     uint32_t bb = 0;
@@ -491,7 +513,7 @@ __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict_
 #pragma unroll
                         for (int q = 0; q < 4; ++q) bb |= (lab[q] == body ? 1u : 0u) << (8 * q);
                     }
-                    *reinterpret_cast<uint32_t*>(body_out + v) = bb;
+                    st_stream(reinterpret_cast<uint32_t*>(body_out + v), bb, hint);
                 }
             }
         }
@@ -521,17 +543,19 @@ cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int
     const int W = (nx + 31) / 32;
     const uint32_t n_words = uint32_t(W) * ny * nz;
     const bool aligned = (nx % 32 == 0) && outs_aligned;
+    static const int stream_hint = [] { const char* e = getenv("MAMRI_STREAM_HINTS"); return e ? atoi(e) : 1; }();
     if (aligned) {
+        // one trip of 32 mask words per warp by default: short-lived CTAs measured faster than a grid-stride loop
         uint32_t blocks = (n_words / 32 + 7) / 8;
-        static const int per_sm = [] { const char* e = getenv("MAMRI_MAT_CTAS_PER_SM"); return e ? atoi(e) : 16; }();
-        if (blocks > uint32_t(148 * per_sm)) blocks = uint32_t(148 * per_sm);
+        static const int per_sm = [] { const char* e = getenv("MAMRI_MAT_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+        if (per_sm > 0 && blocks > uint32_t(148 * per_sm)) blocks = uint32_t(148 * per_sm);
         if (blocks == 0) blocks = 1;
-        LK(k_materialise<true>, blocks, 256, s, true, d_mask, c->d_word_base, c->d_run_label, nx, W, n_words, c->d_dyn, c->d_scalars);
+        LK(k_materialise<true>, blocks, 256, s, true, d_mask, c->d_word_base, c->d_run_label, nx, W, n_words, c->d_dyn, c->d_scalars, stream_hint);
     } else {
         uint32_t blocks = (n_words + 7) / 8;
         if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
         if (blocks == 0) blocks = 1;
-        LK(k_materialise<false>, blocks, 256, s, true, d_mask, c->d_word_base, c->d_run_label, nx, W, n_words, c->d_dyn, c->d_scalars);
+        LK(k_materialise<false>, blocks, 256, s, true, d_mask, c->d_word_base, c->d_run_label, nx, W, n_words, c->d_dyn, c->d_scalars, stream_hint);
     }
     prof_mark(c, s, "materialise");
     return cudaGetLastError();

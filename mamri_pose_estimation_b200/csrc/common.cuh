@@ -96,6 +96,7 @@ struct mamri_ctx {
     // CUDA graph of the whole pipeline (captured on first use of a configuration, relaunched afterwards)
     DynArgs* d_dyn;
     DynArgs* h_dyn;                  // pinned; copied to d_dyn by the graph's first node
+    bool shared_args;                // d_dyn / h_dyn / d_scalars are slices of a pool's arrays (not owned)
     cudaStream_t cap_stream;
     cudaStream_t cap_stream2;        // second branch of the captured graph (materialise || moments + table copies)
     cudaEvent_t ev_fork, ev_join;

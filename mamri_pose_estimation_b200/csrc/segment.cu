@@ -36,6 +36,14 @@ __device__ __forceinline__ uint4 ld_stream_128(const uint4* p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// Same, with an L2 evict-first policy: the voxels are read exactly once, so their lines should leave L2
+// before the bit-packed intermediates of the scans in flight do.
+__device__ __forceinline__ uint4 ld_stream_128(const uint4* p, uint64_t policy) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(policy));
+    return r;
+}
 
 // Fast path: nx % 32 == 0 and 16-byte aligned base, so every row is a whole number of 128-bit vectors
 // and of mask words.  blockIdx.y = slice, warps stride over the rows of the slice two at a time (no
@@ -86,8 +94,11 @@ struct RangeTest16 {
 template <int VOXEL_BYTES, typename Test>
 __global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __restrict__ dyn, uint32_t vec_per_row,
                                                             uint32_t ny, Test test, uint32_t* __restrict__ dst,
-                                                            uint32_t row_stride, uint32_t slice_stride, uint32_t off) {
+                                                            uint32_t row_stride, uint32_t slice_stride, uint32_t off,
+                                                            int evict_first) {
     pdl_wait();
+    uint64_t policy = 0;
+    if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     const uint4* __restrict__ vol = static_cast<const uint4*>(dyn->vol);
     constexpr int E = 16 / VOXEL_BYTES; // voxels per 128-bit load
     constexpr int G = 32 / E;           // lanes per output word
@@ -108,7 +119,8 @@ __global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __res
                 for (int u = 0; u < U; ++u) {
                     const uint32_t i = u0 + u * 32 + lane;
                     ok[r][u] = (y0 + r < ny) && i < vec_per_row;
-                    v[r][u] = ok[r][u] ? ld_stream_128(slice_src + size_t(y0 + r) * vec_per_row + i) : make_uint4(0, 0, 0, 0);
+                    const uint4* src = slice_src + size_t(y0 + r) * vec_per_row + i;
+                    v[r][u] = !ok[r][u] ? make_uint4(0, 0, 0, 0) : evict_first ? ld_stream_128(src, policy) : ld_stream_128(src);
                 }
 #pragma unroll
             for (int r = 0; r < 2; ++r)
@@ -172,6 +184,7 @@ static cudaError_t threshold_pack_t(mamri_ctx* c, int vol_aligned16, int nx, int
         if (gx > want) gx = want;
         if (gx == 0) gx = 1;
         const dim3 grid(gx, uint32_t(nz));
+        static const int evict_first = [] { const char* e = getenv("MAMRI_STREAM_HINTS"); return e ? atoi(e) : 1; }();
         const DynArgs* src = dyn;
         if constexpr (sizeof(T) == 2) {
             constexpr bool SG = std::is_signed<T>::value;
@@ -182,14 +195,14 @@ static cudaError_t threshold_pack_t(mamri_ctx* c, int vol_aligned16, int nx, int
             const bool lm = (l & 0x8000u) != 0, hm = (h & 0x8000u) != 0, ch = h != 0xFFFFu;
             const uint32_t vpr = uint32_t(nx) / E;
 #define MAMRI_T16(LM, HM, CH)                                                                                         \
-    LK(k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>>, grid, 256, s, true, src, vpr, uint32_t(ny), RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off)
+    LK(k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>>, grid, 256, s, true, src, vpr, uint32_t(ny), RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first)
             if (!ch) { if (lm) MAMRI_T16(true, true, false); else MAMRI_T16(false, true, false); }
             else if (lm) { if (hm) MAMRI_T16(true, true, true); else MAMRI_T16(true, false, true); }
             else { if (hm) MAMRI_T16(false, true, true); else MAMRI_T16(false, false, true); }
 #undef MAMRI_T16
         } else {
             RangeTest<T> t{tlo, thi};
-            LK(k_threshold_pack_vec<int(sizeof(T)), RangeTest<T>>, grid, 256, s, true, src, uint32_t(nx) / E, uint32_t(ny), t, dst.p, dst.row_stride, dst.slice_stride, dst.off);
+            LK(k_threshold_pack_vec<int(sizeof(T)), RangeTest<T>>, grid, 256, s, true, src, uint32_t(nx) / E, uint32_t(ny), t, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first);
         }
     } else {
         uint32_t blocks = (n_words + 7) / 8;

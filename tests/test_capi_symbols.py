@@ -57,9 +57,16 @@ def test_no_cpu_fallback_without_gpu(cuda_lib):
     rc = cuda_lib.mamri_create(C.byref(ctx), 0, 64, 64, 64, 0, 0)
     assert rc == _capi.MAMRI_ERR_NO_DEVICE and not ctx.value
     assert b"no CPU fallback" in cuda_lib.mamri_last_error(None)
-    from mamri_pose_estimation_b200.detector import FiducialDetector
+    pool = C.c_void_p()
+    rc = cuda_lib.mamri_pool_create(C.byref(pool), 0, 2, 64, 64, 64, 0, 0)
+    assert rc == _capi.MAMRI_ERR_NO_DEVICE and not pool.value
+    assert b"no CPU fallback" in cuda_lib.mamri_pool_last_error(None)
+    assert cuda_lib.mamri_pool_create(C.byref(pool), 0, 0, 64, 64, 64, 0, 0) == _capi.MAMRI_ERR_INVALID_ARG
+    from mamri_pose_estimation_b200.detector import BatchDetector, FiducialDetector
     with pytest.raises(RuntimeError):
         FiducialDetector((64, 64, 64))
+    with pytest.raises(RuntimeError):
+        BatchDetector((64, 64, 64))
     from mamri_pose_estimation_b200.logic import MamriLogic
     with pytest.raises(RuntimeError):
         MamriLogic()

@@ -92,6 +92,25 @@ def test_c4_merge_stress_reduced(cuda_lib, conn):
     det.close()
 
 
+def test_c4_full_size(cuda_lib):
+    """Config C4 at its full 1024x1024x512 (32 fiducials, 2000 blobs, sigma 20: ~3.2 M runs, ~2.4 M labels):
+    closed mask, label volume, per-label counts and the marker table bit-exact against the C oracle."""
+    from mamri_pose_estimation_b200.detector import FiducialDetector, generate_phantom_cuda
+    ph = phantom.config_c4()
+    d_vol = generate_phantom_cuda(ph)
+    det = FiducialDetector(ph.dims, max_runs=ph.n_voxels // 8, max_markers=16384)
+    res = det.detect(d_vol, spacing=ph.spacing, origin=ph.origin, direction=ph.direction, want_mask=True, want_labels=True)
+    host = d_vol.cpu().numpy()
+    del d_vol
+    ora = c_oracle.detect_fiducials(host, _geom(ph), want_body_mask=False)
+    assert np.array_equal(res.mask.cpu().numpy(), ora.closed)
+    assert np.array_equal(res.labels.cpu().numpy().view(np.uint32), ora.labels)
+    _assert_equal_detection(res, ora)
+    assert np.array_equal(det.label_counts(res.n_labels).astype(np.int64), ora.counts)
+    assert res.n_labels > 100000 and len(res.markers) >= 32
+    det.close()
+
+
 def test_device_phantom_matches_numpy_twin(cuda_lib):
     from mamri_pose_estimation_b200.detector import generate_phantom_cuda
     ph = phantom.small_phantom(dims=(96, 64, 40), seed=8, sigma=15.0)
@@ -200,6 +219,22 @@ def test_batch_detector_matches_single(cuda_lib):
             assert [(m.label, m.count, m.sum_idx, m.sum_mom) for m in r.markers] == \
                    [(m.label, m.count, m.sum_idx, m.sum_mom) for m in r1.markers]
         assert np.array_equal(body.numpy(), r1.body_mask.cpu().numpy())
+    # the pool's ring still holds the mask / label volumes of the last n_contexts scans (7 = waves of 3 + 3 + 1)
+    r_last = one.detect(vols[6], spacing=specs[0].spacing, origin=specs[0].origin, direction=specs[0].direction,
+                        want_mask=True, want_labels=True)
+    assert torch.equal(batch[6].mask, r_last.mask) and torch.equal(batch[6].labels, r_last.labels)
+    # the vectorised table (what the NCCL gather ships) equals the per-object packing
+    from mamri_pose_estimation_b200 import distributed as mdist
+    assert np.array_equal(batch.table(mdist.TABLE_SLOTS), mdist.pack_table(list(batch)))
+    # the per-scan pipelined path (no wave graph) gives the same tables
+    import os
+    os.environ["MAMRI_NO_WAVE_GRAPH"] = "1"
+    try:
+        bd2 = BatchDetector(specs[0].dims, n_contexts=2)
+        assert np.array_equal(bd2.run(vols, specs[0].spacing, specs[0].origin, specs[0].direction).table(), batch.table())
+        bd2.close()
+    finally:
+        del os.environ["MAMRI_NO_WAVE_GRAPH"]
     bd.close(); one.close()
 
 

@@ -1,0 +1,21 @@
+"""Times BatchDetector.run only (device-resident C2 batch), no profiling pass: for experiments."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from mamri_pose_estimation_b200 import phantom
+from mamri_pose_estimation_b200.detector import BatchDetector, generate_phantom_cuda
+S = int(os.environ.get("SCANS", "8")); K = int(os.environ.get("MAMRI_BENCH_CONTEXTS", "8")); steps = int(os.environ.get("STEPS", "20"))
+specs = [phantom.config_c2(scan_index=i) for i in range(S)]
+vols = [generate_phantom_cuda(p) for p in specs]
+bd = BatchDetector(specs[0].dims, n_contexts=K)
+sp, org, dr = specs[0].spacing, specs[0].origin, specs[0].direction
+for _ in range(4):
+    bd.run(vols, sp, org, dr)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(steps):
+    r = bd.run(vols, sp, org, dr)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+print(f"S={S} K={K}: {ms*1e3/S:.1f} us/scan, {S*512*512*256/ms/1e6:.1f} Gvox/s  (labels {r[0].n_labels})")
