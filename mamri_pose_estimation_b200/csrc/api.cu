@@ -419,7 +419,10 @@ struct mamri_pool {
     DynArgs* d_dyn_all;              // [k], contexts' d_dyn point into it -> one copy per wave
     DynArgs* h_dyn_all;              // [k] pinned
     DevScalars* d_scalars_all;       // [k] -> one memset per wave
-    cudaStream_t hbm;                // capture origin: carries the streaming kernels of all scans, one after another
+    cudaStream_t hbm;                // capture origin
+    cudaStream_t chain[4];           // the streaming kernels of scan i run on chain i % n_chains, one after another
+    int n_chains;
+    cudaEvent_t ev_chain[4];
     cudaEvent_t* ev_thr;             // [k] threshold of scan i done
     cudaEvent_t* ev_sel;             // [k] labels of scan i final
     cudaEvent_t* ev_done;            // [k] tables of scan i copied
@@ -450,6 +453,10 @@ extern "C" int mamri_pool_destroy(mamri_pool* pool) {
     for (int i = 0; pool->waves && i <= pool->k; ++i)
         if (pool->waves[i].exec) cudaGraphExecDestroy(pool->waves[i].exec);
     if (pool->hbm) cudaStreamDestroy(pool->hbm);
+    for (int i = 0; i < 4; ++i) {
+        if (pool->chain[i]) cudaStreamDestroy(pool->chain[i]);
+        if (pool->ev_chain[i]) cudaEventDestroy(pool->ev_chain[i]);
+    }
     cudaFree(pool->d_dyn_all); cudaFreeHost(pool->h_dyn_all); cudaFree(pool->d_scalars_all);
     if (pool->fork) cudaEventDestroy(pool->fork);
     delete[] pool->ctx; delete[] pool->streams; delete[] pool->join;
@@ -500,6 +507,12 @@ extern "C" int mamri_pool_create(mamri_pool** out, int device, int32_t n_context
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->hbm, cudaStreamNonBlocking);
+    p->n_chains = 2;
+    if (const char* nc = getenv("MAMRI_HBM_CHAINS")) p->n_chains = atoi(nc) < 1 ? 1 : (atoi(nc) > 4 ? 4 : atoi(nc));
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&p->chain[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_chain[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_dyn_all, sizeof(DynArgs) * n_contexts);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_dyn_all, sizeof(DynArgs) * n_contexts);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_scalars_all, sizeof(DevScalars) * n_contexts);
@@ -544,21 +557,26 @@ extern "C" mamri_ctx* mamri_pool_context(mamri_pool* pool, int32_t k) {
     } while (0)
 
 // One wave = up to k device-resident scans, scan i on context i, as ONE graph.  The two DRAM-bound
-// kernels of every scan sit on a single chain (threshold 0..m-1, then materialise 0..m-1): run one at a
-// time they reach their stand-alone bandwidth, whereas several of them sharing HBM slow each other down.
-// The latency-bound middle of scan i (closing, labelling, filter) branches off after its threshold and
-// runs beside the chain; the chain reaches materialise(0) only after the thresholds of the other scans,
-// by which time labels(0) are final, so the chain never waits.  Moments + table copies of scan i form a
-// third branch off its labels.
+// kernels of every scan sit on a few chains (chain c: threshold of scans c, c + n_chains, ..., then their
+// materialise kernels): with one or two of them in flight they reach close to their stand-alone bandwidth
+// and fill each other's ramp-up / tail, whereas many of them sharing HBM slow each other down.  The
+// latency-bound middle of scan i (closing, labelling, filter) branches off after its threshold and runs
+// beside the chains; a chain reaches materialise(i) only after the thresholds of its later scans, by
+// which time labels(i) are final, so the chains do not wait.  Moments + table copies of scan i form a
+// further branch off its labels.
 static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
 #define TRACE(i, j, st) do { if (pool->trace && pool->ev_trace) CKP(cudaEventRecordWithFlags(pool->ev_trace[(i) * 8 + (j)], st, cudaEventRecordExternal)); } while (0)
     const mamri_volume_desc* desc = &k.desc;
     const mamri_params* prm = &k.prm;
     const int nx = desc->nx, ny = desc->ny, nz = desc->nz;
-    cudaStream_t H = pool->hbm;
-    CKP(cudaMemcpyAsync(pool->d_dyn_all, pool->h_dyn_all, sizeof(DynArgs) * m, cudaMemcpyHostToDevice, H));
-    CKP(cudaMemsetAsync(pool->d_scalars_all, 0, sizeof(DevScalars) * m, H));
+    cudaStream_t H0 = pool->hbm;
+    const int NC = pool->n_chains;
+    CKP(cudaMemcpyAsync(pool->d_dyn_all, pool->h_dyn_all, sizeof(DynArgs) * m, cudaMemcpyHostToDevice, H0));
+    CKP(cudaMemsetAsync(pool->d_scalars_all, 0, sizeof(DevScalars) * m, H0));
+    CKP(cudaEventRecord(pool->fork, H0));
+    for (int c = 0; c < NC; ++c) CKP(cudaStreamWaitEvent(pool->chain[c], pool->fork, 0));
     for (int i = 0; i < m; ++i) {
+        cudaStream_t H = pool->chain[i % NC];
         TRACE(i, 0, H);
         CKP(launch_threshold_pack(pool->ctx[i], k.vol_aligned, desc->dtype, nx, ny, nz, prm->lower, prm->upper, prm->close_radius, H));
         TRACE(i, 1, H);
@@ -579,6 +597,7 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
     }
     if (outputs)
         for (int i = 0; i < m; ++i) {
+            cudaStream_t H = pool->chain[i % NC];
             CKP(cudaStreamWaitEvent(H, pool->ev_sel[i], 0));
             TRACE(i, 5, H);
             CKP(launch_materialise(pool->ctx[i], pool->ctx[i]->d_closed, nx, ny, nz, k.outs_aligned, H));
@@ -593,7 +612,11 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
         CKP(cudaMemcpyAsync(c->h_markers, c->d_markers, size_t(eager) * sizeof(mamri_marker), cudaMemcpyDeviceToHost, s));
         TRACE(i, 7, s);
         CKP(cudaEventRecord(pool->ev_done[i], s));
-        CKP(cudaStreamWaitEvent(H, pool->ev_done[i], 0));
+        CKP(cudaStreamWaitEvent(H0, pool->ev_done[i], 0));
+    }
+    for (int c = 0; c < NC; ++c) {
+        CKP(cudaEventRecord(pool->ev_chain[c], pool->chain[c]));
+        CKP(cudaStreamWaitEvent(H0, pool->ev_chain[c], 0));
     }
 #undef TRACE
     return MAMRI_OK;
