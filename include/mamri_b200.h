@@ -198,6 +198,90 @@ MAMRI_API int mamri_entry_search(mamri_ctx* ctx, const float* d_points, const fl
                        const mamri_volume_desc* mask_desc, const double ras_to_index[12],
                        int32_t path_free_value, mamri_entry_result* result, void* stream);
 
+/* ---- skin-surface candidates: stands in for Mamri.py:994-1003 ---------------------------- */
+/* The reference takes its entry-point candidates from Slicer's closed-surface representation of
+ * "AutoBodySegmentation" (Mamri.py:1338-1339, _get_body_polydata at :994) and vtkPolyDataNormals
+ * (:997-1003).  Neither exists outside Slicer, so the candidate set is defined on the voxel grid:
+ * every body voxel with a face neighbour outside the body, in ascending linear index; point = its
+ * physical centre in RAS (float32 [n][3]); normal = outward unit normal (float32 [n][3], RAS) from
+ * the first moment of the body inside the radius-2 ball around the voxel (zero vector where that
+ * moment vanishes).  The arrays feed mamri_entry_search directly.
+ *   d_body_mask  uint8 [nz*ny*nx] (non-zero = body: `largest_object_img`, :1323), or NULL = the body
+ *                of the scan last collected on this context (no per-voxel pass at all);
+ *   capacity     points the output arrays hold; 0 (outputs may be NULL) only counts.
+ * *n_points receives the number of surface voxels, *n_body_voxels (optional) the body size.
+ * Returns MAMRI_ERR_CAPACITY when capacity > 0 is too small (the first `capacity` points are written). */
+MAMRI_API int mamri_body_surface(mamri_ctx* ctx, const mamri_volume_desc* desc, const uint8_t* d_body_mask,
+                       float* d_points_out, float* d_normals_out, int64_t capacity, int64_t* n_points,
+                       int64_t* n_body_voxels, void* stream);
+
+/* ---- marker table -> robot pose: replaces Mamri.py:1343-1363, 1371-1373, 1771-1792, 1410-1447 ---- */
+/* What MamriLogic.process does with "DetectedFiducials" after the segmentation (Mamri.py:858-870),
+ * batched on the device: L-shape triplet matching per marker-bearing link (joint_detection), the
+ * baseplate y-flatten, the rigid landmark registration of the baseplate (vtkLandmarkTransform, float32
+ * landmarks) and the full-chain IK on the effector (+ weighted secondary) markers.  The IK is a
+ * projected Levenberg-Marquardt with an analytic Jacobian iterated to the minimum; the reference stops
+ * SciPy's TRF at ftol = xtol = 1e-6, so angles agree to that stopping error, not bit for bit. */
+#define MAMRI_MAX_LINKS        16
+#define MAMRI_MAX_CHAIN         8
+#define MAMRI_POSE_MAX_POINTS  64    /* control points per scan the matcher accepts */
+#define MAMRI_AXIS_NONE  0
+#define MAMRI_AXIS_IS    1           /* RotateZ(angle)    Mamri.py:1763 */
+#define MAMRI_AXIS_PA    2           /* RotateY(-angle)   Mamri.py:1765 */
+#define MAMRI_AXIS_LR    3           /* RotateX(angle)    Mamri.py:1767 */
+#define MAMRI_AXIS_TRANS 4           /* "TRANS_X": no rotation (Mamri.py:1498) */
+#define MAMRI_IK_NOT_RUN   0         /* baseplate or effector markers not identified */
+#define MAMRI_IK_CONVERGED 1
+#define MAMRI_IK_MAX_ITER  2
+
+/* One entry of robot_config.json, in file order (joint_detection iterates in this order, :1349). */
+typedef struct mamri_link {
+    int32_t parent;              /* index of the parent link, -1 = root (its parent transform is the baseplate registration) */
+    int32_t axis;                /* MAMRI_AXIS_* ("articulation_axis") */
+    int32_t has_markers;
+    int32_t chain_index;         /* position in the articulated chain (Mamri.py:819), -1 = not an IK unknown */
+    double  translate[3];        /* "fixed_offset_to_parent": translate */
+    double  marker_coords[9];    /* "local_marker_coords": 3 points */
+    double  arm_lengths[2];
+    double  limits_deg[2];       /* "joint_limits" */
+} mamri_link;
+
+typedef struct mamri_robot {
+    int32_t n_links;
+    int32_t base_link;           /* "Baseplate" */
+    int32_t effector_link;       /* "Joint6" */
+    int32_t secondary_link;      /* "Joint4", -1 = none */
+    double  distance_tolerance;  /* DISTANCE_TOLERANCE = 5.0, Mamri.py:813 */
+    double  secondary_weight;    /* joint4_weight = 0.05, Mamri.py:1507 */
+    int32_t apply_correction;    /* effector markers turned 180 deg about z (Mamri.py:1511-1514) */
+    int32_t reserved;
+    mamri_link links[MAMRI_MAX_LINKS];
+} mamri_robot;
+
+typedef struct mamri_pose {
+    int32_t n_points;                        /* control points of the scan */
+    int32_t status;                          /* MAMRI_OK, or MAMRI_ERR_CAPACITY: more than MAMRI_POSE_MAX_POINTS points */
+    int32_t matched[MAMRI_MAX_LINKS][3];     /* per link: control-point indices (corner, short arm, long arm), -1 = not identified */
+    int32_t has_base;                        /* baseplate registered from the scan */
+    int32_t ik_status;                       /* MAMRI_IK_* */
+    int32_t ik_iterations;
+    int32_t reserved;
+    double  base_matrix[16];                 /* row-major 4x4, baseplate model -> world (RAS) */
+    double  joint_angles[MAMRI_MAX_CHAIN];   /* rad, articulated-chain order */
+    double  ik_cost;                         /* 0.5 * sum of squared residuals */
+    double  ik_rms_error;                    /* last_ik_error (Mamri.py:1443-1444): rms of the effector residuals */
+} mamri_pose;
+
+/* Fills in robot_config.json (Baseplate, Joint1..Joint6, Needle) and the reference's constants. */
+MAMRI_API void mamri_default_robot(mamri_robot* robot);
+/* h_points_ras: float64 [n_scans][max_points][3], the control points of each scan's "DetectedFiducials"
+ * in node order (= ascending label; mamri_marker.centroid_ras); h_counts[n_scans] their numbers.
+ * One warp per scan on the device; h_poses[n_scans] receives the results.  A scan with fewer than three
+ * points, or without baseplate / effector markers, is MAMRI_OK with the corresponding fields unset. */
+MAMRI_API int mamri_pose_estimate(mamri_ctx* ctx, const mamri_robot* robot, const double* h_points_ras,
+                        const int32_t* h_counts, int32_t n_scans, int32_t max_points, mamri_pose* h_poses,
+                        void* stream);
+
 /* ---- synthetic phantoms (benchmark utility, not part of the reference path) -------------- */
 /* Paints `n_ellipsoids` (7 floats each: cx,cy,cz,ax,ay,az,intensity; index units; in order)
  * into a zeroed uint16 volume, then adds Rician noise (Philox4x32-10; see phantom.py). */

@@ -47,6 +47,30 @@ class EntryResult(C.Structure):
                 ("n_in_radius", C.c_uint64), ("n_suitable", C.c_uint64)]
 
 
+MAX_LINKS, MAX_CHAIN, POSE_MAX_POINTS = 16, 8, 64
+AXIS_CODES = {None: 0, "IS": 1, "PA": 2, "LR": 3, "TRANS_X": 4}
+IK_NOT_RUN, IK_CONVERGED, IK_MAX_ITER = 0, 1, 2
+
+
+class Link(C.Structure):
+    _fields_ = [("parent", C.c_int32), ("axis", C.c_int32), ("has_markers", C.c_int32), ("chain_index", C.c_int32),
+                ("translate", C.c_double * 3), ("marker_coords", C.c_double * 9), ("arm_lengths", C.c_double * 2),
+                ("limits_deg", C.c_double * 2)]
+
+
+class Robot(C.Structure):
+    _fields_ = [("n_links", C.c_int32), ("base_link", C.c_int32), ("effector_link", C.c_int32),
+                ("secondary_link", C.c_int32), ("distance_tolerance", C.c_double), ("secondary_weight", C.c_double),
+                ("apply_correction", C.c_int32), ("reserved", C.c_int32), ("links", Link * MAX_LINKS)]
+
+
+class Pose(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("status", C.c_int32), ("matched", (C.c_int32 * 3) * MAX_LINKS),
+                ("has_base", C.c_int32), ("ik_status", C.c_int32), ("ik_iterations", C.c_int32), ("reserved", C.c_int32),
+                ("base_matrix", C.c_double * 16), ("joint_angles", C.c_double * MAX_CHAIN), ("ik_cost", C.c_double),
+                ("ik_rms_error", C.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/mamri_b200.h declares
 SIGNATURES = {
     "mamri_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32]),
@@ -77,6 +101,11 @@ SIGNATURES = {
     "mamri_entry_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_double,
                                      C.c_double, C.c_double, C.c_double, C.c_int32, C.c_void_p, C.POINTER(VolumeDesc),
                                      C.POINTER(C.c_double), C.c_int32, C.POINTER(EntryResult), C.c_void_p]),
+    "mamri_body_surface": (C.c_int, [C.c_void_p, C.POINTER(VolumeDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]),
+    "mamri_default_robot": (None, [C.POINTER(Robot)]),
+    "mamri_pose_estimate": (C.c_int, [C.c_void_p, C.POINTER(Robot), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.POINTER(Pose), C.c_void_p]),
     "mamri_phantom_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32,
                                          C.c_float, C.c_uint64, C.c_uint32, C.c_void_p]),
 }

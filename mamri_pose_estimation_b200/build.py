@@ -12,7 +12,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libmamri_b200.so"
-SOURCES = ["segment.cu", "ccl.cu", "stats.cu", "entry.cu", "phantom.cu", "api.cu"]
+SOURCES = ["segment.cu", "ccl.cu", "stats.cu", "entry.cu", "surface.cu", "pose.cu", "phantom.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

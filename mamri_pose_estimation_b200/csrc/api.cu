@@ -88,6 +88,7 @@ extern "C" int mamri_destroy(mamri_ctx* ctx) {
     cudaFree(ctx->d_root_count); cudaFree(ctx->d_scan_runs); cudaFree(ctx->d_scan_rank); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
     cudaFree(ctx->d_summary); if (!ctx->shared_args) cudaFree(ctx->d_scalars); cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
     cudaFree(ctx->d_entry_dist); cudaFree(ctx->d_entry_idx); cudaFree(ctx->d_entry_cnt); cudaFree(ctx->d_entry_res);
+    cudaFree(ctx->d_surf); cudaFreeHost(ctx->h_surf); cudaFree(ctx->d_pose_buf);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 48; ++i) if (ctx->ev_fine[i]) cudaEventDestroy(ctx->ev_fine[i]);
     if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
@@ -178,12 +179,14 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     ALLOC(ctx->d_entry_idx, MAMRI_SCAN_CTAS * sizeof(long long), "entry partials");
     ALLOC(ctx->d_entry_cnt, 2 * sizeof(unsigned long long), "entry counters");
     ALLOC(ctx->d_entry_res, sizeof(mamri_entry_result), "entry result");
+    ALLOC(ctx->d_surf, sizeof(SurfScalars), "surface scalars");
 #undef ALLOC
     if ((e = cudaMallocHost((void**)&ctx->h_markers, size_t(max_markers) * sizeof(mamri_marker))) != cudaSuccess)
         return bail(e, "pinned marker table");
     if ((e = cudaMallocHost((void**)&ctx->h_summary, sizeof(mamri_summary))) != cudaSuccess) return bail(e, "pinned summary");
     if ((e = cudaMallocHost((void**)&ctx->h_entry_res, sizeof(mamri_entry_result))) != cudaSuccess)
         return bail(e, "pinned entry result");
+    if ((e = cudaMallocHost((void**)&ctx->h_surf, sizeof(SurfScalars))) != cudaSuccess) return bail(e, "pinned surface scalars");
     for (int i = 0; i < 6; ++i)
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bail(e, "events");
     if ((e = cudaMalloc((void**)&ctx->d_dyn, sizeof(DynArgs))) != cudaSuccess) return bail(e, "dynamic args");
@@ -815,6 +818,106 @@ extern "C" int mamri_entry_search(mamri_ctx* ctx, const float* d_points, const f
     CK(cudaMemcpyAsync(ctx->h_entry_res, ctx->d_entry_res, sizeof(mamri_entry_result), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     *result = *ctx->h_entry_res;
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_body_surface(mamri_ctx* ctx, const mamri_volume_desc* desc, const uint8_t* d_body_mask,
+                                  float* d_points_out, float* d_normals_out, int64_t capacity, int64_t* n_points,
+                                  int64_t* n_body_voxels, void* stream) {
+    if (!ctx) return MAMRI_ERR_INVALID_ARG;
+    if (!desc || !n_points) return fail(ctx, MAMRI_ERR_INVALID_ARG, "desc/n_points is NULL");
+    if (desc->nx <= 0 || desc->ny <= 0 || desc->nz <= 0 || desc->nx > ctx->max_nx || desc->ny > ctx->max_ny || desc->nz > ctx->max_nz)
+        return fail(ctx, MAMRI_ERR_INVALID_ARG, "volume dimensions outside what the context was created for");
+    for (int i = 0; i < 3; ++i)
+        if (!(desc->spacing[i] > 0.0)) return fail(ctx, MAMRI_ERR_INVALID_ARG, "spacing must be positive");
+    if (capacity < 0 || (capacity > 0 && (!d_points_out || !d_normals_out)))
+        return fail(ctx, MAMRI_ERR_INVALID_ARG, "capacity > 0 needs both output arrays");
+    if (ctx->pending) return fail(ctx, MAMRI_ERR_STATE, "collect the pending detect first");
+    uint32_t body_label = 0;
+    if (!d_body_mask) {                                   // body of the last collected scan, from its run table
+        const mamri_volume_desc& l = ctx->last_desc;
+        if (ctx->last_n_labels == 0 && ctx->h_summary->body_label == 0) { /* empty scan: no candidates */ }
+        else if (l.nx != desc->nx || l.ny != desc->ny || l.nz != desc->nz)
+            return fail(ctx, MAMRI_ERR_STATE, "d_body_mask == NULL needs the geometry of the last collected scan");
+        body_label = ctx->last_n_labels ? ctx->h_summary->body_label : 0;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CK(launch_body_surface(ctx, desc, d_body_mask, body_label, capacity > 0 ? d_points_out : nullptr,
+                           capacity > 0 ? d_normals_out : nullptr, (unsigned long long)capacity, s));
+    CK(cudaMemcpyAsync(ctx->h_surf, ctx->d_surf, sizeof(SurfScalars), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *n_points = (int64_t)ctx->h_surf->n_points;
+    if (n_body_voxels) *n_body_voxels = (int64_t)ctx->h_surf->n_body;
+    if (capacity > 0 && *n_points > capacity)
+        return fail(ctx, MAMRI_ERR_CAPACITY, "more surface voxels than the output arrays hold (n_points is the number needed)");
+    return MAMRI_OK;
+}
+
+extern "C" void mamri_default_robot(mamri_robot* r) {
+    if (!r) return;
+    memset(r, 0, sizeof(*r));
+    // Mamri/Resources/Robot/robot_config.json, in file order
+    struct Row { int parent, axis, markers, chain; double t[3], mc[9], arm[2], lim[2]; };
+    static const Row rows[8] = {
+        {-1, MAMRI_AXIS_NONE, 1, -1, {0, 0, 0}, {-10, 20, 5, 10, 20, 5, -10, -20, 5}, {40, 20}, {0, 0}},                 // Baseplate :2-17
+        {0, MAMRI_AXIS_IS, 0, 0, {0, 0, 20}, {0}, {0, 0}, {-180, 180}},                                                  // Joint1   :18-30
+        {1, MAMRI_AXIS_PA, 1, 1, {0, 0, 30}, {12.5, 45, 110, -12.5, 45, 110, 12.5, 45, 40}, {70, 25}, {-120, 120}},      // Joint2   :31-49
+        {2, MAMRI_AXIS_PA, 0, 2, {0, 0, 150}, {0}, {0, 0}, {-120, 120}},                                                 // Joint3   :50-62
+        {3, MAMRI_AXIS_IS, 1, 3, {0, 0, 0}, {-10, 35, 90, 10, 35, 90, -10, -35, 90}, {70, 20}, {-180, 180}},             // Joint4   :63-81
+        {4, MAMRI_AXIS_PA, 0, 4, {0, 0, 155}, {0}, {0, 0}, {-120, 120}},                                                 // Joint5   :82-94
+        {5, MAMRI_AXIS_IS, 1, 5, {0, 0, 13}, {-10, 22.5, 26, 10, 22.5, 26, -10, -22.5, 26}, {45, 20}, {-270, 270}},      // Joint6   :95-115
+        {6, MAMRI_AXIS_TRANS, 0, -1, {-50, 0, 71}, {0}, {0, 0}, {0, 0}},                                                 // Needle   :116-130
+    };
+    r->n_links = 8;
+    r->base_link = 0; r->effector_link = 6; r->secondary_link = 4;
+    r->distance_tolerance = 5.0;     // Mamri.py:813
+    r->secondary_weight = 0.05;      // Mamri.py:1507
+    r->apply_correction = 0;
+    for (int i = 0; i < 8; ++i) {
+        mamri_link& l = r->links[i];
+        l.parent = rows[i].parent; l.axis = rows[i].axis; l.has_markers = rows[i].markers; l.chain_index = rows[i].chain;
+        for (int k = 0; k < 3; ++k) l.translate[k] = rows[i].t[k];
+        for (int k = 0; k < 9; ++k) l.marker_coords[k] = rows[i].mc[k];
+        for (int k = 0; k < 2; ++k) { l.arm_lengths[k] = rows[i].arm[k]; l.limits_deg[k] = rows[i].lim[k]; }
+    }
+}
+
+extern "C" int mamri_pose_estimate(mamri_ctx* ctx, const mamri_robot* robot, const double* h_points_ras,
+                                   const int32_t* h_counts, int32_t n_scans, int32_t max_points, mamri_pose* h_poses,
+                                   void* stream) {
+    if (!ctx) return MAMRI_ERR_INVALID_ARG;
+    if (!robot || n_scans < 0 || max_points < 0 || (n_scans > 0 && (!h_counts || !h_poses)) ||
+        (n_scans > 0 && max_points > 0 && !h_points_ras))
+        return fail(ctx, MAMRI_ERR_INVALID_ARG, "bad pose arguments");
+    if (robot->n_links < 1 || robot->n_links > MAMRI_MAX_LINKS) return fail(ctx, MAMRI_ERR_INVALID_ARG, "robot: n_links out of range");
+    for (int l = 0; l < robot->n_links; ++l)
+        if (robot->links[l].parent >= l || robot->links[l].chain_index >= MAMRI_MAX_CHAIN)
+            return fail(ctx, MAMRI_ERR_INVALID_ARG, "robot: a link's parent must precede it; chain_index < MAMRI_MAX_CHAIN");
+    if (n_scans == 0) return MAMRI_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t off_pts = (sizeof(mamri_robot) + 255) & ~size_t(255);
+    const size_t pts_bytes = size_t(n_scans) * max_points * 3 * sizeof(double);
+    const size_t off_cnt = (off_pts + pts_bytes + 255) & ~size_t(255);
+    const size_t off_pose = (off_cnt + size_t(n_scans) * sizeof(int32_t) + 255) & ~size_t(255);
+    const size_t total = off_pose + size_t(n_scans) * sizeof(mamri_pose);
+    if (ctx->pose_buf_bytes < total) {                   // first call at this batch size: grow the scratch
+        CK(cudaStreamSynchronize(s));
+        cudaFree(ctx->d_pose_buf);
+        ctx->d_pose_buf = nullptr; ctx->pose_buf_bytes = 0;
+        CK(cudaMalloc(&ctx->d_pose_buf, total));
+        ctx->pose_buf_bytes = total;
+    }
+    char* base = static_cast<char*>(ctx->d_pose_buf);
+    CK(cudaMemcpyAsync(base, robot, sizeof(mamri_robot), cudaMemcpyHostToDevice, s));
+    if (pts_bytes) CK(cudaMemcpyAsync(base + off_pts, h_points_ras, pts_bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(base + off_cnt, h_counts, size_t(n_scans) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CK(launch_pose(reinterpret_cast<const mamri_robot*>(base), reinterpret_cast<const double*>(base + off_pts),
+                   reinterpret_cast<const int32_t*>(base + off_cnt), n_scans, max_points,
+                   reinterpret_cast<mamri_pose*>(base + off_pose), s));
+    CK(cudaMemcpyAsync(h_poses, base + off_pose, size_t(n_scans) * sizeof(mamri_pose), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return MAMRI_OK;
 }
 

@@ -463,7 +463,21 @@ __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict_
             const uint32_t m_l = m_next;
             const uint32_t wn = w0 + n_warps * 32 + lane;
             m_next = (wn < n_words) ? mask[wn] : 0u;
-            const bool resolve = need_labels && ok && __any_sync(0xFFFFFFFFu, m_l != 0u);
+            const bool any_fg = __any_sync(0xFFFFFFFFu, m_l != 0u);
+            if (!any_fg) {
+                // 1024 background voxels (most of an MRI volume is air): nothing to resolve, just the zero stores
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t wi = w0 + k * 4 + (lane >> 3);
+                    if (wi >= n_words) continue;
+                    const uint32_t v = wi * 32 + (lane & 7u) * 4;
+                    if (labels_out) st_stream(reinterpret_cast<uint4*>(labels_out + v), make_uint4(0u, 0u, 0u, 0u), hint);
+                    if (mask_out) st_stream(reinterpret_cast<uint32_t*>(mask_out + v), 0u, hint);
+                    if (body_out) st_stream(reinterpret_cast<uint32_t*>(body_out + v), 0u, hint);
+                }
+                continue;
+            }
+            const bool resolve = need_labels && ok;
             uint32_t starts_l = 0, base_l = 0;
             if (resolve) {
                 uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, m_l, 1);

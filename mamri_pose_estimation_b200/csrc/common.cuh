@@ -27,6 +27,14 @@ struct DevScalars {
     unsigned int done_moments;       // CTAs of k_moments that have finished (last one finalises)
 };
 
+// Device-side scalars of one body-surface extraction (surface.cu).
+struct SurfScalars {
+    unsigned int ticket;             // tile tickets of k_surface
+    unsigned int reserved;
+    unsigned long long n_points;     // surface voxels found (may exceed the caller's capacity)
+    unsigned long long n_body;       // voxels of the body
+};
+
 // Per-call pointers, read by the kernels from device memory so that the captured CUDA graph of the
 // pipeline stays valid when only the caller's buffers change.
 struct DynArgs {
@@ -87,11 +95,15 @@ struct mamri_ctx {
     long long* d_entry_idx;
     unsigned long long* d_entry_cnt; // [2]
     mamri_entry_result* d_entry_res;
+    SurfScalars* d_surf;    // body-surface scalars
+    void* d_pose_buf;       // pose stage: robot + points + counts + poses (grown on demand)
+    size_t pose_buf_bytes;
 
     // pinned host mirrors
     mamri_marker* h_markers;
     mamri_summary* h_summary;
     mamri_entry_result* h_entry_res;
+    SurfScalars* h_surf;
 
     // CUDA graph of the whole pipeline (captured on first use of a configuration, relaunched afterwards)
     DynArgs* d_dyn;
@@ -143,6 +155,10 @@ cudaError_t launch_entry_search(mamri_ctx* c, const float* d_points, const float
                                 const double target[3], double radius, double wx, double wy, double cutoff,
                                 int n_path_samples, const uint8_t* d_path_mask, int mnx, int mny, int mnz,
                                 const double ras_to_index[12], int path_free_value, cudaStream_t s);
+cudaError_t launch_body_surface(mamri_ctx* c, const mamri_volume_desc* desc, const uint8_t* d_body_mask, uint32_t body_label,
+                                float* d_points, float* d_normals, unsigned long long capacity, cudaStream_t s);
+cudaError_t launch_pose(const mamri_robot* d_robot, const double* d_points, const int32_t* d_counts, int n_scans,
+                        int max_points, mamri_pose* d_poses, cudaStream_t s);
 cudaError_t launch_phantom(uint16_t* d_volume, int nx, int ny, int nz, const float* h_ell, int n_ell, float sigma,
                            unsigned long long seed, unsigned int scan_index, cudaStream_t s);
 

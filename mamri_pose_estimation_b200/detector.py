@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._capi import EntryResult, Marker, Params, Summary, VolumeDesc, check
+from ._capi import EntryResult, Marker, Params, Pose, Robot, Summary, VolumeDesc, check
 
 _TORCH_DTYPES = {torch.uint8: "uint8", torch.int16: "int16", torch.uint16: "uint16",
                  torch.int32: "int32", torch.float32: "float32"}
@@ -85,6 +85,32 @@ class DetectionResult:
     @property
     def marker_labels(self) -> List[str]:
         return [f"M_{m.label}_{m.volume_mm3:.0f}mm³" for m in self.markers]   # Mamri.py:1317
+
+
+ROBOT_LINK_NAMES = ("Baseplate", "Joint1", "Joint2", "Joint3", "Joint4", "Joint5", "Joint6", "Needle")   # robot_config.json order
+
+
+@dataclasses.dataclass
+class PoseResult:
+    """What MamriLogic.process derives from "DetectedFiducials" (Mamri.py:858-870) for one scan."""
+    n_points: int
+    identified: dict                             # link name -> [control-point ids] (corner, short arm, long arm): joint_detection
+    base_matrix: Optional[np.ndarray]            # 4x4 baseplate model -> world (RAS), None if no baseplate in the scan
+    joint_angles: Optional[np.ndarray]           # rad, articulated-chain order (Joint1..Joint6), None if the IK did not run
+    ik_converged: bool
+    ik_iterations: int
+    ik_cost: float
+    ik_rms_error: float                          # last_ik_error (Mamri.py:1443-1444)
+
+    @staticmethod
+    def from_c(p: Pose, names=ROBOT_LINK_NAMES, n_chain: int = 6) -> "PoseResult":
+        ident = {names[l]: [int(v) for v in p.matched[l]] for l in range(len(names)) if p.matched[l][0] >= 0}
+        ran = p.ik_status != _capi.IK_NOT_RUN
+        return PoseResult(n_points=int(p.n_points), identified=ident,
+                          base_matrix=np.array(p.base_matrix[:]).reshape(4, 4) if p.has_base else None,
+                          joint_angles=np.array(p.joint_angles[:n_chain]) if ran else None,
+                          ik_converged=p.ik_status == _capi.IK_CONVERGED, ik_iterations=int(p.ik_iterations),
+                          ik_cost=float(p.ik_cost), ik_rms_error=float(p.ik_rms_error))
 
 
 def _desc(shape_zyx, dtype_name, spacing, origin, direction) -> VolumeDesc:
@@ -243,6 +269,71 @@ class FiducialDetector:
         check(rc, self._ctx)
         return {"index": int(res.index), "distance": float(res.distance), "point": np.array(res.point[:]),
                 "n_in_radius": int(res.n_in_radius), "n_suitable": int(res.n_suitable)}
+
+
+    # ------------------------------------------------------------------ marker table -> robot pose
+    def default_robot(self, apply_correction: bool = False) -> Robot:
+        r = Robot()
+        self._lib.mamri_default_robot(C.byref(r))
+        r.apply_correction = int(bool(apply_correction))
+        return r
+
+    def pose_estimate(self, ras_points: Sequence, robot: Optional[Robot] = None, apply_correction: bool = False,
+                      stream: Optional[torch.cuda.Stream] = None) -> List[PoseResult]:
+        """L-shape matching, baseplate registration and full-chain IK (Mamri.py:1343-1447) for a batch of scans on the
+        device, one warp per scan.  `ras_points[i]`: [n_i, 3] control points of scan i in node order
+        (DetectionResult.ras_points)."""
+        n = len(ras_points)
+        if n == 0:
+            return []
+        arrs = [np.asarray(p, dtype=np.float64).reshape(-1, 3) for p in ras_points]
+        max_pts = max(1, max(a.shape[0] for a in arrs))
+        pts = np.zeros((n, max_pts, 3), dtype=np.float64)
+        cnt = np.zeros(n, dtype=np.int32)
+        for i, a in enumerate(arrs):
+            pts[i, :a.shape[0]] = a
+            cnt[i] = a.shape[0]
+        robot = robot if robot is not None else self.default_robot(apply_correction)
+        poses = (Pose * n)()
+        s = stream or torch.cuda.current_stream(self.device)
+        rc = self._lib.mamri_pose_estimate(self._ctx, C.byref(robot), pts.ctypes.data, cnt.ctypes.data, n, max_pts, poses,
+                                           s.cuda_stream)
+        check(rc, self._ctx)
+        out = []
+        for i in range(n):
+            if poses[i].status != _capi.MAMRI_OK:
+                raise _capi.MamriError(poses[i].status, f"scan {i}: {cnt[i]} control points exceed the matcher's limit "
+                                                        f"of {_capi.POSE_MAX_POINTS}")
+            out.append(PoseResult.from_c(poses[i]))
+        return out
+
+    # ------------------------------------------------------------------ skin-surface candidates
+    def body_surface(self, body_mask: Optional[torch.Tensor] = None, shape_zyx=None, spacing=(1.0, 1.0, 1.0),
+                     origin=(0.0, 0.0, 0.0), direction=IDENTITY, stream: Optional[torch.cuda.Stream] = None):
+        """Entry-point candidates of a body labelmap (stands in for Mamri.py:994-1003): float32 CUDA tensors
+        (points [n,3] RAS, normals [n,3] RAS), surface voxels in ascending linear index.  `body_mask`: uint8 CUDA
+        tensor [nz,ny,nx], or None = the body of the scan last collected on this detector (then pass `shape_zyx`).
+        Two calls into the library: count, then emit into exactly-sized arrays."""
+        if body_mask is not None:
+            if not (body_mask.is_cuda and body_mask.is_contiguous() and body_mask.dim() == 3 and body_mask.dtype == torch.uint8):
+                raise ValueError("body_mask must be a contiguous uint8 CUDA tensor [nz, ny, nx]")
+            shape_zyx, ptr, dev = tuple(body_mask.shape), body_mask.data_ptr(), body_mask.device
+        else:
+            if shape_zyx is None:
+                raise ValueError("shape_zyx is needed when the body of the last scan is used")
+            ptr, dev = None, torch.device(f"cuda:{self.device}")
+        d = _desc(shape_zyx, "uint8", spacing, origin, direction)
+        s = stream or torch.cuda.current_stream(dev)
+        n, n_body = C.c_int64(0), C.c_int64(0)
+        check(self._lib.mamri_body_surface(self._ctx, C.byref(d), ptr, None, None, 0, C.byref(n), C.byref(n_body),
+                                           s.cuda_stream), self._ctx)
+        pts = torch.empty((n.value, 3), dtype=torch.float32, device=dev)
+        nrm = torch.empty((n.value, 3), dtype=torch.float32, device=dev)
+        if n.value:
+            check(self._lib.mamri_body_surface(self._ctx, C.byref(d), ptr, pts.data_ptr(), nrm.data_ptr(), n.value,
+                                               C.byref(n), C.byref(n_body), s.cuda_stream), self._ctx)
+        self.last_body_voxels = int(n_body.value)
+        return pts, nrm
 
 
 def _host_view(a):

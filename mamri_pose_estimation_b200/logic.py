@@ -165,6 +165,29 @@ class MamriLogic:
         self.scene["AutoBodySegmentation"] = seg
         pNode.segmentationNode = seg
 
+    # -- Mamri.py:1343-1363 -----------------------------------------------------------------------
+    def joint_detection(self, pNode: MamriParameterNode = None) -> Dict[str, List[Dict]]:
+        '''Identifies known L-shaped fiducial patterns from a list of detected points.'''
+        all_node = self.scene.get("DetectedFiducials")
+        if not (all_node and all_node.GetNumberOfControlPoints() >= 3):
+            return {}
+        det = self._detector or self._detector_for((32, 32, 32))
+        pts = all_node.points()
+        self.last_pose = pose = det.pose_estimate([pts])[0]
+        return {jn: [{"id": i, "ras_coords": [float(c) for c in pts[i]]} for i in ids] for jn, ids in pose.identified.items()}
+
+    # -- Mamri.py:858-870 (the part of process() after the segmentation, on the device) ------------
+    def estimate_pose(self, pNode: MamriParameterNode = None, apply_correction: bool = False):
+        '''Matching, baseplate registration and full-chain IK; returns a detector.PoseResult (or None when fewer
+        than three fiducials were detected).  The reference's SciPy solver remains the parity path for the
+        1e-6 rad criterion; this is its batched on-device counterpart.'''
+        all_node = self.scene.get("DetectedFiducials")
+        if not (all_node and all_node.GetNumberOfControlPoints() >= 3):
+            return None
+        det = self._detector or self._detector_for((32, 32, 32))
+        self.last_pose = det.pose_estimate([all_node.points()], apply_correction=apply_correction)[0]
+        return self.last_pose
+
     # -- Mamri.py:987-1033 -------------------------------------------------------------------------
     def findAndSetEntryPoint(self, pNode: MamriParameterNode) -> None:
         '''Finds and marks the closest suitable entry point on the body surface for the biopsy needle.'''
@@ -174,11 +197,25 @@ class MamriLogic:
             logging.error("Please place a target marker and ensure 'AutoBodySegmentation' exists.")
             return
         pts, nrm = segmentationNode.surface_points, segmentationNode.surface_normals
-        if pts is None or nrm is None or len(pts) == 0:
-            return                                   # `if not body_poly: return` (Mamri.py:995-996)
         dev = torch.device(f"cuda:{self.device}")
-        pts_t = torch.as_tensor(pts, dtype=torch.float32).to(dev).contiguous()
-        nrm_t = torch.as_tensor(nrm, dtype=torch.float32).to(dev).contiguous()
+        if pts is None or nrm is None:
+            # no closed-surface representation supplied by the host application: derive the candidates from
+            # the body labelmap on the GPU (mamri_body_surface; stands in for Mamri.py:994-1003)
+            bm = segmentationNode.body_mask
+            if bm is None:
+                return                               # `if not body_poly: return` (Mamri.py:995-996)
+            bm_t = bm if isinstance(bm, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bm))
+            bm_t = bm_t.to(dev).contiguous()
+            nz, ny, nx = bm_t.shape
+            det = self._detector_for((nx, ny, nz))
+            pts_t, nrm_t = det.body_surface(bm_t, spacing=segmentationNode.spacing, origin=segmentationNode.origin,
+                                            direction=segmentationNode.direction)
+            segmentationNode.surface_points, segmentationNode.surface_normals = pts_t, nrm_t
+        else:
+            pts_t = torch.as_tensor(pts, dtype=torch.float32).to(dev).contiguous()
+            nrm_t = torch.as_tensor(nrm, dtype=torch.float32).to(dev).contiguous()
+        if len(pts_t) == 0:
+            return                                   # `if not body_poly: return` (Mamri.py:995-996)
         target_pos = np.array(targetNode.GetNthControlPointPositionWorld(0), dtype=np.float64)
         det = self._detector or self._detector_for((32, 32, 32))
         best = det.entry_search(pts_t, nrm_t, target_pos, radius=self.SEARCH_RADIUS, wx=1.0, wy=-2.0, cutoff=-0.5)

@@ -35,17 +35,42 @@ def test_ctypes_structs_match_header_sizes(cuda_lib, tmp_path):
     import subprocess
     from mamri_pose_estimation_b200 import _capi
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "mamri_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "mamri_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(mamri_volume_desc),sizeof(mamri_params),sizeof(mamri_marker),sizeof(mamri_summary),'
-                   'sizeof(mamri_entry_result));return 0;}\n')
+                   'sizeof(mamri_entry_result),sizeof(mamri_link),sizeof(mamri_robot),sizeof(mamri_pose));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
-    mirrors = [_capi.VolumeDesc, _capi.Params, _capi.Marker, _capi.Summary, _capi.EntryResult]
+    mirrors = [_capi.VolumeDesc, _capi.Params, _capi.Marker, _capi.Summary, _capi.EntryResult, _capi.Link, _capi.Robot,
+               _capi.Pose]
     assert sizes == [C.sizeof(m) for m in mirrors]
     p = _capi.Params()
     cuda_lib.mamri_default_params(C.byref(p))
     assert (p.lower, p.upper, p.close_radius, p.connectivity, p.min_volume, p.max_volume) == (65.0, 65535.0, 2, 6, 50.0, 1500.0)
+
+
+def test_default_robot_matches_the_oracle_restatement_of_robot_config(cuda_lib):
+    """mamri_default_robot == oracle/kinematics.ROBOT (itself compared with robot_config.json when the
+    reference tree is mounted, tests/test_oracle_kinematics.py)."""
+    from mamri_pose_estimation_b200 import _capi
+    from oracle import kinematics as kin
+    r = _capi.Robot()
+    cuda_lib.mamri_default_robot(C.byref(r))
+    assert r.n_links == len(kin.ROBOT) and r.distance_tolerance == kin.DISTANCE_TOLERANCE and r.secondary_weight == 0.05
+    names = [j["name"] for j in kin.ROBOT]
+    assert (names[r.base_link], names[r.effector_link], names[r.secondary_link]) == ("Baseplate", "Joint6", "Joint4")
+    for i, j in enumerate(kin.ROBOT):
+        l = r.links[i]
+        assert l.parent == (names.index(j["parent"]) if j["parent"] else -1)
+        assert l.axis == _capi.AXIS_CODES[j.get("articulation_axis")]
+        assert bool(l.has_markers) == bool(j.get("has_markers"))
+        assert l.chain_index == (kin.ARTICULATED_CHAIN.index(j["name"]) if j["name"] in kin.ARTICULATED_CHAIN else -1)
+        assert list(l.translate) == [float(v) for v in (j.get("translate") or [0, 0, 0])]
+        if j.get("has_markers"):
+            assert list(l.marker_coords) == [float(v) for p_ in j["local_marker_coords"] for v in p_]
+            assert list(l.arm_lengths) == [float(v) for v in j["arm_lengths"]]
+        if j["name"] in kin.ARTICULATED_CHAIN:
+            assert list(l.limits_deg) == [float(v) for v in j["joint_limits"]]
 
 
 def test_no_cpu_fallback_without_gpu(cuda_lib):
