@@ -59,12 +59,47 @@ class MarkerStats:
                            principal_axes=np.array(m.principal_axes[:]).reshape(3, 3))
 
 
+class _LazyMarkers:
+    """list-like view of a marker table copied out of the C array: MarkerStats objects are built on first access
+    (a noisy high-resolution scan keeps ~1000 labels; building them eagerly would cost more than the scan)."""
+
+    def __init__(self, table: np.ndarray):
+        self.table = table                       # structured array, dtype = np.dtype(Marker), own copy
+        self._items: Optional[List[MarkerStats]] = None
+
+    def _all(self) -> List[MarkerStats]:
+        if self._items is None:
+            mk = (Marker * len(self.table)).from_buffer_copy(self.table.tobytes()) if len(self.table) else []
+            self._items = [MarkerStats.from_c(m) for m in mk]
+        return self._items
+
+    def __len__(self):
+        return len(self.table)
+
+    def __iter__(self):
+        return iter(self._all())
+
+    def __getitem__(self, i):
+        return self._all()[i]
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
+def _marker_table(c_markers, n: int, first: int = 0) -> np.ndarray:
+    """Copies markers [first, first + n) of a ctypes Marker array into a NumPy structured array."""
+    if n <= 0:
+        return np.zeros(0, dtype=np.dtype(Marker))
+    view = np.frombuffer(c_markers, dtype=np.dtype(Marker), count=n, offset=first * C.sizeof(Marker))
+    return view.copy()
+
+
 @dataclasses.dataclass
 class DetectionResult:
     n_labels: int
     n_runs: int
     n_foreground: int
-    markers: List[MarkerStats]                   # ascending label = "DetectedFiducials" control-point order
+    markers: Sequence[MarkerStats]               # ascending label = "DetectedFiducials" control-point order
     body_label: int
     body_count: int
     body: Optional[MarkerStats]
@@ -73,17 +108,32 @@ class DetectionResult:
     body_mask: Optional[object] = None           # uint8 [nz,ny,nx] (device tensor, or host array for detect_host)
 
     @property
+    def marker_table(self) -> Optional[np.ndarray]:
+        """The markers as a NumPy structured array (fields of mamri_marker), when they came from the library."""
+        return self.markers.table if isinstance(self.markers, _LazyMarkers) else None
+
+    @property
     def fiducials_data(self) -> List[dict]:
         """The list the reference builds at Mamri.py:1310."""
+        t = self.marker_table
+        if t is not None:
+            return [{"vol": float(v), "centroid": (float(c[0]), float(c[1]), float(c[2])), "id": int(l)}
+                    for v, c, l in zip(t["volume_mm3"], t["centroid_lps"], t["label"])]
         return [{"vol": m.volume_mm3, "centroid": tuple(float(c) for c in m.centroid_lps), "id": m.label}
                 for m in self.markers]
 
     @property
     def ras_points(self) -> np.ndarray:
+        t = self.marker_table
+        if t is not None:
+            return np.array(t["centroid_ras"], dtype=np.float64).reshape(-1, 3)
         return np.array([m.centroid_ras for m in self.markers], dtype=np.float64).reshape(-1, 3)
 
     @property
     def marker_labels(self) -> List[str]:
+        t = self.marker_table
+        if t is not None:
+            return [f"M_{int(l)}_{float(v):.0f}mm³" for l, v in zip(t["label"], t["volume_mm3"])]      # Mamri.py:1317
         return [f"M_{m.label}_{m.volume_mm3:.0f}mm³" for m in self.markers]   # Mamri.py:1317
 
 
@@ -182,7 +232,7 @@ class FiducialDetector:
         rc = self._lib.mamri_detect_collect(self._ctx, C.byref(summ), self._markers, self.max_markers)
         pend, self._pending = self._pending, None
         check(rc, self._ctx)
-        markers = [MarkerStats.from_c(self._markers[i]) for i in range(summ.n_markers)]
+        markers = _LazyMarkers(_marker_table(self._markers, int(summ.n_markers)))
         body = MarkerStats.from_c(summ.body) if summ.body_label else None
         out_mask, out_labels, out_body = (pend[0], pend[1], pend[2]) if pend else (None, None, None)
         return DetectionResult(n_labels=int(summ.n_labels), n_runs=int(summ.n_runs), n_foreground=int(summ.n_foreground),
@@ -389,7 +439,7 @@ class BatchResult:
         if i not in self._cache:
             summ = self._summ[i]
             k = min(int(summ.n_markers), self._max_m)
-            markers = [MarkerStats.from_c(self._mk[i * self._max_m + j]) for j in range(k)]
+            markers = _LazyMarkers(_marker_table(self._mk, k, first=i * self._max_m))
             body = MarkerStats.from_c(summ.body) if summ.body_label else None
             m, l, b = self._outs(i)
             self._cache[i] = DetectionResult(n_labels=int(summ.n_labels), n_runs=int(summ.n_runs),
