@@ -451,6 +451,13 @@ class BatchResult:
     def __iter__(self):
         return (self[i] for i in range(self.n))
 
+    def ras_points(self) -> List[np.ndarray]:
+        """Per scan: [n_markers, 3] control points of "DetectedFiducials" (node order), straight from the C arrays."""
+        mk = np.frombuffer(self._mk, dtype=np.dtype(Marker)).reshape(self.n, self._max_m)
+        sm = np.frombuffer(self._summ, dtype=np.dtype(Summary))
+        return [np.array(mk[i, :min(int(sm["n_markers"][i]), self._max_m)]["centroid_ras"], dtype=np.float64).reshape(-1, 3)
+                for i in range(self.n)]
+
     def table(self, slots: int = 32) -> np.ndarray:
         """[n, slots, 8] float64: label, count, volume_mm3, RAS x y z, n_labels, body_label (distributed.pack_table)."""
         mk = np.frombuffer(self._mk, dtype=np.dtype(Marker)).reshape(self.n, self._max_m)[:, :slots]
@@ -547,6 +554,10 @@ class BatchDetector:
         _capi.check_pool(rc, self._pool)
         masks, labels = self.masks, self.labels
         return BatchResult(n, summ, mk, self.max_markers, lambda i: (masks[i % k], labels[i % k], None))
+
+    def estimate_poses(self, results: BatchResult, apply_correction: bool = False) -> List[PoseResult]:
+        """Matching + baseplate registration + IK for every scan of a batch in one device call (one warp per scan)."""
+        return self.context(0).pose_estimate(results.ras_points(), apply_correction=apply_correction)
 
     def run_host(self, volumes: Sequence, spacing, origin, direction=IDENTITY, params: Optional[DetectParams] = None,
                  body_out: Optional[Sequence] = None) -> BatchResult:

@@ -171,3 +171,21 @@ def test_c1_scan_to_joint_angles_on_device(cuda_lib):
     pose = logic.estimate_pose()
     assert np.abs(pose.base_matrix - base).max() < MATRIX_TOL
     assert np.abs(pose.joint_angles - ang).max() < ANGLE_TOL
+
+
+def test_batch_detector_poses(cuda_lib):
+    """A batch of scans -> marker tables -> one pose call for the whole batch; equals the per-scan oracle chain."""
+    from mamri_pose_estimation_b200 import phantom
+    from mamri_pose_estimation_b200.detector import BatchDetector
+    from oracle import segmentation as seg
+    specs = [phantom.small_phantom(dims=(96, 80, 48), n_fiducials=6, n_blobs=2, seed=40 + i, spacing=(1.2, 1.2, 2.4)) for i in range(3)]
+    vols = [phantom.generate(p) for p in specs]
+    bd = BatchDetector(specs[0].dims, n_contexts=2)
+    res = bd.run([torch.from_numpy(v).cuda() for v in vols], specs[0].spacing, specs[0].origin, specs[0].direction)
+    poses = bd.estimate_poses(res)
+    assert len(poses) == 3
+    for pose, ph, vol in zip(poses, specs, vols):
+        ora = seg.detect_fiducials(vol, seg.Geometry(ph.spacing, ph.origin, ph.direction))
+        assert pose.n_points == len(ora.fiducials)
+        _compare(pose, ora.ras_points, check_angles=False)
+    bd.close()
