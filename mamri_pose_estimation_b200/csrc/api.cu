@@ -83,6 +83,7 @@ extern "C" const char* mamri_last_error(const mamri_ctx* ctx) { return ctx ? ctx
 extern "C" int mamri_destroy(mamri_ctx* ctx) {
     if (!ctx) return MAMRI_OK;
     DeviceGuard g(ctx->device);
+    cudaFree(ctx->d_occ_raw); cudaFree(ctx->d_occ_dil);
     cudaFree(ctx->d_raw); cudaFree(ctx->d_planes); cudaFree(ctx->d_dil); cudaFree(ctx->d_closed); cudaFree(ctx->d_word_base);
     cudaFree(ctx->d_run_pos); cudaFree(ctx->d_run_len); cudaFree(ctx->d_parent); cudaFree(ctx->d_run_label); cudaFree(ctx->d_label_count); cudaFree(ctx->d_label_slot);
     cudaFree(ctx->d_root_count); cudaFree(ctx->d_scan_runs); cudaFree(ctx->d_scan_rank); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
@@ -155,6 +156,10 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     ALLOC(ctx->d_planes, 3 * ctx->cap_pad_words * 4, "morphology planes");
     ALLOC(ctx->d_dil, ctx->cap_pad_words * 4, "dilated mask");
     ALLOC(ctx->d_closed, ctx->cap_words * 4, "closed mask");
+    ctx->occ_cap = (size_t(max_ny) / 8 + 2) * (size_t(max_nz) / 4 + 2);
+    ALLOC(ctx->d_occ_raw, ctx->occ_cap, "occupancy cells");
+    ALLOC(ctx->d_occ_dil, ctx->occ_cap, "occupancy cells");
+    if ((e = cudaMemset(ctx->d_occ_raw, 0, ctx->occ_cap)) != cudaSuccess) return bail(e, "occupancy cells");
     ALLOC(ctx->d_word_base, ctx->cap_words * 4, "run bases");
     ALLOC(ctx->d_run_pos, size_t(max_runs) * 4, "run positions");
     ALLOC(ctx->d_run_len, size_t(max_runs) * 4, "run lengths");

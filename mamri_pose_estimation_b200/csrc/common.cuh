@@ -70,6 +70,9 @@ struct mamri_ctx {
     uint32_t* d_dil;        // dilation on the r-grown domain, padded layout            [cap_pad_words]
     uint32_t* d_closed;     // closed mask, bit-packed [nz][ny][W]                      [cap_words]
     int raw_nx, raw_ny, raw_nz, raw_r;   // geometry d_raw's zero apron was last cleared for
+    uint8_t* d_occ_raw;     // occupancy cells of the raw mask (set by threshold+pack, cleared by the erosion)  [occ_cap]
+    uint8_t* d_occ_dil;     // per-tile occupancy of the dilated mask (written by the dilation)                 [occ_cap]
+    size_t occ_cap;
     uint32_t* d_word_base;  // runs that start before each word         [cap_words]
     uint32_t* d_run_pos;    // word*32 + bit of each run's first voxel   [max_runs]
     uint32_t* d_run_len;    // voxels in each run                        [max_runs]

@@ -91,11 +91,14 @@ struct RangeTest16 {
     }
 };
 
+// Occupancy cells of the raw mask, in image coordinates (rows x slices; a cell spans all of x).
+constexpr uint32_t OCC_CY = 8, OCC_CZ = 4;
+
 template <int VOXEL_BYTES, typename Test>
 __global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __restrict__ dyn, uint32_t vec_per_row,
                                                             uint32_t ny, Test test, uint32_t* __restrict__ dst,
                                                             uint32_t row_stride, uint32_t slice_stride, uint32_t off,
-                                                            int evict_first) {
+                                                            int evict_first, uint8_t* __restrict__ occ, uint32_t occ_ncy) {
     pdl_wait();
     uint64_t policy = 0;
     if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __res
     const uint4* slice_src = vol + size_t(z) * ny * vec_per_row;
     uint32_t* slice_dst = dst + off + z * slice_stride;
     for (uint32_t y0 = warp * 2; y0 < ny; y0 += n_warps * 2) {
+        uint32_t seen = 0;                                        // any foreground in this pair of rows
         for (uint32_t u0 = 0; u0 < vec_per_row; u0 += 32 * U) {
             uint4 v[2][U];
             bool ok[2][U];
@@ -130,15 +134,18 @@ __global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __res
 #pragma unroll
                     for (int s = 1; s < G; s <<= 1) b |= __shfl_down_sync(0xFFFFFFFFu, b, s) << (E * s);
                     if (ok[r][u] && (lane % G) == 0) slice_dst[(y0 + r) * row_stride + (u0 + u * 32 + lane) / G] = b;
+                    seen |= b;
                 }
         }
+        // occupancy cell (OCC_CY rows x OCC_CZ slices) of the raw mask: lets the closing skip tiles of air unread
+        if (occ && __any_sync(0xFFFFFFFFu, seen != 0u) && lane == 0) occ[(z / OCC_CZ) * occ_ncy + y0 / OCC_CY] = 1;
     }
 }
 
 // General path (ragged nx or unaligned base): one warp per output word, one voxel per lane.
 template <typename T>
 __global__ void __launch_bounds__(256) k_threshold_pack_rows(const DynArgs* __restrict__ dyn, uint32_t nx, uint32_t n_words,
-                                                             T lo, T hi, BitDst dst) {
+                                                             T lo, T hi, BitDst dst, uint8_t* __restrict__ occ, uint32_t occ_ncy) {
     pdl_wait();
     const T* __restrict__ vol = static_cast<const T*>(dyn->vol);
     const unsigned lane = lane_id();
@@ -149,7 +156,10 @@ __global__ void __launch_bounds__(256) k_threshold_pack_rows(const DynArgs* __re
         const uint32_t x = (wi - row * dst.W) * 32 + lane;
         const bool p = x < nx && in_range(vol[size_t(row) * nx + x], lo, hi);
         const uint32_t b = __ballot_sync(0xFFFFFFFFu, p);
-        if (lane == 0) dst.p[dst.index(wi)] = b;
+        if (lane == 0) {
+            dst.p[dst.index(wi)] = b;
+            if (occ && b) { const uint32_t z = row / dst.ny, y = row - z * dst.ny; occ[(z / OCC_CZ) * occ_ncy + y / OCC_CY] = 1; }
+        }
     }
 }
 
@@ -175,6 +185,8 @@ static cudaError_t threshold_pack_t(mamri_ctx* c, int vol_aligned16, int nx, int
     const uint32_t n_words = rows * dst.W;
     const T tlo = cast_bound<T>(lo), thi = cast_bound<T>(hi);
     const bool flat = (nx % 32 == 0) && vol_aligned16;
+    uint8_t* occ = dst.linear ? nullptr : c->d_occ_raw;          // only the closing reads the cells
+    const uint32_t occ_ncy = (uint32_t(ny) + OCC_CY - 1) / OCC_CY;
     if (flat) {
         constexpr int E = 16 / sizeof(T);
         // ~4 waves of 8 resident CTAs per SM; 8 warps per CTA, each warp takes two rows per trip
@@ -195,21 +207,21 @@ static cudaError_t threshold_pack_t(mamri_ctx* c, int vol_aligned16, int nx, int
             const bool lm = (l & 0x8000u) != 0, hm = (h & 0x8000u) != 0, ch = h != 0xFFFFu;
             const uint32_t vpr = uint32_t(nx) / E;
 #define MAMRI_T16(LM, HM, CH)                                                                                         \
-    LK(k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>>, grid, 256, s, true, src, vpr, uint32_t(ny), RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first)
+    LK(k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>>, grid, 256, s, true, src, vpr, uint32_t(ny), RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first, occ, occ_ncy)
             if (!ch) { if (lm) MAMRI_T16(true, true, false); else MAMRI_T16(false, true, false); }
             else if (lm) { if (hm) MAMRI_T16(true, true, true); else MAMRI_T16(true, false, true); }
             else { if (hm) MAMRI_T16(false, true, true); else MAMRI_T16(false, false, true); }
 #undef MAMRI_T16
         } else {
             RangeTest<T> t{tlo, thi};
-            LK(k_threshold_pack_vec<int(sizeof(T)), RangeTest<T>>, grid, 256, s, true, src, uint32_t(nx) / E, uint32_t(ny), t, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first);
+            LK(k_threshold_pack_vec<int(sizeof(T)), RangeTest<T>>, grid, 256, s, true, src, uint32_t(nx) / E, uint32_t(ny), t, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first, occ, occ_ncy);
         }
     } else {
         uint32_t blocks = (n_words + 7) / 8;
         const uint32_t cap = 148 * 8 * 8;
         if (blocks > cap) blocks = cap;
         if (blocks == 0) blocks = 1;
-        LK(k_threshold_pack_rows<T>, blocks, 256, s, true, dyn, uint32_t(nx), n_words, tlo, thi, dst);
+        LK(k_threshold_pack_rows<T>, blocks, 256, s, true, dyn, uint32_t(nx), n_words, tlo, thi, dst, occ, occ_ncy);
     }
     prof_mark(c, s, "threshold_pack");
     return cudaGetLastError();
@@ -481,6 +493,14 @@ struct TileArgs {
     uint32_t TY, TZ;                    // tile: output rows / slices per CTA (TY % SY == 0)
     uint32_t out_w, out_ny;             // TO_IMAGE: row length / rows per slice of the plain mask
     uint32_t tail_mask;
+    // Occupancy of the source: a grid of cells (cy rows x cz slices) over rows [oy, oy + dom_y) and slices
+    // [oz, oz + dom_z) of the padded volume; everything outside that domain is the zero apron.  A tile whose
+    // source cells are all clear writes zeros without reading its source.
+    const uint8_t* occ_in;
+    uint32_t occ_stride, cy, cz, oy, oz, dom_y, dom_z;
+    uint8_t* occ_out;                   // one flag per tile of this pass: any output word non-zero
+    uint8_t* occ_clear;                 // consumed cells, cleared for the context's next scan (first CTA)
+    uint32_t n_clear;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -504,6 +524,39 @@ __global__ void __launch_bounds__(1024) k_morph_tile(const uint32_t* __restrict_
     }
     __syncthreads();
     pdl_wait();                                                    // the source is the previous kernel's output
+    if (a.occ_clear && blockIdx.x == 0 && blockIdx.y == 0)
+        for (uint32_t i = threadIdx.x; i < a.n_clear; i += blockDim.x) a.occ_clear[i] = 0;
+    if (a.occ_in) {
+        // source rows [ys0, ys0 + rows_src) x slices [zs0, zs0 + n_slices), clipped to the occupancy domain
+        const int ya = max(int(ys0) - int(a.oy), 0), yb = min(int(ys0 + rows_src) - int(a.oy), int(a.dom_y));
+        const int za = max(int(zs0) - int(a.oz), 0), zb = min(int(zs0 + n_slices) - int(a.oz), int(a.dom_z));
+        int hit = 0;
+        if (ya < yb && za < zb) {
+            const int c0 = ya / int(a.cy), nyc = (yb - 1) / int(a.cy) - c0 + 1;
+            const int d0 = za / int(a.cz), nzc = (zb - 1) / int(a.cz) - d0 + 1;
+            for (int i = threadIdx.x; i < nyc * nzc; i += blockDim.x)
+                hit |= a.occ_in[(d0 + i / nyc) * a.occ_stride + c0 + i % nyc];
+        }
+        if (!__syncthreads_or(hit)) {                              // air: the output of either pass is zero
+            if (a.occ_out && threadIdx.x == 0) a.occ_out[blockIdx.y * gridDim.x + blockIdx.x] = 0;
+            const uint32_t n_strips = a.TY / SY;
+            if (threadIdx.x >= a.x_cnt * n_strips) return;
+            const uint32_t strip = threadIdx.x / a.x_cnt, xx = threadIdx.x - strip * a.x_cnt;
+            const uint32_t xw = a.x_lo + xx, y0 = y0t + strip * SY;
+            for (uint32_t zo = z0; zo < z1; ++zo)
+#pragma unroll
+                for (int y = 0; y < SY; ++y)
+                    if (y0 + y < y_end) {
+                        if (TO_IMAGE) dst[((zo - a.z_lo) * a.out_ny + (y0 + y - a.y_lo)) * a.out_w + xx] = 0u;
+                        else dst[zo * a.slice + (y0 + y) * a.Wp + xw] = 0u;
+                    }
+            return;
+        }
+    }
+    if (a.occ_out) {
+        if (threadIdx.x == 0) a.occ_out[blockIdx.y * gridDim.x + blockIdx.x] = 0;
+        __syncthreads();                                           // ... before any thread of the CTA raises it
+    }
     if (threadIdx.x == 0) {
         const uint32_t bytes = rows_src * a.Wp * 4u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes * n_slices) : "memory");
@@ -529,6 +582,7 @@ __global__ void __launch_bounds__(1024) k_morph_tile(const uint32_t* __restrict_
     const uint32_t* col = tile + (strip * SY) * a.Wp + xw;         // local row strip*SY = source row y0 - R
 
     uint32_t acc[SY][RING];
+    uint32_t out_any = 0;
 #pragma unroll
     for (int y = 0; y < SY; ++y)
 #pragma unroll
@@ -577,6 +631,7 @@ __global__ void __launch_bounds__(1024) k_morph_tile(const uint32_t* __restrict_
                         dst[((zo - a.z_lo) * a.out_ny + (y0 + y - a.y_lo)) * a.out_w + xx] = v;
                     } else {
                         dst[zo * a.slice + (y0 + y) * a.Wp + xw] = v;
+                        out_any |= v;
                     }
                 }
             }
@@ -588,6 +643,7 @@ __global__ void __launch_bounds__(1024) k_morph_tile(const uint32_t* __restrict_
             acc[y][RING - 1] = NEUTRAL;
         }
     }
+    if (!TO_IMAGE && a.occ_out && out_any) a.occ_out[blockIdx.y * gridDim.x + blockIdx.x] = 1;
 }
 
 // Tile shape for a padded row of Wp words: the largest of a few candidates whose tile + halo fits the
@@ -624,8 +680,22 @@ static cudaError_t closing_tile_r(mamri_ctx* c, int nx, int ny, int nz, uint32_t
     a.out_w = 0; a.out_ny = 0; a.tail_mask = 0xFFFFFFFFu;
     uint32_t threads = ((a.x_cnt * (TY / SY) + 31) / 32) * 32;
     dim3 grid((a.y_cnt + TY - 1) / TY, (a.z_hi - a.z_lo + TZ - 1) / TZ);
+    static const int use_occ = [] { const char* e = getenv("MAMRI_TILE_OCC"); return e ? atoi(e) : 1; }();
+    const uint32_t ncy = (uint32_t(ny) + OCC_CY - 1) / OCC_CY, ncz = (uint32_t(nz) + OCC_CZ - 1) / OCC_CZ;
+    const bool occ = use_occ && size_t(ncy) * ncz <= c->occ_cap && size_t(grid.x) * grid.y <= c->occ_cap;
+    // dilation: source = raw mask, occupancy cells in image coordinates (image row y is padded row y + 2R)
+    a.occ_in = occ ? c->d_occ_raw : nullptr;
+    a.occ_stride = ncy; a.cy = OCC_CY; a.cz = OCC_CZ; a.oy = 2 * R; a.oz = 2 * R; a.dom_y = uint32_t(ny); a.dom_z = uint32_t(nz);
+    a.occ_out = occ ? c->d_occ_dil : nullptr;
+    a.occ_clear = nullptr; a.n_clear = 0;
+    const dim3 dil_grid = grid;
     LKS(k_morph_tile<R, false, false, SY>, grid, threads, smem, s, false, c->d_raw, c->d_dil, a);
     prof_mark(c, s, "dilate");
+    // erosion: source = dilated mask, occupancy = the dilation's per-tile flags (its tiles start at padded row / slice R)
+    a.occ_in = occ ? c->d_occ_dil : nullptr;
+    a.occ_stride = dil_grid.x; a.cy = TY; a.cz = TZ; a.oy = R; a.oz = R; a.dom_y = uint32_t(ny) + 2 * R; a.dom_z = uint32_t(nz) + 2 * R;
+    a.occ_out = nullptr;
+    a.occ_clear = occ ? c->d_occ_raw : nullptr; a.n_clear = ncy * ncz;
     // erosion back on the image domain, straight into the plain [nz][ny][W] mask
     a.x_lo = 1; a.x_cnt = g.W; a.y_lo = 2 * R; a.y_cnt = uint32_t(ny); a.z_lo = 2 * R; a.z_hi = uint32_t(nz) + 2 * R;
     a.out_w = g.W; a.out_ny = uint32_t(ny);

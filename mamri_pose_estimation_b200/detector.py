@@ -85,6 +85,12 @@ class _LazyMarkers:
     def __eq__(self, other):
         return list(self) == list(other)
 
+    def __add__(self, other):
+        return list(self) + list(other)
+
+    def __radd__(self, other):
+        return list(other) + list(self)
+
 
 def _marker_table(c_markers, n: int, first: int = 0) -> np.ndarray:
     """Copies markers [first, first + n) of a ctypes Marker array into a NumPy structured array."""
