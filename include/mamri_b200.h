@@ -166,6 +166,17 @@ MAMRI_API int mamri_pool_detect(mamri_pool* pool, const mamri_volume_desc* desc,
                       const mamri_params* params, uint8_t* const* d_mask_out, uint32_t* const* d_labels_out,
                       uint8_t* const* d_body_out, mamri_summary* summaries, mamri_marker* markers,
                       uint32_t max_markers_per_scan, void* stream);
+/* The same batch in two halves, for callers that have device work to queue behind the scans (the NCCL
+ * gather of the marker tables): _begin enqueues n <= n_contexts scans on `stream` and returns at once;
+ * _end waits and fills summaries / markers as mamri_pool_detect does.  d_tables (optional): device
+ * float64 [n][table_slots][8]; scan i's first table_slots markers are written there as rows of
+ * {label, count, volume_mm3, RAS x, y, z, n_labels, body_label} (unused rows zero) by the scan's last
+ * kernel, so a collective on d_tables can be enqueued on `stream` before _end is called. */
+MAMRI_API int mamri_pool_detect_begin(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* d_volumes, int32_t n,
+                            const mamri_params* params, uint8_t* const* d_mask_out, uint32_t* const* d_labels_out,
+                            uint8_t* const* d_body_out, double* d_tables, uint32_t table_slots, void* stream);
+MAMRI_API int mamri_pool_detect_end(mamri_pool* pool, mamri_summary* summaries, mamri_marker* markers,
+                          uint32_t max_markers_per_scan);
 /* Same from/to HOST buffers (pinned for full PCIe speed): the H2D copy of scan i+1 overlaps the
  * kernels and the body-mask D2H of scan i.  h_body_out is NULL or an array of n host pointers. */
 MAMRI_API int mamri_pool_detect_host(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes,

@@ -285,9 +285,19 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool f
     return MAMRI_OK;
 }
 
+static int detect_async_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* d_volume,
+                             const mamri_params* params, uint8_t* d_mask_out, uint32_t* d_labels_out,
+                             uint8_t* d_body_out, double* d_table, uint32_t table_slots, void* stream);
+
 extern "C" int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* d_volume,
                                   const mamri_params* params, uint8_t* d_mask_out, uint32_t* d_labels_out,
                                   uint8_t* d_body_out, void* stream) {
+    return detect_async_impl(ctx, desc, d_volume, params, d_mask_out, d_labels_out, d_body_out, nullptr, 0, stream);
+}
+
+static int detect_async_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* d_volume,
+                             const mamri_params* params, uint8_t* d_mask_out, uint32_t* d_labels_out,
+                             uint8_t* d_body_out, double* d_table, uint32_t table_slots, void* stream) {
     if (!ctx) return MAMRI_ERR_INVALID_ARG;
     int rc = validate(ctx, desc, params);
     if (rc != MAMRI_OK) return rc;
@@ -307,6 +317,8 @@ extern "C" int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc,
     ctx->h_dyn->mask_out = d_mask_out;
     ctx->h_dyn->labels_out = d_labels_out;
     ctx->h_dyn->body_out = d_body_out;
+    ctx->h_dyn->table_out = d_table;
+    ctx->h_dyn->table_slots = d_table ? table_slots : 0u;
     ctx->h_dyn->gen = ++ctx->gen;            // generation 0 is the cleared state: never used
     if ((ctx->gen & 0x3FFFFFFFu) == 0) ctx->h_dyn->gen = ++ctx->gen;
     CK(prepare_raw_apron(ctx, desc->nx, desc->ny, desc->nz, params->close_radius, s));
@@ -438,6 +450,7 @@ struct mamri_pool {
     bool use_wave_graph;
     bool trace;                      // MAMRI_WAVE_TRACE=1: timing events inside the wave graph, timeline on stderr
     cudaEvent_t* ev_trace;           // [k * 8]
+    int pending_n;                   // scans enqueued by mamri_pool_detect_begin and not yet collected
     char err[512];
 };
 
@@ -630,10 +643,10 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
     return MAMRI_OK;
 }
 
-// Runs scans [first, first + m) as one wave on `cur` and collects them.
-static int pool_wave(mamri_pool* pool, const GraphKey& k, const void* const* volumes, int first, int m,
-                     uint8_t* const* mask_out, uint32_t* const* labels_out, uint8_t* const* body_out,
-                     mamri_summary* summaries, mamri_marker* markers, uint32_t max_m, cudaStream_t cur, int* first_err) {
+// Enqueues scans [first, first + m) as one wave on `cur` (scan first + i on context i).
+static int pool_wave_launch(mamri_pool* pool, const GraphKey& k, const void* const* volumes, int first, int m,
+                            uint8_t* const* mask_out, uint32_t* const* labels_out, uint8_t* const* body_out,
+                            double* tables, uint32_t table_slots, cudaStream_t cur) {
     for (int i = 0; i < m; ++i) {
         mamri_ctx* c = pool->ctx[i];
         DynArgs* d = c->h_dyn;
@@ -641,6 +654,8 @@ static int pool_wave(mamri_pool* pool, const GraphKey& k, const void* const* vol
         d->mask_out = mask_out ? mask_out[first + i] : nullptr;
         d->labels_out = labels_out ? labels_out[first + i] : nullptr;
         d->body_out = body_out ? body_out[first + i] : nullptr;
+        d->table_out = tables ? tables + size_t(first + i) * table_slots * 8 : nullptr;
+        d->table_slots = tables ? table_slots : 0u;
         d->gen = ++c->gen;
         if ((c->gen & 0x3FFFFFFFu) == 0) d->gen = ++c->gen;
         CKP(prepare_raw_apron(c, k.desc.nx, k.desc.ny, k.desc.nz, k.prm.close_radius, cur));
@@ -689,11 +704,41 @@ static int pool_wave(mamri_pool* pool, const GraphKey& k, const void* const* vol
         c->pending = true;
         c->pending_stream = cur;
         c->last_desc = k.desc;
+    }
+    return MAMRI_OK;
+}
+
+// Collects the m scans of the wave in flight into summaries[first ..] / markers.
+static void pool_wave_collect(mamri_pool* pool, int first, int m, mamri_summary* summaries, mamri_marker* markers,
+                              uint32_t max_m, int* first_err) {
+    for (int i = 0; i < m; ++i) {
+        mamri_ctx* c = pool->ctx[i];
         const int rc = mamri_detect_collect(c, &summaries[first + i], markers ? markers + size_t(first + i) * max_m : nullptr, max_m);
         if (rc != MAMRI_OK && *first_err == MAMRI_OK) {
             *first_err = rc;
             snprintf(pool->err, sizeof(pool->err), "scan %d: %s", first + i, mamri_last_error(c));
         }
+    }
+}
+
+// Validates a device-resident batch and fills the key of its wave graph.
+static int wave_key(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* volumes, int n, const mamri_params* params,
+                    uint8_t* const* mask_out, uint32_t* const* labels_out, uint8_t* const* body_out, GraphKey& k) {
+    auto pfail = [&](int code, const char* msg) { snprintf(pool->err, sizeof(pool->err), "%s", msg); return code; };
+    int rc = validate(pool->ctx[0], desc, params);
+    if (rc != MAMRI_OK) return pfail(rc, mamri_last_error(pool->ctx[0]));
+    memset(&k, 0, sizeof(k));
+    k.desc = *desc;
+    k.prm = *params;
+    k.has_mask = mask_out != nullptr; k.has_labels = labels_out != nullptr; k.has_body = body_out != nullptr;
+    k.vol_aligned = 1; k.outs_aligned = 1;
+    for (int i = 0; i < n; ++i) {
+        if (!volumes[i]) return pfail(MAMRI_ERR_INVALID_ARG, "volume pointer is NULL");
+        if (reinterpret_cast<uintptr_t>(volumes[i]) & 15u) k.vol_aligned = 0;
+        if ((mask_out && (reinterpret_cast<uintptr_t>(mask_out[i]) & 15u)) ||
+            (labels_out && (reinterpret_cast<uintptr_t>(labels_out[i]) & 15u)) ||
+            (body_out && (reinterpret_cast<uintptr_t>(body_out[i]) & 15u)))
+            k.outs_aligned = 0;
     }
     return MAMRI_OK;
 }
@@ -713,27 +758,16 @@ static int pool_run(mamri_pool* pool, const mamri_volume_desc* desc, const void*
     int first_err = MAMRI_OK;
     bool profiling = false;
     for (int j = 0; j < K; ++j) profiling = profiling || pool->ctx[j]->profile || pool->ctx[j]->pending;
+    if (pool->pending_n) return pfail(MAMRI_ERR_STATE, "a batch begun with mamri_pool_detect_begin is pending; end it first");
     if (!host && pool->use_wave_graph && !profiling) {
-        int rc = validate(pool->ctx[0], desc, params);
-        if (rc != MAMRI_OK) return pfail(rc, mamri_last_error(pool->ctx[0]));
         GraphKey k;
-        memset(&k, 0, sizeof(k));
-        k.desc = *desc;
-        k.prm = *params;
-        k.has_mask = mask_out != nullptr; k.has_labels = labels_out != nullptr; k.has_body = body_out != nullptr;
-        k.vol_aligned = 1; k.outs_aligned = 1;
-        for (int i = 0; i < n; ++i) {
-            if (!volumes[i]) return pfail(MAMRI_ERR_INVALID_ARG, "volume pointer is NULL");
-            if (reinterpret_cast<uintptr_t>(volumes[i]) & 15u) k.vol_aligned = 0;
-            if ((mask_out && (reinterpret_cast<uintptr_t>(mask_out[i]) & 15u)) ||
-                (labels_out && (reinterpret_cast<uintptr_t>(labels_out[i]) & 15u)) ||
-                (body_out && (reinterpret_cast<uintptr_t>(body_out[i]) & 15u)))
-                k.outs_aligned = 0;
-        }
+        int rc = wave_key(pool, desc, volumes, n, params, mask_out, labels_out, body_out, k);
+        if (rc != MAMRI_OK) return rc;
         for (int first = 0; first < n; first += K) {
             const int m = n - first < K ? n - first : K;
-            rc = pool_wave(pool, k, volumes, first, m, mask_out, labels_out, body_out, summaries, markers, max_m, cur, &first_err);
+            rc = pool_wave_launch(pool, k, volumes, first, m, mask_out, labels_out, body_out, nullptr, 0, cur);
             if (rc != MAMRI_OK) return rc;
+            pool_wave_collect(pool, first, m, summaries, markers, max_m, &first_err);
         }
         return first_err;
     }
@@ -779,6 +813,61 @@ extern "C" int mamri_pool_detect(mamri_pool* pool, const mamri_volume_desc* desc
                                  uint32_t max_markers_per_scan, void* stream) {
     return pool_run(pool, desc, d_volumes, false, n, params, d_mask_out, d_labels_out, d_body_out, summaries, markers,
                     max_markers_per_scan, stream);
+}
+
+extern "C" int mamri_pool_detect_begin(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* d_volumes, int32_t n,
+                                       const mamri_params* params, uint8_t* const* d_mask_out, uint32_t* const* d_labels_out,
+                                       uint8_t* const* d_body_out, double* d_tables, uint32_t table_slots, void* stream) {
+    if (!pool) return MAMRI_ERR_INVALID_ARG;
+    auto pfail = [&](int code, const char* msg) { snprintf(pool->err, sizeof(pool->err), "%s", msg); return code; };
+    if (n < 1 || n > pool->k || !d_volumes) return pfail(MAMRI_ERR_INVALID_ARG, "begin/end handles 1..n_contexts scans per call");
+    if (d_tables && table_slots == 0) return pfail(MAMRI_ERR_INVALID_ARG, "table_slots must be positive");
+    if (pool->pending_n) return pfail(MAMRI_ERR_STATE, "a batch is already pending; end it first");
+    for (int j = 0; j < pool->k; ++j)
+        if (pool->ctx[j]->pending) return pfail(MAMRI_ERR_STATE, "a context of the pool has a detect pending");
+    DeviceGuard g(pool->device);
+    cudaStream_t cur = static_cast<cudaStream_t>(stream);
+    bool profiling = false;
+    for (int j = 0; j < pool->k; ++j) profiling = profiling || pool->ctx[j]->profile;
+    if (pool->use_wave_graph && !profiling) {
+        GraphKey k;
+        int rc = wave_key(pool, desc, d_volumes, n, params, d_mask_out, d_labels_out, d_body_out, k);
+        if (rc != MAMRI_OK) return rc;
+        rc = pool_wave_launch(pool, k, d_volumes, 0, n, d_mask_out, d_labels_out, d_body_out, d_tables, table_slots, cur);
+        if (rc != MAMRI_OK) return rc;
+    } else {                                          // no wave graph: one context and stream per scan
+        if (cudaEventRecord(pool->fork, cur) != cudaSuccess) return pfail(MAMRI_ERR_CUDA, "recording the fork event failed");
+        for (int i = 0; i < n; ++i) {
+            if (cudaStreamWaitEvent(pool->streams[i], pool->fork, 0) != cudaSuccess) return pfail(MAMRI_ERR_CUDA, "forking failed");
+            const int rc = detect_async_impl(pool->ctx[i], desc, d_volumes[i], params, d_mask_out ? d_mask_out[i] : nullptr,
+                                             d_labels_out ? d_labels_out[i] : nullptr, d_body_out ? d_body_out[i] : nullptr,
+                                             d_tables ? d_tables + size_t(i) * table_slots * 8 : nullptr, table_slots, pool->streams[i]);
+            if (rc != MAMRI_OK) {
+                snprintf(pool->err, sizeof(pool->err), "scan %d: %s", i, mamri_last_error(pool->ctx[i]));
+                for (int j = 0; j < i; ++j) { mamri_summary tmp; mamri_detect_collect(pool->ctx[j], &tmp, nullptr, 0); }
+                return rc;
+            }
+            if (cudaEventRecord(pool->join[i], pool->streams[i]) != cudaSuccess ||
+                cudaStreamWaitEvent(cur, pool->join[i], 0) != cudaSuccess)
+                return pfail(MAMRI_ERR_CUDA, "joining the pool's streams failed");
+        }
+    }
+    pool->pending_n = n;
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_pool_detect_end(mamri_pool* pool, mamri_summary* summaries, mamri_marker* markers,
+                                     uint32_t max_markers_per_scan) {
+    if (!pool) return MAMRI_ERR_INVALID_ARG;
+    auto pfail = [&](int code, const char* msg) { snprintf(pool->err, sizeof(pool->err), "%s", msg); return code; };
+    if (!pool->pending_n) return pfail(MAMRI_ERR_STATE, "no batch pending on this pool");
+    if (!summaries || (max_markers_per_scan > 0 && !markers)) return pfail(MAMRI_ERR_INVALID_ARG, "bad result arrays");
+    DeviceGuard g(pool->device);
+    int first_err = MAMRI_OK;
+    const int n = pool->pending_n;
+    pool->pending_n = 0;
+    pool_wave_collect(pool, 0, n, summaries, markers, max_markers_per_scan, &first_err);
+    return first_err;
 }
 
 extern "C" int mamri_pool_detect_host(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes,

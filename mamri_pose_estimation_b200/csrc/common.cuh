@@ -43,6 +43,9 @@ struct DynArgs {
     uint32_t* labels_out;
     uint8_t* body_out;
     uint32_t gen;                    // launch generation (tags the look-back states of the single-pass scans)
+    uint32_t table_slots;            // rows of table_out
+    double* table_out;               // NULL or [table_slots][8]: fixed-size marker table of the scan, written by the
+                                     // finaliser so that a collective can be enqueued right behind the scan
 };
 
 // Everything else a captured pipeline depends on.

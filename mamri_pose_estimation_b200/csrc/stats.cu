@@ -95,14 +95,15 @@ __device__ __forceinline__ unsigned long long sum_sq_upto(long long k) {   // su
 
 __device__ void finalize_block(const uint32_t* cand_label, const uint32_t* label_count, const unsigned long long* sums,
                                uint32_t max_markers, const GeomArgs& g, mamri_marker* markers, mamri_summary* summary,
-                               const DevScalars* sc);
+                               const DevScalars* sc, const DynArgs* dyn);
 
 __global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_len,
                                                  const uint32_t* __restrict__ parent, const uint32_t* __restrict__ run_label,
                                                  const uint32_t* __restrict__ label_slot, int W, int ny,
                                                  unsigned long long* sums, const uint32_t* __restrict__ cand_label,
                                                  const uint32_t* __restrict__ label_count, uint32_t max_markers, GeomArgs g,
-                                                 mamri_marker* __restrict__ markers, mamri_summary* summary, DevScalars* sc) {
+                                                 mamri_marker* __restrict__ markers, mamri_summary* summary, DevScalars* sc,
+                                                 const DynArgs* __restrict__ dyn) {
     __shared__ CtaCache<9, unsigned long long, 16> cache;
     pdl_wait();
     cache.init();
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ ru
     __syncthreads();
     if (!last) return;
     __threadfence();
-    finalize_block(cand_label, label_count, sums, max_markers, g, markers, summary, sc);
+    finalize_block(cand_label, label_count, sums, max_markers, g, markers, summary, sc, dyn);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -245,12 +246,18 @@ __device__ void make_marker(mamri_marker* out, uint32_t label, unsigned long lon
 
 // One CTA (the last of k_moments): orders the kept labels ascending (= GetLabels order), emits their
 // records and the summary.  Sums were accumulated with L2 atomics; read them past L1.
+// Also fills the scan's fixed-size table (DynArgs::table_out, rows of {label, count, volume_mm3, RAS x y z,
+// n_labels, body_label}: the layout distributed.pack_table builds on the host) when the caller asked for it.
 __device__ void finalize_block(const uint32_t* cand_label, const uint32_t* label_count, const unsigned long long* sums,
                                uint32_t max_markers, const GeomArgs& g, mamri_marker* markers, mamri_summary* summary,
-                               const DevScalars* sc) {
+                               const DevScalars* sc, const DynArgs* dyn) {
     const bool ok = sc->status == MAMRI_OK;
     const uint32_t n_all = sc->n_cand;
     const uint32_t n = ok ? (n_all < max_markers ? n_all : max_markers) : 0u;
+    double* __restrict__ table = dyn->table_out;
+    const uint32_t slots = table ? dyn->table_slots : 0u;
+    const unsigned long long bpk = sc->body_packed;
+    const double body_d = (ok && (bpk >> 32) != 0ull) ? double(0xFFFFFFFFu - uint32_t(bpk & 0xFFFFFFFFull)) : 0.0;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t lab = cand_label[i];
         uint32_t rank = 0;
@@ -258,7 +265,15 @@ __device__ void finalize_block(const uint32_t* cand_label, const uint32_t* label
         unsigned long long s9[9];
         for (int k = 0; k < 9; ++k) s9[k] = __ldcg(sums + i * 9u + k);
         make_marker(markers + rank, lab, __ldcg(label_count + lab - 1u), s9, g);
+        if (rank < slots) {
+            const mamri_marker& m = markers[rank];
+            double* row = table + size_t(rank) * 8;
+            row[0] = double(m.label); row[1] = double(m.count); row[2] = m.volume_mm3;
+            row[3] = m.centroid_ras[0]; row[4] = m.centroid_ras[1]; row[5] = m.centroid_ras[2];
+            row[6] = double(sc->n_labels); row[7] = body_d;
+        }
     }
+    for (uint32_t i = n * 8 + threadIdx.x; i < slots * 8; i += blockDim.x) table[i] = 0.0;   // unused rows
     if (threadIdx.x == 0) {
         summary->n_labels = sc->n_labels;
         summary->n_runs = sc->n_runs;
@@ -308,7 +323,7 @@ cudaError_t launch_moments(mamri_ctx* c, const mamri_volume_desc* desc, const ma
     const GeomArgs g = geom_args(desc, prm);
     const int W = (desc->nx + 31) / 32;
     LK(k_moments, MAMRI_RUN_CTAS, 256, s, false, c->d_run_pos, c->d_run_len, c->d_parent, c->d_run_label, c->d_label_slot, W, desc->ny,
-       c->d_cand_sums, c->d_cand_label, c->d_label_count, c->max_markers, g, c->d_markers, c->d_summary, c->d_scalars);
+       c->d_cand_sums, c->d_cand_label, c->d_label_count, c->max_markers, g, c->d_markers, c->d_summary, c->d_scalars, c->d_dyn);
     prof_mark(c, s, "moments_finalize");
     return cudaGetLastError();
 }

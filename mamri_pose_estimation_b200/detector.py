@@ -561,6 +561,49 @@ class BatchDetector:
         masks, labels = self.masks, self.labels
         return BatchResult(n, summ, mk, self.max_markers, lambda i: (masks[i % k], labels[i % k], None))
 
+    def begin(self, volumes: Sequence[torch.Tensor], spacing, origin, direction=IDENTITY,
+              params: Optional[DetectParams] = None, tables: Optional[torch.Tensor] = None) -> None:
+        """First half of `run` for up to n_contexts scans: enqueues them on the current stream and returns at once.
+        `tables` (optional): float64 CUDA tensor [n, slots, 8] that the scans' last kernels fill with the fixed-size
+        marker tables (distributed.pack_table layout), so that the gather of the tables can be queued behind the
+        scans before `end()` makes the host wait."""
+        n, k = len(volumes), self.n_contexts
+        if not 1 <= n <= k:
+            raise ValueError(f"begin/end handles 1..{k} scans per call")
+        v0 = volumes[0]
+        for v in volumes:
+            if not (v.is_cuda and v.is_contiguous() and v.dim() == 3 and v.dtype == v0.dtype and v.shape == v0.shape):
+                raise ValueError("volumes must be contiguous CUDA tensors [nz, ny, nx] of one shape and type")
+        tptr, slots = None, 0
+        if tables is not None:
+            if not (tables.is_cuda and tables.is_contiguous() and tables.dtype == torch.float64 and tables.dim() == 3
+                    and tables.shape[0] >= n and tables.shape[2] == 8):
+                raise ValueError("tables must be a contiguous float64 CUDA tensor [n, slots, 8]")
+            tptr, slots = tables.data_ptr(), int(tables.shape[1])
+        d = _desc(tuple(v0.shape), _TORCH_DTYPES[v0.dtype], spacing, origin, direction)
+        p = (params or DetectParams()).to_c()
+        vp = self._ptrs([v.data_ptr() for v in volumes], n)
+        mp = self._ptrs([self.masks[i % k].data_ptr() for i in range(n)], n) if self.materialise else None
+        lp = self._ptrs([self.labels[i % k].data_ptr() for i in range(n)], n) if self.materialise else None
+        s = torch.cuda.current_stream(self.device)
+        rc = self._lib.mamri_pool_detect_begin(self._pool, C.byref(d), vp, n, C.byref(p), mp, lp, None, tptr, slots,
+                                               s.cuda_stream)
+        _capi.check_pool(rc, self._pool)
+        self._begun = (n, volumes, tables)           # keep the buffers alive until end()
+
+    def end(self) -> BatchResult:
+        """Second half of `run`: waits for the scans begun with `begin` and returns their results."""
+        if getattr(self, "_begun", None) is None:
+            raise RuntimeError("no batch pending: call begin() first")
+        n = self._begun[0]
+        self._begun = None
+        summ = (Summary * n)()
+        mk = (Marker * (n * self.max_markers))()
+        rc = self._lib.mamri_pool_detect_end(self._pool, summ, mk, self.max_markers)
+        _capi.check_pool(rc, self._pool)
+        masks, labels, k = self.masks, self.labels, self.n_contexts
+        return BatchResult(n, summ, mk, self.max_markers, lambda i: (masks[i % k], labels[i % k], None))
+
     def estimate_poses(self, results: BatchResult, apply_correction: bool = False) -> List[PoseResult]:
         """Matching + baseplate registration + IK for every scan of a batch in one device call (one warp per scan)."""
         return self.context(0).pose_estimate(results.ras_points(), apply_correction=apply_correction)

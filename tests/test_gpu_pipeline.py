@@ -275,3 +275,35 @@ def test_size_independent_properties(cuda_lib):
     assert pair.shape[1] == r6.n_labels + 1, "every 6-component lies in exactly one 26-component"
     assert int(det.label_counts(r26.n_labels).astype(np.int64).sum()) == r26.n_foreground == int(r6.mask.sum())
     det.close()
+
+
+def test_begin_end_and_device_tables(cuda_lib):
+    """mamri_pool_detect_begin/_end: same results as the one-call form, and the fixed-size marker tables the scans'
+    last kernels write on the device equal the host-packed ones bit for bit (what the NCCL gather ships)."""
+    from mamri_pose_estimation_b200.detector import BatchDetector
+    from mamri_pose_estimation_b200.distributed import TABLE_SLOTS, pack_table
+    from mamri_pose_estimation_b200 import _capi
+    specs = [phantom.small_phantom(dims=(96, 80, 48), n_fiducials=5 + i, n_blobs=3, seed=60 + i, spacing=(1.2, 1.2, 2.4)) for i in range(3)]
+    vols = [torch.from_numpy(phantom.generate(p)).cuda() for p in specs]
+    sp, org, dr = specs[0].spacing, specs[0].origin, specs[0].direction
+    for env_graph in (True, False):
+        bd = BatchDetector(specs[0].dims, n_contexts=4)
+        if not env_graph:
+            bd.context(0).set_profiling(True)               # forces the per-context (no wave graph) path
+        want = bd.run(vols, sp, org, dr) if env_graph else None
+        tables = torch.full((3, TABLE_SLOTS, 8), -1.0, dtype=torch.float64, device="cuda")
+        bd.begin(vols, sp, org, dr, tables=tables)
+        with pytest.raises(_capi.MamriError):
+            bd.begin(vols, sp, org, dr)                     # one batch at a time
+        got = bd.end()
+        assert np.array_equal(tables.cpu().numpy(), pack_table(got))
+        for i, (ph, v) in enumerate(zip(specs, vols)):
+            ora = seg.detect_fiducials(v.cpu().numpy(), _geom(ph))
+            _assert_equal_detection(got[i], ora)
+            if want is not None:
+                assert [m.label for m in got[i].markers] == [m.label for m in want[i].markers]
+        with pytest.raises(RuntimeError):
+            bd.end()
+        with pytest.raises(ValueError):
+            bd.begin(vols * 2, sp, org, dr)                 # more scans than contexts
+        bd.close()
