@@ -42,12 +42,13 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region, sampled every 5 ms through NVML on a
+    """SM clock + throttle reasons DURING the timed region, sampled every 2 ms through NVML on a
     background thread (nvidia-smi -lms needs longer to start than a short run lasts)."""
 
     def __init__(self, gpu_index: int):
         import threading
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.recording = False               # samples are kept only while the timed region runs
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -68,6 +69,9 @@ class ClockSampler:
         flags = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
                  "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         while not self._stop.is_set():
+            if not self.recording:
+                self._stop.wait(0.001)
+                continue
             try:
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
                 try:
@@ -79,7 +83,10 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.005)
+            self._stop.wait(0.002)
+
+    def begin(self) -> None:
+        self.recording = True
 
     def stop(self) -> dict:
         if self._thread is None:
@@ -176,9 +183,11 @@ def run_native(args):
     # ---------------- device-resident throughput
     for _ in range(max(args.warmup, 3)):
         res = step()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None       # NVML thread, 5 ms period, timed region only
+    sampler = ClockSampler(local) if rank == 0 else None       # NVML thread (set up before the barrier: nvmlInit takes ms)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if sampler:
+        sampler.begin()                                        # 2 ms period, timed region only
     e0.record()
     for _ in range(args.steps):
         res = step()
@@ -335,7 +344,7 @@ def main():
         args.warmup = args.warmup if args.warmup is not None else 1
         run_reference(args)
     else:
-        args.steps = args.steps if args.steps is not None else 20
+        args.steps = args.steps if args.steps is not None else 100     # ~0.1 s timed: enough NVML clock samples
         args.warmup = args.warmup if args.warmup is not None else 3
         run_native(args)
 
