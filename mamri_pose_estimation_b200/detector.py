@@ -636,3 +636,49 @@ class BatchDetector:
         _capi.check_pool(rc, self._pool)
         return BatchResult(n, summ, mk, self.max_markers,
                            lambda i: (None, None, body_out[i] if body_out is not None else None))
+
+
+class BatchPipeline:
+    """A stream of batches through `depth` pools that alternate: batch k+1 is enqueued (on its own stream) before
+    the results of batch k are collected, so the thresholds of one batch overlap the materialise kernels of the
+    previous one and the host-side collection of one batch hides behind the kernels of the next.  Same kernels, same
+    results as `BatchDetector.run`; every batch still has at most n_contexts scans."""
+
+    def __init__(self, dims_xyz: Sequence[int], device: int = 0, n_contexts: int = 8, depth: int = 2, **kw):
+        self.device = int(device)
+        self.pools = [BatchDetector(dims_xyz, device=device, n_contexts=n_contexts, **kw) for _ in range(int(depth))]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.pools]
+        self.n_contexts = n_contexts
+        self.kernel_launches_per_scan = self.pools[0].kernel_launches_per_scan
+        self._in_flight: List[int] = []
+        self._next = 0
+
+    def close(self):
+        for p in self.pools:
+            p.close()
+
+    def submit(self, volumes: Sequence[torch.Tensor], spacing, origin, direction=IDENTITY,
+               params: Optional[DetectParams] = None, tables: Optional[torch.Tensor] = None) -> torch.cuda.Stream:
+        """Enqueues one batch; returns the stream it runs on (queue device work that consumes `tables` there)."""
+        i = self._next
+        if i in self._in_flight:
+            raise RuntimeError("pipeline full: collect a result() first")
+        self._next = (i + 1) % len(self.pools)
+        s = self.streams[i]
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.pools[i].begin(volumes, spacing, origin, direction, params, tables=tables)
+        self._in_flight.append(i)
+        return s
+
+    def result(self) -> BatchResult:
+        """Results of the oldest batch in flight; the current stream then also waits for that batch's stream."""
+        if not self._in_flight:
+            raise RuntimeError("no batch in flight")
+        i = self._in_flight.pop(0)
+        res = self.pools[i].end()
+        torch.cuda.current_stream(self.device).wait_stream(self.streams[i])
+        return res
+
+    def pending(self) -> int:
+        return len(self._in_flight)

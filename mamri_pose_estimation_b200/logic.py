@@ -34,6 +34,21 @@ class ScalarVolumeNode:
     direction: Sequence[float] = IDENTITY
     name: str = "inputVolume"
 
+    @staticmethod
+    def from_ijk_to_ras(array, ijk_to_ras, name: str = "inputVolume") -> "ScalarVolumeNode":
+        """The geometry conversion `PullVolumeFromSlicer` performs (Mamri.py:1306): a MRML volume node carries a 4x4
+        IJK-to-RAS matrix; the SimpleITK image it becomes has spacing = the column norms, direction = the
+        normalised columns and origin = the translation, both turned RAS -> LPS (x and y negated)."""
+        m = np.asarray(ijk_to_ras, dtype=np.float64).reshape(4, 4)
+        spacing = np.linalg.norm(m[:3, :3], axis=0)
+        if not np.all(spacing > 0):
+            raise ValueError("IJK-to-RAS matrix has a zero column")
+        flip = np.diag([-1.0, -1.0, 1.0])
+        direction = flip @ (m[:3, :3] / spacing)
+        origin = flip @ m[:3, 3]
+        return ScalarVolumeNode(array, tuple(float(v) for v in spacing), tuple(float(v) for v in origin),
+                                tuple(float(v) for v in direction.reshape(9)), name)
+
 
 class MarkupsFiducialNode:
     """vtkMRMLMarkupsFiducialNode subset used by the reference (Mamri.py:1313-1317, 1345-1347)."""

@@ -122,3 +122,30 @@ def test_empty_and_full(cuda_lib):
         res, counts = _run_gpu(vol, geom, DetectParams())
         _compare(res, counts, ora, geom, check_axes=False)
         assert res.n_labels == (1 if fill else 0)
+
+
+def test_one_context_across_different_scans(cuda_lib):
+    """State that outlives a scan on a context (zero apron of the padded mask, occupancy cells, look-back
+    generations, captured graphs) must never leak into the next scan: one detector, a sequence of scans that
+    differ in content, geometry, radius and connectivity."""
+    from mamri_pose_estimation_b200.detector import DetectParams, FiducialDetector
+    det = FiducialDetector((128, 96, 64), max_markers=8192)
+    rng = np.random.default_rng(77)
+    seq = []
+    for dims, seed in (((96, 80, 48), 1), ((128, 96, 64), 2), ((64, 48, 40), 3), ((37, 29, 23), 4)):
+        seq.append(phantom.generate(phantom.small_phantom(dims=dims, seed=seed, touch_border=bool(seed % 2))))
+    seq.insert(1, np.zeros_like(seq[0]))                                  # air after a populated scan of the same shape
+    seq.insert(3, np.full((64, 96, 128), 300, dtype=np.uint16))           # completely full
+    seq.append((rng.random((40, 48, 64)) < 0.3).astype(np.uint16) * 100)  # dense noise
+    seq.append(seq[0])
+    geom = seg.Geometry((1.1, 0.9, 1.7), (3.0, -4.0, 5.0), (1, 0, 0, 0, 1, 0, 0, 0, 1))
+    for i, vol in enumerate(seq * 2):
+        radius, conn = (2, 1, 0, 3)[i % 4], (6, 26)[(i // 2) % 2]
+        prm = DetectParams(close_radius=radius, connectivity=conn, min_volume=20.0, max_volume=600.0)
+        ora = seg.detect_fiducials(vol, geom, close_radius=radius, connectivity=conn, min_vol=20.0, max_vol=600.0)
+        res = det.detect(torch.from_numpy(vol).cuda(), spacing=geom.spacing, origin=geom.origin, direction=geom.direction,
+                         params=prm, want_mask=True, want_labels=True, want_body=True)
+        assert np.array_equal(res.mask.cpu().numpy(), ora.closed), f"scan {i}: closed mask differs"
+        assert np.array_equal(res.labels.cpu().numpy().view(np.uint32), ora.labels), f"scan {i}: labels differ"
+        assert [m.label for m in res.markers] == [f["id"] for f in ora.fiducials] and res.body_label == ora.body_label
+    det.close()

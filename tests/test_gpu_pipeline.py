@@ -307,3 +307,31 @@ def test_begin_end_and_device_tables(cuda_lib):
         with pytest.raises(ValueError):
             bd.begin(vols * 2, sp, org, dr)                 # more scans than contexts
         bd.close()
+
+
+def test_batch_pipeline_matches_single_batches(cuda_lib):
+    """BatchPipeline: batches enqueued ahead of the collection of the previous one give the results of plain runs."""
+    from mamri_pose_estimation_b200.detector import BatchPipeline
+    specs = [[phantom.small_phantom(dims=(96, 80, 48), n_fiducials=4 + i, n_blobs=2, seed=80 + 10 * b + i, spacing=(1.2, 1.2, 2.4))
+              for i in range(3)] for b in range(4)]
+    vols = [[torch.from_numpy(phantom.generate(p)).cuda() for p in batch] for batch in specs]
+    sp, org, dr = specs[0][0].spacing, specs[0][0].origin, specs[0][0].direction
+    bp = BatchPipeline(specs[0][0].dims, n_contexts=3, depth=2)
+    got = []
+    bp.submit(vols[0], sp, org, dr)
+    for b in range(4):
+        if b + 1 < 4:
+            bp.submit(vols[b + 1], sp, org, dr)
+        got.append(bp.result())
+    with pytest.raises(RuntimeError):
+        bp.result()
+    for b in range(4):
+        for i in range(3):
+            ora = seg.detect_fiducials(vols[b][i].cpu().numpy(), _geom(specs[b][i]))
+            _assert_equal_detection(got[b][i], ora)
+    bp.submit(vols[0], sp, org, dr)
+    bp.submit(vols[1], sp, org, dr)
+    with pytest.raises(RuntimeError):
+        bp.submit(vols[2], sp, org, dr)                    # both pools busy
+    bp.result(); bp.result()
+    bp.close()

@@ -58,3 +58,28 @@ def test_pack_table_layout():
     t = mdist.pack_table([r, r])
     assert t.shape == (2, mdist.TABLE_SLOTS, mdist.TABLE_FIELDS)
     assert t[1, 0].tolist() == [3, 100, 51.2, 1.0, 2.0, 3.0, 7, 1] and not t[:, 1:].any()
+
+
+def test_ijk_to_ras_geometry_conversion():
+    """ScalarVolumeNode.from_ijk_to_ras == the RAS->LPS conversion of PullVolumeFromSlicer (Mamri.py:1306): the
+    physical point of every index, computed the ITK way from (spacing, origin, direction), is the LPS image of the
+    RAS point the MRML matrix gives."""
+    import torch  # noqa: F401  (logic imports torch)
+    from mamri_pose_estimation_b200.logic import ScalarVolumeNode
+    from oracle import segmentation as seg
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-0.4, 0.4)
+    rot = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    m = np.eye(4)
+    m[:3, :3] = (rot @ np.diag([-1.0, -1.0, 1.0])) * np.array([0.8, 0.9, 1.6])     # an axial MR volume, LPS-ish axes
+    m[:3, 3] = [110.0, 95.0, -60.0]
+    node = ScalarVolumeNode.from_ijk_to_ras(np.zeros((4, 5, 6), np.uint16), m)
+    assert np.allclose(node.spacing, [0.8, 0.9, 1.6])
+    geom = seg.Geometry(node.spacing, node.origin, node.direction)
+    idx = rng.integers(0, 50, (20, 3)).astype(np.float64)
+    ras = idx @ m[:3, :3].T + m[:3, 3]
+    lps = np.array([geom.index_to_physical(i) for i in idx]) if hasattr(geom, "index_to_physical") else \
+        np.array(node.origin) + (idx * np.array(node.spacing)) @ np.array(node.direction).reshape(3, 3).T
+    assert np.allclose(lps, ras * np.array([-1.0, -1.0, 1.0]), atol=1e-9)
+    d = np.array(node.direction).reshape(3, 3)
+    assert np.allclose(d @ d.T, np.eye(3), atol=1e-12)
