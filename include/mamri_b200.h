@@ -293,6 +293,29 @@ MAMRI_API int mamri_pose_estimate(mamri_ctx* ctx, const mamri_robot* robot, cons
                         const int32_t* h_counts, int32_t n_scans, int32_t max_points, mamri_pose* h_poses,
                         void* stream);
 
+/* ---- robot-vs-body collision sampling: stands in for Mamri.py:1555-1575 ------------------- */
+/* _check_collision runs vtkCollisionDetectionFilter between each link's collision mesh and the body
+ * mesh, one joint configuration per call (per configuration of a planned path, :976-982; inside the
+ * trajectory IK's error function, :1541).  Here a batch of configurations is tested on the device:
+ * every sample point of every link (float32 [total][3], link-local coordinates, e.g. the vertices of
+ * the *_collision.STL meshes; h_part_offsets[n_links + 1] delimits each link's points, empty ranges
+ * for links that are not checked) goes through the link's forward-kinematics transform
+ * (base_matrix = baseplate -> world, row-major 4x4) and the RAS -> voxel affine, and hits if it lands
+ * on a non-zero voxel of d_body_mask (uint8 [nz*ny*nx]; outside the volume = free).  Points inside the
+ * body instead of surface intersection: decisions agree with the mesh test on clear and on colliding
+ * poses, not on grazing contacts. */
+typedef struct mamri_collision_result {
+    uint32_t link_mask;        /* bit l set: link l has a sample point inside the body */
+    uint32_t n_points_inside;
+    int32_t  first_link;       /* lowest colliding link (the reference returns at the first contact), -1 = clear */
+    int32_t  reserved;
+} mamri_collision_result;
+MAMRI_API int mamri_collision_check(mamri_ctx* ctx, const mamri_robot* robot, const double base_matrix[16],
+                          const double* h_joint_angles /* [n_configs][MAMRI_MAX_CHAIN] rad */, int32_t n_configs,
+                          const float* d_part_points, const int32_t* h_part_offsets, const uint8_t* d_body_mask,
+                          const mamri_volume_desc* mask_desc, const double ras_to_index[12],
+                          mamri_collision_result* h_results, void* stream);
+
 /* ---- synthetic phantoms (benchmark utility, not part of the reference path) -------------- */
 /* Paints `n_ellipsoids` (7 floats each: cx,cy,cz,ax,ay,az,intensity; index units; in order)
  * into a zeroed uint16 volume, then adds Rician noise (Philox4x32-10; see phantom.py). */

@@ -71,6 +71,10 @@ class Pose(C.Structure):
                 ("ik_rms_error", C.c_double)]
 
 
+class CollisionResult(C.Structure):
+    _fields_ = [("link_mask", C.c_uint32), ("n_points_inside", C.c_uint32), ("first_link", C.c_int32), ("reserved", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/mamri_b200.h declares
 SIGNATURES = {
     "mamri_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32]),
@@ -110,6 +114,9 @@ SIGNATURES = {
     "mamri_default_robot": (None, [C.POINTER(Robot)]),
     "mamri_pose_estimate": (C.c_int, [C.c_void_p, C.POINTER(Robot), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.POINTER(Pose), C.c_void_p]),
+    "mamri_collision_check": (C.c_int, [C.c_void_p, C.POINTER(Robot), C.POINTER(C.c_double), C.c_void_p, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.POINTER(VolumeDesc), C.POINTER(C.c_double),
+                                        C.POINTER(CollisionResult), C.c_void_p]),
     "mamri_phantom_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32,
                                          C.c_float, C.c_uint64, C.c_uint32, C.c_void_p]),
 }

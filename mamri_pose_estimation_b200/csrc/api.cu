@@ -1015,6 +1015,48 @@ extern "C" int mamri_pose_estimate(mamri_ctx* ctx, const mamri_robot* robot, con
     return MAMRI_OK;
 }
 
+extern "C" int mamri_collision_check(mamri_ctx* ctx, const mamri_robot* robot, const double base_matrix[16],
+                                     const double* h_joint_angles, int32_t n_configs, const float* d_part_points,
+                                     const int32_t* h_part_offsets, const uint8_t* d_body_mask,
+                                     const mamri_volume_desc* mask_desc, const double ras_to_index[12],
+                                     mamri_collision_result* h_results, void* stream) {
+    if (!ctx) return MAMRI_ERR_INVALID_ARG;
+    if (!robot || !base_matrix || n_configs < 0 || !h_part_offsets || !d_body_mask || !mask_desc || !ras_to_index ||
+        (n_configs > 0 && (!h_joint_angles || !h_results)))
+        return fail(ctx, MAMRI_ERR_INVALID_ARG, "bad collision arguments");
+    if (robot->n_links < 1 || robot->n_links > MAMRI_MAX_LINKS) return fail(ctx, MAMRI_ERR_INVALID_ARG, "robot: n_links out of range");
+    for (int l = 0; l < robot->n_links; ++l) {
+        if (robot->links[l].parent >= l) return fail(ctx, MAMRI_ERR_INVALID_ARG, "robot: a link's parent must precede it");
+        if (h_part_offsets[l + 1] < h_part_offsets[l] || h_part_offsets[l] < 0)
+            return fail(ctx, MAMRI_ERR_INVALID_ARG, "part offsets must be non-negative and non-decreasing");
+    }
+    if (h_part_offsets[robot->n_links] > 0 && !d_part_points) return fail(ctx, MAMRI_ERR_INVALID_ARG, "part points are NULL");
+    if (mask_desc->nx <= 0 || mask_desc->ny <= 0 || mask_desc->nz <= 0) return fail(ctx, MAMRI_ERR_INVALID_ARG, "mask dimensions must be positive");
+    if (n_configs == 0) return MAMRI_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t off_ang = (sizeof(mamri_robot) + 255) & ~size_t(255);
+    const size_t ang_bytes = size_t(n_configs) * MAMRI_MAX_CHAIN * sizeof(double);
+    const size_t off_res = (off_ang + ang_bytes + 255) & ~size_t(255);
+    const size_t total = off_res + size_t(n_configs) * sizeof(mamri_collision_result);
+    if (ctx->pose_buf_bytes < total) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(ctx->d_pose_buf);
+        ctx->d_pose_buf = nullptr; ctx->pose_buf_bytes = 0;
+        CK(cudaMalloc(&ctx->d_pose_buf, total));
+        ctx->pose_buf_bytes = total;
+    }
+    char* base = static_cast<char*>(ctx->d_pose_buf);
+    CK(cudaMemcpyAsync(base, robot, sizeof(mamri_robot), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(base + off_ang, h_joint_angles, ang_bytes, cudaMemcpyHostToDevice, s));
+    CK(launch_collision(reinterpret_cast<const mamri_robot*>(base), base_matrix, ras_to_index, mask_desc->nx, mask_desc->ny,
+                        mask_desc->nz, h_part_offsets, robot->n_links, reinterpret_cast<const double*>(base + off_ang), n_configs,
+                        d_part_points, d_body_mask, reinterpret_cast<mamri_collision_result*>(base + off_res), s));
+    CK(cudaMemcpyAsync(h_results, base + off_res, size_t(n_configs) * sizeof(mamri_collision_result), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MAMRI_OK;
+}
+
 extern "C" int mamri_phantom_generate(uint16_t* d_volume, int32_t nx, int32_t ny, int32_t nz, const float* h_ellipsoids,
                                       int32_t n_ellipsoids, float sigma, uint64_t seed, uint32_t scan_index, void* stream) {
     if (!d_volume || nx <= 0 || ny <= 0 || nz <= 0 || n_ellipsoids < 0 || (n_ellipsoids && !h_ellipsoids)) {

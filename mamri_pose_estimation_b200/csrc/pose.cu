@@ -356,6 +356,87 @@ __global__ void __launch_bounds__(32) k_pose(const mamri_robot* __restrict__ rob
     solve_ik(P, out);
 }
 
+// ------------------------------------------------------------------------------------------------
+// robot-vs-body collision sampling: stands in for MamriLogic._check_collision
+// (Mamri/Mamri.py:1555-1575), which runs vtkCollisionDetectionFilter between every link's collision mesh and
+// the body mesh for one joint configuration at a time (called per configuration of a path, :976-982, and inside
+// the trajectory IK's error function, :1541).  Here: a batch of configurations, one CTA each; every sample point
+// of every link (link-local coordinates, e.g. the vertices of the *_collision.STL meshes) goes through the
+// link's forward-kinematics transform and the RAS -> voxel affine, and hits if it lands on a non-zero voxel of
+// the body labelmap.  A different geometric predicate than VTK's triangle test (points inside the volume, not
+// surface intersection): decisions agree on clear / colliding poses, not on grazing contacts.
+// ------------------------------------------------------------------------------------------------
+struct CollisionArgs {
+    double base[16];
+    double m[12];              // RAS mm -> voxel index, row-major 3x4
+    int nx, ny, nz;
+    int n_links;
+    int offsets[MAMRI_MAX_LINKS + 1];
+};
+
+__global__ void __launch_bounds__(256) k_collision(const mamri_robot* __restrict__ robot, CollisionArgs a,
+                                                   const double* __restrict__ angles, const float* __restrict__ pts,
+                                                   const uint8_t* __restrict__ mask, mamri_collision_result* __restrict__ out) {
+    __shared__ M34 world[MAMRI_MAX_LINKS];
+    __shared__ unsigned s_mask, s_count;
+    __shared__ int s_first;
+    const int cfg = blockIdx.x;
+    if (threadIdx.x == 0) {
+        M34 base;
+        for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) base.r[3 * i + j] = a.base[4 * i + j]; base.t[i] = a.base[4 * i + 3]; }
+        for (int l = 0; l < robot->n_links; ++l) {
+            const mamri_link& L = robot->links[l];
+            const double ang = (L.chain_index >= 0 && L.chain_index < MAMRI_MAX_CHAIN) ? angles[size_t(cfg) * MAMRI_MAX_CHAIN + L.chain_index] : 0.0;
+            world[l] = mul(L.parent >= 0 ? world[L.parent] : base, local_tf(L, ang));
+        }
+        s_mask = 0u; s_count = 0u; s_first = MAMRI_MAX_LINKS;
+    }
+    __syncthreads();
+    unsigned hits = 0, lmask = 0;
+    int first = MAMRI_MAX_LINKS;
+    for (int l = 0; l < a.n_links; ++l) {
+        const M34& T = world[l];
+        for (int i = a.offsets[l] + int(threadIdx.x); i < a.offsets[l + 1]; i += blockDim.x) {
+            const double lx = pts[3 * size_t(i)], ly = pts[3 * size_t(i) + 1], lz = pts[3 * size_t(i) + 2];
+            double w[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                w[k] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.r[3 * k], lx), __dmul_rn(T.r[3 * k + 1], ly)), __dmul_rn(T.r[3 * k + 2], lz)), T.t[k]);
+            long long idx[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                idx[k] = llrint(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a.m[4 * k], w[0]), __dmul_rn(a.m[4 * k + 1], w[1])), __dmul_rn(a.m[4 * k + 2], w[2])), a.m[4 * k + 3]));
+            if (idx[0] >= 0 && idx[0] < a.nx && idx[1] >= 0 && idx[1] < a.ny && idx[2] >= 0 && idx[2] < a.nz &&
+                mask[(size_t(idx[2]) * a.ny + idx[1]) * a.nx + idx[0]] != 0) {
+                ++hits;
+                lmask |= 1u << l;
+                if (l < first) first = l;
+            }
+        }
+    }
+    if (hits) { atomicAdd(&s_count, hits); atomicOr(&s_mask, lmask); atomicMin(&s_first, first); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out[cfg].link_mask = s_mask;
+        out[cfg].n_points_inside = s_count;
+        out[cfg].first_link = s_mask ? s_first : -1;
+        out[cfg].reserved = 0;
+    }
+}
+
+cudaError_t launch_collision(const mamri_robot* d_robot, const double base[16], const double m[12], int nx, int ny, int nz,
+                             const int* offsets, int n_links, const double* d_angles, int n_configs, const float* d_points,
+                             const uint8_t* d_mask, mamri_collision_result* d_out, cudaStream_t s) {
+    if (n_configs <= 0) return cudaSuccess;
+    CollisionArgs a;
+    for (int i = 0; i < 16; ++i) a.base[i] = base[i];
+    for (int i = 0; i < 12; ++i) a.m[i] = m[i];
+    a.nx = nx; a.ny = ny; a.nz = nz; a.n_links = n_links;
+    for (int i = 0; i <= MAMRI_MAX_LINKS; ++i) a.offsets[i] = i <= n_links ? offsets[i] : offsets[n_links];
+    k_collision<<<n_configs, 256, 0, s>>>(d_robot, a, d_angles, d_points, d_mask, d_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pose(const mamri_robot* d_robot, const double* d_points, const int32_t* d_counts, int n_scans,
                         int max_points, mamri_pose* d_poses, cudaStream_t s) {
     if (n_scans <= 0) return cudaSuccess;

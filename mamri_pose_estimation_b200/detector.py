@@ -363,6 +363,52 @@ class FiducialDetector:
             out.append(PoseResult.from_c(poses[i]))
         return out
 
+    # ------------------------------------------------------------------ robot-vs-body collision sampling
+    def collision_check(self, part_points: dict, joint_angles, base_matrix, body_mask: torch.Tensor, ras_to_index,
+                        robot: Optional[Robot] = None, stream: Optional[torch.cuda.Stream] = None) -> List[dict]:
+        """Stands in for MamriLogic._check_collision (Mamri.py:1555-1575) for a batch of joint configurations.
+        `part_points`: link name -> float32 [n,3] sample points in the link's own frame (e.g. the vertices of its
+        *_collision.STL); `joint_angles`: [n_configs, 6] rad; `body_mask`: uint8 CUDA tensor [nz,ny,nx];
+        `ras_to_index`: 3x4 affine RAS mm -> voxel index.  Returns per configuration
+        {"collision": bool, "links": [names], "first_link": name or None, "n_points_inside": int}."""
+        if not (body_mask.is_cuda and body_mask.is_contiguous() and body_mask.dtype == torch.uint8 and body_mask.dim() == 3):
+            raise ValueError("body_mask must be a contiguous uint8 CUDA tensor [nz, ny, nx]")
+        if len(joint_angles) == 0:
+            return []
+        robot = robot if robot is not None else self.default_robot()
+        names = ROBOT_LINK_NAMES[:robot.n_links]
+        unknown = set(part_points) - set(names)
+        if unknown:
+            raise ValueError(f"unknown links: {sorted(unknown)}")
+        offs = (C.c_int32 * (robot.n_links + 1))()
+        chunks = []
+        for l, nm in enumerate(names):
+            p = np.asarray(part_points.get(nm, np.zeros((0, 3))), dtype=np.float32).reshape(-1, 3)
+            chunks.append(p)
+            offs[l + 1] = offs[l] + p.shape[0]
+        allp = np.ascontiguousarray(np.concatenate(chunks)) if offs[robot.n_links] else np.zeros((1, 3), np.float32)
+        pts_d = torch.from_numpy(allp).to(body_mask.device)
+        ang = np.zeros((len(joint_angles), _capi.MAX_CHAIN), dtype=np.float64)
+        ja = np.asarray(joint_angles, dtype=np.float64).reshape(len(joint_angles), -1)
+        ang[:, :ja.shape[1]] = ja
+        n = ang.shape[0]
+        res = (_capi.CollisionResult * max(n, 1))()
+        base = (C.c_double * 16)(*[float(v) for v in np.asarray(base_matrix, dtype=np.float64).reshape(16)])
+        m2i = (C.c_double * 12)(*[float(v) for v in np.asarray(ras_to_index, dtype=np.float64).reshape(12)])
+        d = _desc(tuple(body_mask.shape), "uint8", (1, 1, 1), (0, 0, 0), IDENTITY)
+        s = stream or torch.cuda.current_stream(body_mask.device)
+        rc = self._lib.mamri_collision_check(self._ctx, C.byref(robot), base, ang.ctypes.data, n, pts_d.data_ptr(), offs,
+                                             body_mask.data_ptr(), C.byref(d), m2i, res, s.cuda_stream)
+        check(rc, self._ctx)
+        out = []
+        for i in range(n):
+            r = res[i]
+            links = [names[l] for l in range(robot.n_links) if (r.link_mask >> l) & 1]
+            out.append({"collision": bool(r.link_mask), "links": links,
+                        "first_link": names[r.first_link] if r.first_link >= 0 else None,
+                        "n_points_inside": int(r.n_points_inside)})
+        return out
+
     # ------------------------------------------------------------------ skin-surface candidates
     def body_surface(self, body_mask: Optional[torch.Tensor] = None, shape_zyx=None, spacing=(1.0, 1.0, 1.0),
                      origin=(0.0, 0.0, 0.0), direction=IDENTITY, stream: Optional[torch.cuda.Stream] = None):

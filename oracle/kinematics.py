@@ -290,3 +290,33 @@ def find_entry_point(points: np.ndarray, normals: np.ndarray, target: Sequence[f
     cand = np.flatnonzero(ok)
     best = cand[np.argmin(dist[cand])]
     return int(best), float(dist[best])
+
+
+# ------------------------------ robot-vs-body collision sampling ------------------------------
+def check_collision_voxel(angles_rad: Sequence[float], base: np.ndarray, part_points: Dict[str, np.ndarray],
+                          body_mask: np.ndarray, ras_to_index: np.ndarray):
+    """Voxel-sampling stand-in for MamriLogic._check_collision (Mamri.py:1555-1575), the definition
+    ``pose.cu:k_collision`` implements: every sample point of every link (link-local float32 coordinates) goes
+    through the link's world transform (_get_world_transform_for_joint, :1486-1505) and the RAS -> voxel affine
+    (nearest voxel, ties to even) and hits if the body labelmap ``body_mask[z, y, x]`` is non-zero there; outside
+    the volume is free.  Returns (colliding link names in robot order, number of points inside)."""
+    vals = dict(zip(ARTICULATED_CHAIN, angles_rad))
+    m = np.asarray(ras_to_index, dtype=np.float64).reshape(3, 4)
+    nz, ny, nx = body_mask.shape
+    links, inside = [], 0
+    for j in ROBOT:
+        p = part_points.get(j["name"])
+        if p is None or len(p) == 0:
+            continue
+        tf = world_transform_for_joint(vals, j["name"], base)
+        loc = np.asarray(p, dtype=np.float32).astype(np.float64).reshape(-1, 3)
+        w = np.stack([((tf[k, 0] * loc[:, 0] + tf[k, 1] * loc[:, 1]) + tf[k, 2] * loc[:, 2]) + tf[k, 3] for k in range(3)], axis=1)
+        idx = np.stack([np.rint(((m[k, 0] * w[:, 0] + m[k, 1] * w[:, 1]) + m[k, 2] * w[:, 2]) + m[k, 3]) for k in range(3)], axis=1).astype(np.int64)
+        ok = (idx[:, 0] >= 0) & (idx[:, 0] < nx) & (idx[:, 1] >= 0) & (idx[:, 1] < ny) & (idx[:, 2] >= 0) & (idx[:, 2] < nz)
+        hit = np.zeros(len(loc), dtype=bool)
+        ii = idx[ok]
+        hit[ok] = body_mask[ii[:, 2], ii[:, 1], ii[:, 0]] != 0
+        if hit.any():
+            links.append(j["name"])
+            inside += int(hit.sum())
+    return links, inside

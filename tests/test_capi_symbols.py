@@ -35,14 +35,14 @@ def test_ctypes_structs_match_header_sizes(cuda_lib, tmp_path):
     import subprocess
     from mamri_pose_estimation_b200 import _capi
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "mamri_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "mamri_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(mamri_volume_desc),sizeof(mamri_params),sizeof(mamri_marker),sizeof(mamri_summary),'
-                   'sizeof(mamri_entry_result),sizeof(mamri_link),sizeof(mamri_robot),sizeof(mamri_pose));return 0;}\n')
+                   'sizeof(mamri_entry_result),sizeof(mamri_link),sizeof(mamri_robot),sizeof(mamri_pose),sizeof(mamri_collision_result));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     mirrors = [_capi.VolumeDesc, _capi.Params, _capi.Marker, _capi.Summary, _capi.EntryResult, _capi.Link, _capi.Robot,
-               _capi.Pose]
+               _capi.Pose, _capi.CollisionResult]
     assert sizes == [C.sizeof(m) for m in mirrors]
     p = _capi.Params()
     cuda_lib.mamri_default_params(C.byref(p))

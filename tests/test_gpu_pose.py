@@ -189,3 +189,40 @@ def test_batch_detector_poses(cuda_lib):
         assert pose.n_points == len(ora.fiducials)
         _compare(pose, ora.ras_points, check_angles=False)
     bd.close()
+
+
+def test_collision_sampling_matches_the_oracle(cuda_lib):
+    """mamri_collision_check (stand-in for _check_collision, Mamri.py:1555-1575): per configuration the set of links
+    with a sample point inside the body labelmap and the number of such points equal the NumPy restatement."""
+    from mamri_pose_estimation_b200 import phantom
+    from mamri_pose_estimation_b200.detector import FiducialDetector
+    rng = np.random.default_rng(99)
+    dims = (160, 144, 96)                                          # x, y, z
+    sp = np.array([2.5, 2.5, 4.0])
+    org = -0.5 * sp * (np.array(dims) - 1)                         # volume centred on the LPS origin
+    z, y, x = np.meshgrid(np.arange(dims[2]), np.arange(dims[1]), np.arange(dims[0]), indexing="ij")
+    body = ((((x - 79.5) / 44.0) ** 2 + ((y - 40.0) / 26.0) ** 2 + ((z - 47.5) / 36.0) ** 2) <= 1.0).astype(np.uint8)
+    m = np.array([[-1 / sp[0], 0, 0, -org[0] / sp[0]], [0, -1 / sp[1], 0, -org[1] / sp[1]], [0, 0, 1 / sp[2], -org[2] / sp[2]]])
+    base = phantom.robot_base_matrix()
+    base[:3, 3] = [20.0, -170.0, -60.0]                            # baseplate on the table under the body
+    parts = {}                                                     # boxes around each link's axis as stand-ins for the STL vertices
+    for name, (lo, hi) in {"Joint1": (0, 30), "Joint2": (0, 150), "Joint3": (0, 10), "Joint4": (0, 155), "Joint5": (0, 13),
+                           "Joint6": (0, 60)}.items():
+        n = 400
+        parts[name] = np.stack([rng.uniform(-15, 15, n), rng.uniform(-15, 15, n), rng.uniform(lo, hi, n)], axis=1).astype(np.float32)
+    configs = np.radians(rng.uniform(-100, 100, (40, 6)))
+    configs[0] = 0.0                                               # arm straight up: through the body
+    det = FiducialDetector((32, 32, 32))
+    got = det.collision_check(parts, configs, base, torch.from_numpy(body).cuda(), m)
+    n_hit = 0
+    for cfg, g in zip(configs, got):
+        links, inside = kin.check_collision_voxel(cfg, base, parts, body, m)
+        assert g["links"] == links and g["n_points_inside"] == inside
+        assert g["collision"] == bool(links) and g["first_link"] == (links[0] if links else None)
+        n_hit += bool(links)
+    assert 0 < n_hit < len(configs), "the test poses should include clear and colliding ones"
+    # no points / no configurations
+    assert det.collision_check({}, configs[:2], base, torch.from_numpy(body).cuda(), m) == [
+        {"collision": False, "links": [], "first_link": None, "n_points_inside": 0}] * 2
+    assert det.collision_check(parts, np.zeros((0, 6)), base, torch.from_numpy(body).cuda(), m) == []
+    det.close()
