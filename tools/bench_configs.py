@@ -179,5 +179,30 @@ if rank == 0 and want("pose"):
          ik_iterations_mean=float(np.mean([p.ik_iterations for p in out[0]])), note="host tables in, poses out (H2D + kernel + D2H + sync + Python unpacking)")
     det.close()
 
+# ---- CPU baselines of SURVEY 8d on the box's host cores: (B1) the NumPy/SciPy oracle, single-threaded, and
+# (B2) the C/OpenMP restatement on all host threads -- both on config C1 (B2 also on C2); restatements, not SimpleITK
+if rank == 0 and want("cpu"):
+    import time
+    from oracle import c_oracle
+    from oracle import segmentation as seg
+    ph = phantom.config_c1()
+    vol = phantom.generate(ph)
+    geom = seg.Geometry(ph.spacing, ph.origin, ph.direction)
+    t0 = time.perf_counter()
+    ora = seg.detect_fiducials(vol, geom)
+    dt = time.perf_counter() - t0
+    emit(config="cpu/B1", what="oracle/segmentation.py (NumPy + scipy.ndimage), one thread", dims=list(ph.dims), seconds=dt,
+         gvoxel_per_s=vol.size / dt / 1e9, n_labels=ora.n_labels, n_markers=len(ora.fiducials))
+    c_oracle.use_all_cores()
+    for nm, p in (("C1", ph), ("C2", phantom.config_c2())):
+        v = vol if nm == "C1" else phantom.generate(p)
+        c_oracle.run_pipeline(v)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            c_oracle.run_pipeline(v)
+        dt = (time.perf_counter() - t0) / 3
+        emit(config="cpu/B2", what="oracle/c (C + OpenMP), all host threads", scan=nm, dims=list(p.dims), threads=c_oracle.num_threads(),
+             cpu_count=os.cpu_count(), seconds=dt, gvoxel_per_s=v.size / dt / 1e9)
+
 if world > 1:
     dist.destroy_process_group()
