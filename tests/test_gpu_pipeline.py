@@ -335,3 +335,36 @@ def test_batch_pipeline_matches_single_batches(cuda_lib):
         bp.submit(vols[2], sp, org, dr)                    # both pools busy
     bp.result(); bp.result()
     bp.close()
+
+
+def test_c3_batch_full_size(cuda_lib):
+    """Config C3 at full size (512x512x256, Rician sigma 15 -> thousands of noise voxels above the threshold before
+    closing), 12 of the 64 scans through the pipelined pools: every scan against the C oracle (labels, markers, body),
+    mask + label volumes bit-exact for the scans whose ring buffers are still live, and the pose stage on the batch."""
+    from mamri_pose_estimation_b200.detector import BatchPipeline, generate_phantom_cuda
+    specs = [phantom.config_c3(scan_index=i) for i in range(12)]
+    vols = [generate_phantom_cuda(p) for p in specs]
+    sp, org, dr = specs[0].spacing, specs[0].origin, specs[0].direction
+    bp = BatchPipeline(specs[0].dims, n_contexts=4, depth=2)
+    got = []
+    bp.submit(vols[0:4], sp, org, dr)
+    for b in range(3):
+        if b + 1 < 3:
+            bp.submit(vols[4 * (b + 1):4 * (b + 2)], sp, org, dr)
+        res = bp.result()
+        if b == 2:                                            # its ring buffers are not overwritten any more
+            last_masks = [res[i].mask.cpu().numpy() for i in range(4)]
+            last_labels = [res[i].labels.cpu().numpy().view(np.uint32) for i in range(4)]
+        got.extend(res[i] for i in range(4))
+    for i, (ph, v) in enumerate(zip(specs, vols)):
+        ora = c_oracle.detect_fiducials(v.cpu().numpy(), _geom(ph), want_body_mask=False)
+        if i >= 8:
+            _assert_equal_detection(got[i], ora, last_masks[i - 8], last_labels[i - 8])
+        else:
+            _assert_equal_detection(got[i], ora)
+        assert len(got[i].markers) == 6 and got[i].n_labels == ora.n_labels
+    poses = bp.pools[0].context(0).pose_estimate([g.ras_points for g in got])
+    for pose, g in zip(poses, got):
+        ident = kin.joint_detection(g.ras_points)
+        assert pose.identified == {jn: [m["id"] for m in ms] for jn, ms in ident.items()}
+    bp.close()
