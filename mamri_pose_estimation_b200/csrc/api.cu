@@ -27,12 +27,26 @@ const LaunchTuning& launch_tuning() {
         v.prio_small = greatest;     // numerically lowest = scheduled first
         v.prio_big = least;
         v.pdl = 1;
+        v.run_ctas = 0;                 // 0 = follow the work (run_grid_class)
+        if (const char* e = getenv("MAMRI_RUN_CTAS")) v.run_ctas = atoi(e) < 1 ? 1 : atoi(e);
         if (const char* e = getenv("MAMRI_PRIO_SMALL")) v.prio_small = atoi(e);
         if (const char* e = getenv("MAMRI_PRIO_BIG")) v.prio_big = atoi(e);
         if (const char* e = getenv("MAMRI_PDL")) v.pdl = atoi(e);
         return v;
     }();
     return t;
+}
+
+int run_grid_class(int current, uint32_t hint) {
+    const int forced = launch_tuning().run_ctas;
+    if (forced > 0) return forced > MAMRI_RUN_CTAS ? MAMRI_RUN_CTAS : forced;
+    if (hint == 0) return current > 0 ? current : MAMRI_RUN_CTAS;       // nothing known yet: the full grid
+    const unsigned long long need = (hint + 511ull) / 512ull;           // CTAs of 256 threads at two runs per thread
+    int want = 37;                                                      // classes 37, 74, 148, 296, 592 (148 SMs / 4 ... x 4)
+    while (want < MAMRI_RUN_CTAS && (unsigned long long)want < need) want *= 2;
+    if (current <= 0 || want > current) return want;                    // grow at once
+    if (want * 4 <= current) return want * 2;                           // shrink only on a 4x drop, keep 2x headroom
+    return current;
 }
 
 namespace {
@@ -313,6 +327,7 @@ static int detect_async_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, cons
     k.outs_aligned = ((reinterpret_cast<uintptr_t>(d_labels_out) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(d_mask_out) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_body_out) & 15u) == 0);
     k.has_mask = d_mask_out != nullptr; k.has_labels = d_labels_out != nullptr; k.has_body = d_body_out != nullptr;
+    k.run_ctas = ctx->run_ctas = run_grid_class(ctx->run_ctas, ctx->last_n_runs);
     ctx->h_dyn->vol = d_volume;
     ctx->h_dyn->mask_out = d_mask_out;
     ctx->h_dyn->labels_out = d_labels_out;
@@ -397,6 +412,7 @@ extern "C" int mamri_detect_collect(mamri_ctx* ctx, mamri_summary* summary, mamr
     CK(cudaStreamSynchronize(ctx->pending_stream));
     const mamri_summary* hs = ctx->h_summary;
     ctx->last_n_labels = hs->n_labels;
+    ctx->last_n_runs = hs->device_status == MAMRI_OK ? hs->n_runs : ctx->max_runs;
     if (summary) *summary = *hs;
     if (hs->device_status != MAMRI_OK) {
         snprintf(ctx->err, sizeof(ctx->err),
@@ -732,6 +748,12 @@ static int wave_key(mamri_pool* pool, const mamri_volume_desc* desc, const void*
     k.prm = *params;
     k.has_mask = mask_out != nullptr; k.has_labels = labels_out != nullptr; k.has_body = body_out != nullptr;
     k.vol_aligned = 1; k.outs_aligned = 1;
+    {   // one grid class for the wave, from the largest run count the pool's contexts have seen last
+        uint32_t hint = 0;
+        for (int j = 0; j < pool->k; ++j) hint = pool->ctx[j]->last_n_runs > hint ? pool->ctx[j]->last_n_runs : hint;
+        k.run_ctas = run_grid_class(pool->ctx[0]->run_ctas, hint);
+        for (int j = 0; j < pool->k; ++j) pool->ctx[j]->run_ctas = k.run_ctas;
+    }
     for (int i = 0; i < n; ++i) {
         if (!volumes[i]) return pfail(MAMRI_ERR_INVALID_ARG, "volume pointer is NULL");
         if (reinterpret_cast<uintptr_t>(volumes[i]) & 15u) k.vol_aligned = 0;

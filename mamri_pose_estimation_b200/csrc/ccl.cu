@@ -238,9 +238,9 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
     const uint32_t n = r1 - r0;
     if (n == 0) return;
     uint32_t* P = (n <= SLICE_SMEM_RUNS) ? sp : parent + r0;
-    for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) P[i] = i;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) P[i] = i;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t pos = run_pos[r0 + i];
         const uint32_t wi = pos >> 5, row = wi / W;
         if (row == z * ny) continue;                                        // y == 0: no row above in this slice
@@ -253,13 +253,13 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
     while (again) {
         __syncthreads();
         bool changed = false;
-        for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
             const uint32_t p = P[i], pp = P[p];   // a concurrent update of P[p] still yields an ancestor
             if (pp != p) { P[i] = pp; changed = true; }
         }
         again = __syncthreads_or(changed);
     }
-    for (uint32_t i = threadIdx.x; i < n; i += SLICE_THREADS) parent[r0 + i] = r0 + P[i];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) parent[r0 + i] = r0 + P[i];
 }
 
 // Phase 2 -- global boundary merge between slices, with atomicMin on the roots.  Joining all slice
@@ -391,9 +391,12 @@ cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int
     prof_mark(c, s, "runs_scan");
     int radix = 1;
     while (radix * radix < nz) radix <<= 1;
-    const int RG = MAMRI_RUN_CTAS;
+    const int RG = c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS;
+    // threads per slice CTA: about one per run of an average slice (RG * 512 runs are expected at most), 128..512
+    int slice_threads = SLICE_THREADS;
+    while (slice_threads > 128 && (long long)(slice_threads / 2) * nz >= (long long)RG * 512) slice_threads /= 2;
     if (connectivity == 26) {
-        LK(k_union_slices<true>, nz, SLICE_THREADS, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, nz, c->d_scalars);
+        LK(k_union_slices<true>, nz, slice_threads, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, nz, c->d_scalars);
         prof_mark(c, s, "union_slices");
         if (nz > 1) {
             LK(k_union_z<true>, RG, 256, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 0, c->d_scalars);
@@ -404,7 +407,7 @@ cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int
             prof_mark(c, s, "union_z_between_blocks");
         }
     } else {
-        LK(k_union_slices<false>, nz, SLICE_THREADS, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, nz, c->d_scalars);
+        LK(k_union_slices<false>, nz, slice_threads, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, nz, c->d_scalars);
         prof_mark(c, s, "union_slices");
         if (nz > 1) {
             LK(k_union_z<false>, RG, 256, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 0, c->d_scalars);

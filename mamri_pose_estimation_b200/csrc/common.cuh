@@ -10,7 +10,7 @@
 
 #define MAMRI_RMAX 3                 // largest closing radius the scratch layout is sized for
 #define MAMRI_SCAN_CTAS 592          // 148 SMs x 4: CTA count of the chunked scans
-#define MAMRI_RUN_CTAS (148 * 4)     // CTA count of the per-run kernels (grid-stride over the run table)
+#define MAMRI_RUN_CTAS (148 * 4)     // largest CTA count of the per-run kernels (grid-stride over the run table)
 #define MAMRI_NONE 0xFFFFFFFFu
 
 // Device-side scalars of one scan (one cudaMemsetAsync clears them).
@@ -53,6 +53,7 @@ struct GraphKey {
     mamri_volume_desc desc;
     mamri_params prm;
     int vol_aligned, outs_aligned, has_mask, has_labels, has_body;
+    int run_ctas;                    // grid of the per-run kernels (sized from the previous scans' run counts)
 };
 
 // Bit-packed volume: `w` 32-voxel words per row, `h` rows per slice, `d` slices.
@@ -135,6 +136,8 @@ struct mamri_ctx {
     cudaStream_t pending_stream;
     mamri_volume_desc last_desc;
     uint32_t last_n_labels;
+    uint32_t last_n_runs;             // x-runs of the last collected scan: sizes the next scan's per-run grids
+    int run_ctas;                     // CTAs of the per-run kernels for the scan being enqueued
 
     char err[512];
 };
@@ -179,8 +182,13 @@ cudaError_t launch_phantom(uint16_t* d_volume, int nx, int ny, int nz, const flo
 // dependent launch: the next kernel's CTAs are set up while the current kernel drains; every kernel
 // therefore starts with pdl_wait() (griddepcontrol.wait) before it touches memory.
 // MAMRI_PRIO_SMALL / MAMRI_PRIO_BIG / MAMRI_PDL override the defaults (experiments only).
-struct LaunchTuning { int prio_small, prio_big, pdl; };
+struct LaunchTuning { int prio_small, prio_big, pdl, run_ctas; };
 const LaunchTuning& launch_tuning();
+// The run-table kernels (boundary merge, ranking, filter, moments) are latency-bound; CTAs they do not need
+// still take SM slots away from the streaming kernels of the scans running beside them, so their grid follows
+// the work: two runs per thread, from the run count of the scans just processed (`hint`, 0 = unknown), in
+// power-of-two classes with hysteresis so that a captured graph is only re-captured when the load really changes.
+int run_grid_class(int current, uint32_t hint);
 
 template <typename... KA, typename... A>
 inline cudaError_t launch_ks(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool big, A&&... args) {

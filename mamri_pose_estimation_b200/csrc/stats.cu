@@ -312,7 +312,7 @@ static GeomArgs geom_args(const mamri_volume_desc* desc, const mamri_params* prm
 // Volume filter + body label + final label of every run: everything `materialise` needs.
 cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
     const GeomArgs g = geom_args(desc, prm);
-    LK(k_select, MAMRI_RUN_CTAS, 256, s, false, c->d_parent, c->d_root_count, c->d_run_label, c->d_label_count, c->d_label_slot,
+    LK(k_select, c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS, 256, s, false, c->d_parent, c->d_root_count, c->d_run_label, c->d_label_count, c->d_label_slot,
        c->d_cand_label, c->d_cand_sums, c->max_markers, g, c->d_scalars);
     prof_mark(c, s, "select");
     return cudaGetLastError();
@@ -322,7 +322,7 @@ cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mam
 cudaError_t launch_moments(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
     const GeomArgs g = geom_args(desc, prm);
     const int W = (desc->nx + 31) / 32;
-    LK(k_moments, MAMRI_RUN_CTAS, 256, s, false, c->d_run_pos, c->d_run_len, c->d_parent, c->d_run_label, c->d_label_slot, W, desc->ny,
+    LK(k_moments, c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS, 256, s, false, c->d_run_pos, c->d_run_len, c->d_parent, c->d_run_label, c->d_label_slot, W, desc->ny,
        c->d_cand_sums, c->d_cand_label, c->d_label_count, c->max_markers, g, c->d_markers, c->d_summary, c->d_scalars, c->d_dyn);
     prof_mark(c, s, "moments_finalize");
     return cudaGetLastError();
