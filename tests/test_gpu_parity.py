@@ -149,3 +149,33 @@ def test_one_context_across_different_scans(cuda_lib):
         assert np.array_equal(res.labels.cpu().numpy().view(np.uint32), ora.labels), f"scan {i}: labels differ"
         assert [m.label for m in res.markers] == [f["id"] for f in ora.fiducials] and res.body_label == ora.body_label
     det.close()
+
+
+def test_random_geometry_sweep(cuda_lib):
+    """Seeded sweep over ragged volume shapes, radii and connectivities with sparse content (air tiles, objects that
+    touch the border, tile- and cell-straddling blobs): masks and labels bit-exact against the C oracle."""
+    from mamri_pose_estimation_b200.detector import DetectParams, FiducialDetector
+    from oracle import c_oracle
+    rng = np.random.default_rng(2026)
+    det = FiducialDetector((200, 96, 72), max_markers=8192)
+    for case in range(24):
+        dims = (int(rng.integers(8, 201)), int(rng.integers(5, 97)), int(rng.integers(3, 73)))
+        if case % 6 == 0:
+            dims = (32 * int(rng.integers(1, 7)), dims[1], dims[2])            # aligned fast paths too
+        radius, conn = int(rng.integers(0, 4)), (6, 26)[int(rng.integers(0, 2))]
+        ph = phantom.small_phantom(dims=dims, n_fiducials=int(rng.integers(0, 6)), n_blobs=int(rng.integers(0, 10)),
+                                   sigma=float(rng.choice([0.0, 8.0, 14.0])), seed=1000 + case, touch_border=bool(case % 2))
+        vol = phantom.generate(ph)
+        geom = seg.Geometry(ph.spacing, ph.origin, ph.direction)
+        ora = c_oracle.detect_fiducials(vol, geom, close_radius=radius, connectivity=conn, min_vol=20.0, max_vol=600.0)
+        res = det.detect(torch.from_numpy(vol).cuda(), spacing=ph.spacing, origin=ph.origin, direction=ph.direction,
+                         params=DetectParams(close_radius=radius, connectivity=conn, min_volume=20.0, max_volume=600.0),
+                         want_mask=True, want_labels=True, want_body=True)
+        tag = f"case {case}: dims {dims} r {radius} conn {conn}"
+        assert np.array_equal(res.mask.cpu().numpy(), ora.closed), tag
+        assert np.array_equal(res.labels.cpu().numpy().view(np.uint32), ora.labels), tag
+        assert [m.label for m in res.markers] == [f["id"] for f in ora.fiducials], tag
+        assert res.body_label == ora.body_label, tag
+        if ora.body_label:
+            assert np.array_equal(res.body_mask.cpu().numpy(), ora.body_mask), tag
+    det.close()
