@@ -293,6 +293,12 @@ MAMRI_API int mamri_pose_estimate(mamri_ctx* ctx, const mamri_robot* robot, cons
                         const int32_t* h_counts, int32_t n_scans, int32_t max_points, mamri_pose* h_poses,
                         void* stream);
 
+/* Same, fed from the device-written marker tables of mamri_pool_detect_begin (float64
+ * [n_scans][table_slots][8]; a row is a control point while its label is non-zero): enqueued on `stream`
+ * right behind the scans, no host round trip of the tables.  Waits for the poses. */
+MAMRI_API int mamri_pose_from_tables(mamri_ctx* ctx, const mamri_robot* robot, const double* d_tables, int32_t n_scans,
+                           uint32_t table_slots, mamri_pose* h_poses, void* stream);
+
 /* ---- robot-vs-body collision sampling: stands in for Mamri.py:1555-1575 ------------------- */
 /* _check_collision runs vtkCollisionDetectionFilter between each link's collision mesh and the body
  * mesh, one joint configuration per call (per configuration of a planned path, :976-982; inside the

@@ -114,6 +114,8 @@ SIGNATURES = {
     "mamri_default_robot": (None, [C.POINTER(Robot)]),
     "mamri_pose_estimate": (C.c_int, [C.c_void_p, C.POINTER(Robot), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.POINTER(Pose), C.c_void_p]),
+    "mamri_pose_from_tables": (C.c_int, [C.c_void_p, C.POINTER(Robot), C.c_void_p, C.c_int32, C.c_uint32, C.POINTER(Pose),
+                                         C.c_void_p]),
     "mamri_collision_check": (C.c_int, [C.c_void_p, C.POINTER(Robot), C.POINTER(C.c_double), C.c_void_p, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.POINTER(VolumeDesc), C.POINTER(C.c_double),
                                         C.POINTER(CollisionResult), C.c_void_p]),

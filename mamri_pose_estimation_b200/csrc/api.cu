@@ -1037,6 +1037,36 @@ extern "C" int mamri_pose_estimate(mamri_ctx* ctx, const mamri_robot* robot, con
     return MAMRI_OK;
 }
 
+extern "C" int mamri_pose_from_tables(mamri_ctx* ctx, const mamri_robot* robot, const double* d_tables, int32_t n_scans,
+                                      uint32_t table_slots, mamri_pose* h_poses, void* stream) {
+    if (!ctx) return MAMRI_ERR_INVALID_ARG;
+    if (!robot || n_scans < 0 || (n_scans > 0 && (!d_tables || !h_poses || table_slots == 0)))
+        return fail(ctx, MAMRI_ERR_INVALID_ARG, "bad pose arguments");
+    if (robot->n_links < 1 || robot->n_links > MAMRI_MAX_LINKS) return fail(ctx, MAMRI_ERR_INVALID_ARG, "robot: n_links out of range");
+    for (int l = 0; l < robot->n_links; ++l)
+        if (robot->links[l].parent >= l || robot->links[l].chain_index >= MAMRI_MAX_CHAIN)
+            return fail(ctx, MAMRI_ERR_INVALID_ARG, "robot: a link's parent must precede it; chain_index < MAMRI_MAX_CHAIN");
+    if (n_scans == 0) return MAMRI_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t off_pose = (sizeof(mamri_robot) + 255) & ~size_t(255);
+    const size_t total = off_pose + size_t(n_scans) * sizeof(mamri_pose);
+    if (ctx->pose_buf_bytes < total) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(ctx->d_pose_buf);
+        ctx->d_pose_buf = nullptr; ctx->pose_buf_bytes = 0;
+        CK(cudaMalloc(&ctx->d_pose_buf, total));
+        ctx->pose_buf_bytes = total;
+    }
+    char* base = static_cast<char*>(ctx->d_pose_buf);
+    CK(cudaMemcpyAsync(base, robot, sizeof(mamri_robot), cudaMemcpyHostToDevice, s));
+    CK(launch_pose(reinterpret_cast<const mamri_robot*>(base), d_tables, nullptr, n_scans, int(table_slots),
+                   reinterpret_cast<mamri_pose*>(base + off_pose), s));
+    CK(cudaMemcpyAsync(h_poses, base + off_pose, size_t(n_scans) * sizeof(mamri_pose), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MAMRI_OK;
+}
+
 extern "C" int mamri_collision_check(mamri_ctx* ctx, const mamri_robot* robot, const double base_matrix[16],
                                      const double* h_joint_angles, int32_t n_configs, const float* d_part_points,
                                      const int32_t* h_part_offsets, const uint8_t* d_body_mask,

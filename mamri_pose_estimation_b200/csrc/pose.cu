@@ -239,6 +239,9 @@ __device__ void solve_ik(const IkProblem& P, mamri_pose* out) {
 
 }  // namespace
 
+// Points of scan s: either packed [n_scans][max_points][3] with counts[] (host tables), or -- counts == NULL -- the
+// device-written marker tables [n_scans][max_points][8] (rows {label, count, volume, RAS x y z, n_labels, body};
+// a row is in use while its label is non-zero), so the stage can be queued right behind the scans.
 __global__ void __launch_bounds__(32) k_pose(const mamri_robot* __restrict__ robot, const double* __restrict__ points,
                                              const int32_t* __restrict__ counts, int max_points, mamri_pose* __restrict__ poses) {
     __shared__ mamri_robot rb;
@@ -246,11 +249,28 @@ __global__ void __launch_bounds__(32) k_pose(const mamri_robot* __restrict__ rob
     __shared__ int s_match[MAMRI_MAX_LINKS][3];
     const int scan = blockIdx.x, lane = threadIdx.x;
     for (int i = lane; i < int(sizeof(mamri_robot) / 4); i += 32) reinterpret_cast<uint32_t*>(&rb)[i] = reinterpret_cast<const uint32_t*>(robot)[i];
-    int n = counts[scan];
+    const bool tables = counts == nullptr;
+    int n_in;
+    if (tables) {
+        const double* t = points + size_t(scan) * max_points * 8;
+        int c = 0;
+        for (int i = lane; i < max_points; i += 32) c += t[size_t(i) * 8] != 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+        n_in = c;
+    } else {
+        n_in = counts[scan];
+    }
+    int n = n_in;
     mamri_pose* out = poses + scan;
     const bool too_many = n > MAMRI_POSE_MAX_POINTS || n > max_points;
     if (too_many) n = 0;
-    for (int i = lane; i < n * 3; i += 32) pt[i / 3][i % 3] = points[(size_t(scan) * max_points) * 3 + i];
+    if (tables) {
+        const double* t = points + size_t(scan) * max_points * 8;
+        for (int i = lane; i < n * 3; i += 32) pt[i / 3][i % 3] = t[size_t(i / 3) * 8 + 3 + i % 3];
+    } else {
+        for (int i = lane; i < n * 3; i += 32) pt[i / 3][i % 3] = points[(size_t(scan) * max_points) * 3 + i];
+    }
     for (int i = lane; i < MAMRI_MAX_LINKS * 3; i += 32) s_match[i / 3][i % 3] = -1;
     __syncwarp();
 
@@ -303,7 +323,7 @@ __global__ void __launch_bounds__(32) k_pose(const mamri_robot* __restrict__ rob
     if (lane != 0) return;
 
     // ---- results, registration, IK (lane 0)
-    out->n_points = counts[scan];
+    out->n_points = n_in;
     out->status = too_many ? MAMRI_ERR_CAPACITY : MAMRI_OK;
     for (int l = 0; l < MAMRI_MAX_LINKS; ++l) for (int q = 0; q < 3; ++q) out->matched[l][q] = s_match[l][q];
     out->has_base = 0;

@@ -363,6 +363,29 @@ class FiducialDetector:
             out.append(PoseResult.from_c(poses[i]))
         return out
 
+    def pose_from_tables(self, tables: torch.Tensor, n_scans: Optional[int] = None, robot: Optional[Robot] = None,
+                         apply_correction: bool = False, stream: Optional[torch.cuda.Stream] = None) -> List[PoseResult]:
+        """`pose_estimate` fed from the device-written marker tables of `BatchDetector.begin(tables=...)`: queued on the
+        stream right behind the scans (call it between begin() and end()); only the poses travel to the host."""
+        if not (tables.is_cuda and tables.is_contiguous() and tables.dtype == torch.float64 and tables.dim() == 3
+                and tables.shape[2] == 8):
+            raise ValueError("tables must be a contiguous float64 CUDA tensor [n, slots, 8]")
+        n = int(tables.shape[0]) if n_scans is None else int(n_scans)
+        if n == 0:
+            return []
+        robot = robot if robot is not None else self.default_robot(apply_correction)
+        poses = (Pose * n)()
+        s = stream or torch.cuda.current_stream(tables.device)
+        check(self._lib.mamri_pose_from_tables(self._ctx, C.byref(robot), tables.data_ptr(), n, int(tables.shape[1]), poses,
+                                               s.cuda_stream), self._ctx)
+        out = []
+        for i in range(n):
+            if poses[i].status != _capi.MAMRI_OK:
+                raise _capi.MamriError(poses[i].status, f"scan {i}: more control points than the matcher's limit of "
+                                                        f"{_capi.POSE_MAX_POINTS}")
+            out.append(PoseResult.from_c(poses[i]))
+        return out
+
     # ------------------------------------------------------------------ robot-vs-body collision sampling
     def collision_check(self, part_points: dict, joint_angles, base_matrix, body_mask: torch.Tensor, ras_to_index,
                         robot: Optional[Robot] = None, stream: Optional[torch.cuda.Stream] = None) -> List[dict]:

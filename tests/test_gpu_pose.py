@@ -180,10 +180,23 @@ def test_batch_detector_poses(cuda_lib):
     from oracle import segmentation as seg
     specs = [phantom.small_phantom(dims=(96, 80, 48), n_fiducials=6, n_blobs=2, seed=40 + i, spacing=(1.2, 1.2, 2.4)) for i in range(3)]
     vols = [phantom.generate(p) for p in specs]
-    bd = BatchDetector(specs[0].dims, n_contexts=2)
+    bd = BatchDetector(specs[0].dims, n_contexts=4)
     res = bd.run([torch.from_numpy(v).cuda() for v in vols], specs[0].spacing, specs[0].origin, specs[0].direction)
     poses = bd.estimate_poses(res)
     assert len(poses) == 3
+    # the same stage queued on the device right behind the scans, fed from the device-written tables
+    tables = torch.zeros((3, 32, 8), dtype=torch.float64, device="cuda")
+    bd.begin([torch.from_numpy(v).cuda() for v in vols], specs[0].spacing, specs[0].origin, specs[0].direction, tables=tables)
+    dev_poses = bd.context(0).pose_from_tables(tables)
+    bd.end()
+    for a, b in zip(dev_poses, poses):
+        assert a.identified == b.identified and a.n_points == b.n_points
+        assert (a.base_matrix is None) == (b.base_matrix is None)
+        if a.base_matrix is not None:
+            assert np.array_equal(a.base_matrix, b.base_matrix)
+        assert (a.joint_angles is None) == (b.joint_angles is None)
+        if a.joint_angles is not None:
+            assert np.array_equal(a.joint_angles, b.joint_angles)
     for pose, ph, vol in zip(poses, specs, vols):
         ora = seg.detect_fiducials(vol, seg.Geometry(ph.spacing, ph.origin, ph.direction))
         assert pose.n_points == len(ora.fiducials)
