@@ -175,6 +175,11 @@ MAMRI_API int mamri_pool_detect(mamri_pool* pool, const mamri_volume_desc* desc,
 MAMRI_API int mamri_pool_detect_begin(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* d_volumes, int32_t n,
                             const mamri_params* params, uint8_t* const* d_mask_out, uint32_t* const* d_labels_out,
                             uint8_t* const* d_body_out, double* d_tables, uint32_t table_slots, void* stream);
+/* _begin for HOST buffers (as mamri_pool_detect_host; n <= n_contexts): every scan's H2D copy, kernels and
+ * body-mask D2H are enqueued before the call returns, so a second pool can start feeding the link while
+ * this one drains.  Ended by mamri_pool_detect_end. */
+MAMRI_API int mamri_pool_detect_host_begin(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes,
+                                 int32_t n, const mamri_params* params, uint8_t* const* h_body_out, void* stream);
 MAMRI_API int mamri_pool_detect_end(mamri_pool* pool, mamri_summary* summaries, mamri_marker* markers,
                           uint32_t max_markers_per_scan);
 /* Same from/to HOST buffers (pinned for full PCIe speed): the H2D copy of scan i+1 overlaps the

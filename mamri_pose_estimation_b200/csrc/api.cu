@@ -878,6 +878,34 @@ extern "C" int mamri_pool_detect_begin(mamri_pool* pool, const mamri_volume_desc
     return MAMRI_OK;
 }
 
+extern "C" int mamri_pool_detect_host_begin(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes,
+                                            int32_t n, const mamri_params* params, uint8_t* const* h_body_out, void* stream) {
+    if (!pool) return MAMRI_ERR_INVALID_ARG;
+    auto pfail = [&](int code, const char* msg) { snprintf(pool->err, sizeof(pool->err), "%s", msg); return code; };
+    if (n < 1 || n > pool->k || !h_volumes) return pfail(MAMRI_ERR_INVALID_ARG, "begin/end handles 1..n_contexts scans per call");
+    if (pool->pending_n) return pfail(MAMRI_ERR_STATE, "a batch is already pending; end it first");
+    for (int j = 0; j < pool->k; ++j)
+        if (pool->ctx[j]->pending) return pfail(MAMRI_ERR_STATE, "a context of the pool has a detect pending");
+    DeviceGuard g(pool->device);
+    cudaStream_t cur = static_cast<cudaStream_t>(stream);
+    if (cudaEventRecord(pool->fork, cur) != cudaSuccess) return pfail(MAMRI_ERR_CUDA, "recording the fork event failed");
+    for (int i = 0; i < n; ++i) {                     // scan i: H2D, kernels, body-mask D2H on stream i
+        if (cudaStreamWaitEvent(pool->streams[i], pool->fork, 0) != cudaSuccess) return pfail(MAMRI_ERR_CUDA, "forking failed");
+        const int rc = mamri_detect_host_async(pool->ctx[i], desc, h_volumes[i], params, h_body_out ? h_body_out[i] : nullptr,
+                                               pool->streams[i]);
+        if (rc != MAMRI_OK) {
+            snprintf(pool->err, sizeof(pool->err), "scan %d: %s", i, mamri_last_error(pool->ctx[i]));
+            for (int j = 0; j < i; ++j) { mamri_summary tmp; mamri_detect_collect(pool->ctx[j], &tmp, nullptr, 0); }
+            return rc;
+        }
+        if (cudaEventRecord(pool->join[i], pool->streams[i]) != cudaSuccess ||
+            cudaStreamWaitEvent(cur, pool->join[i], 0) != cudaSuccess)
+            return pfail(MAMRI_ERR_CUDA, "joining the pool's streams failed");
+    }
+    pool->pending_n = n;
+    return MAMRI_OK;
+}
+
 extern "C" int mamri_pool_detect_end(mamri_pool* pool, mamri_summary* summaries, mamri_marker* markers,
                                      uint32_t max_markers_per_scan) {
     if (!pool) return MAMRI_ERR_INVALID_ARG;

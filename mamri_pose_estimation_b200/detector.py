@@ -660,6 +660,34 @@ class BatchDetector:
         _capi.check_pool(rc, self._pool)
         self._begun = (n, volumes, tables)           # keep the buffers alive until end()
 
+    def begin_host(self, volumes: Sequence, spacing, origin, direction=IDENTITY, params: Optional[DetectParams] = None,
+                   body_out: Optional[Sequence] = None) -> None:
+        """First half of `run_host` for up to n_contexts scans: every scan's H2D copy, kernels and body-mask D2H are
+        enqueued; `end()` waits."""
+        n = len(volumes)
+        if not 1 <= n <= self.n_contexts:
+            raise ValueError(f"begin/end handles 1..{self.n_contexts} scans per call")
+        views = [_host_view(v) for v in volumes]
+        a0 = views[0][0]
+        for a, _ in views:
+            if a["dtype"] != a0["dtype"] or tuple(a["shape"]) != tuple(a0["shape"]):
+                raise ValueError("host volumes must share one shape and type")
+        d = _desc(a0["shape"], a0["dtype"], spacing, origin, direction)
+        p = (params or DetectParams()).to_c()
+        vp = self._ptrs([a["ptr"] for a, _ in views], n)
+        bp, bviews = None, None
+        if body_out is not None:
+            bviews = [_host_view(b) for b in body_out]
+            for b, _ in bviews:
+                if b["dtype"] != "uint8" or tuple(b["shape"]) != tuple(a0["shape"]):
+                    raise ValueError("body_out must be uint8 with the volume's shape")
+            bp = self._ptrs([b["ptr"] for b, _ in bviews], n)
+        s = torch.cuda.current_stream(self.device)
+        rc = self._lib.mamri_pool_detect_host_begin(self._pool, C.byref(d), vp, n, C.byref(p), bp, s.cuda_stream)
+        _capi.check_pool(rc, self._pool)
+        self._begun = (n, views, bviews)
+        self._begun_body = body_out if body_out is not None else ()
+
     def end(self) -> BatchResult:
         """Second half of `run`: waits for the scans begun with `begin` and returns their results."""
         if getattr(self, "_begun", None) is None:
@@ -671,6 +699,9 @@ class BatchDetector:
         rc = self._lib.mamri_pool_detect_end(self._pool, summ, mk, self.max_markers)
         _capi.check_pool(rc, self._pool)
         masks, labels, k = self.masks, self.labels, self.n_contexts
+        body, self._begun_body = getattr(self, "_begun_body", None), None
+        if body is not None:                         # begun with begin_host: no device volumes, host body masks if asked for
+            return BatchResult(n, summ, mk, self.max_markers, lambda i: (None, None, body[i] if len(body) else None))
         return BatchResult(n, summ, mk, self.max_markers, lambda i: (masks[i % k], labels[i % k], None))
 
     def estimate_poses(self, results: BatchResult, apply_correction: bool = False) -> List[PoseResult]:
@@ -737,6 +768,21 @@ class BatchPipeline:
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             self.pools[i].begin(volumes, spacing, origin, direction, params, tables=tables)
+        self._in_flight.append(i)
+        return s
+
+    def submit_host(self, volumes: Sequence, spacing, origin, direction=IDENTITY, params: Optional[DetectParams] = None,
+                    body_out: Optional[Sequence] = None) -> torch.cuda.Stream:
+        """`submit` for HOST buffers (pinned for full PCIe speed): the next batch's copies start feeding the link while
+        the previous batch's last scans still compute and drain."""
+        i = self._next
+        if i in self._in_flight:
+            raise RuntimeError("pipeline full: collect a result() first")
+        self._next = (i + 1) % len(self.pools)
+        s = self.streams[i]
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.pools[i].begin_host(volumes, spacing, origin, direction, params, body_out=body_out)
         self._in_flight.append(i)
         return s
 

@@ -368,3 +368,32 @@ def test_c3_batch_full_size(cuda_lib):
         ident = kin.joint_detection(g.ras_points)
         assert pose.identified == {jn: [m["id"] for m in ms] for jn, ms in ident.items()}
     bp.close()
+
+
+def test_host_pipeline_matches_run_host(cuda_lib):
+    """BatchPipeline.submit_host / result (mamri_pool_detect_host_begin / _end): host volumes in, host body masks +
+    markers out, batches enqueued ahead of the previous batch's collection."""
+    from mamri_pose_estimation_b200.detector import BatchPipeline
+    specs = [[phantom.small_phantom(dims=(96, 80, 48), n_fiducials=4 + i, n_blobs=2, seed=120 + 10 * b + i, spacing=(1.2, 1.2, 2.4))
+              for i in range(3)] for b in range(3)]
+    vols = [[phantom.generate(p) for p in batch] for batch in specs]
+    bodies = [[np.zeros(v.shape, np.uint8) for v in batch] for batch in vols]
+    sp, org, dr = specs[0][0].spacing, specs[0][0].origin, specs[0][0].direction
+    bp = BatchPipeline(specs[0][0].dims, n_contexts=3, depth=2)
+    got = []
+    bp.submit_host(vols[0], sp, org, dr, body_out=bodies[0])
+    for b in range(3):
+        if b + 1 < 3:
+            bp.submit_host(vols[b + 1], sp, org, dr, body_out=bodies[b + 1])
+        got.append(bp.result())
+    torch.cuda.synchronize()
+    for b in range(3):
+        for i in range(3):
+            ora = seg.detect_fiducials(vols[b][i], _geom(specs[b][i]))
+            _assert_equal_detection(got[b][i], ora)
+            assert np.array_equal(bodies[b][i], ora.body_mask)
+            assert got[b][i].body_mask is bodies[b][i]
+    bp.submit_host(vols[0], sp, org, dr)                      # no body masks asked for
+    r = bp.result()
+    assert r[0].body_mask is None and r[0].mask is None
+    bp.close()
