@@ -143,6 +143,23 @@ def run_native(args):
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    numa = None
+    if world > 1 and os.environ.get("MAMRI_BENCH_NUMA", "1") != "0":
+        # one process per GPU: run on the CPUs next to this GPU *before* any pinned host buffer is allocated, so that
+        # the staging memory of the e2e path is local to the GPU's PCIe root (first touch)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[local]) if visible and visible.split(",")[local].isdigit() else local
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1} & os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = f"{min(cpus)}-{max(cpus)} ({len(cpus)} cpus)"
+        except Exception as e:                      # no NVML / not permitted: run unpinned
+            numa = f"unpinned: {e}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -358,6 +375,8 @@ def run_native(args):
                 "gpu_launches": args.steps * S * bd.kernel_launches_per_scan, "parity": parity}
         if gathered_ok is not None:
             line["gathered_tables_equal_host_packed"] = gathered_ok
+        if numa is not None:
+            line["config"]["cpu_affinity_rank0"] = numa
         print(json.dumps(line), flush=True)
     bp.close()
     if world > 1:
