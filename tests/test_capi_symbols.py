@@ -30,6 +30,12 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     assert cuda_lib.mamri_version().decode().startswith("mamri_b200")
 
 
+def test_integration_doc_names_every_entry_point():
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in declared_symbols() if n not in doc]
+    assert not missing, f"INTEGRATION.md does not say what {missing} replace"
+
+
 def test_ctypes_structs_match_header_sizes(cuda_lib, tmp_path):
     """sizeof of every struct as gcc sees the header == sizeof of the ctypes mirror."""
     import subprocess
