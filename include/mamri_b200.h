@@ -47,13 +47,14 @@ extern "C" {
 #define MAMRI_U16  2
 #define MAMRI_I32  3
 #define MAMRI_F32  4
+#define MAMRI_F64  5
 
 typedef struct mamri_ctx mamri_ctx;
 
 /* Geometry of a SimpleITK image (LPS): physical = origin + direction * (spacing .* index). */
 typedef struct mamri_volume_desc {
     int32_t nx, ny, nz;
-    int32_t dtype;            /* MAMRI_U8 .. MAMRI_F32 */
+    int32_t dtype;            /* MAMRI_U8 .. MAMRI_F64 */
     double  spacing[3];
     double  origin[3];
     double  direction[9];     /* row-major 3x3 */

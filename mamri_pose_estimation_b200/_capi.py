@@ -13,7 +13,7 @@ MAMRI_ERR_CAPACITY = -3
 MAMRI_ERR_NO_DEVICE = -4
 MAMRI_ERR_STATE = -5
 
-DTYPE_CODES = {"uint8": 0, "int16": 1, "uint16": 2, "int32": 3, "float32": 4}
+DTYPE_CODES = {"uint8": 0, "int16": 1, "uint16": 2, "int32": 3, "float32": 4, "float64": 5}
 
 LIB_PATH = Path(__file__).resolve().parent / "libmamri_b200.so"
 

@@ -70,6 +70,7 @@ size_t dtype_size(int dtype) {
         case MAMRI_U8: return 1;
         case MAMRI_I16: case MAMRI_U16: return 2;
         case MAMRI_I32: case MAMRI_F32: return 4;
+        case MAMRI_F64: return 8;
         default: return 0;
     }
 }

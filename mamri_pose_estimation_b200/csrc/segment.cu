@@ -176,6 +176,8 @@ static T cast_bound(double v) {
 }
 template <>
 float cast_bound<float>(double v) { return float(v); }
+template <>
+double cast_bound<double>(double v) { return v; }
 
 template <typename T>
 static cudaError_t threshold_pack_t(mamri_ctx* c, int vol_aligned16, int nx, int ny, int nz, double lo, double hi,
@@ -273,6 +275,7 @@ cudaError_t launch_threshold_pack(mamri_ctx* c, int vol_aligned16, int dtype, in
         case MAMRI_U16: return threshold_pack_t<uint16_t>(c, vol_aligned16, nx, ny, nz, lo, hi, dst, s);
         case MAMRI_I32: return threshold_pack_t<int32_t>(c, vol_aligned16, nx, ny, nz, lo, hi, dst, s);
         case MAMRI_F32: return threshold_pack_t<float>(c, vol_aligned16, nx, ny, nz, lo, hi, dst, s);
+        case MAMRI_F64: return threshold_pack_t<double>(c, vol_aligned16, nx, ny, nz, lo, hi, dst, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -18,7 +18,7 @@ from . import _capi
 from ._capi import EntryResult, Marker, Params, Pose, Robot, Summary, VolumeDesc, check
 
 _TORCH_DTYPES = {torch.uint8: "uint8", torch.int16: "int16", torch.uint16: "uint16",
-                 torch.int32: "int32", torch.float32: "float32"}
+                 torch.int32: "int32", torch.float32: "float32", torch.float64: "float64"}
 
 IDENTITY = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)
 

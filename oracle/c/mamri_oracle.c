@@ -56,6 +56,11 @@ static void thresh_f32(const float* v, size_t n, double lo, double hi, uint8_t* 
     for (size_t i = 0; i < n; ++i) out[i] = (v[i] >= l && v[i] <= h) ? 1 : 0;   /* NaN -> 0 */
 }
 
+static void thresh_f64(const double* v, size_t n, double lo, double hi, uint8_t* out) {
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) out[i] = (v[i] >= lo && v[i] <= hi) ? 1 : 0;   /* NaN -> 0 */
+}
+
 API int oracle_threshold(const void* vol, int dtype, size_t n, double lo, double hi, uint8_t* out) {
     switch (dtype) {
         case 0: thresh_u8((const uint8_t*)vol, n, lo, hi, out); return 0;
@@ -63,6 +68,7 @@ API int oracle_threshold(const void* vol, int dtype, size_t n, double lo, double
         case 2: thresh_u16((const uint16_t*)vol, n, lo, hi, out); return 0;
         case 3: thresh_i32((const int32_t*)vol, n, lo, hi, out); return 0;
         case 4: thresh_f32((const float*)vol, n, lo, hi, out); return 0;
+        case 5: thresh_f64((const double*)vol, n, lo, hi, out); return 0;
         default: return -1;
     }
 }

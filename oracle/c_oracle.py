@@ -12,7 +12,7 @@ import numpy as np
 from . import build_c
 from . import segmentation as seg
 
-_DT = {"uint8": 0, "int16": 1, "uint16": 2, "int32": 3, "float32": 4}
+_DT = {"uint8": 0, "int16": 1, "uint16": 2, "int32": 3, "float32": 4, "float64": 5}
 _lib = None
 
 

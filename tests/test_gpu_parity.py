@@ -97,13 +97,13 @@ def test_random_masks_all_radii(cuda_lib, radius):
             _compare(res, counts, ora, geom, check_axes=False)
 
 
-@pytest.mark.parametrize("dtype", ["uint8", "int16", "uint16", "int32", "float32"])
+@pytest.mark.parametrize("dtype", ["uint8", "int16", "uint16", "int32", "float32", "float64"])
 def test_voxel_types(cuda_lib, dtype):
     from mamri_pose_estimation_b200.detector import DetectParams
     rng = np.random.default_rng(7)
     base = rng.integers(0, 200, size=(12, 20, 64))
-    if dtype == "float32":
-        vol = base.astype(np.float32) + rng.random(base.shape).astype(np.float32)
+    if dtype in ("float32", "float64"):
+        vol = base.astype(dtype) + rng.random(base.shape).astype(dtype)
         vol[0, 0, :5] = np.nan
     else:
         vol = base.astype(dtype)

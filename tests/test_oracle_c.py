@@ -31,7 +31,7 @@ def test_c_closing_all_radii(radius):
     assert np.array_equal(out, seg.binary_closing_safe_border(m, radius))
 
 
-@pytest.mark.parametrize("dtype", ["uint8", "int16", "uint16", "int32", "float32"])
+@pytest.mark.parametrize("dtype", ["uint8", "int16", "uint16", "int32", "float32", "float64"])
 def test_c_threshold_types(dtype):
     rng = np.random.default_rng(11)
     vol = rng.integers(0, 200, size=(5, 6, 40)).astype(dtype)
