@@ -42,7 +42,7 @@ int run_grid_class(int current, uint32_t hint) {
     if (forced > 0) return forced > MAMRI_RUN_CTAS ? MAMRI_RUN_CTAS : forced;
     if (hint == 0) return current > 0 ? current : MAMRI_RUN_CTAS;       // nothing known yet: the full grid
     const unsigned long long need = (hint + 511ull) / 512ull;           // CTAs of 256 threads at two runs per thread
-    int want = 37;                                                      // classes 37, 74, 148, 296, 592 (148 SMs / 4 ... x 4)
+    int want = 37;                                                      // classes 37, 74, ..., 1184 (148 SMs / 4 ... x 8)
     while (want < MAMRI_RUN_CTAS && (unsigned long long)want < need) want *= 2;
     if (current <= 0 || want > current) return want;                    // grow at once
     if (want * 4 <= current) return want * 2;                           // shrink only on a 4x drop, keep 2x headroom

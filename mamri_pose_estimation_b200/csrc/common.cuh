@@ -10,7 +10,7 @@
 
 #define MAMRI_RMAX 3                 // largest closing radius the scratch layout is sized for
 #define MAMRI_SCAN_CTAS 592          // 148 SMs x 4: CTA count of the chunked scans
-#define MAMRI_RUN_CTAS (148 * 4)     // largest CTA count of the per-run kernels (grid-stride over the run table)
+#define MAMRI_RUN_CTAS (148 * 8)     // largest CTA count of the per-run kernels (grid-stride over the run table)
 #define MAMRI_NONE 0xFFFFFFFFu
 
 // Device-side scalars of one scan (one cudaMemsetAsync clears them).
@@ -24,7 +24,7 @@ struct DevScalars {
     unsigned int ticket_runs;        // tile tickets of k_runs_scan / k_flatten_rank
     unsigned int ticket_rank;
     unsigned int done_select;        // CTAs of k_select that have finished (last one prepares the moment table)
-    unsigned int done_moments;       // CTAs of k_moments that have finished (last one finalises)
+    unsigned int reserved_;
 };
 
 // Device-side scalars of one body-surface extraction (surface.cu).
@@ -334,6 +334,7 @@ template <int NV, typename V, int SLOTS>
 __device__ __forceinline__ void warp_agg_add(uint32_t key, V (&v)[NV], CtaCache<NV, V, SLOTS>& cache, V* table) {
     const unsigned lane = lane_id();
     const bool valid = key != MAMRI_NONE;
+    if (!__any_sync(FULL, valid)) return;                    // nothing to add in this warp
     const unsigned peers = __match_any_sync(FULL, key);
     const bool single = valid && peers == (1u << lane);
     if (single) cache.add(key, v, table);

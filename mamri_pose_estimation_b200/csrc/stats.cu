@@ -32,9 +32,11 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ par
     const uint32_t n = sc->status == MAMRI_OK ? sc->n_runs : 0u;
     const uint32_t warp0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;
     const uint32_t stride = gridDim.x * blockDim.x;
+    // per-thread body bid and foreground count over all of the thread's runs: one pair of atomics per warp at the
+    // end (a noisy scan has millions of one-voxel components, every one of them a root that bids)
+    unsigned long long packed = 0ull, cnt64 = 0ull;
     for (uint32_t r0 = warp0; r0 < n; r0 += stride) {
         const uint32_t r = r0 + lane;
-        unsigned long long packed = 0ull, cnt64 = 0ull;
         if (r < n) {
             const uint32_t root = parent[r];
             if (root != r) {
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ par
             } else {
                 const uint32_t cnt = root_count[r], label = run_label[r];
                 label_count[label - 1u] = cnt;
-                cnt64 = cnt;
+                cnt64 += cnt;
                 const double vol = double(cnt) * g.voxel_volume;        // GetPhysicalSize
                 uint32_t slot = MAMRI_NONE;
                 if (vol >= g.min_volume && vol <= g.max_volume) {         // inclusive bounds
@@ -50,21 +52,22 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ par
                     if (slot < max_markers) cand_label[slot] = label; else slot = MAMRI_NONE;
                 } else {
                     // max(..., key=GetPhysicalSize) returns the FIRST maximum -> lowest label on ties
-                    packed = (cnt64 << 32) | (unsigned long long)(0xFFFFFFFFu - label);
+                    const unsigned long long bid = ((unsigned long long)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - label);
+                    packed = bid > packed ? bid : packed;
                 }
                 label_slot[r] = slot;
             }
         }
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long p2 = __shfl_xor_sync(FULL, packed, o);
-            packed = p2 > packed ? p2 : packed;
-            cnt64 += __shfl_xor_sync(FULL, cnt64, o);
-        }
-        if (lane == 0) {
-            if (packed) atomicMax(&sc->body_packed, packed);
-            if (cnt64) atomicAdd(&sc->n_foreground, cnt64);
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long p2 = __shfl_xor_sync(FULL, packed, o);
+        packed = p2 > packed ? p2 : packed;
+        cnt64 += __shfl_xor_sync(FULL, cnt64, o);
+    }
+    if (lane == 0) {
+        if (packed) atomicMax(&sc->body_packed, packed);
+        if (cnt64) atomicAdd(&sc->n_foreground, cnt64);
     }
     // The last CTA to finish clamps the candidate count, names the body's label in slot `max_markers`
     // and zeroes the moment sums of the slots in use.
@@ -93,17 +96,11 @@ __device__ __forceinline__ unsigned long long sum_sq_upto(long long k) {   // su
     return (unsigned long long)(k * (k + 1) * (2 * k + 1) / 6);
 }
 
-__device__ void finalize_block(const uint32_t* cand_label, const uint32_t* label_count, const unsigned long long* sums,
-                               uint32_t max_markers, const GeomArgs& g, mamri_marker* markers, mamri_summary* summary,
-                               const DevScalars* sc, const DynArgs* dyn);
-
 __global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_len,
                                                  const uint32_t* __restrict__ parent, const uint32_t* __restrict__ run_label,
                                                  const uint32_t* __restrict__ label_slot, int W, int ny,
                                                  unsigned long long* sums, const uint32_t* __restrict__ cand_label,
-                                                 const uint32_t* __restrict__ label_count, uint32_t max_markers, GeomArgs g,
-                                                 mamri_marker* __restrict__ markers, mamri_summary* summary, DevScalars* sc,
-                                                 const DynArgs* __restrict__ dyn) {
+                                                 uint32_t max_markers, DevScalars* sc) {
     __shared__ CtaCache<9, unsigned long long, 16> cache;
     pdl_wait();
     cache.init();
@@ -140,15 +137,6 @@ __global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ ru
         warp_agg_add(key, v, cache, sums);
     }
     cache.flush(sums);
-    // The last CTA to finish turns the sums into the marker table and the summary.
-    __shared__ bool last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(&sc->done_moments, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    finalize_block(cand_label, label_count, sums, max_markers, g, markers, summary, sc, dyn);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -244,13 +232,21 @@ __device__ void make_marker(mamri_marker* out, uint32_t label, unsigned long lon
     *out = m;
 }
 
-// One CTA (the last of k_moments): orders the kept labels ascending (= GetLabels order), emits their
-// records and the summary.  Sums were accumulated with L2 atomics; read them past L1.
-// Also fills the scan's fixed-size table (DynArgs::table_out, rows of {label, count, volume_mm3, RAS x y z,
-// n_labels, body_label}: the layout distributed.pack_table builds on the host) when the caller asked for it.
-__device__ void finalize_block(const uint32_t* cand_label, const uint32_t* label_count, const unsigned long long* sums,
-                               uint32_t max_markers, const GeomArgs& g, mamri_marker* markers, mamri_summary* summary,
-                               const DevScalars* sc, const DynArgs* dyn) {
+// Turns the sums into the marker table and the summary: one thread per kept label (its rank among the kept labels =
+// its place in GetLabels order; the labels of a noisy high-resolution scan number in the thousands, so they are
+// staged in shared memory and the work is spread over a few CTAs), thread 0 of CTA 0 writes the summary and the body.
+// Sums were accumulated with L2 atomics by the kernel before.  Also fills the scan's fixed-size table
+// (DynArgs::table_out, rows of {label, count, volume_mm3, RAS x y z, n_labels, body_label}: the layout
+// distributed.pack_table builds on the host) when the caller asked for it.
+constexpr int FIN_THREADS = 128, FIN_SMEM_LABELS = 8192;
+
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint32_t* __restrict__ cand_label,
+                                                          const uint32_t* __restrict__ label_count,
+                                                          const unsigned long long* __restrict__ sums, uint32_t max_markers,
+                                                          GeomArgs g, mamri_marker* __restrict__ markers, mamri_summary* summary,
+                                                          const DevScalars* __restrict__ sc, const DynArgs* __restrict__ dyn) {
+    extern __shared__ uint32_t s_lab[];
+    pdl_wait();
     const bool ok = sc->status == MAMRI_OK;
     const uint32_t n_all = sc->n_cand;
     const uint32_t n = ok ? (n_all < max_markers ? n_all : max_markers) : 0u;
@@ -258,10 +254,16 @@ __device__ void finalize_block(const uint32_t* cand_label, const uint32_t* label
     const uint32_t slots = table ? dyn->table_slots : 0u;
     const unsigned long long bpk = sc->body_packed;
     const double body_d = (ok && (bpk >> 32) != 0ull) ? double(0xFFFFFFFFu - uint32_t(bpk & 0xFFFFFFFFull)) : 0.0;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t lab = cand_label[i];
+    const bool staged = n <= FIN_SMEM_LABELS && max_markers <= FIN_SMEM_LABELS;
+    if (staged && blockIdx.x * blockDim.x < n) {
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) s_lab[j] = cand_label[j];
+    }
+    __syncthreads();
+    const uint32_t* __restrict__ labs = staged ? s_lab : cand_label;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t lab = labs[i];
         uint32_t rank = 0;
-        for (uint32_t j = 0; j < n; ++j) rank += cand_label[j] < lab;
+        for (uint32_t j = 0; j < n; ++j) rank += labs[j] < lab;
         unsigned long long s9[9];
         for (int k = 0; k < 9; ++k) s9[k] = __ldcg(sums + i * 9u + k);
         make_marker(markers + rank, lab, __ldcg(label_count + lab - 1u), s9, g);
@@ -273,8 +275,8 @@ __device__ void finalize_block(const uint32_t* cand_label, const uint32_t* label
             row[6] = double(sc->n_labels); row[7] = body_d;
         }
     }
-    for (uint32_t i = n * 8 + threadIdx.x; i < slots * 8; i += blockDim.x) table[i] = 0.0;   // unused rows
-    if (threadIdx.x == 0) {
+    for (uint32_t i = n * 8 + blockIdx.x * blockDim.x + threadIdx.x; i < slots * 8; i += gridDim.x * blockDim.x) table[i] = 0.0;   // unused rows
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         summary->n_labels = sc->n_labels;
         summary->n_runs = sc->n_runs;
         summary->n_markers = n_all;
@@ -323,7 +325,14 @@ cudaError_t launch_moments(mamri_ctx* c, const mamri_volume_desc* desc, const ma
     const GeomArgs g = geom_args(desc, prm);
     const int W = (desc->nx + 31) / 32;
     LK(k_moments, c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS, 256, s, false, c->d_run_pos, c->d_run_len, c->d_parent, c->d_run_label, c->d_label_slot, W, desc->ny,
-       c->d_cand_sums, c->d_cand_label, c->d_label_count, c->max_markers, g, c->d_markers, c->d_summary, c->d_scalars, c->d_dyn);
-    prof_mark(c, s, "moments_finalize");
+       c->d_cand_sums, c->d_cand_label, c->max_markers, c->d_scalars);
+    prof_mark(c, s, "moments");
+    // one thread per kept label, a few CTAs at most; a handful of labels (the usual scan) need only the first
+    uint32_t fin_ctas = (c->max_markers + FIN_THREADS - 1) / FIN_THREADS;
+    if (fin_ctas > 32) fin_ctas = 32;
+    const size_t fin_smem = size_t(c->max_markers <= FIN_SMEM_LABELS ? c->max_markers : 0) * sizeof(uint32_t);
+    LKS(k_finalize, fin_ctas, FIN_THREADS, fin_smem, s, false, c->d_cand_label, c->d_label_count, c->d_cand_sums, c->max_markers, g,
+        c->d_markers, c->d_summary, c->d_scalars, c->d_dyn);
+    prof_mark(c, s, "finalize");
     return cudaGetLastError();
 }

@@ -578,7 +578,7 @@ class BatchDetector:
                       for _ in range(self.n_contexts)]
         self.labels = [torch.empty((nz, ny, nx), dtype=torch.int32, device=dev) if materialise else None
                        for _ in range(self.n_contexts)]
-        self.kernel_launches_per_scan = 11          # threshold 1, closing 2, ccl 5, stats 2, materialise 1
+        self.kernel_launches_per_scan = 12          # threshold 1, closing 2, ccl 5, stats 3, materialise 1
 
     def close(self):
         if getattr(self, "_pool", None) and self._pool.value:
