@@ -227,7 +227,22 @@ def run_native(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    # NVML can be slow to answer on some hosts: if the timed region saw fewer than 5 clock samples, keep the same load
+    # running (untimed) until the sampler has them -- every rank takes part, rank 0 decides
+    extra_steps = 0
+    t_stop = time.perf_counter() + 2.0
+    while True:
+        more = torch.tensor([1 if (sampler is not None and sampler._thread is not None and len(sampler.samples) < 5
+                                   and time.perf_counter() < t_stop) else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(more, op=dist.ReduceOp.MAX)
+        if not int(more.item()):
+            break
+        run_steps(10)
+        extra_steps += 10
     clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["untimed_load_steps_for_sampling"] = extra_steps
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
