@@ -111,3 +111,43 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{f} imports the oracle"
                 assert "libmamri_oracle" not in text, f"{f} links the oracle"
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    exe = tmp_path / "detect_host"
+    lib_dir = os.path.join(ROOT, "mamri_pose_estimation_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "detect_host.c"), "-o", str(exe), "-L", lib_dir, "-lmamri_b200",
+                    f"-Wl,-rpath,{lib_dir}"], check=True)
+    return exe
+
+
+def test_plain_c_caller_compiles_and_links(cuda_lib, tmp_path):
+    """examples/detect_host.c: the header is valid C99 and the library links from a plain C program."""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_matches_the_oracle(cuda_lib, tmp_path):
+    import subprocess
+    import numpy as np
+    from mamri_pose_estimation_b200 import phantom
+    from oracle import segmentation as seg
+    ph = phantom.small_phantom(dims=(96, 80, 48), n_fiducials=6, seed=12, spacing=(1.2, 1.2, 2.4))
+    vol = phantom.generate(ph)
+    ora = seg.detect_fiducials(vol, seg.Geometry(ph.spacing, (0, 0, 0), (1, 0, 0, 0, 1, 0, 0, 0, 1)))
+    path = tmp_path / "vol.u16"
+    vol.tofile(path)
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([str(exe), str(path), "96", "80", "48", "1.2", "1.2", "2.4"], capture_output=True, text=True, check=True)
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == f"labels {ora.n_labels} markers {len(ora.fiducials)} body {ora.body_label} body_voxels {int(ora.body_mask.sum())}"
+    for line, label, f, ras in zip(lines[1:], ora.marker_labels, ora.fiducials, ora.ras_points):
+        tok = line.split()
+        assert tok[0] == label.replace("mm³", "mm3")
+        assert np.allclose([float(v) for v in tok[2:5]], ras, atol=1e-5)
+    assert lines[-1] == f"body_mask_voxels {int(ora.body_mask.sum())}"
