@@ -94,7 +94,9 @@ struct RangeTest16 {
 // Occupancy cells of the raw mask, in image coordinates (rows x slices; a cell spans all of x).
 constexpr uint32_t OCC_CY = 8, OCC_CZ = 4;
 
-template <int VOXEL_BYTES, typename Test>
+// WHOLE: ny is even and a row is a whole number of warp trips (vec_per_row % 64 == 0), so nothing in the loop needs a
+// bounds predicate -- the common case (512- and 1024-voxel rows), and the kernel is close to issue-bound.
+template <int VOXEL_BYTES, typename Test, bool WHOLE>
 __global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __restrict__ dyn, uint32_t vec_per_row,
                                                             uint32_t ny, Test test, uint32_t* __restrict__ dst,
                                                             uint32_t row_stride, uint32_t slice_stride, uint32_t off,
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __res
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const uint32_t i = u0 + u * 32 + lane;
-                    ok[r][u] = (y0 + r < ny) && i < vec_per_row;
+                    ok[r][u] = WHOLE || ((y0 + r < ny) && i < vec_per_row);
                     const uint4* src = slice_src + size_t(y0 + r) * vec_per_row + i;
                     v[r][u] = !ok[r][u] ? make_uint4(0, 0, 0, 0) : evict_first ? ld_stream_128(src, policy) : ld_stream_128(src);
                 }
@@ -208,15 +210,17 @@ static cudaError_t threshold_pack_t(mamri_ctx* c, int vol_aligned16, int nx, int
             const uint32_t lo_c = (l & 0x7FFFu) * 0x10001u, hi_c = (h | 0x8000u) * 0x10001u;
             const bool lm = (l & 0x8000u) != 0, hm = (h & 0x8000u) != 0, ch = h != 0xFFFFu;
             const uint32_t vpr = uint32_t(nx) / E;
+            const bool full = (ny % 2 == 0) && (vpr % 64u == 0);
 #define MAMRI_T16(LM, HM, CH)                                                                                         \
-    LK(k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>>, grid, 256, s, true, src, vpr, uint32_t(ny), RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first, occ, occ_ncy)
+    do { if (full) LK(k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>, true>, grid, 256, s, true, src, vpr, uint32_t(ny), RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first, occ, occ_ncy); \
+         else LK(k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>, false>, grid, 256, s, true, src, vpr, uint32_t(ny), RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first, occ, occ_ncy); } while (0)
             if (!ch) { if (lm) MAMRI_T16(true, true, false); else MAMRI_T16(false, true, false); }
             else if (lm) { if (hm) MAMRI_T16(true, true, true); else MAMRI_T16(true, false, true); }
             else { if (hm) MAMRI_T16(false, true, true); else MAMRI_T16(false, false, true); }
 #undef MAMRI_T16
         } else {
             RangeTest<T> t{tlo, thi};
-            LK(k_threshold_pack_vec<int(sizeof(T)), RangeTest<T>>, grid, 256, s, true, src, uint32_t(nx) / E, uint32_t(ny), t, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first, occ, occ_ncy);
+            LK(k_threshold_pack_vec<int(sizeof(T)), RangeTest<T>, false>, grid, 256, s, true, src, uint32_t(nx) / E, uint32_t(ny), t, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first, occ, occ_ncy);
         }
     } else {
         uint32_t blocks = (n_words + 7) / 8;
