@@ -203,6 +203,21 @@ class MamriLogic:
         self.last_pose = det.pose_estimate([all_node.points()], apply_correction=apply_correction)[0]
         return self.last_pose
 
+    # -- Mamri.py:850-881 (without the scene/model building and the motor-step conversion) ----------
+    def process(self, pNode: MamriParameterNode, apply_correction: bool = False):
+        '''Executes the pipeline: segmentation, fiducial detection, baseplate registration and inverse kinematics.
+        Returns the joint angles (rad, Joint1..Joint6) or None, like the first element of the reference's result:
+        None when no baseplate was registered from the scan (`:861-864`) or the Joint6 markers were not found
+        (`:868-875`).  Details of the run stay in `last_detection` / `last_pose`.'''
+        self.volume_threshold_segmentation(pNode)
+        pose = self.estimate_pose(pNode, apply_correction=apply_correction)
+        if pose is None or pose.base_matrix is None:
+            return None
+        if pose.joint_angles is None:
+            logging.info("Prerequisites for full-chain IK not met (e.g., Joint6 markers not found). Cannot estimate pose.")
+            return None
+        return pose.joint_angles
+
     # -- Mamri.py:987-1033 -------------------------------------------------------------------------
     def findAndSetEntryPoint(self, pNode: MamriParameterNode) -> None:
         '''Finds and marks the closest suitable entry point on the body surface for the biopsy needle.'''

@@ -171,6 +171,11 @@ def test_c1_scan_to_joint_angles_on_device(cuda_lib):
     pose = logic.estimate_pose()
     assert np.abs(pose.base_matrix - base).max() < MATRIX_TOL
     assert np.abs(pose.joint_angles - ang).max() < ANGLE_TOL
+    # the whole of process() (Mamri.py:850-881) in one call, from a device-resident volume this time
+    angles = MamriLogic().process(MamriParameterNode(inputVolume=ScalarVolumeNode(torch.from_numpy(vol).cuda(), ph.spacing, ph.origin,
+                                                                                   ph.direction)))
+    assert np.abs(angles - ang).max() < ANGLE_TOL
+    assert MamriLogic().process(MamriParameterNode(inputVolume=ScalarVolumeNode(np.zeros((16, 32, 64), np.uint16)))) is None
 
 
 def test_batch_detector_poses(cuda_lib):
