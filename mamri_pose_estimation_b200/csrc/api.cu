@@ -49,6 +49,18 @@ int run_grid_class(int current, uint32_t hint) {
     return current;
 }
 
+int slice_threads_class(int current, uint32_t hint, int nz) {
+    static const int forced = [] { const char* e = getenv("MAMRI_SLICE_THREADS"); return e ? atoi(e) : 0; }();
+    if (forced >= 32 && forced <= 512) return forced;
+    if (hint == 0 || nz <= 0) return current != 0 ? current : -512;
+    const unsigned long long per_slice = hint / (unsigned long long)nz;
+    int want = 128;
+    while (want < 512 && (unsigned long long)want < per_slice) want *= 2;
+    if (current <= 0 || want > current) return want;
+    if (want * 4 <= current) return want * 2;
+    return current;
+}
+
 namespace {
 struct DeviceGuard {
     int prev = -1;
@@ -329,6 +341,8 @@ static int detect_async_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, cons
                      ((reinterpret_cast<uintptr_t>(d_mask_out) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_body_out) & 15u) == 0);
     k.has_mask = d_mask_out != nullptr; k.has_labels = d_labels_out != nullptr; k.has_body = d_body_out != nullptr;
     k.run_ctas = ctx->run_ctas = run_grid_class(ctx->run_ctas, ctx->last_n_runs);
+    ctx->slice_threads = slice_threads_class(ctx->slice_threads, ctx->last_n_runs, desc->nz);
+    k.slice_threads = ctx->slice_threads < 0 ? -ctx->slice_threads : ctx->slice_threads;
     ctx->h_dyn->vol = d_volume;
     ctx->h_dyn->mask_out = d_mask_out;
     ctx->h_dyn->labels_out = d_labels_out;
@@ -753,7 +767,9 @@ static int wave_key(mamri_pool* pool, const mamri_volume_desc* desc, const void*
         uint32_t hint = 0;
         for (int j = 0; j < pool->k; ++j) hint = pool->ctx[j]->last_n_runs > hint ? pool->ctx[j]->last_n_runs : hint;
         k.run_ctas = run_grid_class(pool->ctx[0]->run_ctas, hint);
-        for (int j = 0; j < pool->k; ++j) pool->ctx[j]->run_ctas = k.run_ctas;
+        const int st = slice_threads_class(pool->ctx[0]->slice_threads, hint, desc->nz);
+        k.slice_threads = st < 0 ? -st : st;
+        for (int j = 0; j < pool->k; ++j) { pool->ctx[j]->run_ctas = k.run_ctas; pool->ctx[j]->slice_threads = st; }
     }
     for (int i = 0; i < n; ++i) {
         if (!volumes[i]) return pfail(MAMRI_ERR_INVALID_ARG, "volume pointer is NULL");

@@ -392,9 +392,8 @@ cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int
     int radix = 1;
     while (radix * radix < nz) radix <<= 1;
     const int RG = c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS;
-    // threads per slice CTA: about one per run of an average slice (RG * 512 runs are expected at most), 128..512
-    int slice_threads = SLICE_THREADS;
-    while (slice_threads > 128 && (long long)(slice_threads / 2) * nz >= (long long)RG * 512) slice_threads /= 2;
+    // threads per slice CTA: about one per run of an average slice of the scans just processed (slice_threads_class)
+    const int slice_threads = c->slice_threads > 0 ? c->slice_threads : (c->slice_threads < 0 ? -c->slice_threads : SLICE_THREADS);
     if (connectivity == 26) {
         LK(k_union_slices<true>, nz, slice_threads, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, nz, c->d_scalars);
         prof_mark(c, s, "union_slices");

@@ -54,6 +54,7 @@ struct GraphKey {
     mamri_params prm;
     int vol_aligned, outs_aligned, has_mask, has_labels, has_body;
     int run_ctas;                    // grid of the per-run kernels (sized from the previous scans' run counts)
+    int slice_threads;               // threads of the per-slice union-find CTAs (same source)
 };
 
 // Bit-packed volume: `w` 32-voxel words per row, `h` rows per slice, `d` slices.
@@ -138,6 +139,7 @@ struct mamri_ctx {
     uint32_t last_n_labels;
     uint32_t last_n_runs;             // x-runs of the last collected scan: sizes the next scan's per-run grids
     int run_ctas;                     // CTAs of the per-run kernels for the scan being enqueued
+    int slice_threads;                // threads of the per-slice union-find CTAs (negative: default, nothing known yet)
 
     char err[512];
 };
@@ -189,6 +191,9 @@ const LaunchTuning& launch_tuning();
 // the work: two runs per thread, from the run count of the scans just processed (`hint`, 0 = unknown), in
 // power-of-two classes with hysteresis so that a captured graph is only re-captured when the load really changes.
 int run_grid_class(int current, uint32_t hint);
+// Same idea for the per-slice union-find CTAs: 128..512 threads, about one per run of an average slice.  A negative
+// value means "default, nothing known yet" (the first hint then sets the class without hysteresis).
+int slice_threads_class(int current, uint32_t hint, int nz);
 
 template <typename... KA, typename... A>
 inline cudaError_t launch_ks(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool big, A&&... args) {
