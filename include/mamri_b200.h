@@ -200,6 +200,15 @@ MAMRI_API int mamri_stage_times(mamri_ctx* ctx, float ms[5]);
  * written (<= max_n) or a negative status. */
 MAMRI_API int mamri_kernel_times(mamri_ctx* ctx, float* ms, const char** names, int max_n);
 
+/* Kernels one scan took on the path it was last enqueued / captured with (6 with the cluster labelling kernel that
+ * small run tables get, 10 with the scalable kernels of large ones). */
+MAMRI_API int mamri_kernel_launches(const mamri_ctx* ctx);
+/* In-pipeline kernel timeline, trace build only (libmamri_b200_trace.so, -DMAMRI_KTRACE; MAMRI_ERR_STATE otherwise):
+ * every kernel stamps the GPU's nanosecond timer when its first CTA gets past the dependency on the kernel before it.
+ * _read fills out_ns[32] (slot order: csrc/common.cuh KId; ~0 = not stamped since the last _reset). */
+MAMRI_API int mamri_ktrace_reset(void);
+MAMRI_API int mamri_ktrace_read(unsigned long long* out_ns, int n);
+
 /* ---- stage 4b: replaces the loop at Mamri.py:1008-1023 ---------------------------------- */
 /* d_points / d_normals: float32 [n][3] (RAS mm / unit normals), as vtkPolyData stores them.
  * Keeps points with |p - target|^2 <= radius^2 and wx*|nx| + wy*|ny| > cutoff (reference:

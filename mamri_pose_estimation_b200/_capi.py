@@ -15,7 +15,10 @@ MAMRI_ERR_STATE = -5
 
 DTYPE_CODES = {"uint8": 0, "int16": 1, "uint16": 2, "int32": 3, "float32": 4, "float64": 5}
 
-LIB_PATH = Path(__file__).resolve().parent / "libmamri_b200.so"
+import os
+
+# MAMRI_LIB: another build of the same library (the trace build libmamri_b200_trace.so of tools/ktrace.py)
+LIB_PATH = Path(os.environ.get("MAMRI_LIB") or Path(__file__).resolve().parent / "libmamri_b200.so")
 
 
 class VolumeDesc(C.Structure):
@@ -106,6 +109,9 @@ SIGNATURES = {
                                          C.c_uint32, C.c_void_p]),
     "mamri_label_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "mamri_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "mamri_kernel_launches": (C.c_int, [C.c_void_p]),
+    "mamri_ktrace_reset": (C.c_int, []),
+    "mamri_ktrace_read": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "mamri_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mamri_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.c_int]),
     "mamri_entry_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_double,

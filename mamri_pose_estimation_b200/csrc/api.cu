@@ -61,6 +61,18 @@ int slice_threads_class(int current, uint32_t hint, int nz) {
     return current;
 }
 
+// Labelling path for the scan being enqueued: one cluster kernel while the run table is small (about 8 K runs per CTA
+// of the cluster, so that every chunk's parents fit shared memory), the scalable kernels above that.  `hint` = runs of
+// the scans just processed (0 = nothing known yet: decided by the volume size).
+int label_cluster_class(int current, uint32_t hint, unsigned long long voxels, int max_cluster) {
+    if (max_cluster < 2) return 0;
+    static const long long limit_env = [] { const char* e = getenv("MAMRI_LABEL_CLUSTER_RUNS"); return e ? atoll(e) : 0ll; }();
+    const unsigned long long limit = limit_env > 0 ? (unsigned long long)limit_env : (unsigned long long)max_cluster * 8192ull;
+    if (hint == 0) return voxels <= (1ull << 27) ? max_cluster : 0;
+    if (current > 0) return hint <= limit + limit / 4 ? max_cluster : 0;   // hysteresis: leave the path only on a clear excess
+    return hint <= limit ? max_cluster : 0;
+}
+
 namespace {
 struct DeviceGuard {
     int prev = -1;
@@ -93,6 +105,33 @@ int fail(mamri_ctx* ctx, int code, const char* msg) {
 }
 }  // namespace
 
+#ifdef MAMRI_KTRACE
+void ktrace_reset_segment(); void ktrace_merge_segment(unsigned long long*);
+void ktrace_reset_ccl(); void ktrace_merge_ccl(unsigned long long*);
+void ktrace_reset_stats(); void ktrace_merge_stats(unsigned long long*);
+#endif
+// Trace build only (libmamri_b200_trace.so): reset / read the in-pipeline kernel timeline (common.cuh: ktrace).
+extern "C" int mamri_ktrace_reset(void) {
+#ifdef MAMRI_KTRACE
+    ktrace_reset_segment(); ktrace_reset_ccl(); ktrace_reset_stats();
+    return cudaDeviceSynchronize() == cudaSuccess ? MAMRI_OK : MAMRI_ERR_CUDA;
+#else
+    return MAMRI_ERR_STATE;
+#endif
+}
+extern "C" int mamri_ktrace_read(unsigned long long* out_ns, int n) {
+#ifdef MAMRI_KTRACE
+    if (!out_ns || n < KT_SLOTS) return MAMRI_ERR_INVALID_ARG;
+    if (cudaDeviceSynchronize() != cudaSuccess) return MAMRI_ERR_CUDA;
+    for (int i = 0; i < KT_SLOTS; ++i) out_ns[i] = ~0ull;
+    ktrace_merge_segment(out_ns); ktrace_merge_ccl(out_ns); ktrace_merge_stats(out_ns);
+    return KT_SLOTS;
+#else
+    (void)out_ns; (void)n;
+    return MAMRI_ERR_STATE;
+#endif
+}
+
 extern "C" const char* mamri_version(void) { return "mamri_b200 0.1 (sm_100a)"; }
 
 extern "C" void mamri_default_params(mamri_params* p) {
@@ -113,8 +152,8 @@ extern "C" int mamri_destroy(mamri_ctx* ctx) {
     cudaFree(ctx->d_occ_raw); cudaFree(ctx->d_occ_dil);
     cudaFree(ctx->d_raw); cudaFree(ctx->d_planes); cudaFree(ctx->d_dil); cudaFree(ctx->d_closed); cudaFree(ctx->d_word_base);
     cudaFree(ctx->d_run_pos); cudaFree(ctx->d_run_len); cudaFree(ctx->d_parent); cudaFree(ctx->d_run_label); cudaFree(ctx->d_label_count); cudaFree(ctx->d_label_slot);
-    cudaFree(ctx->d_root_count); cudaFree(ctx->d_scan_runs); cudaFree(ctx->d_scan_rank); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
-    cudaFree(ctx->d_summary); if (!ctx->shared_args) cudaFree(ctx->d_scalars); cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
+    cudaFree(ctx->d_root_count); cudaFree(ctx->d_scan_runs); cudaFree(ctx->d_scan_rank); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_rank); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
+    cudaFree(ctx->d_summary); cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
     cudaFree(ctx->d_entry_dist); cudaFree(ctx->d_entry_idx); cudaFree(ctx->d_entry_cnt); cudaFree(ctx->d_entry_res);
     cudaFree(ctx->d_surf); cudaFreeHost(ctx->h_surf); cudaFree(ctx->d_pose_buf);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -124,7 +163,7 @@ extern "C" int mamri_destroy(mamri_ctx* ctx) {
     if (ctx->cap_stream2) cudaStreamDestroy(ctx->cap_stream2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    if (!ctx->shared_args) { cudaFree(ctx->d_dyn); cudaFreeHost(ctx->h_dyn); }
+    if (!ctx->shared_args) { cudaFree(ctx->d_args); cudaFreeHost(ctx->h_args); }
     cudaFreeHost(ctx->h_markers); cudaFreeHost(ctx->h_summary); cudaFreeHost(ctx->h_entry_res);
     delete ctx;
     return MAMRI_OK;
@@ -195,18 +234,18 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     ALLOC(ctx->d_label_count, size_t(max_runs) * 4, "label counts");
     ALLOC(ctx->d_label_slot, size_t(max_runs) * 4, "label slots");
     ALLOC(ctx->d_root_count, size_t(max_runs) * 4, "root counts");
-    {   // look-back states of the two single-pass scans (tile sizes: ccl.cu RS_TILE = 8192 words, FR_TILE = 1024 runs)
-        const size_t t_runs = ctx->cap_words / 8192 + 2, t_rank = size_t(max_runs) / 1024 + 2;
+    {   // look-back states of the two single-pass scans (smallest tiles: ccl.cu k_runs_scan<4> = 2048 words, FR_TILE = 1024 runs)
+        const size_t t_runs = ctx->cap_words / 2048 + 2, t_rank = size_t(max_runs) / 1024 + 2;
         ALLOC(ctx->d_scan_runs, t_runs * 8, "scan states");
         ALLOC(ctx->d_scan_rank, t_rank * 8, "scan states");
         if ((e = cudaMemset(ctx->d_scan_runs, 0, t_runs * 8)) != cudaSuccess) return bail(e, "scan states");
         if ((e = cudaMemset(ctx->d_scan_rank, 0, t_rank * 8)) != cudaSuccess) return bail(e, "scan states");
     }
     ALLOC(ctx->d_cand_label, (size_t(max_markers) + 1) * 4, "candidate labels");
+    ALLOC(ctx->d_cand_rank, size_t(max_markers) * 4, "candidate ranks");
     ALLOC(ctx->d_cand_sums, (size_t(max_markers) + 1) * 9 * 8, "candidate sums");
     ALLOC(ctx->d_markers, size_t(max_markers) * sizeof(mamri_marker), "marker table");
     ALLOC(ctx->d_summary, sizeof(mamri_summary), "summary");
-    ALLOC(ctx->d_scalars, sizeof(DevScalars), "scalars");
     ALLOC(ctx->d_entry_dist, MAMRI_SCAN_CTAS * sizeof(double), "entry partials");
     ALLOC(ctx->d_entry_idx, MAMRI_SCAN_CTAS * sizeof(long long), "entry partials");
     ALLOC(ctx->d_entry_cnt, 2 * sizeof(unsigned long long), "entry counters");
@@ -221,8 +260,18 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     if ((e = cudaMallocHost((void**)&ctx->h_surf, sizeof(SurfScalars))) != cudaSuccess) return bail(e, "pinned surface scalars");
     for (int i = 0; i < 6; ++i)
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return bail(e, "events");
-    if ((e = cudaMalloc((void**)&ctx->d_dyn, sizeof(DynArgs))) != cudaSuccess) return bail(e, "dynamic args");
-    if ((e = cudaMallocHost((void**)&ctx->h_dyn, sizeof(DynArgs))) != cudaSuccess) return bail(e, "pinned dynamic args");
+    if ((e = cudaMalloc((void**)&ctx->d_args, sizeof(ScanArgs))) != cudaSuccess) return bail(e, "scan arguments");
+    if ((e = cudaMallocHost((void**)&ctx->h_args, sizeof(ScanArgs))) != cudaSuccess) return bail(e, "pinned scan arguments");
+    memset(ctx->h_args, 0, sizeof(ScanArgs));
+    ctx->d_dyn = &ctx->d_args->dyn; ctx->d_scalars = &ctx->d_args->sc; ctx->h_dyn = &ctx->h_args->dyn;
+    // per-device function attributes (dynamic shared memory above 48 KB, cluster size): every context sets them for
+    // its own device, so one process can drive several GPUs
+    if ((e = segment_init_device()) != cudaSuccess) return bail(e, "kernel attributes");
+    ctx->max_cluster = ccl_init_device();
+    if (const char* lc = getenv("MAMRI_LABEL_CLUSTER")) {          // experiments: 0 = scalable kernels only, N = cluster size
+        const int want = atoi(lc);
+        ctx->max_cluster = want < ctx->max_cluster ? (want < 0 ? 0 : want) : ctx->max_cluster;
+    }
     if ((e = cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "capture stream");
     if ((e = cudaStreamCreateWithFlags(&ctx->cap_stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "capture stream");
     if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "events");
@@ -234,6 +283,8 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     *out = ctx;
     return MAMRI_OK;
 }
+
+extern "C" int mamri_kernel_launches(const mamri_ctx* ctx) { return ctx ? ctx->n_launches : MAMRI_ERR_INVALID_ARG; }
 
 extern "C" int mamri_set_profiling(mamri_ctx* ctx, int enable) {
     if (!ctx) return MAMRI_ERR_INVALID_ARG;
@@ -282,17 +333,16 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool f
     const mamri_volume_desc* desc = &k.desc;
     const mamri_params* params = &k.prm;
     const int nx = desc->nx, ny = desc->ny, nz = desc->nz;
-    CK(cudaMemcpyAsync(ctx->d_dyn, ctx->h_dyn, sizeof(DynArgs), cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(DevScalars), s));
+    launch_counter() = 0;
+    CK(cudaMemcpyAsync(ctx->d_args, ctx->h_args, sizeof(ScanArgs), cudaMemcpyHostToDevice, s));   // pointers + zeroed scalars
     if (prof) { ctx->n_fine = 0; CK(cudaEventRecord(ctx->ev[0], s)); }
     CK(launch_threshold_pack(ctx, k.vol_aligned, desc->dtype, nx, ny, nz, params->lower, params->upper, params->close_radius, s));
     if (prof) CK(cudaEventRecord(ctx->ev[1], s));
     const uint32_t* mask = ctx->d_closed;
     if (params->close_radius > 0) CK(launch_closing(ctx, nx, ny, nz, params->close_radius, s));
     if (prof) CK(cudaEventRecord(ctx->ev[2], s));
-    CK(launch_ccl(ctx, mask, nx, ny, nz, params->connectivity, s));
+    CK(launch_label(ctx, mask, desc, params, s));
     if (prof) CK(cudaEventRecord(ctx->ev[3], s));
-    CK(launch_select(ctx, desc, params, s));
     const bool outputs = k.has_mask || k.has_labels || k.has_body;
     const bool forked = fork && outputs;
     if (forked) {
@@ -301,7 +351,7 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool f
         CK(launch_materialise(ctx, mask, nx, ny, nz, k.outs_aligned, ctx->cap_stream2));
         CK(cudaEventRecord(ctx->ev_join, ctx->cap_stream2));
     }
-    CK(launch_moments(ctx, desc, params, s));
+    CK(launch_stats(ctx, desc, params, s));
     if (prof) CK(cudaEventRecord(ctx->ev[4], s));
     if (outputs && !forked) CK(launch_materialise(ctx, mask, nx, ny, nz, k.outs_aligned, s));
     if (prof) CK(cudaEventRecord(ctx->ev[5], s));
@@ -309,6 +359,7 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool f
     const uint32_t eager = ctx->max_markers < EAGER_MARKERS ? ctx->max_markers : EAGER_MARKERS;
     CK(cudaMemcpyAsync(ctx->h_markers, ctx->d_markers, size_t(eager) * sizeof(mamri_marker), cudaMemcpyDeviceToHost, s));
     if (forked) CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    ctx->n_launches = launch_counter();
     return MAMRI_OK;
 }
 
@@ -336,13 +387,15 @@ static int detect_async_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, cons
     memset(&k, 0, sizeof(k));
     k.desc = *desc;
     k.prm = *params;
-    k.vol_aligned = (reinterpret_cast<uintptr_t>(d_volume) & 15u) == 0;
+    k.vol_aligned = (reinterpret_cast<uintptr_t>(d_volume) & 15u) ? 0 : ((reinterpret_cast<uintptr_t>(d_volume) & 31u) ? 1 : 2);   // 16 / 32 bytes
     k.outs_aligned = ((reinterpret_cast<uintptr_t>(d_labels_out) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(d_mask_out) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_body_out) & 15u) == 0);
     k.has_mask = d_mask_out != nullptr; k.has_labels = d_labels_out != nullptr; k.has_body = d_body_out != nullptr;
     k.run_ctas = ctx->run_ctas = run_grid_class(ctx->run_ctas, ctx->last_n_runs);
     ctx->slice_threads = slice_threads_class(ctx->slice_threads, ctx->last_n_runs, desc->nz);
     k.slice_threads = ctx->slice_threads < 0 ? -ctx->slice_threads : ctx->slice_threads;
+    k.label_cluster = ctx->label_cluster = label_cluster_class(ctx->label_cluster, ctx->last_n_runs,
+                                                               (unsigned long long)desc->nx * desc->ny * desc->nz, ctx->max_cluster);
     ctx->h_dyn->vol = d_volume;
     ctx->h_dyn->mask_out = d_mask_out;
     ctx->h_dyn->labels_out = d_labels_out;
@@ -467,9 +520,8 @@ struct mamri_pool {
     cudaEvent_t fork;
     cudaEvent_t* join;
     // device-resident batches run as ONE captured graph per wave of up to k scans (see enqueue_wave)
-    DynArgs* d_dyn_all;              // [k], contexts' d_dyn point into it -> one copy per wave
-    DynArgs* h_dyn_all;              // [k] pinned
-    DevScalars* d_scalars_all;       // [k] -> one memset per wave
+    ScanArgs* d_args_all;            // [k], the contexts' d_args point into it -> one copy per wave sets the
+    ScanArgs* h_args_all;            // [k] pinned                                 pointers and resets the scalars
     cudaStream_t hbm;                // capture origin
     cudaStream_t chain[4];           // the streaming kernels of scan i run on chain i % n_chains, one after another
     int n_chains;
@@ -509,7 +561,7 @@ extern "C" int mamri_pool_destroy(mamri_pool* pool) {
         if (pool->chain[i]) cudaStreamDestroy(pool->chain[i]);
         if (pool->ev_chain[i]) cudaEventDestroy(pool->ev_chain[i]);
     }
-    cudaFree(pool->d_dyn_all); cudaFreeHost(pool->h_dyn_all); cudaFree(pool->d_scalars_all);
+    cudaFree(pool->d_args_all); cudaFreeHost(pool->h_args_all);
     if (pool->fork) cudaEventDestroy(pool->fork);
     delete[] pool->ctx; delete[] pool->streams; delete[] pool->join;
     delete[] pool->ev_thr; delete[] pool->ev_sel; delete[] pool->ev_done; delete[] pool->waves;
@@ -565,15 +617,16 @@ extern "C" int mamri_pool_create(mamri_pool** out, int device, int32_t n_context
         e = cudaStreamCreateWithFlags(&p->chain[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_chain[i], cudaEventDisableTiming);
     }
-    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_dyn_all, sizeof(DynArgs) * n_contexts);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_dyn_all, sizeof(DynArgs) * n_contexts);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_scalars_all, sizeof(DevScalars) * n_contexts);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_args_all, sizeof(ScanArgs) * n_contexts);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_args_all, sizeof(ScanArgs) * n_contexts);
+    if (e == cudaSuccess) memset(p->h_args_all, 0, sizeof(ScanArgs) * n_contexts);
     if (e == cudaSuccess) {
         // the contexts' per-call arguments and scalars become slices of the pool's arrays
         for (int i = 0; i < n_contexts; ++i) {
             mamri_ctx* c = p->ctx[i];
-            cudaFree(c->d_dyn); cudaFreeHost(c->h_dyn); cudaFree(c->d_scalars);
-            c->d_dyn = p->d_dyn_all + i; c->h_dyn = p->h_dyn_all + i; c->d_scalars = p->d_scalars_all + i;
+            cudaFree(c->d_args); cudaFreeHost(c->h_args);
+            c->d_args = p->d_args_all + i; c->h_args = p->h_args_all + i;
+            c->d_dyn = &c->d_args->dyn; c->d_scalars = &c->d_args->sc; c->h_dyn = &c->h_args->dyn;
             c->shared_args = true;
         }
         const char* tr = getenv("MAMRI_WAVE_TRACE");
@@ -623,8 +676,8 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
     const int nx = desc->nx, ny = desc->ny, nz = desc->nz;
     cudaStream_t H0 = pool->hbm;
     const int NC = pool->n_chains;
-    CKP(cudaMemcpyAsync(pool->d_dyn_all, pool->h_dyn_all, sizeof(DynArgs) * m, cudaMemcpyHostToDevice, H0));
-    CKP(cudaMemsetAsync(pool->d_scalars_all, 0, sizeof(DevScalars) * m, H0));
+    launch_counter() = 0;
+    CKP(cudaMemcpyAsync(pool->d_args_all, pool->h_args_all, sizeof(ScanArgs) * m, cudaMemcpyHostToDevice, H0));
     CKP(cudaEventRecord(pool->fork, H0));
     for (int c = 0; c < NC; ++c) CKP(cudaStreamWaitEvent(pool->chain[c], pool->fork, 0));
     for (int i = 0; i < m; ++i) {
@@ -641,9 +694,8 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
         CKP(cudaStreamWaitEvent(s, pool->ev_thr[i], 0));
         if (prm->close_radius > 0) CKP(launch_closing(c, nx, ny, nz, prm->close_radius, s));
         TRACE(i, 2, s);
-        CKP(launch_ccl(c, c->d_closed, nx, ny, nz, prm->connectivity, s));
         TRACE(i, 3, s);
-        CKP(launch_select(c, desc, prm, s));
+        CKP(launch_label(c, c->d_closed, desc, prm, s));
         TRACE(i, 4, s);
         CKP(cudaEventRecord(pool->ev_sel[i], s));
     }
@@ -658,7 +710,7 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
     for (int i = 0; i < m; ++i) {
         mamri_ctx* c = pool->ctx[i];
         cudaStream_t s = pool->streams[i];
-        CKP(launch_moments(c, desc, prm, s));
+        CKP(launch_stats(c, desc, prm, s));
         CKP(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(mamri_summary), cudaMemcpyDeviceToHost, s));
         const uint32_t eager = c->max_markers < EAGER_MARKERS ? c->max_markers : EAGER_MARKERS;
         CKP(cudaMemcpyAsync(c->h_markers, c->d_markers, size_t(eager) * sizeof(mamri_marker), cudaMemcpyDeviceToHost, s));
@@ -671,6 +723,7 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
         CKP(cudaStreamWaitEvent(H0, pool->ev_chain[c], 0));
     }
 #undef TRACE
+    for (int i = 0; i < m; ++i) pool->ctx[i]->n_launches = launch_counter() / m;
     return MAMRI_OK;
 }
 
@@ -762,18 +815,23 @@ static int wave_key(mamri_pool* pool, const mamri_volume_desc* desc, const void*
     k.desc = *desc;
     k.prm = *params;
     k.has_mask = mask_out != nullptr; k.has_labels = labels_out != nullptr; k.has_body = body_out != nullptr;
-    k.vol_aligned = 1; k.outs_aligned = 1;
+    k.vol_aligned = 2; k.outs_aligned = 1;
     {   // one grid class for the wave, from the largest run count the pool's contexts have seen last
         uint32_t hint = 0;
         for (int j = 0; j < pool->k; ++j) hint = pool->ctx[j]->last_n_runs > hint ? pool->ctx[j]->last_n_runs : hint;
         k.run_ctas = run_grid_class(pool->ctx[0]->run_ctas, hint);
         const int st = slice_threads_class(pool->ctx[0]->slice_threads, hint, desc->nz);
         k.slice_threads = st < 0 ? -st : st;
-        for (int j = 0; j < pool->k; ++j) { pool->ctx[j]->run_ctas = k.run_ctas; pool->ctx[j]->slice_threads = st; }
+        k.label_cluster = label_cluster_class(pool->ctx[0]->label_cluster, hint, (unsigned long long)desc->nx * desc->ny * desc->nz,
+                                              pool->ctx[0]->max_cluster);
+        for (int j = 0; j < pool->k; ++j) {
+            pool->ctx[j]->run_ctas = k.run_ctas; pool->ctx[j]->slice_threads = st; pool->ctx[j]->label_cluster = k.label_cluster;
+        }
     }
     for (int i = 0; i < n; ++i) {
         if (!volumes[i]) return pfail(MAMRI_ERR_INVALID_ARG, "volume pointer is NULL");
         if (reinterpret_cast<uintptr_t>(volumes[i]) & 15u) k.vol_aligned = 0;
+        else if ((reinterpret_cast<uintptr_t>(volumes[i]) & 31u) && k.vol_aligned > 1) k.vol_aligned = 1;
         if ((mask_out && (reinterpret_cast<uintptr_t>(mask_out[i]) & 15u)) ||
             (labels_out && (reinterpret_cast<uintptr_t>(labels_out[i]) & 15u)) ||
             (body_out && (reinterpret_cast<uintptr_t>(body_out[i]) & 15u)))

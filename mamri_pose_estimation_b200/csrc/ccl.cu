@@ -33,7 +33,9 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 // first voxel) and length of every run, in raster order.  One pass over the mask: a CTA takes a tile of
 // RS_TILE words (16 consecutive words per thread, 128-bit loads), scans its run-start counts, gets
 // the count of all earlier tiles by decoupled look-back and writes its part of both tables.
-constexpr int RS_THREADS = 512, RS_ITEMS = 16, RS_TILE = RS_THREADS * RS_ITEMS;   // few, large tiles: short look-back chains
+// Tiles of RS_THREADS x ITEMS words: 16 words per thread on large masks (few, large tiles), 4 on small ones (enough
+// CTAs to use the machine).  The prefix of a tile comes from a CTA-wide look-back (scan_lookback_cta).
+constexpr int RS_THREADS = 512;
 
 template <int WARPS>
 __device__ __forceinline__ uint32_t block_excl_scan_w(uint32_t v, uint32_t* ws /*[WARPS]*/, uint32_t& total) {
@@ -53,14 +55,18 @@ __device__ __forceinline__ uint32_t block_excl_scan_w(uint32_t v, uint32_t* ws /
     return off + inc - v;
 }
 
+template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
                                                           volatile unsigned long long* state, const DynArgs* __restrict__ dyn,
                                                           uint32_t* __restrict__ word_base, uint32_t* __restrict__ run_pos,
                                                           uint32_t* __restrict__ run_len, uint32_t* __restrict__ root_count,
                                                           uint32_t max_runs, DevScalars* sc) {
+    constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     pdl_wait();
+    ktrace(KT_RUNS);
     __shared__ uint32_t ws[RS_THREADS / 32];
-    __shared__ uint32_t s_tile, s_prefix;
+    __shared__ uint32_t red[34];
+    __shared__ uint32_t s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(&sc->ticket_runs, 1u);
     __syncthreads();
     const uint32_t tile = s_tile, n_tiles = gridDim.x;
@@ -93,18 +99,13 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
     }
     uint32_t total;
     const uint32_t ex = block_excl_scan_w<RS_THREADS / 32>(cnt, ws, total);
-    if (threadIdx.x < 32) {
-        const uint32_t before = scan_lookback(state, tile, total, dyn->gen);
-        if (threadIdx.x == 0) {
-            s_prefix = before;
-            if (tile == n_tiles - 1) {                   // grand total: every later stage keys off n_runs / status
-                if (before + total > max_runs) { sc->status = MAMRI_ERR_CAPACITY; sc->n_runs = 0; }
-                else sc->n_runs = before + total;
-            }
-        }
+    const uint32_t before = scan_lookback_cta(state, tile, total, dyn->gen, red);
+    if (threadIdx.x == 0 && tile == n_tiles - 1) {      // grand total: every later stage keys off n_runs / status
+        if (before + total > max_runs) { sc->status = MAMRI_ERR_CAPACITY; sc->n_runs = 0; }
+        else sc->n_runs = before + total;
     }
-    __syncthreads();
-    uint32_t base = s_prefix + ex;
+    ktrace(KT_RUNS_LB);
+    uint32_t base = before + ex;
     uint32_t wb[RS_ITEMS];
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; ++k) {
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
                                                                const uint32_t* __restrict__ run_len, uint32_t* parent,
                                                                int W, int ny, int nz, const DevScalars* sc) {
     pdl_wait();
+    ktrace(KT_USLICE);
     __shared__ uint32_t sp[SLICE_SMEM_RUNS];
     if (sc->status != MAMRI_OK) return;
     const uint32_t z = blockIdx.x;
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ ma
                                                  uint32_t* parent, int W, int ny, int radix, int between_blocks,
                                                  const DevScalars* sc) {
     pdl_wait();
+    ktrace(between_blocks ? KT_UZ2 : KT_UZ1);
     if (sc->status != MAMRI_OK) return;
     const uint32_t n = sc->n_runs;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
@@ -306,6 +309,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_flatten_rank(uint32_t* parent, c
                                                              const DynArgs* __restrict__ dyn, uint32_t* __restrict__ run_label,
                                                              uint32_t* root_count, DevScalars* sc) {
     pdl_wait();
+    ktrace(KT_RANK);
     __shared__ CtaCache<1, uint32_t, 64> cache;
     __shared__ uint32_t ws[9];
     __shared__ uint32_t s_tile, s_prefix;
@@ -382,13 +386,318 @@ __global__ void __launch_bounds__(FR_THREADS) k_flatten_rank(uint32_t* parent, c
     cache.flush(root_count);
 }
 
-cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int connectivity, cudaStream_t s) {
+
+// ------------------------------------------------------------------------------------------------
+// small run tables: union-find, ranking and the candidate filter in ONE launch by one thread-block cluster
+// ------------------------------------------------------------------------------------------------
+// A clinical scan has a few ten thousand x-runs; on such a table the five kernels above (per-slice union, two
+// boundary-merge rounds, flatten + rank, filter) are five dependent launches of microseconds of work each.  Here one
+// cluster of NC CTAs does all of it, with hardware cluster barriers (barrier.cluster, ~0.2 us) where the kernels
+// had launch boundaries.  CTA c owns a chunk of consecutive slices holding about 1/NC of the runs:
+//   U1  block-local union-find in shared memory over the chunk: joins with the row above AND with the slice below
+//       when it belongs to the chunk; pointer-jumping flatten; parents published as global run ids
+//   U2  global boundary merge: the runs of each chunk's first slice join the slice below (atomicMin on the roots;
+//       at most NC - 1 boundaries, so root chains stay shorter than NC)
+//   F   every run finds its root; voxel counts per root (warp shuffles -> CTA cache -> atomics); roots of the chunk
+//       are ranked locally in raster order, the CTA totals are exchanged through DevScalars::cl_roots
+//   FIX roots get their ITK-consecutive label = 1 + roots of the earlier chunks + local rank
+//   S   the volume filter, marker slots, the body bid and the final label of every run (as k_select)
+// The result is bit-identical to the multi-kernel path (run ids are raster-ordered, the smaller id wins every hook).
+// Any run count is handled correctly (a chunk that does not fit shared memory works on the global array); the host
+// picks this path when the previous scans had few enough runs for it to be the faster one.
+constexpr int LC_THREADS = 1024;
+constexpr uint32_t LC_SMEM_RUNS = 10240;             // 40 KB of parents per CTA
+
+struct LabelArgs {
+    const uint32_t* mask;
+    const uint32_t* word_base;
+    const uint32_t* run_pos;
+    const uint32_t* run_len;
+    uint32_t* parent;
+    uint32_t* run_label;
+    uint32_t* root_count;
+    uint32_t* label_count;
+    uint32_t* label_slot;
+    uint32_t* cand_label;
+    unsigned long long* sums;
+    DevScalars* sc;
+    int W, ny, nz;
+    uint32_t max_markers;
+    int fence;                          // explicit gpu-scope fence before each cluster barrier (MAMRI_CLUSTER_FENCE, default 1)
+    double voxel_volume, min_volume, max_volume;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// Barrier over the whole cluster; global-memory writes made before it are visible to every CTA after it.
+__device__ __forceinline__ void cluster_barrier(int fence) {
+    if (fence) __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+template <bool CONN26>
+__global__ void __launch_bounds__(LC_THREADS, 1) k_label_cluster(LabelArgs a) {
+    __shared__ uint32_t sp[LC_SMEM_RUNS];
+    __shared__ CtaCache<1, uint32_t, 64> cache;
+    __shared__ uint32_t s_zcnt[2];
+    __shared__ uint32_t s_wsum[LC_THREADS / 32];
+    __shared__ uint32_t s_carry;
+    __shared__ unsigned long long s_bid, s_fg;
+    pdl_wait();
+    ktrace(KT_LABEL);
+    DevScalars* sc = a.sc;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t rank = cluster_rank(), NC = cluster_size();
+    const uint32_t n = sc->status == MAMRI_OK ? sc->n_runs : 0u;     // uniform over the cluster (written by k_runs_scan)
+    if (n == 0) return;                                               // n_labels, n_cand, body: all zero already
+    const int W = a.W, ny = a.ny, nz = a.nz;
+    const uint32_t slice_words = uint32_t(W) * uint32_t(ny);
+    // ---- chunk of slices: [zlo, zhi) with zlo = #{z : first run of slice z < rank n / NC} (the slice bases are sorted)
+    const uint32_t t_lo = uint32_t((unsigned long long)rank * n / NC), t_hi = uint32_t((unsigned long long)(rank + 1) * n / NC);
+    if (tid < 2) s_zcnt[tid] = 0;
+    if (tid == 0) { s_bid = 0ull; s_fg = 0ull; }
+    __syncthreads();
+    {
+        uint32_t c_lo = 0, c_hi = 0;
+        for (uint32_t z = tid; z < uint32_t(nz); z += blockDim.x) {
+            const uint32_t b = a.word_base[z * slice_words];
+            c_lo += b < t_lo;
+            c_hi += b < t_hi;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { c_lo += __shfl_xor_sync(FULL, c_lo, o); c_hi += __shfl_xor_sync(FULL, c_hi, o); }
+        if (lane == 0) { if (c_lo) atomicAdd(&s_zcnt[0], c_lo); if (c_hi) atomicAdd(&s_zcnt[1], c_hi); }
+    }
+    __syncthreads();
+    const uint32_t zlo = s_zcnt[0], zhi = rank + 1 == NC ? uint32_t(nz) : s_zcnt[1];
+    const uint32_t r0 = zlo < uint32_t(nz) ? a.word_base[zlo * slice_words] : n;
+    const uint32_t r1 = zhi < uint32_t(nz) ? a.word_base[zhi * slice_words] : n;
+    const uint32_t nr = r1 - r0;                                      // runs of this chunk (ids r0 .. r1 - 1)
+
+    // ---- U1: block-local union-find over the chunk
+    uint32_t* P = nr <= LC_SMEM_RUNS ? sp : a.parent + r0;
+    for (uint32_t i = tid; i < nr; i += blockDim.x) P[i] = i;
+    __syncthreads();
+    for (uint32_t i = tid; i < nr; i += blockDim.x) {
+        const uint32_t pos = a.run_pos[r0 + i];
+        const uint32_t wi = pos >> 5, row = wi / uint32_t(W);
+        const uint32_t z = row / uint32_t(ny), y = row - z * uint32_t(ny);
+        const int gx0 = int((wi - row * uint32_t(W)) * 32 + (pos & 31u));
+        const int len = int(a.run_len[r0 + i]);
+        if (y > 0) join_run<CONN26>(a.mask, a.word_base, P, r0, W, i, gx0, len, (row - 1) * uint32_t(W));
+        if (z > zlo) {
+            const uint32_t below = (row - uint32_t(ny)) * uint32_t(W);
+            join_run<CONN26>(a.mask, a.word_base, P, r0, W, i, gx0, len, below);
+            if (CONN26) {
+                if (y > 0) join_run<true>(a.mask, a.word_base, P, r0, W, i, gx0, len, below - uint32_t(W));
+                if (y + 1 < uint32_t(ny)) join_run<true>(a.mask, a.word_base, P, r0, W, i, gx0, len, below + uint32_t(W));
+            }
+        }
+    }
+    {
+        bool again = true;
+        while (again) {
+            __syncthreads();
+            bool changed = false;
+            for (uint32_t i = tid; i < nr; i += blockDim.x) {
+                const uint32_t p = ld_vol(P + i), pp = ld_vol(P + p);
+                if (pp != p) { P[i] = pp; changed = true; }
+            }
+            again = __syncthreads_or(changed);
+        }
+    }
+    for (uint32_t i = tid; i < nr; i += blockDim.x) a.parent[r0 + i] = r0 + P[i];   // in place when P is the global array
+    cluster_barrier(a.fence);
+    ktrace(KT_L_U1);
+
+    // ---- U2: the chunk's first slice joins the slice below it (owned by an earlier chunk)
+    if (zlo > 0 && zlo < uint32_t(nz) && nr > 0) {
+        const uint32_t e0 = r0;
+        const uint32_t e1 = zlo + 1 < uint32_t(nz) ? a.word_base[(zlo + 1) * slice_words] : n;
+        for (uint32_t r = e0 + tid; r < e1; r += blockDim.x) {
+            const uint32_t pos = a.run_pos[r];
+            const uint32_t wi = pos >> 5, row = wi / uint32_t(W);
+            const uint32_t y = row - zlo * uint32_t(ny);
+            const int gx0 = int((wi - row * uint32_t(W)) * 32 + (pos & 31u));
+            const int len = int(a.run_len[r]);
+            const uint32_t below = (row - uint32_t(ny)) * uint32_t(W);
+            join_run<CONN26>(a.mask, a.word_base, a.parent, 0u, W, r, gx0, len, below);
+            if (CONN26) {
+                if (y > 0) join_run<true>(a.mask, a.word_base, a.parent, 0u, W, r, gx0, len, below - uint32_t(W));
+                if (y + 1 < uint32_t(ny)) join_run<true>(a.mask, a.word_base, a.parent, 0u, W, r, gx0, len, below + uint32_t(W));
+            }
+        }
+    }
+    cluster_barrier(a.fence);
+    ktrace(KT_L_U2);
+
+    // ---- F: roots, voxel counts per root, local rank of the chunk's roots (kept in run_label until FIX)
+    cache.init();
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t b = 0; b < nr; b += blockDim.x) {
+        const uint32_t i = b + tid;
+        uint32_t key = MAMRI_NONE, v[1] = {0u};
+        bool is_root = false;
+        if (i < nr) {
+            const uint32_t r = r0 + i;
+            uint32_t x = r, p = ld_vol(a.parent + x);
+            while (p != x) { x = p; p = ld_vol(a.parent + x); }
+            a.parent[r] = x;                                           // roots stay fixed points: concurrent walkers stay correct
+            is_root = x == r;
+            key = x;
+            v[0] = a.run_len[r];
+        }
+        warp_agg_add(key, v, cache, a.root_count);
+        const unsigned bal = __ballot_sync(FULL, is_root);
+        if (lane == 0) s_wsum[wid] = __popc(bal);
+        __syncthreads();
+        uint32_t off = 0, tot = 0;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) {
+            const uint32_t t = s_wsum[w];
+            if (w < wid) off += t;
+            tot += t;
+        }
+        const uint32_t carry = s_carry;
+        if (is_root) a.run_label[r0 + i] = carry + off + __popc(bal & ((1u << lane) - 1u));
+        __syncthreads();
+        if (tid == 0) s_carry = carry + tot;
+    }
+    cache.flush(a.root_count);
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile unsigned int*>(&sc->cl_roots[rank]) = s_carry;
+    cluster_barrier(a.fence);
+    ktrace(KT_L_F);
+
+    // ---- FIX: consecutive labels in raster order of the roots
+    uint32_t base = 0;
+    for (uint32_t c = 0; c < rank; ++c) base += ld_vol(&sc->cl_roots[c]);
+    if (rank + 1 == NC && tid == 0) sc->n_labels = base + s_carry;
+    for (uint32_t i = tid; i < nr; i += blockDim.x) {
+        const uint32_t r = r0 + i;
+        if (ld_vol(a.parent + r) == r) a.run_label[r] = ld_vol(a.run_label + r) + base + 1u;
+    }
+    cluster_barrier(a.fence);
+    ktrace(KT_L_FIX);
+
+    // ---- S: volume filter (Mamri.py:1310), body bid (:1320-1322), final label of every run
+    {
+        unsigned long long packed = 0ull, cnt64 = 0ull;
+        for (uint32_t i = tid; i < nr; i += blockDim.x) {
+            const uint32_t r = r0 + i;
+            const uint32_t root = ld_vol(a.parent + r);
+            if (root != r) {
+                a.run_label[r] = ld_vol(a.run_label + root);
+            } else {
+                const uint32_t cnt = ld_vol(a.root_count + r), label = ld_vol(a.run_label + r);
+                a.label_count[label - 1u] = cnt;
+                cnt64 += cnt;
+                const double vol = double(cnt) * a.voxel_volume;        // GetPhysicalSize
+                uint32_t slot = MAMRI_NONE;
+                if (vol >= a.min_volume && vol <= a.max_volume) {         // inclusive bounds
+                    slot = atomicAdd(&sc->n_cand, 1u);
+                    if (slot < a.max_markers) a.cand_label[slot] = label; else slot = MAMRI_NONE;
+                } else {
+                    const unsigned long long bid = ((unsigned long long)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - label);
+                    packed = bid > packed ? bid : packed;
+                }
+                a.label_slot[r] = slot;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long p2 = __shfl_xor_sync(FULL, packed, o);
+            packed = p2 > packed ? p2 : packed;
+            cnt64 += __shfl_xor_sync(FULL, cnt64, o);
+        }
+        if (lane == 0) {
+            if (packed) atomicMax(&s_bid, packed);
+            if (cnt64) atomicAdd(&s_fg, cnt64);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (s_bid) atomicMax(&sc->body_packed, s_bid);
+            if (s_fg) atomicAdd(&sc->n_foreground, s_fg);
+        }
+    }
+    cluster_barrier(a.fence);
+    ktrace(KT_L_S);
+    // ---- the first CTA clamps the candidate count, names the body's label in slot `max_markers` and zeroes the
+    // moment sums of the slots in use (as the last CTA of k_select does)
+    if (rank == 0) {
+        uint32_t nc = *(volatile unsigned int*)&sc->n_cand;
+        if (nc > a.max_markers) {
+            nc = a.max_markers;
+            if (tid == 0) sc->status = MAMRI_ERR_CAPACITY;
+        }
+        const unsigned long long bp = *(volatile unsigned long long*)&sc->body_packed;
+        if (tid == 0 && (bp >> 32) != 0ull) a.cand_label[a.max_markers] = 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull);
+        for (uint32_t i = tid; i < nc * 9u; i += blockDim.x) a.sums[i] = 0ull;
+        for (uint32_t i = tid; i < 9u; i += blockDim.x) a.sums[uint32_t(a.max_markers) * 9u + i] = 0ull;
+    }
+}
+
+// Largest cluster the labelling kernel can be launched with on the current device (16 needs the non-portable opt-in),
+// 0 = none.  Also sets the per-device function attributes; called from mamri_create under its device guard.
+template <bool C26>
+static int label_cluster_probe() {
+    int best = 0;
+    cudaFuncSetAttribute(k_label_cluster<C26>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (int nc = 16; nc >= 2 && best == 0; nc >>= 1) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(nc); cfg.blockDim = dim3(LC_THREADS);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, k_label_cluster<C26>, &cfg) == cudaSuccess && n_clusters >= 1) best = nc;
+    }
+    cudaGetLastError();
+    return best;
+}
+
+int ccl_init_device() {
+    const int a = label_cluster_probe<false>(), b = label_cluster_probe<true>();
+    return a < b ? a : b;
+}
+
+// Labelling of the closed mask, the volume filter and the body label: everything `materialise` needs.
+// c->label_cluster > 0: one cluster of that many CTAs (small run tables); otherwise the scalable kernels.
+cudaError_t launch_label(mamri_ctx* c, const uint32_t* d_mask, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
+    const int nx = desc->nx, ny = desc->ny, nz = desc->nz, connectivity = prm->connectivity;
     const int W = (nx + 31) / 32;
     const uint32_t n_words = uint32_t(W) * ny * nz;
-    const uint32_t scan_tiles = (n_words + RS_TILE - 1) / RS_TILE;
-    LK(k_runs_scan, scan_tiles, RS_THREADS, s, false, d_mask, W, n_words, c->d_scan_runs, c->d_dyn, c->d_word_base,
-       c->d_run_pos, c->d_run_len, c->d_root_count, c->max_runs, c->d_scalars);
+    if (n_words >= 148u * RS_THREADS * 16u) {
+        LK(k_runs_scan<16>, (n_words + RS_THREADS * 16 - 1) / (RS_THREADS * 16), RS_THREADS, s, false, d_mask, W, n_words, c->d_scan_runs,
+           c->d_dyn, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_root_count, c->max_runs, c->d_scalars);
+    } else {
+        LK(k_runs_scan<4>, (n_words + RS_THREADS * 4 - 1) / (RS_THREADS * 4), RS_THREADS, s, false, d_mask, W, n_words, c->d_scan_runs,
+           c->d_dyn, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_root_count, c->max_runs, c->d_scalars);
+    }
     prof_mark(c, s, "runs_scan");
+    if (c->label_cluster > 0) {
+        static const int fence = [] { const char* e = getenv("MAMRI_CLUSTER_FENCE"); return e ? atoi(e) : 1; }();
+        LabelArgs a;
+        a.mask = d_mask; a.word_base = c->d_word_base; a.run_pos = c->d_run_pos; a.run_len = c->d_run_len;
+        a.parent = c->d_parent; a.run_label = c->d_run_label; a.root_count = c->d_root_count; a.label_count = c->d_label_count;
+        a.label_slot = c->d_label_slot; a.cand_label = c->d_cand_label; a.sums = c->d_cand_sums; a.sc = c->d_scalars;
+        a.W = W; a.ny = ny; a.nz = nz; a.max_markers = c->max_markers; a.fence = fence;
+        double vv = 1.0;
+        for (int i = 0; i < 3; ++i) vv *= desc->spacing[i];       // ITK: sizePerPixel *= spacing[i]
+        a.voxel_volume = vv; a.min_volume = prm->min_volume; a.max_volume = prm->max_volume;
+        const unsigned nc = unsigned(c->label_cluster);
+        cudaError_t e = connectivity == 26
+            ? launch_kc(k_label_cluster<true>, dim3(nc), dim3(LC_THREADS), 0, nc, s, false, a)
+            : launch_kc(k_label_cluster<false>, dim3(nc), dim3(LC_THREADS), 0, nc, s, false, a);
+        if (e != cudaSuccess) return e;
+        prof_mark(c, s, "label_cluster");
+        return cudaGetLastError();
+    }
     int radix = 1;
     while (radix * radix < nz) radix <<= 1;
     const int RG = c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS;
@@ -420,7 +729,7 @@ cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int
     LK(k_flatten_rank, RG, FR_THREADS, s, false, c->d_parent, c->d_run_len, c->d_scan_rank, c->d_dyn, c->d_run_label,
        c->d_root_count, c->d_scalars);
     prof_mark(c, s, "flatten_rank");
-    return cudaGetLastError();
+    return launch_select(c, desc, prm, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -445,6 +754,7 @@ __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict_
                                                      uint32_t n_words, const DynArgs* __restrict__ dyn,
                                                      const DevScalars* sc, int stream_hint) {
     pdl_wait();
+    ktrace(KT_MAT);
     const bool hint = stream_hint != 0;
     uint8_t* __restrict__ mask_out = dyn->mask_out;
     uint32_t* __restrict__ labels_out = dyn->labels_out;
@@ -551,7 +861,7 @@ __global__ void __launch_bounds__(256) k_materialise(const uint32_t* __restrict_
             if (mask_out) mask_out[v] = on ? 1 : 0;
             if (body_out) body_out[v] = (has_body && lab == body) ? 1 : 0;
         }
-    }
+    }    ktrace_last(KT_END);
 }
 
 cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int outs_aligned,
@@ -576,3 +886,5 @@ cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int
     prof_mark(c, s, "materialise");
     return cudaGetLastError();
 }
+
+KTRACE_TU(ccl)

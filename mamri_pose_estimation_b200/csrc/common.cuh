@@ -24,7 +24,8 @@ struct DevScalars {
     unsigned int ticket_runs;        // tile tickets of k_runs_scan / k_flatten_rank
     unsigned int ticket_rank;
     unsigned int done_select;        // CTAs of k_select that have finished (last one prepares the moment table)
-    unsigned int reserved_;
+    unsigned int done_stats;         // CTAs of k_stats that have finished their moment sums (last one finalises)
+    unsigned int cl_roots[16];       // k_label_cluster: roots found by each CTA of the cluster (rank exchange)
 };
 
 // Device-side scalars of one body-surface extraction (surface.cu).
@@ -48,6 +49,14 @@ struct DynArgs {
                                      // finaliser so that a collective can be enqueued right behind the scan
 };
 
+// One device block per context: the per-call pointers followed by the scan's scalars.  The host keeps a pinned
+// image whose scalar part is all zero, so ONE host-to-device copy per scan (per wave for a pool) both sets
+// the pointers and resets the scalars.
+struct ScanArgs {
+    DynArgs dyn;
+    DevScalars sc;
+};
+
 // Everything else a captured pipeline depends on.
 struct GraphKey {
     mamri_volume_desc desc;
@@ -55,6 +64,7 @@ struct GraphKey {
     int vol_aligned, outs_aligned, has_mask, has_labels, has_body;
     int run_ctas;                    // grid of the per-run kernels (sized from the previous scans' run counts)
     int slice_threads;               // threads of the per-slice union-find CTAs (same source)
+    int label_cluster;               // 0: labelling by the scalable multi-kernel path; N > 0: one cluster of N CTAs
 };
 
 // Bit-packed volume: `w` 32-voxel words per row, `h` rows per slice, `d` slices.
@@ -90,6 +100,7 @@ struct mamri_ctx {
     unsigned long long* d_scan_rank;  // look-back states of k_flatten_rank  [tiles of max_runs]
     uint32_t gen;
     uint32_t* d_cand_label; // label of each slot                       [max_markers + 1]
+    uint32_t* d_cand_rank;  // place of each slot in ascending label order [max_markers]
     unsigned long long* d_cand_sums; // 9 sums per slot (sx sy sz xx yy zz xy xz yz) [(max_markers+1)*9]
     mamri_marker* d_markers;         // sorted marker table              [max_markers]
     mamri_summary* d_summary;
@@ -114,9 +125,11 @@ struct mamri_ctx {
     SurfScalars* h_surf;
 
     // CUDA graph of the whole pipeline (captured on first use of a configuration, relaunched afterwards)
+    ScanArgs* d_args;                // {per-call pointers, scalars}: d_dyn / d_scalars point into it
+    ScanArgs* h_args;                // pinned image (scalars zero); copied to d_args by the graph's first node
     DynArgs* d_dyn;
-    DynArgs* h_dyn;                  // pinned; copied to d_dyn by the graph's first node
-    bool shared_args;                // d_dyn / h_dyn / d_scalars are slices of a pool's arrays (not owned)
+    DynArgs* h_dyn;
+    bool shared_args;                // d_args / h_args are slices of a pool's arrays (not owned)
     cudaStream_t cap_stream;
     cudaStream_t cap_stream2;        // second branch of the captured graph (materialise || moments + table copies)
     cudaEvent_t ev_fork, ev_join;
@@ -140,6 +153,9 @@ struct mamri_ctx {
     uint32_t last_n_runs;             // x-runs of the last collected scan: sizes the next scan's per-run grids
     int run_ctas;                     // CTAs of the per-run kernels for the scan being enqueued
     int slice_threads;                // threads of the per-slice union-find CTAs (negative: default, nothing known yet)
+    int label_cluster;                // CTAs of the labelling cluster for the scan being enqueued (0 = scalable path)
+    int max_cluster;                  // largest cluster size k_label_cluster can be launched with on this device
+    int n_launches;                   // kernels of one scan on the path last enqueued / captured
 
     char err[512];
 };
@@ -157,9 +173,13 @@ cudaError_t prepare_raw_apron(mamri_ctx* c, int nx, int ny, int nz, int radius, 
 cudaError_t launch_threshold_pack(mamri_ctx* c, int vol_aligned16, int dtype, int nx, int ny, int nz, double lo,
                                   double hi, int radius, cudaStream_t s);
 cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s);
-cudaError_t launch_ccl(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int connectivity, cudaStream_t s);
+// run numbering + union-find + ranking + volume filter + body label (one cluster kernel or the scalable kernels)
+cudaError_t launch_label(mamri_ctx* c, const uint32_t* d_mask, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
 cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
-cudaError_t launch_moments(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
+cudaError_t launch_stats(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
+// per-device function attributes (dynamic shared memory opt-in, non-portable cluster size); called by mamri_create
+cudaError_t segment_init_device();
+int ccl_init_device();               // returns the largest cluster size the labelling kernel can use (0 = none)
 cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int outs_aligned,
                                cudaStream_t s);
 cudaError_t launch_entry_search(mamri_ctx* c, const float* d_points, const float* d_normals, long long n,
@@ -195,13 +215,19 @@ int run_grid_class(int current, uint32_t hint);
 // value means "default, nothing known yet" (the first hint then sets the class without hysteresis).
 int slice_threads_class(int current, uint32_t hint, int nz);
 
+// Kernels launched through launch_kc on this thread since the counter was last reset: the enqueue functions read it
+// to report how many kernels one scan takes on the path it was given (mamri_kernel_launches).
+inline int& launch_counter() { static thread_local int n = 0; return n; }
+
+// `cluster` > 1: the grid is launched as thread-block clusters of that many CTAs along x.
 template <typename... KA, typename... A>
-inline cudaError_t launch_ks(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool big, A&&... args) {
+inline cudaError_t launch_kc(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, unsigned cluster, cudaStream_t s, bool big,
+                             A&&... args) {
     const LaunchTuning& t = launch_tuning();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[2];
+    cudaLaunchAttribute at[3];
     unsigned n = 0;
     at[n].id = cudaLaunchAttributePriority;
     at[n].val.priority = big ? t.prio_big : t.prio_small;
@@ -211,8 +237,19 @@ inline cudaError_t launch_ks(void (*kern)(KA...), dim3 grid, dim3 block, size_t 
         at[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;
     }
+    if (cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+        ++n;
+    }
     cfg.attrs = at; cfg.numAttrs = n;
+    ++launch_counter();
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
+
+template <typename... KA, typename... A>
+inline cudaError_t launch_ks(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool big, A&&... args) {
+    return launch_kc(kern, grid, block, smem, 1u, s, big, static_cast<A&&>(args)...);
 }
 
 template <typename... KA, typename... A>
@@ -245,6 +282,48 @@ __device__ __forceinline__ void pdl_wait() {
 
 
 #define FULL 0xFFFFFFFFu
+
+// ---- in-pipeline kernel timeline (trace build only: -DMAMRI_KTRACE, libmamri_b200_trace.so) -------
+// Every kernel stamps %globaltimer when its first CTA passes griddepcontrol.wait (= the kernel before it
+// has completed) into slot `id`; ktrace_mark adds in-kernel phase stamps.  mamri_ktrace_read() returns
+// the earliest stamp per slot.  One scan in flight at a time; the production library compiles this away.
+enum KId { KT_THRESHOLD = 0, KT_CLOSE, KT_ERODE, KT_RUNS, KT_USLICE, KT_UZ1, KT_UZ2, KT_RANK, KT_SELECT, KT_LABEL,
+           KT_STATS, KT_FINAL, KT_MAT, KT_END, KT_L_U1, KT_L_U2, KT_L_F, KT_L_FIX, KT_L_S, KT_L_END, KT_RUNS_LB, KT_RUNS_WR,
+           KT_CLOSE_LD, KT_CLOSE_DIL, KT_CLOSE_ERO, KT_STATS_FIN, KT_SLOTS = 32 };
+#ifdef MAMRI_KTRACE
+static __device__ unsigned long long g_ktrace[KT_SLOTS];      // one copy per translation unit (no -rdc)
+__device__ __forceinline__ void ktrace(int id) {
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(&g_ktrace[id], t);
+    }
+}
+// latest stamp of a slot instead of the earliest (stored complemented; tools/ktrace.py complements KT_END back)
+__device__ __forceinline__ void ktrace_last(int id) {
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(&g_ktrace[id], ~t);
+    }
+}
+// reset / min-merge of this translation unit's stamps (called by mamri_ktrace_reset / mamri_ktrace_read)
+#define KTRACE_TU(name)                                                                         \
+    void ktrace_reset_##name() {                                                                \
+        unsigned long long v[KT_SLOTS];                                                         \
+        memset(v, 0xFF, sizeof(v));                                                             \
+        cudaMemcpyToSymbol(g_ktrace, v, sizeof(v));                                             \
+    }                                                                                           \
+    void ktrace_merge_##name(unsigned long long* out) {                                         \
+        unsigned long long v[KT_SLOTS];                                                         \
+        if (cudaMemcpyFromSymbol(v, g_ktrace, sizeof(v)) != cudaSuccess) return;                \
+        for (int i = 0; i < KT_SLOTS; ++i) out[i] = v[i] < out[i] ? v[i] : out[i];              \
+    }
+#else
+__device__ __forceinline__ void ktrace(int) {}
+__device__ __forceinline__ void ktrace_last(int) {}
+#define KTRACE_TU(name)
+#endif
 
 // ---- single-pass prefix sums over tiles (decoupled look-back) ------------------------------------
 // One 64-bit word per tile: [63:34] generation of the launch that wrote it, [33:2] value, [1:0] flag
@@ -289,6 +368,58 @@ __device__ __forceinline__ uint32_t scan_lookback(volatile unsigned long long* s
         pos -= 32;
     }
     if (lane == 0) state[tile] = scan_pack(gen, excl + total, 2u);
+    return excl;
+}
+
+// Same, called by EVERY thread of the CTA (blockDim.x a multiple of 32, at most 1024): one window covers blockDim.x
+// earlier tiles, so with no more tiles than threads -- all of them resident -- the prefix is one round trip to L2 and
+// one block reduction instead of a chain of 32-tile windows.  `red` is shared scratch of 34 words.
+__device__ __forceinline__ uint32_t scan_lookback_cta(volatile unsigned long long* state, uint32_t tile, uint32_t total,
+                                                      uint32_t gen, uint32_t* red) {
+    const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5, nw = blockDim.x >> 5;
+    if (tile == 0) {
+        if (tid == 0) state[0] = scan_pack(gen, total, 2u);
+        return 0u;
+    }
+    if (tid == 0) state[tile] = scan_pack(gen, total, 1u);
+    const unsigned long long g30 = gen & 0x3FFFFFFFu;
+    uint32_t excl = 0;
+    int pos = int(tile);
+    while (true) {
+        const int idx = pos - 1 - int(tid);
+        uint32_t flag = 2u, val = 0u;                    // before the first tile: inclusive prefix 0
+        if (idx >= 0) {
+            unsigned long long v;
+            do {
+                v = state[idx];
+                flag = ((v >> 34) == g30) ? uint32_t(v & 3u) : 0u;
+            } while (flag == 0u);
+            val = uint32_t(v >> 2);
+        }
+        if (tid == 0) red[33] = 0xFFFFFFFFu;
+        __syncthreads();
+        // nearest earlier tile with an inclusive prefix = smallest thread index that saw flag 2
+        const unsigned incl = __ballot_sync(FULL, flag == 2u);
+        if (lane == 0 && incl) atomicMin(&red[33], wid * 32u + uint32_t(__ffs(incl) - 1));
+        __syncthreads();
+        const uint32_t first = red[33];
+        uint32_t c = tid <= first ? val : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+        if (lane == 0) red[wid] = c;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t t = lane < nw ? red[lane] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+            if (lane == 0) red[32] = t;
+        }
+        __syncthreads();
+        excl += red[32];
+        if (first != 0xFFFFFFFFu) break;
+        pos -= int(blockDim.x);
+    }
+    if (tid == 0) state[tile] = scan_pack(gen, excl + total, 2u);
     return excl;
 }
 

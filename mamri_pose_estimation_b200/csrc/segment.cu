@@ -91,8 +91,11 @@ struct RangeTest16 {
     }
 };
 
-// Occupancy cells of the raw mask, in image coordinates (rows x slices; a cell spans all of x).
+// Occupancy cells of the raw mask, in image coordinates (rows x slices; a cell spans all of x).  A cell holds the
+// tag of the last scan that saw foreground in it (occ_tag: 1..255 from the launch generation), so the cells never
+// need clearing: a stale tag that happens to equal the current one only makes the closing read a tile of air.
 constexpr uint32_t OCC_CY = 8, OCC_CZ = 4;
+__device__ __forceinline__ uint8_t occ_tag(uint32_t gen) { return uint8_t(gen % 255u + 1u); }
 
 // WHOLE: ny is even and a row is a whole number of warp trips (vec_per_row % 64 == 0), so nothing in the loop needs a
 // bounds predicate -- the common case (512- and 1024-voxel rows), and the kernel is close to issue-bound.
@@ -102,9 +105,11 @@ __global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __res
                                                             uint32_t row_stride, uint32_t slice_stride, uint32_t off,
                                                             int evict_first, uint8_t* __restrict__ occ, uint32_t occ_ncy) {
     pdl_wait();
+    ktrace(KT_THRESHOLD);
     uint64_t policy = 0;
     if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     const uint4* __restrict__ vol = static_cast<const uint4*>(dyn->vol);
+    const uint8_t tag = occ_tag(dyn->gen);
     constexpr int E = 16 / VOXEL_BYTES; // voxels per 128-bit load
     constexpr int G = 32 / E;           // lanes per output word
     constexpr int U = 2;                // vectors per lane per row in flight (x 2 rows)
@@ -140,7 +145,59 @@ __global__ void __launch_bounds__(256) k_threshold_pack_vec(const DynArgs* __res
                 }
         }
         // occupancy cell (OCC_CY rows x OCC_CZ slices) of the raw mask: lets the closing skip tiles of air unread
-        if (occ && __any_sync(0xFFFFFFFFu, seen != 0u) && lane == 0) occ[(z / OCC_CZ) * occ_ncy + y0 / OCC_CY] = 1;
+        if (occ && __any_sync(0xFFFFFFFFu, seen != 0u) && lane == 0) occ[(z / OCC_CZ) * occ_ncy + y0 / OCC_CY] = tag;
+    }
+}
+
+
+// 16-bit voxels, rows that are a whole number of 512-voxel warp trips, 32-byte aligned base: 256-bit loads
+// (ld.global.nc.v8.u32, sm_100).  A lane turns its 32 bytes = 16 voxels into 16 mask bits, two lanes make a word (one
+// shuffle), ROWS rows are in flight per warp.  About half the instructions per voxel of the 128-bit kernel above
+// (which sits between the issue and the memory limit): the compare is the same SWAR test, but the lane merge, the
+// address arithmetic and the loop overhead are paid once per 16 voxels instead of once per 8.
+__device__ __forceinline__ void ld_stream_256(const void* p, uint64_t policy, bool hint, uint4& a, uint4& b) {
+    if (hint)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p), "l"(policy));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
+template <typename Test, int ROWS>
+__global__ void __launch_bounds__(256) k_threshold_pack_v8(const DynArgs* __restrict__ dyn, uint32_t vec_per_row /* 32-byte vectors */,
+                                                           uint32_t ny, Test test, uint32_t* __restrict__ dst, uint32_t row_stride,
+                                                           uint32_t slice_stride, uint32_t off, int evict_first,
+                                                           uint8_t* __restrict__ occ, uint32_t occ_ncy) {
+    pdl_wait();
+    ktrace(KT_THRESHOLD);
+    uint64_t policy = 0;
+    if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    const char* __restrict__ vol = static_cast<const char*>(dyn->vol);
+    const uint8_t tag = occ_tag(dyn->gen);
+    const unsigned lane = lane_id();
+    const uint32_t z = blockIdx.y;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    const char* slice_src = vol + size_t(z) * ny * vec_per_row * 32u;
+    uint32_t* slice_dst = dst + off + z * slice_stride;
+    for (uint32_t y0 = warp * ROWS; y0 < ny; y0 += n_warps * ROWS) {           // ny % ROWS == 0
+        uint32_t seen = 0;
+        for (uint32_t u0 = 0; u0 < vec_per_row; u0 += 32) {                    // vec_per_row % 32 == 0
+            uint4 a[ROWS], b[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+                ld_stream_256(slice_src + (size_t(y0 + r) * vec_per_row + u0 + lane) * 32u, policy, evict_first != 0, a[r], b[r]);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const uint32_t h = test.pack(a[r]) | (test.pack(b[r]) << 8);   // 16 voxels of this lane
+                const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, h, 1);
+                const uint32_t w = (lane & 1u) ? 0u : (h | (other << 16));
+                if (!(lane & 1u)) slice_dst[(y0 + r) * row_stride + ((u0 + lane) >> 1)] = w;
+                seen |= w;
+            }
+        }
+        if (occ && __any_sync(0xFFFFFFFFu, seen != 0u) && lane == 0) occ[(z / OCC_CZ) * occ_ncy + y0 / OCC_CY] = tag;
     }
 }
 
@@ -149,7 +206,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_threshold_pack_rows(const DynArgs* __restrict__ dyn, uint32_t nx, uint32_t n_words,
                                                              T lo, T hi, BitDst dst, uint8_t* __restrict__ occ, uint32_t occ_ncy) {
     pdl_wait();
+    ktrace(KT_THRESHOLD);
     const T* __restrict__ vol = static_cast<const T*>(dyn->vol);
+    const uint8_t tag = occ_tag(dyn->gen);
     const unsigned lane = lane_id();
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -160,7 +219,7 @@ __global__ void __launch_bounds__(256) k_threshold_pack_rows(const DynArgs* __re
         const uint32_t b = __ballot_sync(0xFFFFFFFFu, p);
         if (lane == 0) {
             dst.p[dst.index(wi)] = b;
-            if (occ && b) { const uint32_t z = row / dst.ny, y = row - z * dst.ny; occ[(z / OCC_CZ) * occ_ncy + y / OCC_CY] = 1; }
+            if (occ && b) { const uint32_t z = row / dst.ny, y = row - z * dst.ny; occ[(z / OCC_CZ) * occ_ncy + y / OCC_CY] = tag; }
         }
     }
 }
@@ -213,6 +272,23 @@ static cudaError_t threshold_pack_t(mamri_ctx* c, int vol_aligned16, int nx, int
             const bool lm = (l & 0x8000u) != 0, hm = (h & 0x8000u) != 0, ch = h != 0xFFFFu;
             const uint32_t vpr = uint32_t(nx) / E;
             const bool full = (ny % 2 == 0) && (vpr % 64u == 0);
+            static const int use_v8 = [] { const char* e = getenv("MAMRI_THR_V8"); return e ? atoi(e) : 1; }();
+            const bool wide = use_v8 && vol_aligned16 >= 2 && (nx % 512 == 0) && (ny % 4 == 0);
+            if (wide) {
+                // ROWS = 4 rows per warp trip; the grid keeps the same number of warps per SM as the 128-bit kernel
+                uint32_t gx8 = (uint32_t(ny) + 31) / 32;
+                if (gx8 > want) gx8 = want;
+                if (gx8 == 0) gx8 = 1;
+                const dim3 grid8(gx8, uint32_t(nz));
+                const uint32_t vpr8 = uint32_t(nx) / 16u;
+#define MAMRI_T8(LM, HM, CH) LK(k_threshold_pack_v8<RangeTest16<LM, HM, CH, SG>, 4>, grid8, 256, s, true, src, vpr8, uint32_t(ny), RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first, occ, occ_ncy)
+                if (!ch) { if (lm) MAMRI_T8(true, true, false); else MAMRI_T8(false, true, false); }
+                else if (lm) { if (hm) MAMRI_T8(true, true, true); else MAMRI_T8(true, false, true); }
+                else { if (hm) MAMRI_T8(false, true, true); else MAMRI_T8(false, false, true); }
+#undef MAMRI_T8
+                prof_mark(c, s, "threshold_pack");
+                return cudaGetLastError();
+            }
 #define MAMRI_T16(LM, HM, CH)                                                                                         \
     do { if (full) LK(k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>, true>, grid, 256, s, true, src, vpr, uint32_t(ny), RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first, occ, occ_ncy); \
          else LK(k_threshold_pack_vec<2, RangeTest16<LM, HM, CH, SG>, false>, grid, 256, s, true, src, vpr, uint32_t(ny), RangeTest16<LM, HM, CH, SG>{lo_c, hi_c}, dst.p, dst.row_stride, dst.slice_stride, dst.off, evict_first, occ, occ_ncy); } while (0)
@@ -508,14 +584,14 @@ struct TileArgs {
     const uint8_t* occ_in;
     uint32_t occ_stride, cy, cz, oy, oz, dom_y, dom_z;
     uint8_t* occ_out;                   // one flag per tile of this pass: any output word non-zero
-    uint8_t* occ_clear;                 // consumed cells, cleared for the context's next scan (first CTA)
-    uint32_t n_clear;
+    uint32_t occ_tagged;                // occ_in holds scan tags (raw-mask cells) instead of 0/1 flags
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
 template <int R, bool ERODE, bool TO_IMAGE, int SY>
-__global__ void __launch_bounds__(1024) k_morph_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, TileArgs a) {
+__global__ void __launch_bounds__(1024) k_morph_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                     const DynArgs* __restrict__ dyn, TileArgs a) {
     extern __shared__ __align__(128) uint32_t tile[];              // [TZ+2R][TY+2R][Wp], then the mbarrier
     constexpr int RING = 2 * R + 1, NC = BallZ<R>::n_cls();
     constexpr uint32_t NEUTRAL = ERODE ? 0xFFFFFFFFu : 0u;
@@ -533,9 +609,9 @@ __global__ void __launch_bounds__(1024) k_morph_tile(const uint32_t* __restrict_
     }
     __syncthreads();
     pdl_wait();                                                    // the source is the previous kernel's output
-    if (a.occ_clear && blockIdx.x == 0 && blockIdx.y == 0)
-        for (uint32_t i = threadIdx.x; i < a.n_clear; i += blockDim.x) a.occ_clear[i] = 0;
+    ktrace(ERODE ? KT_ERODE : KT_CLOSE);
     if (a.occ_in) {
+        const uint8_t want = a.occ_tagged ? occ_tag(dyn->gen) : uint8_t(1);
         // source rows [ys0, ys0 + rows_src) x slices [zs0, zs0 + n_slices), clipped to the occupancy domain
         const int ya = max(int(ys0) - int(a.oy), 0), yb = min(int(ys0 + rows_src) - int(a.oy), int(a.dom_y));
         const int za = max(int(zs0) - int(a.oz), 0), zb = min(int(zs0 + n_slices) - int(a.oz), int(a.dom_z));
@@ -544,7 +620,7 @@ __global__ void __launch_bounds__(1024) k_morph_tile(const uint32_t* __restrict_
             const int c0 = ya / int(a.cy), nyc = (yb - 1) / int(a.cy) - c0 + 1;
             const int d0 = za / int(a.cz), nzc = (zb - 1) / int(a.cz) - d0 + 1;
             for (int i = threadIdx.x; i < nyc * nzc; i += blockDim.x)
-                hit |= a.occ_in[(d0 + i / nyc) * a.occ_stride + c0 + i % nyc];
+                hit |= a.occ_in[(d0 + i / nyc) * a.occ_stride + c0 + i % nyc] == want;
         }
         if (!__syncthreads_or(hit)) {                              // air: the output of either pass is zero
             if (a.occ_out && threadIdx.x == 0) a.occ_out[blockIdx.y * gridDim.x + blockIdx.x] = 0;
@@ -674,14 +750,6 @@ template <int R, int SY>
 static cudaError_t closing_tile_r(mamri_ctx* c, int nx, int ny, int nz, uint32_t TY, uint32_t TZ, uint32_t smem,
                                   cudaStream_t s) {
     const PadGeom g(nx, ny, nz, R);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_morph_tile<R, false, false, SY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 + 16);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_morph_tile<R, true, true, SY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 + 16);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
     TileArgs a;
     a.Wp = g.Wp; a.slice = g.slice; a.TY = TY; a.TZ = TZ;
     // dilation on the r-grown domain: rows [R, ny+3R), slices [R, nz+3R), every padded word column
@@ -696,29 +764,290 @@ static cudaError_t closing_tile_r(mamri_ctx* c, int nx, int ny, int nz, uint32_t
     a.occ_in = occ ? c->d_occ_raw : nullptr;
     a.occ_stride = ncy; a.cy = OCC_CY; a.cz = OCC_CZ; a.oy = 2 * R; a.oz = 2 * R; a.dom_y = uint32_t(ny); a.dom_z = uint32_t(nz);
     a.occ_out = occ ? c->d_occ_dil : nullptr;
-    a.occ_clear = nullptr; a.n_clear = 0;
+    a.occ_tagged = 1;
     const dim3 dil_grid = grid;
-    LKS(k_morph_tile<R, false, false, SY>, grid, threads, smem, s, false, c->d_raw, c->d_dil, a);
+    LKS(k_morph_tile<R, false, false, SY>, grid, threads, smem, s, false, c->d_raw, c->d_dil, c->d_dyn, a);
     prof_mark(c, s, "dilate");
     // erosion: source = dilated mask, occupancy = the dilation's per-tile flags (its tiles start at padded row / slice R)
     a.occ_in = occ ? c->d_occ_dil : nullptr;
     a.occ_stride = dil_grid.x; a.cy = TY; a.cz = TZ; a.oy = R; a.oz = R; a.dom_y = uint32_t(ny) + 2 * R; a.dom_z = uint32_t(nz) + 2 * R;
     a.occ_out = nullptr;
-    a.occ_clear = occ ? c->d_occ_raw : nullptr; a.n_clear = ncy * ncz;
+    a.occ_tagged = 0;
     // erosion back on the image domain, straight into the plain [nz][ny][W] mask
     a.x_lo = 1; a.x_cnt = g.W; a.y_lo = 2 * R; a.y_cnt = uint32_t(ny); a.z_lo = 2 * R; a.z_hi = uint32_t(nz) + 2 * R;
     a.out_w = g.W; a.out_ny = uint32_t(ny);
     a.tail_mask = (nx % 32) ? (0xFFFFFFFFu >> (32 - nx % 32)) : 0xFFFFFFFFu;
     threads = ((a.x_cnt * (TY / SY) + 31) / 32) * 32;
     grid = dim3((a.y_cnt + TY - 1) / TY, (a.z_hi - a.z_lo + TZ - 1) / TZ);
-    LKS(k_morph_tile<R, true, true, SY>, grid, threads, smem, s, false, c->d_dil, c->d_closed, a);
+    LKS(k_morph_tile<R, true, true, SY>, grid, threads, smem, s, false, c->d_dil, c->d_closed, c->d_dyn, a);
     prof_mark(c, s, "erode");
     return cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Fused closing: dilation and erosion of one tile in ONE kernel, the dilated tile never leaves shared memory
+// ------------------------------------------------------------------------------------------------
+// A CTA produces TY rows x TZ slices x all word columns of the closed mask.  It fetches the raw tile with a halo
+// of 2R rows / slices (one bulk copy per slice, completion on an mbarrier), dilates it into a second shared-memory
+// tile that carries a halo of R (the r-grown domain of the safe-border rule falls out of the zero apron of the
+// padded layout), and erodes that tile straight into the plain [nz][ny][W] mask.  Both passes use the same
+// strip walk as k_morph_tile: a unit of work is one word column x a strip of SY rows x a chunk of slices, walked
+// with a register ring of 2R+1 partial results.  The source is read (TY+4R)(TZ+4R)/(TY TZ) times from L2 instead of
+// the dilated volume making a round trip through memory, and one launch replaces two.
+struct FusedArgs {
+    uint32_t Wp, slice;                 // padded row / slice strides (words); Wp % 4 == 0
+    uint32_t W, ny, nz;                 // image: words per row, rows, slices
+    uint32_t pad;                       // apron rows / slices on each side of the padded volume (>= 2R)
+    uint32_t TY, TZ;                    // output tile; (TY + 2R) % SYD == 0 and TY % SYE == 0
+    uint32_t zs_d, zs_e;                // slice chunks per strip in the dilation / erosion (more, shorter walks)
+    uint32_t tail_mask;
+    const uint8_t* occ;                 // occupancy cells of the raw mask (scan tags), NULL = read every tile
+    uint32_t occ_stride;
+};
+
+// The strip walk: `col` points at (first source row of the strip, word column) of the first source slice of a
+// shared-memory tile; source slices [k0, k1) are folded, output slice m (centred on source slice m + R) is
+// complete after source slice m + 2R and handed to store(m, y, value) for the SY rows of the strip.
+template <int R, bool ERODE, int SY, typename StoreF>
+__device__ __forceinline__ void ball_walk(const uint32_t* col, uint32_t row_stride, uint32_t slice_stride, uint32_t k0,
+                                          uint32_t k1, bool has_l, bool has_r, StoreF&& store) {
+    constexpr int RING = 2 * R + 1, NC = BallZ<R>::n_cls();
+    constexpr uint32_t NEUTRAL = ERODE ? 0xFFFFFFFFu : 0u;
+    uint32_t acc[SY][RING];
+#pragma unroll
+    for (int y = 0; y < SY; ++y)
+#pragma unroll
+        for (int j = 0; j < RING; ++j) acc[y][j] = NEUTRAL;
+    for (uint32_t k = k0; k < k1; ++k) {
+        uint32_t Q[NC][SY];
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int y = 0; y < SY; ++y) Q[c][y] = NEUTRAL;
+        const uint32_t* p = col + k * slice_stride;
+        static_for<0, SY + 2 * R>([&](auto ir) {
+            constexpr int r = decltype(ir)::value;
+            uint32_t S[R + 1];
+            load_shifted<R, ERODE>(p + r * row_stride, has_l, has_r, S);
+            static_for<0, SY>([&](auto iy) {
+                constexpr int y = decltype(iy)::value;
+                constexpr int dy = r - R - y;
+                if constexpr (dy >= -R && dy <= R) {
+                    static_for<0, NC>([&](auto ic) {
+                        constexpr int c = decltype(ic)::value;
+                        constexpr int hh = Ball<R>::h(dy < 0 ? -dy : dy, BallZ<R>::rep(c));
+                        if constexpr (hh >= 0) Q[c][y] = ERODE ? (Q[c][y] & S[hh]) : (Q[c][y] | S[hh]);
+                    });
+                }
+            });
+        });
+#pragma unroll
+        for (int y = 0; y < SY; ++y)
+            static_for<0, RING>([&](auto ij) {
+                constexpr int j = decltype(ij)::value;
+                constexpr int adz = (R - j) < 0 ? (j - R) : (R - j);
+                constexpr int c = BallZ<R>::cls(adz);
+                acc[y][j] = ERODE ? (acc[y][j] & Q[c][y]) : (acc[y][j] | Q[c][y]);
+            });
+        if (k - k0 >= 2 * R) {
+#pragma unroll
+            for (int y = 0; y < SY; ++y) store(k - 2 * R, y, acc[y][0]);
+        }
+#pragma unroll
+        for (int y = 0; y < SY; ++y) {
+#pragma unroll
+            for (int j = 0; j + 1 < RING; ++j) acc[y][j] = acc[y][j + 1];
+            acc[y][RING - 1] = NEUTRAL;
+        }
+    }
+}
+
+template <int R, int SYD, int SYE>
+__global__ void __launch_bounds__(512) k_close_fused(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                     const DynArgs* __restrict__ dyn, FusedArgs a) {
+    extern __shared__ __align__(128) uint32_t tile[];
+    const uint32_t SY_ = a.TY + 4 * R, SZ_ = a.TZ + 4 * R;          // source rows / slices held
+    const uint32_t DY = a.TY + 2 * R, DZ = a.TZ + 2 * R;            // dilated rows / slices held
+    uint32_t* s_src = tile;                                         // [SZ_][SY_][Wp]
+    uint32_t* s_dil = tile + SZ_ * SY_ * a.Wp;                      // [DZ][DY][Wp]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_dil + DZ * DY * a.Wp);
+    const uint32_t bar_s = smem_u32(bar);
+    const uint32_t Y0 = blockIdx.x * a.TY, Z0 = blockIdx.y * a.TZ;  // first output row / slice (image coordinates)
+    const uint32_t py0 = Y0 + a.pad - 2 * R, pz0 = Z0 + a.pad - 2 * R;   // first source row / slice (padded coordinates)
+    const uint32_t rows_src = min(SY_, a.ny + 2 * a.pad - py0);     // rows / slices past the padded volume feed no output
+    const uint32_t n_sl = min(SZ_, a.nz + 2 * a.pad - pz0);
+    const uint32_t out_rows = min(a.TY, a.ny - Y0), out_sl = min(a.TZ, a.nz - Z0);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();
+    ktrace(KT_CLOSE);
+    if (a.occ) {
+        const uint8_t want = occ_tag(dyn->gen);
+        // source rows / slices of the tile in image coordinates, clipped to the image (the apron is air)
+        const int ya = max(int(Y0) - 2 * R, 0), yb = min(int(Y0 + a.TY) + 2 * R, int(a.ny));
+        const int za = max(int(Z0) - 2 * R, 0), zb = min(int(Z0 + a.TZ) + 2 * R, int(a.nz));
+        const int c0 = ya / int(OCC_CY), nyc = (yb - 1) / int(OCC_CY) - c0 + 1;
+        const int d0 = za / int(OCC_CZ), nzc = (zb - 1) / int(OCC_CZ) - d0 + 1;
+        int hit = 0;
+        for (int i = threadIdx.x; i < nyc * nzc; i += blockDim.x)
+            hit |= a.occ[(d0 + i / nyc) * a.occ_stride + c0 + i % nyc] == want;
+        if (!__syncthreads_or(hit)) {                               // air: the closing of nothing is nothing
+            const uint32_t per_slice = out_rows * a.W;
+            for (uint32_t i = threadIdx.x; i < per_slice * out_sl; i += blockDim.x) {
+                const uint32_t zo = i / per_slice;
+                dst[(size_t(Z0 + zo) * a.ny + Y0) * a.W + (i - zo * per_slice)] = 0u;
+            }
+            return;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = rows_src * a.Wp * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes * n_sl) : "memory");
+        for (uint32_t k = 0; k < n_sl; ++k) {
+            const uint32_t* g = src + size_t(pz0 + k) * a.slice + py0 * a.Wp;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(s_src + k * SY_ * a.Wp)), "l"(g), "r"(bytes), "r"(bar_s) : "memory");
+        }
+    }
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar_s) : "memory");
+    }
+    ktrace(KT_CLOSE_LD);
+    // ---- dilation: dilated row j (image row Y0 - R + j) folds source rows j .. j + 2R; same along the slices.
+    // Slices / rows past the data that was fetched hold stale shared memory; they only reach outputs that are dropped.
+    {
+        const uint32_t n_strips = DY / SYD;
+        const uint32_t cz = (DZ + a.zs_d - 1) / a.zs_d;
+        const uint32_t n_units = a.Wp * n_strips * a.zs_d;
+        for (uint32_t u = threadIdx.x; u < n_units; u += blockDim.x) {
+            const uint32_t xw = u % a.Wp, rest = u / a.Wp;
+            const uint32_t strip = rest % n_strips, q = rest / n_strips;
+            const uint32_t m0 = q * cz, m1 = min(m0 + cz, DZ);
+            if (m0 >= m1) continue;
+            uint32_t* out = s_dil + (strip * SYD) * a.Wp + xw;
+            ball_walk<R, false, SYD>(s_src + (strip * SYD) * a.Wp + xw, a.Wp, SY_ * a.Wp, m0, m1 + 2 * R, xw > 0, xw + 1 < a.Wp,
+                                     [&](uint32_t m, int y, uint32_t v) { out[m * DY * a.Wp + uint32_t(y) * a.Wp] = v; });
+        }
+    }
+    __syncthreads();
+    ktrace(KT_CLOSE_DIL);
+    // ---- erosion: output row y (image row Y0 + y) folds dilated rows y .. y + 2R
+    {
+        const uint32_t n_strips = a.TY / SYE;
+        const uint32_t cz = (a.TZ + a.zs_e - 1) / a.zs_e;
+        const uint32_t n_units = a.W * n_strips * a.zs_e;
+        for (uint32_t u = threadIdx.x; u < n_units; u += blockDim.x) {
+            const uint32_t xx = u % a.W, rest = u / a.W;
+            const uint32_t strip = rest % n_strips, q = rest / n_strips;
+            const uint32_t m0 = q * cz, m1 = min(min(m0 + cz, a.TZ), out_sl);
+            if (m0 >= m1 || strip * SYE >= out_rows) continue;
+            const uint32_t tail = (xx == a.W - 1) ? a.tail_mask : 0xFFFFFFFFu;
+            uint32_t* out = dst + (size_t(Z0) * a.ny + Y0 + strip * SYE) * a.W + xx;
+            const uint32_t rows_left = out_rows - strip * SYE;
+            ball_walk<R, true, SYE>(s_dil + (strip * SYE) * a.Wp + xx + 1, a.Wp, DY * a.Wp, m0, m1 + 2 * R, true, true,
+                                    [&](uint32_t m, int y, uint32_t v) {
+                                        if (uint32_t(y) < rows_left) out[size_t(m) * a.ny * a.W + uint32_t(y) * a.W] = v & tail;
+                                    });
+        }
+    }
+    ktrace(KT_CLOSE_ERO);
+}
+
+// Tile of the fused kernel for rows of Wp padded words: TY from {SYD k - 2R} with TY % SYE == 0 near the wanted size,
+// TZ halved until source + dilated tile fit the shared-memory budget.  false = does not fit (very wide rows).
+template <int R, int SYD, int SYE>
+static bool fused_plan(uint32_t Wp, uint32_t want_ty, uint32_t want_tz, uint32_t budget, uint32_t& TY, uint32_t& TZ, uint32_t& smem) {
+    for (uint32_t tz = want_tz; tz >= 2; tz >>= 1) {
+        for (uint32_t ty = want_ty + 2; ty >= 4; --ty) {
+            if ((ty + 2 * R) % SYD != 0 || ty % SYE != 0) continue;
+            const uint32_t bytes = Wp * 4u * ((ty + 4 * R) * (tz + 4 * R) + (ty + 2 * R) * (tz + 2 * R)) + 16u;
+            if (bytes <= budget) { TY = ty; TZ = tz; smem = bytes; return true; }
+        }
+    }
+    return false;
+}
+
+constexpr uint32_t FUSED_SMEM_MAX = 200u * 1024u;
+
+template <int R, int SYD, int SYE>
+static cudaError_t closing_fused_r(mamri_ctx* c, int nx, int ny, int nz, bool& done, cudaStream_t s) {
+    static const int e_ty = [] { const char* e = getenv("MAMRI_CLOSE_TY"); return e ? atoi(e) : 16; }();
+    static const int e_tz = [] { const char* e = getenv("MAMRI_CLOSE_TZ"); return e ? atoi(e) : 16; }();
+    static const int e_zsd = [] { const char* e = getenv("MAMRI_CLOSE_ZSD"); return e ? atoi(e) : 1; }();
+    static const int e_zse = [] { const char* e = getenv("MAMRI_CLOSE_ZSE"); return e ? atoi(e) : 1; }();
+    static const int e_budget = [] { const char* e = getenv("MAMRI_CLOSE_SMEM_KB"); return e ? atoi(e) : 100; }();
+    static const int use_occ = [] { const char* e = getenv("MAMRI_TILE_OCC"); return e ? atoi(e) : 1; }();
+    const PadGeom g(nx, ny, nz, R);
+    FusedArgs a;
+    uint32_t smem = 0;
+    done = false;
+    uint32_t budget = uint32_t(e_budget) * 1024u;
+    if (budget > FUSED_SMEM_MAX) budget = FUSED_SMEM_MAX;
+    if (!fused_plan<R, SYD, SYE>(g.Wp, uint32_t(e_ty), uint32_t(e_tz), budget, a.TY, a.TZ, smem) &&
+        !fused_plan<R, SYD, SYE>(g.Wp, uint32_t(e_ty), uint32_t(e_tz), FUSED_SMEM_MAX, a.TY, a.TZ, smem))
+        return cudaSuccess;                                         // too wide: the caller takes the two-pass kernels
+    a.Wp = g.Wp; a.slice = g.slice; a.W = g.W; a.ny = uint32_t(ny); a.nz = uint32_t(nz); a.pad = 2 * R;
+    a.zs_d = uint32_t(e_zsd < 1 ? 1 : e_zsd); a.zs_e = uint32_t(e_zse < 1 ? 1 : e_zse);
+    a.tail_mask = (nx % 32) ? (0xFFFFFFFFu >> (32 - nx % 32)) : 0xFFFFFFFFu;
+    const uint32_t ncy = (uint32_t(ny) + OCC_CY - 1) / OCC_CY, ncz = (uint32_t(nz) + OCC_CZ - 1) / OCC_CZ;
+    a.occ = (use_occ && size_t(ncy) * ncz <= c->occ_cap) ? c->d_occ_raw : nullptr;
+    a.occ_stride = ncy;
+    const uint32_t units_d = a.Wp * ((a.TY + 2 * R) / SYD) * a.zs_d, units_e = a.W * (a.TY / SYE) * a.zs_e;
+    uint32_t threads = ((units_d > units_e ? units_d : units_e) + 31) / 32 * 32;
+    if (threads > 512) threads = 512;
+    const dim3 grid((uint32_t(ny) + a.TY - 1) / a.TY, (uint32_t(nz) + a.TZ - 1) / a.TZ);
+    LKS(k_close_fused<R, SYD, SYE>, grid, threads, smem, s, false, c->d_raw, c->d_closed, c->d_dyn, a);
+    prof_mark(c, s, "close_fused");
+    done = true;
+    return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t closing_fused_dispatch(mamri_ctx* c, int nx, int ny, int nz, bool& done, cudaStream_t s) {
+    // strip heights of the two passes: 4 rows amortise the shifted loads best, 2 rows give more, shorter walks
+    static const int syd = [] { const char* e = getenv("MAMRI_CLOSE_SYD"); return e ? atoi(e) : 4; }();
+    static const int sye = [] { const char* e = getenv("MAMRI_CLOSE_SYE"); return e ? atoi(e) : 2; }();
+    if (syd == 4 && sye == 4 && R % 2 == 0) return closing_fused_r<R, 4, 4>(c, nx, ny, nz, done, s);
+    if (syd == 4) return closing_fused_r<R, 4, 2>(c, nx, ny, nz, done, s);
+    return closing_fused_r<R, 2, 2>(c, nx, ny, nz, done, s);
+}
+
+// Opt-in to more than 48 KB of dynamic shared memory is a per-device function attribute: set for every tile kernel
+// whenever a context is created on a device (mamri_create, under its device guard, outside any stream capture).
+template <int R>
+static cudaError_t tile_attrs_r() {
+    cudaError_t e = cudaFuncSetAttribute(k_morph_tile<R, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 + 16);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_morph_tile<R, true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 + 16);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_close_fused<R, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(FUSED_SMEM_MAX));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_close_fused<R, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(FUSED_SMEM_MAX));
+    if constexpr (R % 2 == 0)
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_close_fused<R, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(FUSED_SMEM_MAX));
+    return e;
+}
+
+cudaError_t segment_init_device() {
+    cudaError_t e = tile_attrs_r<1>();
+    if (e == cudaSuccess) e = tile_attrs_r<2>();
+    if (e == cudaSuccess) e = tile_attrs_r<3>();
+    return e;
 }
 
 template <int R, int SY>
 static cudaError_t closing_dispatch(mamri_ctx* c, int nx, int ny, int nz, cudaStream_t s) {
     static const int use_planes = [] { const char* e = getenv("MAMRI_MORPH_PLANES"); return e ? atoi(e) : 0; }();
+    static const int use_fused = [] { const char* e = getenv("MAMRI_CLOSE_FUSED"); return e ? atoi(e) : 1; }();
+    if (use_fused && !use_planes) {
+        bool done = false;
+        const cudaError_t e = closing_fused_dispatch<R>(c, nx, ny, nz, done, s);
+        if (e != cudaSuccess || done) return e;
+    }
     uint32_t TY, TZ, smem;
     if (!use_planes && tile_plan<R, SY>(PadGeom(nx, ny, nz, R).Wp, TY, TZ, smem)) {
         if (const char* e = getenv("MAMRI_TILE_TZ")) {              // experiments only
@@ -738,3 +1067,5 @@ cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, cud
         default: return cudaErrorInvalidValue;
     }
 }
+
+KTRACE_TU(segment)

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ par
                                                 unsigned long long* __restrict__ sums, uint32_t max_markers, GeomArgs g,
                                                 DevScalars* sc) {
     pdl_wait();
+    ktrace(KT_SELECT);
     const unsigned lane = lane_id();
     const uint32_t n = sc->status == MAMRI_OK ? sc->n_runs : 0u;
     const uint32_t warp0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;
@@ -92,51 +93,15 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ par
 // ------------------------------------------------------------------------------------------------
 // phase 2: first and second moments of the kept labels (+ body)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long sum_sq_upto(long long k) {   // sum_{i=0..k} i^2, k >= -1
-    return (unsigned long long)(k * (k + 1) * (2 * k + 1) / 6);
-}
-
-__global__ void __launch_bounds__(256) k_moments(const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_len,
-                                                 const uint32_t* __restrict__ parent, const uint32_t* __restrict__ run_label,
-                                                 const uint32_t* __restrict__ label_slot, int W, int ny,
-                                                 unsigned long long* sums, const uint32_t* __restrict__ cand_label,
-                                                 uint32_t max_markers, DevScalars* sc) {
-    __shared__ CtaCache<9, unsigned long long, 16> cache;
-    pdl_wait();
-    cache.init();
-    const bool ok = sc->status == MAMRI_OK;
-    const uint32_t n = ok ? sc->n_runs : 0u;
-    const unsigned long long bp = sc->body_packed;
-    const uint32_t body = (bp >> 32) != 0ull ? 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull) : 0u;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t r0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < n; r0 += stride) {
-        const uint32_t r = r0 + lane_id();
-        uint32_t key = MAMRI_NONE;
-        unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (r < n) {
-            key = label_slot[parent[r]];
-            if (key == MAMRI_NONE && run_label[r] == body) key = max_markers;   // the body has the extra slot
-            if (key != MAMRI_NONE) {
-                const uint32_t pos = run_pos[r];
-                const uint32_t wi = pos >> 5, row = wi / W;
-                const long long z = row / ny, y = row - uint32_t(z) * ny;
-                const long long xs = (long long)(wi - row * W) * 32 + (pos & 31u);
-                const long long len = run_len[r], xe = xs + len - 1;
-                const unsigned long long sx = (unsigned long long)((xs + xe) * len / 2);
-                v[0] = sx;                                              // sum x
-                v[1] = (unsigned long long)(len * y);                   // sum y
-                v[2] = (unsigned long long)(len * z);                   // sum z
-                v[3] = sum_sq_upto(xe) - sum_sq_upto(xs - 1);           // sum xx
-                v[4] = (unsigned long long)(len * y * y);               // sum yy
-                v[5] = (unsigned long long)(len * z * z);               // sum zz
-                v[6] = sx * (unsigned long long)y;                      // sum xy
-                v[7] = sx * (unsigned long long)z;                      // sum xz
-                v[8] = (unsigned long long)(len * y * z);               // sum yz
-            }
-        }
-        warp_agg_add(key, v, cache, sums);
-    }
-    cache.flush(sums);
+// sum_{i=0..k} i^2 = k(k+1)(2k+1)/6, k >= -1.  One of k, k+1 is even and one of k, k+1, 2k+1 is a multiple of 3, so
+// the divisions are done on the factors first: the product then never exceeds the result (exact in 64 bits for any
+// row length a 2^32-voxel volume can have).
+__device__ __forceinline__ unsigned long long sum_sq_upto(long long k) {
+    if (k <= 0) return 0ull;
+    unsigned long long a = (unsigned long long)k, b = a + 1ull, c = 2ull * a + 1ull;
+    if (a % 2ull == 0ull) a /= 2ull; else b /= 2ull;
+    if (a % 3ull == 0ull) a /= 3ull; else if (b % 3ull == 0ull) b /= 3ull; else c /= 3ull;
+    return a * b * c;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -232,38 +197,85 @@ __device__ void make_marker(mamri_marker* out, uint32_t label, unsigned long lon
     *out = m;
 }
 
-// Turns the sums into the marker table and the summary: one thread per kept label (its rank among the kept labels =
-// its place in GetLabels order; the labels of a noisy high-resolution scan number in the thousands, so they are
-// staged in shared memory and the work is spread over a few CTAs), thread 0 of CTA 0 writes the summary and the body.
-// Sums were accumulated with L2 atomics by the kernel before.  Also fills the scan's fixed-size table
-// (DynArgs::table_out, rows of {label, count, volume_mm3, RAS x y z, n_labels, body_label}: the layout
-// distributed.pack_table builds on the host) when the caller asked for it.
-constexpr int FIN_THREADS = 128, FIN_SMEM_LABELS = 8192;
-
-__global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint32_t* __restrict__ cand_label,
-                                                          const uint32_t* __restrict__ label_count,
-                                                          const unsigned long long* __restrict__ sums, uint32_t max_markers,
-                                                          GeomArgs g, mamri_marker* __restrict__ markers, mamri_summary* summary,
-                                                          const DevScalars* __restrict__ sc, const DynArgs* __restrict__ dyn) {
-    extern __shared__ uint32_t s_lab[];
+// Turns the sums into the marker table and the summary.  One kernel does three things:
+//   ranks    every kept label's place in GetLabels order = number of kept labels below it (slots are claimed by
+//            atomics in arbitrary order); spread over the whole grid, it only needs the slot table
+//   moments  exact integer sums per run for the kept labels + the body, as described above
+//   finalise by the LAST CTA to finish its sums (ticket in DevScalars::done_stats): one thread per kept label turns
+//            the sums into a mamri_marker (float64 centroid, physical size, Jacobi eigen-decomposition), another
+//            warp's thread does the body, thread 0 the summary scalars.  Also fills the scan's fixed-size table
+//            (DynArgs::table_out, rows of {label, count, volume_mm3, RAS x y z, n_labels, body_label}: the layout
+//            distributed.pack_table builds on the host) when the caller asked for it.
+// It runs beside `materialise` on the second branch of the graph.
+__global__ void __launch_bounds__(256) k_stats(const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_len,
+                                               const uint32_t* __restrict__ parent, const uint32_t* __restrict__ run_label,
+                                               const uint32_t* __restrict__ label_slot, int W, int ny,
+                                               unsigned long long* sums, const uint32_t* __restrict__ cand_label,
+                                               uint32_t* cand_rank, const uint32_t* __restrict__ label_count,
+                                               uint32_t max_markers, GeomArgs g, mamri_marker* __restrict__ markers,
+                                               mamri_summary* summary, DevScalars* sc, const DynArgs* __restrict__ dyn) {
+    __shared__ CtaCache<9, unsigned long long, 16> cache;
+    __shared__ bool last;
     pdl_wait();
+    ktrace(KT_STATS);
+    cache.init();
     const bool ok = sc->status == MAMRI_OK;
+    const uint32_t n = ok ? sc->n_runs : 0u;
     const uint32_t n_all = sc->n_cand;
-    const uint32_t n = ok ? (n_all < max_markers ? n_all : max_markers) : 0u;
+    const uint32_t n_kept = ok ? (n_all < max_markers ? n_all : max_markers) : 0u;
+    const unsigned long long bp = sc->body_packed;
+    const uint32_t body = (ok && (bp >> 32) != 0ull) ? 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull) : 0u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // ---- ranks of the kept labels
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_kept; i += stride) {
+        const uint32_t lab = cand_label[i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n_kept; ++j) rank += cand_label[j] < lab;
+        cand_rank[i] = rank;
+    }
+    // ---- moments
+    for (uint32_t r0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < n; r0 += stride) {
+        const uint32_t r = r0 + lane_id();
+        uint32_t key = MAMRI_NONE;
+        unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (r < n) {
+            key = label_slot[parent[r]];
+            if (key == MAMRI_NONE && body != 0u && run_label[r] == body) key = max_markers;   // the body has the extra slot
+            if (key != MAMRI_NONE) {
+                const uint32_t pos = run_pos[r];
+                const uint32_t wi = pos >> 5, row = wi / W;
+                const long long z = row / ny, y = row - uint32_t(z) * ny;
+                const long long xs = (long long)(wi - row * W) * 32 + (pos & 31u);
+                const long long len = run_len[r], xe = xs + len - 1;
+                const unsigned long long sx = (unsigned long long)((xs + xe) * len / 2);
+                v[0] = sx;                                              // sum x
+                v[1] = (unsigned long long)(len * y);                   // sum y
+                v[2] = (unsigned long long)(len * z);                   // sum z
+                v[3] = sum_sq_upto(xe) - sum_sq_upto(xs - 1);           // sum xx
+                v[4] = (unsigned long long)(len * y * y);               // sum yy
+                v[5] = (unsigned long long)(len * z * z);               // sum zz
+                v[6] = sx * (unsigned long long)y;                      // sum xy
+                v[7] = sx * (unsigned long long)z;                      // sum xz
+                v[8] = (unsigned long long)(len * y * z);               // sum yz
+            }
+        }
+        warp_agg_add(key, v, cache, sums);
+    }
+    cache.flush(sums);
+    // ---- the last CTA to get here finalises
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&sc->done_stats, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    ktrace(KT_STATS_FIN);
     double* __restrict__ table = dyn->table_out;
     const uint32_t slots = table ? dyn->table_slots : 0u;
-    const unsigned long long bpk = sc->body_packed;
-    const double body_d = (ok && (bpk >> 32) != 0ull) ? double(0xFFFFFFFFu - uint32_t(bpk & 0xFFFFFFFFull)) : 0.0;
-    const bool staged = n <= FIN_SMEM_LABELS && max_markers <= FIN_SMEM_LABELS;
-    if (staged && blockIdx.x * blockDim.x < n) {
-        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) s_lab[j] = cand_label[j];
-    }
-    __syncthreads();
-    const uint32_t* __restrict__ labs = staged ? s_lab : cand_label;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t lab = labs[i];
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < n; ++j) rank += labs[j] < lab;
+    const double body_d = double(body);
+    const uint32_t n_labels = sc->n_labels;
+    for (uint32_t i = threadIdx.x; i < n_kept; i += blockDim.x) {
+        const uint32_t lab = __ldcg(cand_label + i), rank = __ldcg(cand_rank + i);
         unsigned long long s9[9];
         for (int k = 0; k < 9; ++k) s9[k] = __ldcg(sums + i * 9u + k);
         make_marker(markers + rank, lab, __ldcg(label_count + lab - 1u), s9, g);
@@ -272,31 +284,29 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint32_t* __rest
             double* row = table + size_t(rank) * 8;
             row[0] = double(m.label); row[1] = double(m.count); row[2] = m.volume_mm3;
             row[3] = m.centroid_ras[0]; row[4] = m.centroid_ras[1]; row[5] = m.centroid_ras[2];
-            row[6] = double(sc->n_labels); row[7] = body_d;
+            row[6] = double(n_labels); row[7] = body_d;
         }
     }
-    for (uint32_t i = n * 8 + blockIdx.x * blockDim.x + threadIdx.x; i < slots * 8; i += gridDim.x * blockDim.x) table[i] = 0.0;   // unused rows
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        summary->n_labels = sc->n_labels;
+    for (uint32_t i = n_kept * 8 + threadIdx.x; i < slots * 8; i += blockDim.x) table[i] = 0.0;   // unused rows
+    if (threadIdx.x == blockDim.x - 1) {                     // the body: a thread of another warp than marker 0's
+        if (body != 0u) {
+            unsigned long long s9[9];
+            for (int k = 0; k < 9; ++k) s9[k] = __ldcg(sums + max_markers * 9u + k);
+            make_marker(&summary->body, body, bp >> 32, s9, g);
+        } else {
+            memset(&summary->body, 0, sizeof(mamri_marker));
+        }
+    }
+    if (threadIdx.x == 0) {
+        summary->n_labels = n_labels;
         summary->n_runs = sc->n_runs;
         summary->n_markers = n_all;
         summary->n_foreground = sc->n_foreground;
         summary->device_status = sc->status;
         summary->reserved = 0;
-        const unsigned long long bp = sc->body_packed;
-        if (ok && (bp >> 32) != 0ull) {
-            const uint32_t body = 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull);
-            summary->body_label = body;
-            summary->body_count = bp >> 32;
-            unsigned long long s9[9];
-            for (int k = 0; k < 9; ++k) s9[k] = __ldcg(sums + max_markers * 9u + k);
-            make_marker(&summary->body, body, bp >> 32, s9, g);
-        } else {
-            summary->body_label = 0;
-            summary->body_count = 0;
-            memset(&summary->body, 0, sizeof(mamri_marker));
-        }
-    }
+        summary->body_label = body;
+        summary->body_count = body != 0u ? (bp >> 32) : 0ull;
+    }    ktrace_last(KT_FINAL);
 }
 
 static GeomArgs geom_args(const mamri_volume_desc* desc, const mamri_params* prm) {
@@ -321,18 +331,14 @@ cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mam
 }
 
 // Moments of the kept labels + body, and the marker table / summary (independent of `materialise`).
-cudaError_t launch_moments(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
+cudaError_t launch_stats(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
     const GeomArgs g = geom_args(desc, prm);
     const int W = (desc->nx + 31) / 32;
-    LK(k_moments, c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS, 256, s, false, c->d_run_pos, c->d_run_len, c->d_parent, c->d_run_label, c->d_label_slot, W, desc->ny,
-       c->d_cand_sums, c->d_cand_label, c->max_markers, c->d_scalars);
-    prof_mark(c, s, "moments");
-    // one thread per kept label, a few CTAs at most; a handful of labels (the usual scan) need only the first
-    uint32_t fin_ctas = (c->max_markers + FIN_THREADS - 1) / FIN_THREADS;
-    if (fin_ctas > 32) fin_ctas = 32;
-    const size_t fin_smem = size_t(c->max_markers <= FIN_SMEM_LABELS ? c->max_markers : 0) * sizeof(uint32_t);
-    LKS(k_finalize, fin_ctas, FIN_THREADS, fin_smem, s, false, c->d_cand_label, c->d_label_count, c->d_cand_sums, c->max_markers, g,
-        c->d_markers, c->d_summary, c->d_scalars, c->d_dyn);
-    prof_mark(c, s, "finalize");
+    LK(k_stats, c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS, 256, s, false, c->d_run_pos, c->d_run_len, c->d_parent, c->d_run_label,
+       c->d_label_slot, W, desc->ny, c->d_cand_sums, c->d_cand_label, c->d_cand_rank, c->d_label_count, c->max_markers, g, c->d_markers,
+       c->d_summary, c->d_scalars, c->d_dyn);
+    prof_mark(c, s, "stats");
     return cudaGetLastError();
 }
+
+KTRACE_TU(stats)

@@ -276,6 +276,11 @@ class FiducialDetector:
 
     STAGES = ("threshold_pack", "closing", "ccl", "stats_filter", "materialise")
 
+    @property
+    def kernel_launches(self) -> int:
+        """Kernels per scan on the path the last scan was enqueued with (6: cluster labelling, 10: scalable kernels)."""
+        return int(self._lib.mamri_kernel_launches(self._ctx))
+
     def set_profiling(self, enable: bool) -> None:
         check(self._lib.mamri_set_profiling(self._ctx, int(bool(enable))), self._ctx)
 
@@ -578,7 +583,11 @@ class BatchDetector:
                       for _ in range(self.n_contexts)]
         self.labels = [torch.empty((nz, ny, nx), dtype=torch.int32, device=dev) if materialise else None
                        for _ in range(self.n_contexts)]
-        self.kernel_launches_per_scan = 12          # threshold 1, closing 2, ccl 5, stats 3, materialise 1
+
+    @property
+    def kernel_launches_per_scan(self) -> int:
+        """Kernels per scan on the path of the last batch (counted by the library while it enqueues / captures)."""
+        return int(self._lib.mamri_kernel_launches(C.c_void_p(self._lib.mamri_pool_context(self._pool, 0))))
 
     def close(self):
         if getattr(self, "_pool", None) and self._pool.value:
@@ -749,9 +758,12 @@ class BatchPipeline:
         self.pools = [BatchDetector(dims_xyz, device=device, n_contexts=n_contexts, **kw) for _ in range(int(depth))]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in self.pools]
         self.n_contexts = n_contexts
-        self.kernel_launches_per_scan = self.pools[0].kernel_launches_per_scan
         self._in_flight: List[int] = []
         self._next = 0
+
+    @property
+    def kernel_launches_per_scan(self) -> int:
+        return self.pools[0].kernel_launches_per_scan
 
     def close(self):
         for p in self.pools:
