@@ -87,8 +87,6 @@ struct DeviceGuard {
     }
 };
 
-constexpr uint32_t EAGER_MARKERS = 64;   // marker records copied back together with the summary
-
 size_t dtype_size(int dtype) {
     switch (dtype) {
         case MAMRI_U8: return 1;
@@ -151,9 +149,9 @@ extern "C" int mamri_destroy(mamri_ctx* ctx) {
     DeviceGuard g(ctx->device);
     cudaFree(ctx->d_occ_raw); cudaFree(ctx->d_occ_dil);
     cudaFree(ctx->d_raw); cudaFree(ctx->d_planes); cudaFree(ctx->d_dil); cudaFree(ctx->d_closed); cudaFree(ctx->d_word_base);
-    cudaFree(ctx->d_run_pos); cudaFree(ctx->d_run_len); cudaFree(ctx->d_parent); cudaFree(ctx->d_run_label); cudaFree(ctx->d_label_count); cudaFree(ctx->d_label_slot);
-    cudaFree(ctx->d_root_count); cudaFree(ctx->d_scan_runs); cudaFree(ctx->d_scan_rank); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_rank); cudaFree(ctx->d_cand_sums); cudaFree(ctx->d_markers);
-    cudaFree(ctx->d_summary); cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
+    cudaFree(ctx->d_run_pos); cudaFree(ctx->d_run_end); cudaFree(ctx->d_parent); cudaFree(ctx->d_run_label); cudaFree(ctx->d_label_count); cudaFree(ctx->d_label_slot);
+    cudaFree(ctx->d_root_count); cudaFree(ctx->d_scan_runs); cudaFree(ctx->d_scan_rank); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_rank); cudaFree(ctx->d_cand_sums);
+    cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
     cudaFree(ctx->d_entry_dist); cudaFree(ctx->d_entry_idx); cudaFree(ctx->d_entry_cnt); cudaFree(ctx->d_entry_res);
     cudaFree(ctx->d_surf); cudaFreeHost(ctx->h_surf); cudaFree(ctx->d_pose_buf);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -228,7 +226,7 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     if ((e = cudaMemset(ctx->d_occ_raw, 0, ctx->occ_cap)) != cudaSuccess) return bail(e, "occupancy cells");
     ALLOC(ctx->d_word_base, ctx->cap_words * 4, "run bases");
     ALLOC(ctx->d_run_pos, size_t(max_runs) * 4, "run positions");
-    ALLOC(ctx->d_run_len, size_t(max_runs) * 4, "run lengths");
+    ALLOC(ctx->d_run_end, size_t(max_runs) * 4, "run lengths");
     ALLOC(ctx->d_parent, size_t(max_runs) * 4, "union-find parents");
     ALLOC(ctx->d_run_label, size_t(max_runs) * 4, "run labels");
     ALLOC(ctx->d_label_count, size_t(max_runs) * 4, "label counts");
@@ -244,8 +242,6 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     ALLOC(ctx->d_cand_label, (size_t(max_markers) + 1) * 4, "candidate labels");
     ALLOC(ctx->d_cand_rank, size_t(max_markers) * 4, "candidate ranks");
     ALLOC(ctx->d_cand_sums, (size_t(max_markers) + 1) * 9 * 8, "candidate sums");
-    ALLOC(ctx->d_markers, size_t(max_markers) * sizeof(mamri_marker), "marker table");
-    ALLOC(ctx->d_summary, sizeof(mamri_summary), "summary");
     ALLOC(ctx->d_entry_dist, MAMRI_SCAN_CTAS * sizeof(double), "entry partials");
     ALLOC(ctx->d_entry_idx, MAMRI_SCAN_CTAS * sizeof(long long), "entry partials");
     ALLOC(ctx->d_entry_cnt, 2 * sizeof(unsigned long long), "entry counters");
@@ -345,19 +341,21 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool f
     if (prof) CK(cudaEventRecord(ctx->ev[3], s));
     const bool outputs = k.has_mask || k.has_labels || k.has_body;
     const bool forked = fork && outputs;
+    // Statistics (marker table + summary, written straight into the pinned host buffers) and the per-voxel outputs
+    // both depend on the labels only.  The statistics kernel goes FIRST, on the second branch: its few CTAs take their
+    // slots before `materialise` floods the machine with thousands of CTAs (launched after it, a small kernel only
+    // gets in when that grid has drained -- measured: it then ran after materialise instead of beside it).
     if (forked) {
         CK(cudaEventRecord(ctx->ev_fork, s));
         CK(cudaStreamWaitEvent(ctx->cap_stream2, ctx->ev_fork, 0));
-        CK(launch_materialise(ctx, mask, nx, ny, nz, k.outs_aligned, ctx->cap_stream2));
+        CK(launch_stats(ctx, desc, params, ctx->cap_stream2));
         CK(cudaEventRecord(ctx->ev_join, ctx->cap_stream2));
+    } else {
+        CK(launch_stats(ctx, desc, params, s));
     }
-    CK(launch_stats(ctx, desc, params, s));
     if (prof) CK(cudaEventRecord(ctx->ev[4], s));
-    if (outputs && !forked) CK(launch_materialise(ctx, mask, nx, ny, nz, k.outs_aligned, s));
+    if (outputs) CK(launch_materialise(ctx, mask, nx, ny, nz, k.outs_aligned, s));
     if (prof) CK(cudaEventRecord(ctx->ev[5], s));
-    CK(cudaMemcpyAsync(ctx->h_summary, ctx->d_summary, sizeof(mamri_summary), cudaMemcpyDeviceToHost, s));
-    const uint32_t eager = ctx->max_markers < EAGER_MARKERS ? ctx->max_markers : EAGER_MARKERS;
-    CK(cudaMemcpyAsync(ctx->h_markers, ctx->d_markers, size_t(eager) * sizeof(mamri_marker), cudaMemcpyDeviceToHost, s));
     if (forked) CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     ctx->n_launches = launch_counter();
     return MAMRI_OK;
@@ -490,12 +488,6 @@ extern "C" int mamri_detect_collect(mamri_ctx* ctx, mamri_summary* summary, mamr
         return MAMRI_ERR_CAPACITY;
     }
     const uint32_t n = hs->n_markers;
-    const uint32_t eager = ctx->max_markers < EAGER_MARKERS ? ctx->max_markers : EAGER_MARKERS;
-    if (n > eager) {
-        CK(cudaMemcpyAsync(ctx->h_markers + eager, ctx->d_markers + eager, size_t(n - eager) * sizeof(mamri_marker),
-                           cudaMemcpyDeviceToHost, ctx->pending_stream));
-        CK(cudaStreamSynchronize(ctx->pending_stream));
-    }
     if (n > max_markers || (n && !h_markers)) {
         if (h_markers && max_markers) memcpy(h_markers, ctx->h_markers, size_t(max_markers) * sizeof(mamri_marker));
         return fail(ctx, MAMRI_ERR_CAPACITY, "caller's marker array is smaller than n_markers");
@@ -698,6 +690,11 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
         CKP(launch_label(c, c->d_closed, desc, prm, s));
         TRACE(i, 4, s);
         CKP(cudaEventRecord(pool->ev_sel[i], s));
+        // statistics + tables (straight into the pinned host buffers) right behind the labels, before the wave's
+        // materialise kernels are queued: a small kernel launched after those only gets in when they have drained
+        CKP(launch_stats(c, desc, prm, s));
+        TRACE(i, 7, s);
+        CKP(cudaEventRecord(pool->ev_done[i], s));
     }
     if (outputs)
         for (int i = 0; i < m; ++i) {
@@ -707,17 +704,7 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
             CKP(launch_materialise(pool->ctx[i], pool->ctx[i]->d_closed, nx, ny, nz, k.outs_aligned, H));
             TRACE(i, 6, H);
         }
-    for (int i = 0; i < m; ++i) {
-        mamri_ctx* c = pool->ctx[i];
-        cudaStream_t s = pool->streams[i];
-        CKP(launch_stats(c, desc, prm, s));
-        CKP(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(mamri_summary), cudaMemcpyDeviceToHost, s));
-        const uint32_t eager = c->max_markers < EAGER_MARKERS ? c->max_markers : EAGER_MARKERS;
-        CKP(cudaMemcpyAsync(c->h_markers, c->d_markers, size_t(eager) * sizeof(mamri_marker), cudaMemcpyDeviceToHost, s));
-        TRACE(i, 7, s);
-        CKP(cudaEventRecord(pool->ev_done[i], s));
-        CKP(cudaStreamWaitEvent(H0, pool->ev_done[i], 0));
-    }
+    for (int i = 0; i < m; ++i) CKP(cudaStreamWaitEvent(H0, pool->ev_done[i], 0));
     for (int c = 0; c < NC; ++c) {
         CKP(cudaEventRecord(pool->ev_chain[c], pool->chain[c]));
         CKP(cudaStreamWaitEvent(H0, pool->ev_chain[c], 0));

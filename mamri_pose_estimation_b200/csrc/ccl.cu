@@ -29,8 +29,8 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 // ------------------------------------------------------------------------------------------------
 // run numbering: single-pass exclusive scan of run starts per word, and the run table
 // ------------------------------------------------------------------------------------------------
-// word_base[w] = number of runs that start before word w; run table: position (word*32 + bit of the
-// first voxel) and length of every run, in raster order.  One pass over the mask: a CTA takes a tile of
+// word_base[w] = number of runs that start before word w; run table: position (word*32 + bit) of the
+// first and of the last voxel of every run (run_pos, run_end), in raster order.  One pass over the mask: a CTA takes a tile of
 // RS_TILE words (16 consecutive words per thread, 128-bit loads), scans its run-start counts, gets
 // the count of all earlier tiles by decoupled look-back and writes its part of both tables.
 // Tiles of RS_THREADS x ITEMS words: 16 words per thread on large masks (few, large tiles), 4 on small ones (enough
@@ -59,7 +59,7 @@ template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
                                                           volatile unsigned long long* state, const DynArgs* __restrict__ dyn,
                                                           uint32_t* __restrict__ word_base, uint32_t* __restrict__ run_pos,
-                                                          uint32_t* __restrict__ run_len, uint32_t* __restrict__ root_count,
+                                                          uint32_t* __restrict__ run_end, uint32_t* __restrict__ root_count,
                                                           uint32_t max_runs, DevScalars* sc) {
     constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     pdl_wait();
@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
     __syncthreads();
     const uint32_t tile = s_tile, n_tiles = gridDim.x;
     const uint32_t i0 = tile * RS_TILE + threadIdx.x * RS_ITEMS;
-    uint32_t m[RS_ITEMS], starts[RS_ITEMS];
-    uint32_t cnt = 0;
+    uint32_t m[RS_ITEMS], starts[RS_ITEMS], ends[RS_ITEMS];
+    uint32_t cnt = 0, open = 0;
     if (i0 + RS_ITEMS <= n_words) {
 #pragma unroll
         for (int k = 0; k < RS_ITEMS; k += 4) {
@@ -84,14 +84,22 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
         for (int k = 0; k < RS_ITEMS; ++k) m[k] = (i0 + k < n_words) ? mask[i0 + k] : 0u;
     }
     {
-        uint32_t any = 0;
-#pragma unroll
-        for (int k = 0; k < RS_ITEMS; ++k) any |= m[k];
-        uint32_t prev = (any && i0 > 0) ? mask[i0 - 1] : 0u;
-        uint32_t xw = i0 % uint32_t(W);
+        // a run starts where a set bit follows a clear one and ends where a clear one follows a set one (row ends
+        // cut runs); the j-th start and the j-th end in raster order belong to the same run, so lengths need no walk
+        // along the run: starts go to run_pos, ends to run_end, both indexed by the same scan
+        const uint32_t xw0 = i0 % uint32_t(W);
+        const bool any_first = m[0] != 0u, any_last = m[RS_ITEMS - 1] != 0u;
+        uint32_t prev = (any_first && i0 > 0) ? mask[i0 - 1] : 0u;
+        const uint32_t after = (any_last && i0 + RS_ITEMS < n_words) ? mask[i0 + RS_ITEMS] : 0u;
+        uint32_t xw = xw0;
+        open = (xw0 != 0u && (prev >> 31) && (m[0] & 1u)) ? 1u : 0u;      // a run is open across this thread's first word
 #pragma unroll
         for (int k = 0; k < RS_ITEMS; ++k) {
-            starts[k] = run_starts(m[k], xw ? prev : 0u);
+            const bool row_first = xw == 0u, row_last = xw + 1u == uint32_t(W);
+            uint32_t nxt = after;
+            if (k + 1 < RS_ITEMS) nxt = m[(k + 1) % RS_ITEMS];
+            starts[k] = run_starts(m[k], row_first ? 0u : prev);
+            ends[k] = m[k] & ~((m[k] >> 1) | (row_last ? 0u : (nxt << 31)));
             cnt += __popc(starts[k]);
             prev = m[k];
             if (++xw == uint32_t(W)) xw = 0;
@@ -106,37 +114,29 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
     }
     ktrace(KT_RUNS_LB);
     uint32_t base = before + ex;
+    uint32_t e_idx = base - open;                                        // ends before this thread = starts before - open runs
     uint32_t wb[RS_ITEMS];
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; ++k) {
         wb[k] = base;
-        const uint32_t i = i0 + k;
-        uint32_t st = starts[k], r = base;
+        const uint32_t bit0 = (i0 + uint32_t(k)) * 32u;
+        uint32_t st = starts[k];
         while (st) {
             const int b = __ffs(st) - 1;
             st &= st - 1;
-            const uint32_t t = m[k] >> b;                        // run bits from its start
-            uint32_t len;
-            if (t != (0xFFFFFFFFu >> b)) {
-                len = __ffs(~t) - 1;                             // ends inside this word
-            } else {
-                len = 32 - b;                                    // reaches bit 31: follow it through the next words
-                const uint32_t xw = i % uint32_t(W);
-                for (uint32_t j = 1; xw + j < uint32_t(W); ++j) {
-                    const uint32_t nm = mask[i + j];
-                    if (nm == 0xFFFFFFFFu) { len += 32; continue; }
-                    len += __ffs(~nm) - 1;
-                    break;
-                }
+            if (base < max_runs) {
+                run_pos[base] = bit0 + uint32_t(b);
+                root_count[base] = 0u;                                   // accumulated on the roots by the labelling
             }
-            if (r < max_runs) {
-                run_pos[r] = i * 32u + uint32_t(b);
-                run_len[r] = len;
-                root_count[r] = 0u;                              // accumulated by k_flatten_rank on the roots
-            }
-            ++r;
+            ++base;
         }
-        base += __popc(starts[k]);
+        uint32_t en = ends[k];
+        while (en) {
+            const int b = __ffs(en) - 1;
+            en &= en - 1;
+            if (e_idx < max_runs) run_end[e_idx] = bit0 + uint32_t(b);
+            ++e_idx;
+        }
     }
     if (i0 + RS_ITEMS <= n_words) {
 #pragma unroll
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
         for (int k = 0; k < RS_ITEMS; ++k)
             if (i0 + k < n_words) word_base[i0 + k] = wb[k];
     }
+    ktrace_last(KT_RUNS_LAST);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -178,38 +179,29 @@ __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t 
     }
 }
 
-// Joins run `node` (x range [gx0, gx0+len) of its row) with every run of one earlier neighbour row
-// that touches it: same x for face connectivity; DIAG widens the range by one voxel each side
-// (26-connectivity).  Every maximal piece of neighbour bits inside the range lies in exactly one
-// neighbour run, so one union per piece start suffices (a piece continuing from the previous word
-// belongs to the run already joined).  Node ids are run ids minus `id_off`.
+// Joins run `node` (x range [gx0, gx0+len) of its row) with every run of one earlier neighbour row that touches
+// it: same x for face connectivity; DIAG widens the range by one voxel each side (26-connectivity).  The neighbour
+// runs come from the run table, not from the mask: word_base gives the ids of the runs that start inside the words
+// the range covers, plus the one run that may reach into the range from the left -- two or three dependent loads
+// whatever the length of the run (walking the mask costs one load per 32 voxels, and the body's runs are hundreds of
+// voxels long).  `nbr_row` = word index of the neighbour row's first word; node ids are run ids minus `id_off`.
 template <bool DIAG>
-__device__ __forceinline__ void join_run(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
-                                         uint32_t* parent, uint32_t id_off, int W, uint32_t node, int gx0, int len,
-                                         uint32_t nbr_row) {
+__device__ __forceinline__ void join_run(const uint32_t* __restrict__ word_base, const uint32_t* __restrict__ run_pos,
+                                         const uint32_t* __restrict__ run_end, uint32_t* parent, uint32_t id_off, int W,
+                                         uint32_t node, int gx0, int len, uint32_t nbr_row) {
     int lo = gx0 - (DIAG ? 1 : 0), hi = gx0 + len - 1 + (DIAG ? 1 : 0);
     if (lo < 0) lo = 0;
     if (hi > W * 32 - 1) hi = W * 32 - 1;
-    const int w_lo = lo >> 5, w_hi = hi >> 5;
-    uint32_t carry = 0;
-    for (int w = w_lo; w <= w_hi; ++w) {
-        const uint32_t up = mask[nbr_row + w];
-        uint32_t seg = 0xFFFFFFFFu;
-        if (w == w_lo) seg &= 0xFFFFFFFFu << (lo & 31);
-        if (w == w_hi) seg &= 0xFFFFFFFFu >> (31 - (hi & 31));
-        const uint32_t t = up & seg;
-        uint32_t ps = t & ~((t << 1) | carry);
-        if (ps) {
-            const uint32_t up_prev = w > 0 ? mask[nbr_row + w - 1] : 0u;
-            const uint32_t starts_up = run_starts(up, up_prev);
-            const uint32_t base_up = word_base[nbr_row + w] - id_off;
-            while (ps) {
-                const int bit = __ffs(ps) - 1;
-                ps &= ps - 1;
-                uf_union(parent, node, run_id_in_word(base_up, starts_up, bit));
-            }
-        }
-        carry = t >> 31;
+    const uint32_t lo_abs = nbr_row * 32u + uint32_t(lo), hi_abs = nbr_row * 32u + uint32_t(hi);
+    const uint32_t j_lo = word_base[nbr_row + uint32_t(lo >> 5)];          // runs that start before the first word of the range
+    const uint32_t j_hi = word_base[nbr_row + uint32_t(hi >> 5) + 1u];     // ... before the word after its last (a later row at most)
+    // the last run that starts left of the range reaches into it iff it ends at or after lo (a run of an earlier row
+    // ends before this row begins, so it fails the test by itself)
+    if (j_lo > 0u && run_end[j_lo - 1u] >= lo_abs) uf_union(parent, node, j_lo - 1u - id_off);
+    for (uint32_t j = j_lo; j < j_hi; ++j) {
+        const uint32_t sj = run_pos[j];
+        if (sj > hi_abs) break;                                            // starts right of the range: so do the rest
+        if (run_end[j] >= lo_abs) uf_union(parent, node, j - id_off);
     }
 }
 
@@ -223,10 +215,9 @@ constexpr int SLICE_THREADS = 512;
 constexpr uint32_t SLICE_SMEM_RUNS = 12000;      // 48 KB static shared memory
 
 template <bool CONN26>
-__global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* __restrict__ mask,
-                                                               const uint32_t* __restrict__ word_base,
+__global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* __restrict__ word_base,
                                                                const uint32_t* __restrict__ run_pos,
-                                                               const uint32_t* __restrict__ run_len, uint32_t* parent,
+                                                               const uint32_t* __restrict__ run_end, uint32_t* parent,
                                                                int W, int ny, int nz, const DevScalars* sc) {
     pdl_wait();
     ktrace(KT_USLICE);
@@ -247,7 +238,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
         const uint32_t wi = pos >> 5, row = wi / W;
         if (row == z * ny) continue;                                        // y == 0: no row above in this slice
         const int gx0 = int((wi - row * W) * 32 + (pos & 31u));
-        join_run<CONN26>(mask, word_base, P, r0, W, i, gx0, int(run_len[r0 + i]), (row - 1) * W);
+        join_run<CONN26>(word_base, run_pos, run_end, P, r0, W, i, gx0, int(run_end[r0 + i] - pos + 1u), (row - 1) * W);
     }
     // flatten by pointer jumping: a convex object leaves a chain as long as it is tall, which a per-run
     // walk would follow hop by hop; doubling reaches the root in log2(height) rounds
@@ -269,8 +260,8 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
 // boundaries are merged in two rounds: first those inside blocks of `radix` slices (chains <= radix),
 // then the boundaries between blocks (again <= radix of them per chain).
 template <bool CONN26>
-__global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
-                                                 const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_len,
+__global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ word_base,
+                                                 const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_end,
                                                  uint32_t* parent, int W, int ny, int radix, int between_blocks,
                                                  const DevScalars* sc) {
     pdl_wait();
@@ -284,12 +275,12 @@ __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ ma
         if (z == 0 || ((z % radix) == 0) != (between_blocks != 0)) continue;
         const uint32_t y = row - z * ny;
         const int gx0 = int((wi - row * W) * 32 + (pos & 31u));
-        const int len = int(run_len[r]);
+        const int len = int(run_end[r] - pos + 1u);
         const uint32_t below = (row - ny) * W;                              // row (y, z-1)
-        join_run<CONN26>(mask, word_base, parent, 0u, W, r, gx0, len, below);
+        join_run<CONN26>(word_base, run_pos, run_end, parent, 0u, W, r, gx0, len, below);
         if (CONN26) {
-            if (y > 0) join_run<true>(mask, word_base, parent, 0u, W, r, gx0, len, below - W);
-            if (y + 1 < uint32_t(ny)) join_run<true>(mask, word_base, parent, 0u, W, r, gx0, len, below + W);
+            if (y > 0) join_run<true>(word_base, run_pos, run_end, parent, 0u, W, r, gx0, len, below - W);
+            if (y + 1 < uint32_t(ny)) join_run<true>(word_base, run_pos, run_end, parent, 0u, W, r, gx0, len, below + W);
         }
     }
 }
@@ -304,7 +295,8 @@ __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ ma
 // minimum linear index, so this is ITK's consecutive numbering.
 constexpr int FR_THREADS = 256, FR_ITEMS = 4, FR_TILE = FR_THREADS * FR_ITEMS;
 
-__global__ void __launch_bounds__(FR_THREADS) k_flatten_rank(uint32_t* parent, const uint32_t* __restrict__ run_len,
+__global__ void __launch_bounds__(FR_THREADS) k_flatten_rank(uint32_t* parent, const uint32_t* __restrict__ run_pos,
+                                                             const uint32_t* __restrict__ run_end,
                                                              volatile unsigned long long* state,
                                                              const DynArgs* __restrict__ dyn, uint32_t* __restrict__ run_label,
                                                              uint32_t* root_count, DevScalars* sc) {
@@ -344,7 +336,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_flatten_rank(uint32_t* parent, c
                 parent[r] = x;                                       // roots stay fixed points: concurrent walkers stay correct
                 is_root[k] = (x == r);
                 key = x;
-                v[0] = run_len[r];
+                v[0] = run_end[r] - run_pos[r] + 1u;
             }
             roots += is_root[k];
             warp_agg_add(key, v, cache, root_count);
@@ -409,10 +401,9 @@ constexpr int LC_THREADS = 1024;
 constexpr uint32_t LC_SMEM_RUNS = 10240;             // 40 KB of parents per CTA
 
 struct LabelArgs {
-    const uint32_t* mask;
     const uint32_t* word_base;
     const uint32_t* run_pos;
-    const uint32_t* run_len;
+    const uint32_t* run_end;
     uint32_t* parent;
     uint32_t* run_label;
     uint32_t* root_count;
@@ -477,29 +468,31 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_label_cluster(LabelArgs a) {
     const uint32_t r1 = zhi < uint32_t(nz) ? a.word_base[zhi * slice_words] : n;
     const uint32_t nr = r1 - r0;                                      // runs of this chunk (ids r0 .. r1 - 1)
 
-    // ---- U1: block-local union-find over the chunk
+    // ---- U1: block-local union-find over the chunk, in two rounds so that no root chain grows longer than a slice is
+    // tall or the chunk is deep: (a) every run joins the row above it, flatten; (b) joins with the slice below, flatten
     uint32_t* P = nr <= LC_SMEM_RUNS ? sp : a.parent + r0;
     for (uint32_t i = tid; i < nr; i += blockDim.x) P[i] = i;
     __syncthreads();
-    for (uint32_t i = tid; i < nr; i += blockDim.x) {
-        const uint32_t pos = a.run_pos[r0 + i];
-        const uint32_t wi = pos >> 5, row = wi / uint32_t(W);
-        const uint32_t z = row / uint32_t(ny), y = row - z * uint32_t(ny);
-        const int gx0 = int((wi - row * uint32_t(W)) * 32 + (pos & 31u));
-        const int len = int(a.run_len[r0 + i]);
-        if (y > 0) join_run<CONN26>(a.mask, a.word_base, P, r0, W, i, gx0, len, (row - 1) * uint32_t(W));
-        if (z > zlo) {
-            const uint32_t below = (row - uint32_t(ny)) * uint32_t(W);
-            join_run<CONN26>(a.mask, a.word_base, P, r0, W, i, gx0, len, below);
-            if (CONN26) {
-                if (y > 0) join_run<true>(a.mask, a.word_base, P, r0, W, i, gx0, len, below - uint32_t(W));
-                if (y + 1 < uint32_t(ny)) join_run<true>(a.mask, a.word_base, P, r0, W, i, gx0, len, below + uint32_t(W));
+    for (int round = 0; round < 2; ++round) {
+        for (uint32_t i = tid; i < nr; i += blockDim.x) {
+            const uint32_t pos = a.run_pos[r0 + i];
+            const uint32_t wi = pos >> 5, row = wi / uint32_t(W);
+            const uint32_t z = row / uint32_t(ny), y = row - z * uint32_t(ny);
+            const int gx0 = int((wi - row * uint32_t(W)) * 32 + (pos & 31u));
+            const int len = int(a.run_end[r0 + i] - pos + 1u);
+            if (round == 0) {
+                if (y > 0) join_run<CONN26>(a.word_base, a.run_pos, a.run_end, P, r0, W, i, gx0, len, (row - 1) * uint32_t(W));
+            } else if (z > zlo) {
+                const uint32_t below = (row - uint32_t(ny)) * uint32_t(W);
+                join_run<CONN26>(a.word_base, a.run_pos, a.run_end, P, r0, W, i, gx0, len, below);
+                if (CONN26) {
+                    if (y > 0) join_run<true>(a.word_base, a.run_pos, a.run_end, P, r0, W, i, gx0, len, below - uint32_t(W));
+                    if (y + 1 < uint32_t(ny)) join_run<true>(a.word_base, a.run_pos, a.run_end, P, r0, W, i, gx0, len, below + uint32_t(W));
+                }
             }
         }
-    }
-    {
         bool again = true;
-        while (again) {
+        while (again) {                                               // pointer jumping: log2(depth) rounds
             __syncthreads();
             bool changed = false;
             for (uint32_t i = tid; i < nr; i += blockDim.x) {
@@ -522,12 +515,12 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_label_cluster(LabelArgs a) {
             const uint32_t wi = pos >> 5, row = wi / uint32_t(W);
             const uint32_t y = row - zlo * uint32_t(ny);
             const int gx0 = int((wi - row * uint32_t(W)) * 32 + (pos & 31u));
-            const int len = int(a.run_len[r]);
+            const int len = int(a.run_end[r] - pos + 1u);
             const uint32_t below = (row - uint32_t(ny)) * uint32_t(W);
-            join_run<CONN26>(a.mask, a.word_base, a.parent, 0u, W, r, gx0, len, below);
+            join_run<CONN26>(a.word_base, a.run_pos, a.run_end, a.parent, 0u, W, r, gx0, len, below);
             if (CONN26) {
-                if (y > 0) join_run<true>(a.mask, a.word_base, a.parent, 0u, W, r, gx0, len, below - uint32_t(W));
-                if (y + 1 < uint32_t(ny)) join_run<true>(a.mask, a.word_base, a.parent, 0u, W, r, gx0, len, below + uint32_t(W));
+                if (y > 0) join_run<true>(a.word_base, a.run_pos, a.run_end, a.parent, 0u, W, r, gx0, len, below - uint32_t(W));
+                if (y + 1 < uint32_t(ny)) join_run<true>(a.word_base, a.run_pos, a.run_end, a.parent, 0u, W, r, gx0, len, below + uint32_t(W));
             }
         }
     }
@@ -549,7 +542,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_label_cluster(LabelArgs a) {
             a.parent[r] = x;                                           // roots stay fixed points: concurrent walkers stay correct
             is_root = x == r;
             key = x;
-            v[0] = a.run_len[r];
+            v[0] = a.run_end[r] - a.run_pos[r] + 1u;
         }
         warp_agg_add(key, v, cache, a.root_count);
         const unsigned bal = __ballot_sync(FULL, is_root);
@@ -674,16 +667,16 @@ cudaError_t launch_label(mamri_ctx* c, const uint32_t* d_mask, const mamri_volum
     const uint32_t n_words = uint32_t(W) * ny * nz;
     if (n_words >= 148u * RS_THREADS * 16u) {
         LK(k_runs_scan<16>, (n_words + RS_THREADS * 16 - 1) / (RS_THREADS * 16), RS_THREADS, s, false, d_mask, W, n_words, c->d_scan_runs,
-           c->d_dyn, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_root_count, c->max_runs, c->d_scalars);
+           c->d_dyn, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_root_count, c->max_runs, c->d_scalars);
     } else {
         LK(k_runs_scan<4>, (n_words + RS_THREADS * 4 - 1) / (RS_THREADS * 4), RS_THREADS, s, false, d_mask, W, n_words, c->d_scan_runs,
-           c->d_dyn, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_root_count, c->max_runs, c->d_scalars);
+           c->d_dyn, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_root_count, c->max_runs, c->d_scalars);
     }
     prof_mark(c, s, "runs_scan");
     if (c->label_cluster > 0) {
         static const int fence = [] { const char* e = getenv("MAMRI_CLUSTER_FENCE"); return e ? atoi(e) : 1; }();
         LabelArgs a;
-        a.mask = d_mask; a.word_base = c->d_word_base; a.run_pos = c->d_run_pos; a.run_len = c->d_run_len;
+        a.word_base = c->d_word_base; a.run_pos = c->d_run_pos; a.run_end = c->d_run_end;
         a.parent = c->d_parent; a.run_label = c->d_run_label; a.root_count = c->d_root_count; a.label_count = c->d_label_count;
         a.label_slot = c->d_label_slot; a.cand_label = c->d_cand_label; a.sums = c->d_cand_sums; a.sc = c->d_scalars;
         a.W = W; a.ny = ny; a.nz = nz; a.max_markers = c->max_markers; a.fence = fence;
@@ -704,29 +697,29 @@ cudaError_t launch_label(mamri_ctx* c, const uint32_t* d_mask, const mamri_volum
     // threads per slice CTA: about one per run of an average slice of the scans just processed (slice_threads_class)
     const int slice_threads = c->slice_threads > 0 ? c->slice_threads : (c->slice_threads < 0 ? -c->slice_threads : SLICE_THREADS);
     if (connectivity == 26) {
-        LK(k_union_slices<true>, nz, slice_threads, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, nz, c->d_scalars);
+        LK(k_union_slices<true>, nz, slice_threads, s, false, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_parent, W, ny, nz, c->d_scalars);
         prof_mark(c, s, "union_slices");
         if (nz > 1) {
-            LK(k_union_z<true>, RG, 256, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 0, c->d_scalars);
+            LK(k_union_z<true>, RG, 256, s, false, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_parent, W, ny, radix, 0, c->d_scalars);
             prof_mark(c, s, "union_z_within_blocks");
         }
         if (nz > radix) {
-            LK(k_union_z<true>, RG, 256, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 1, c->d_scalars);
+            LK(k_union_z<true>, RG, 256, s, false, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_parent, W, ny, radix, 1, c->d_scalars);
             prof_mark(c, s, "union_z_between_blocks");
         }
     } else {
-        LK(k_union_slices<false>, nz, slice_threads, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, nz, c->d_scalars);
+        LK(k_union_slices<false>, nz, slice_threads, s, false, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_parent, W, ny, nz, c->d_scalars);
         prof_mark(c, s, "union_slices");
         if (nz > 1) {
-            LK(k_union_z<false>, RG, 256, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 0, c->d_scalars);
+            LK(k_union_z<false>, RG, 256, s, false, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_parent, W, ny, radix, 0, c->d_scalars);
             prof_mark(c, s, "union_z_within_blocks");
         }
         if (nz > radix) {
-            LK(k_union_z<false>, RG, 256, s, false, d_mask, c->d_word_base, c->d_run_pos, c->d_run_len, c->d_parent, W, ny, radix, 1, c->d_scalars);
+            LK(k_union_z<false>, RG, 256, s, false, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_parent, W, ny, radix, 1, c->d_scalars);
             prof_mark(c, s, "union_z_between_blocks");
         }
     }
-    LK(k_flatten_rank, RG, FR_THREADS, s, false, c->d_parent, c->d_run_len, c->d_scan_rank, c->d_dyn, c->d_run_label,
+    LK(k_flatten_rank, RG, FR_THREADS, s, false, c->d_parent, c->d_run_pos, c->d_run_end, c->d_scan_rank, c->d_dyn, c->d_run_label,
        c->d_root_count, c->d_scalars);
     prof_mark(c, s, "flatten_rank");
     return launch_select(c, desc, prm, s);

@@ -90,7 +90,7 @@ struct mamri_ctx {
     size_t occ_cap;
     uint32_t* d_word_base;  // runs that start before each word         [cap_words]
     uint32_t* d_run_pos;    // word*32 + bit of each run's first voxel   [max_runs]
-    uint32_t* d_run_len;    // voxels in each run                        [max_runs]
+    uint32_t* d_run_end;    // word*32 + bit of each run's last voxel    [max_runs]
     uint32_t* d_parent;     // union-find over runs                     [max_runs]
     uint32_t* d_run_label;  // final label of each run                  [max_runs]
     uint32_t* d_root_count; // voxels of the component rooted at each run (roots only) [max_runs]
@@ -102,8 +102,6 @@ struct mamri_ctx {
     uint32_t* d_cand_label; // label of each slot                       [max_markers + 1]
     uint32_t* d_cand_rank;  // place of each slot in ascending label order [max_markers]
     unsigned long long* d_cand_sums; // 9 sums per slot (sx sy sz xx yy zz xy xz yz) [(max_markers+1)*9]
-    mamri_marker* d_markers;         // sorted marker table              [max_markers]
-    mamri_summary* d_summary;
     DevScalars* d_scalars;
     void* d_stage_in;       // staging for mamri_detect_host_async (lazy)
     size_t stage_in_bytes;
@@ -289,7 +287,7 @@ __device__ __forceinline__ void pdl_wait() {
 // the earliest stamp per slot.  One scan in flight at a time; the production library compiles this away.
 enum KId { KT_THRESHOLD = 0, KT_CLOSE, KT_ERODE, KT_RUNS, KT_USLICE, KT_UZ1, KT_UZ2, KT_RANK, KT_SELECT, KT_LABEL,
            KT_STATS, KT_FINAL, KT_MAT, KT_END, KT_L_U1, KT_L_U2, KT_L_F, KT_L_FIX, KT_L_S, KT_L_END, KT_RUNS_LB, KT_RUNS_WR,
-           KT_CLOSE_LD, KT_CLOSE_DIL, KT_CLOSE_ERO, KT_STATS_FIN, KT_SLOTS = 32 };
+           KT_CLOSE_LD, KT_CLOSE_DIL, KT_CLOSE_ERO, KT_STATS_FIN, KT_CLOSE_LAST, KT_RUNS_LAST, KT_THR_LAST, KT_SLOTS = 32 };
 #ifdef MAMRI_KTRACE
 static __device__ unsigned long long g_ktrace[KT_SLOTS];      // one copy per translation unit (no -rdc)
 __device__ __forceinline__ void ktrace(int id) {

@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(256) k_threshold_pack_v8(const DynArgs* __rest
         }
         if (occ && __any_sync(0xFFFFFFFFu, seen != 0u) && lane == 0) occ[(z / OCC_CZ) * occ_ncy + y0 / OCC_CY] = tag;
     }
+    ktrace_last(KT_THR_LAST);
 }
 
 // General path (ragged nx or unaligned base): one warp per output word, one voxel per lane.
@@ -958,6 +959,7 @@ __global__ void __launch_bounds__(512) k_close_fused(const uint32_t* __restrict_
         }
     }
     ktrace(KT_CLOSE_ERO);
+    ktrace_last(KT_CLOSE_LAST);
 }
 
 // Tile of the fused kernel for rows of Wp padded words: TY from {SYD k - 2R} with TY % SYE == 0 near the wanted size,

@@ -146,9 +146,8 @@ __device__ void jacobi_eigen3(double a[3][3], double w[3], double v[3][3]) {
             }
 }
 
-__device__ void make_marker(mamri_marker* out, uint32_t label, unsigned long long count, const unsigned long long* s9,
+__device__ void make_marker(mamri_marker& m, uint32_t label, unsigned long long count, const unsigned long long* s9,
                             const GeomArgs& g) {
-    mamri_marker m;
     m.label = label;
     m.reserved = 0;
     m.count = count;
@@ -194,7 +193,6 @@ __device__ void make_marker(mamri_marker* out, uint32_t label, unsigned long lon
         m.principal_moments[i] = w[i];
         for (int j = 0; j < 3; ++j) m.principal_axes[3 * i + j] = ax[i][j];
     }
-    *out = m;
 }
 
 // Turns the sums into the marker table and the summary.  One kernel does three things:
@@ -203,11 +201,13 @@ __device__ void make_marker(mamri_marker* out, uint32_t label, unsigned long lon
 //   moments  exact integer sums per run for the kept labels + the body, as described above
 //   finalise by the LAST CTA to finish its sums (ticket in DevScalars::done_stats): one thread per kept label turns
 //            the sums into a mamri_marker (float64 centroid, physical size, Jacobi eigen-decomposition), another
-//            warp's thread does the body, thread 0 the summary scalars.  Also fills the scan's fixed-size table
+//            warp's thread does the body, thread 0 the summary scalars.  `markers` and `summary` are the context's
+//            PINNED HOST buffers: the records go straight over PCIe as posted writes and are visible to the host when
+//            the stream has drained, so no copy nodes follow the kernel.  Also fills the scan's fixed-size table
 //            (DynArgs::table_out, rows of {label, count, volume_mm3, RAS x y z, n_labels, body_label}: the layout
 //            distributed.pack_table builds on the host) when the caller asked for it.
 // It runs beside `materialise` on the second branch of the graph.
-__global__ void __launch_bounds__(256) k_stats(const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_len,
+__global__ void __launch_bounds__(256) k_stats(const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_end,
                                                const uint32_t* __restrict__ parent, const uint32_t* __restrict__ run_label,
                                                const uint32_t* __restrict__ label_slot, int W, int ny,
                                                unsigned long long* sums, const uint32_t* __restrict__ cand_label,
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256) k_stats(const uint32_t* __restrict__ run_
                 const uint32_t wi = pos >> 5, row = wi / W;
                 const long long z = row / ny, y = row - uint32_t(z) * ny;
                 const long long xs = (long long)(wi - row * W) * 32 + (pos & 31u);
-                const long long len = run_len[r], xe = xs + len - 1;
+                const long long len = (long long)(run_end[r] - pos) + 1, xe = xs + len - 1;
                 const unsigned long long sx = (unsigned long long)((xs + xe) * len / 2);
                 v[0] = sx;                                              // sum x
                 v[1] = (unsigned long long)(len * y);                   // sum y
@@ -278,9 +278,10 @@ __global__ void __launch_bounds__(256) k_stats(const uint32_t* __restrict__ run_
         const uint32_t lab = __ldcg(cand_label + i), rank = __ldcg(cand_rank + i);
         unsigned long long s9[9];
         for (int k = 0; k < 9; ++k) s9[k] = __ldcg(sums + i * 9u + k);
-        make_marker(markers + rank, lab, __ldcg(label_count + lab - 1u), s9, g);
+        mamri_marker m;
+        make_marker(m, lab, __ldcg(label_count + lab - 1u), s9, g);
+        markers[rank] = m;
         if (rank < slots) {
-            const mamri_marker& m = markers[rank];
             double* row = table + size_t(rank) * 8;
             row[0] = double(m.label); row[1] = double(m.count); row[2] = m.volume_mm3;
             row[3] = m.centroid_ras[0]; row[4] = m.centroid_ras[1]; row[5] = m.centroid_ras[2];
@@ -289,13 +290,15 @@ __global__ void __launch_bounds__(256) k_stats(const uint32_t* __restrict__ run_
     }
     for (uint32_t i = n_kept * 8 + threadIdx.x; i < slots * 8; i += blockDim.x) table[i] = 0.0;   // unused rows
     if (threadIdx.x == blockDim.x - 1) {                     // the body: a thread of another warp than marker 0's
+        mamri_marker m;
         if (body != 0u) {
             unsigned long long s9[9];
             for (int k = 0; k < 9; ++k) s9[k] = __ldcg(sums + max_markers * 9u + k);
-            make_marker(&summary->body, body, bp >> 32, s9, g);
+            make_marker(m, body, bp >> 32, s9, g);
         } else {
-            memset(&summary->body, 0, sizeof(mamri_marker));
+            memset(&m, 0, sizeof(m));
         }
+        summary->body = m;
     }
     if (threadIdx.x == 0) {
         summary->n_labels = n_labels;
@@ -334,9 +337,9 @@ cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mam
 cudaError_t launch_stats(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
     const GeomArgs g = geom_args(desc, prm);
     const int W = (desc->nx + 31) / 32;
-    LK(k_stats, c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS, 256, s, false, c->d_run_pos, c->d_run_len, c->d_parent, c->d_run_label,
-       c->d_label_slot, W, desc->ny, c->d_cand_sums, c->d_cand_label, c->d_cand_rank, c->d_label_count, c->max_markers, g, c->d_markers,
-       c->d_summary, c->d_scalars, c->d_dyn);
+    LK(k_stats, c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS, 256, s, false, c->d_run_pos, c->d_run_end, c->d_parent, c->d_run_label,
+       c->d_label_slot, W, desc->ny, c->d_cand_sums, c->d_cand_label, c->d_cand_rank, c->d_label_count, c->max_markers, g, c->h_markers,
+       c->h_summary, c->d_scalars, c->d_dyn);
     prof_mark(c, s, "stats");
     return cudaGetLastError();
 }

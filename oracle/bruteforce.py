@@ -66,6 +66,18 @@ def closing_itk_pipeline(mask: np.ndarray, radius: int) -> np.ndarray:
     return e[r:-r, r:-r, r:-r].astype(np.uint8)
 
 
+def opening_itk_pipeline(mask: np.ndarray, radius: int) -> np.ndarray:
+    """itk::BinaryMorphologicalOpeningImageFilter literally: erode with the outside
+    of the image counted as foreground (BinaryErodeImageFilter's BoundaryToForeground
+    = true), then dilate with the outside as background; no padding."""
+    r = int(radius)
+    if r == 0:
+        return mask.astype(np.uint8).copy()
+    b = ball(r)
+    e = erode(mask.astype(bool), b, outside=True)
+    return dilate(e, b, outside=False).astype(np.uint8)
+
+
 def flood_fill_labels(mask: np.ndarray, connectivity: int = 6):
     """Raster scan; every unlabelled foreground voxel starts the next label and
     is flooded -- labels are consecutive in order of first voxel by construction."""

@@ -47,7 +47,13 @@ def cast_threshold(value: float, dtype: np.dtype) -> object:
 def binary_threshold(vol: np.ndarray, lo: float = INTENSITY_THRESHOLD,
                      hi: float = UPPER_THRESHOLD) -> np.ndarray:
     """uint8 {0,1}: 1 where lo <= v <= hi (both inclusive), compared in the
-    input pixel type.  NaN compares false."""
+    input pixel type.  NaN compares false.
+
+    Restates itk::BinaryThresholdImageFilter (ITK 5.x,
+    Modules/Filtering/Thresholding/include/itkBinaryThresholdImageFilter.h:
+    Functor::BinaryThreshold::operator() ``m_LowerThreshold <= A && A <=
+    m_UpperThreshold ? m_InsideValue : m_OutsideValue``; the bounds reach the functor
+    through ``static_cast<InputPixelType>`` of SimpleITK's double arguments)."""
     lo_c = cast_threshold(lo, vol.dtype)
     hi_c = cast_threshold(hi, vol.dtype)
     return ((vol >= lo_c) & (vol <= hi_c)).astype(np.uint8)
@@ -59,7 +65,15 @@ def binary_threshold(vol: np.ndarray, lo: float = INTENSITY_THRESHOLD,
 def ball_offsets(radius: int) -> np.ndarray:
     """Offsets (dz, dy, dx) of ITK's ball: voxel centres inside the ellipsoid of
     axes 2r+1, i.e. dx^2+dy^2+dz^2 <= (r+0.5)^2  <=>  <= r*r + r for integers.
-    r=1 -> 19 voxels, r=2 -> 81, r=3 -> 179."""
+    r=1 -> 19 voxels, r=2 -> 81, r=3 -> 179.
+
+    Restates itk::FlatStructuringElement<3>::Ball(radius, radiusIsParametric=false)
+    (Modules/Filtering/MathematicalMorphology/include/itkFlatStructuringElement.hxx):
+    an EllipsoidInteriorExteriorSpatialFunction with axes = size = 2r+1 centred at
+    r + 0.5, flood-filled from the centre pixel with the centre-inclusion strategy
+    (a pixel belongs iff its centre index + 0.5 is inside).  SimpleITK's sitkBall
+    maps to this constructor.  tools/make_itk_golden.py records the element ITK
+    really used (dilation of one voxel) as ``ball{r}``."""
     r = int(radius)
     g = np.arange(-r, r + 1)
     dz, dy, dx = np.meshgrid(g, g, g, indexing="ij")
@@ -78,8 +92,33 @@ def ball_structure(radius: int) -> np.ndarray:
 # --------------------------------------------------------------------------- #
 # (c-3) sitk.BinaryMorphologicalClosing(binary, [r]*3, sitkBall)  Mamri.py:1308
 # --------------------------------------------------------------------------- #
+def binary_opening(mask: np.ndarray, radius: int) -> np.ndarray:
+    """sitk.BinaryMorphologicalOpening(mask, [r]*3, sitkBall): the north_star's
+    "open/close" -- the reference itself only closes (Mamri.py:1308), so this is
+    an extension (``mamri_params.open_radius``, 0 = off = the reference).
+
+    Restates itk::BinaryMorphologicalOpeningImageFilter::GenerateData
+    (Modules/Filtering/BinaryMathematicalMorphology/include/
+    itkBinaryMorphologicalOpeningImageFilter.hxx): BinaryErodeImageFilter, whose
+    constructor sets BoundaryToForeground = true (outside the image counts as
+    foreground: an object is not eroded from the image border), then
+    BinaryDilateImageFilter (outside = background).  There is no safe-border
+    padding in the opening filter."""
+    r = int(radius)
+    if r == 0:
+        return mask.astype(np.uint8).copy()
+    st = ball_structure(r)
+    e = ndimage.binary_erosion(mask.astype(bool), structure=st, border_value=1)
+    d = ndimage.binary_dilation(e, structure=st, border_value=0)
+    return d.astype(np.uint8)
+
+
 def binary_closing_safe_border(mask: np.ndarray, radius: int = CLOSE_RADIUS) -> np.ndarray:
-    """itk::BinaryMorphologicalClosingImageFilter with SafeBorder=true:
+    """itk::BinaryMorphologicalClosingImageFilter with SafeBorder=true
+    (Modules/Filtering/BinaryMathematicalMorphology/include/
+    itkBinaryMorphologicalClosingImageFilter.hxx, GenerateData: ConstantPadImageFilter
+    by the kernel radius -> BinaryDilateImageFilter -> BinaryErodeImageFilter ->
+    CropImageFilter; SimpleITK's procedural call leaves safeBorder at its default true):
     ConstantPad(r, 0) -> BinaryDilate (outside = background) -> BinaryErode
     (outside = foreground) -> Crop(r).  For voxels of the original domain this is
     the closing of the zero-extended mask on an unbounded grid.  Restated as:
@@ -120,7 +159,14 @@ def canonical_relabel(labels: np.ndarray) -> Tuple[np.ndarray, int]:
 
 def connected_components(mask: np.ndarray, connectivity: int = 6) -> Tuple[np.ndarray, int]:
     """itk::ConnectedComponentImageFilter; SimpleITK default fullyConnected=False
-    is face connectivity (6), True is 26.  uint32 labels, background 0."""
+    is face connectivity (6), True is 26.  uint32 labels, background 0.
+
+    Restates Modules/Segmentation/ConnectedComponents/include/
+    itkConnectedComponentImageFilter.hxx + itkScanlineFilterCommon.h: provisional
+    labels per x-run in raster order, LinkLabels keeps the smaller label as the
+    root of a union, CreateConsecutive numbers the roots 1..K in increasing order
+    of provisional label -- i.e. by each object's first voxel in raster order,
+    which is what ``canonical_relabel`` produces."""
     if connectivity == 6:
         st = ndimage.generate_binary_structure(3, 1)
     elif connectivity == 26:
@@ -186,7 +232,13 @@ def integer_sums(labels: np.ndarray, n_labels: int):
 
 
 def moments_from_sums(count: int, sum_idx, sum_mom, geom: Geometry):
-    """ShapeLabelMapFilter's second central moments from exact index sums.
+    """ShapeLabelMapFilter's second central moments from exact index sums
+    (itk::ShapeLabelMapFilter::ThreadedProcessLabelObject,
+    Modules/Filtering/LabelMap/include/itkShapeLabelMapFilter.hxx: sums over the
+    label object's lines, "Normalize using the total mass", "Center the second
+    order moments", then ``centralMoments[i][i] += spacing[i]^2 / 12`` -- the
+    second moment of one pixel --, vnl_symmetric_eigensystem (ascending), principal
+    axes = V^T with the last row multiplied by the determinant).
     With p = o + A i (A = direction*spacing):  E[pp^T]-cc^T = A Cov(i) A^T, plus
     spacing_i^2/12 on the diagonal (second moment of one voxel box).  Principal
     moments ascending; principal axes = rows of V^T with the last row multiplied
@@ -261,10 +313,12 @@ def select_candidates(counts: np.ndarray, voxel_volume: float,
 def detect_fiducials(vol: np.ndarray, geom: Geometry, lo: float = INTENSITY_THRESHOLD,
                      hi: float = UPPER_THRESHOLD, close_radius: int = CLOSE_RADIUS,
                      connectivity: int = 6, min_vol: float = MIN_VOLUME_THRESHOLD,
-                     max_vol: float = MAX_VOLUME_THRESHOLD, full_stats: bool = False) -> Detection:
-    """The whole of Mamri.py:1308-1323 on one volume."""
+                     max_vol: float = MAX_VOLUME_THRESHOLD, full_stats: bool = False,
+                     open_radius: int = 0) -> Detection:
+    """The whole of Mamri.py:1308-1323 on one volume (``open_radius`` > 0: the
+    thresholded mask is opened first -- north_star extension, not in the reference)."""
     binary = binary_threshold(vol, lo, hi)
-    closed = binary_closing_safe_border(binary, close_radius)
+    closed = binary_closing_safe_border(binary_opening(binary, open_radius), close_radius)
     labels, k = connected_components(closed, connectivity)
     counts = np.bincount(labels.ravel(), minlength=k + 1)[1:].astype(np.int64)
     kept, body = select_candidates(counts, geom.voxel_volume(), min_vol, max_vol)

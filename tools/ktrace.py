@@ -25,7 +25,8 @@ from mamri_pose_estimation_b200.detector import DetectParams, FiducialDetector, 
 # slot order of csrc/common.cuh: enum KId
 NAMES = ["threshold", "close", "erode", "runs_scan", "union_slices", "union_z1", "union_z2", "flatten_rank", "select",
          "label_cluster", "stats", "final", "materialise", "end", "label.U1", "label.U2", "label.F", "label.FIX", "label.S",
-         "label.end", "runs.lookback", "runs.write", "close.loaded", "close.dilated", "close.eroded", "stats.finalise"]
+         "label.end", "runs.lookback", "runs.write", "close.loaded", "close.dilated", "close.eroded", "stats.finalise",
+         "close.lastCTA", "runs.lastCTA", "threshold.lastCTA"]
 
 
 def main():
@@ -61,7 +62,7 @@ def main():
         totals.append(e0.elapsed_time(e1) * 1e3)
         lib.mamri_ktrace_read(buf, 32)
         row = [int(v) for v in buf]
-        for j in (11, 13):                               # KT_FINAL / KT_END hold the complement of the LAST stamp (ktrace_last)
+        for j in (11, 13, 26, 27, 28):                               # KT_FINAL / KT_END hold the complement of the LAST stamp (ktrace_last)
             if row[j] != (1 << 64) - 1:
                 row[j] = ~row[j] & ((1 << 64) - 1)
         rows.append(row)
