@@ -69,6 +69,9 @@ typedef struct mamri_params {
     int32_t connectivity;     /* 6 = SimpleITK default, or 26          Mamri.py:1309 */
     double  min_volume;       /* MIN_VOLUME_THRESHOLD = 50.0 mm^3      Mamri.py:811  */
     double  max_volume;       /* MAX_VOLUME_THRESHOLD = 1500.0 mm^3    Mamri.py:812  */
+    int32_t open_radius;      /* 0 = off (the reference only closes); 1..3: the thresholded mask is opened with the
+                                 ITK ball first (sitk.BinaryMorphologicalOpening: north_star "open/close") */
+    int32_t reserved;
 } mamri_params;
 
 /* One label kept by the list comprehension at Mamri.py:1310, in ascending label order

@@ -28,7 +28,8 @@ class VolumeDesc(C.Structure):
 
 class Params(C.Structure):
     _fields_ = [("lower", C.c_double), ("upper", C.c_double), ("close_radius", C.c_int32),
-                ("connectivity", C.c_int32), ("min_volume", C.c_double), ("max_volume", C.c_double)]
+                ("connectivity", C.c_int32), ("min_volume", C.c_double), ("max_volume", C.c_double),
+                ("open_radius", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Marker(C.Structure):

@@ -137,6 +137,8 @@ extern "C" void mamri_default_params(mamri_params* p) {
     p->lower = 65.0;          // Mamri.py:810
     p->upper = 65535.0;       // Mamri.py:1308
     p->close_radius = 2;      // Mamri.py:1308
+    p->open_radius = 0;       // the reference does not open
+    p->reserved = 0;
     p->connectivity = 6;      // Mamri.py:1309 (SimpleITK default fullyConnected=False)
     p->min_volume = 50.0;     // Mamri.py:811
     p->max_volume = 1500.0;   // Mamri.py:812
@@ -148,7 +150,7 @@ extern "C" int mamri_destroy(mamri_ctx* ctx) {
     if (!ctx) return MAMRI_OK;
     DeviceGuard g(ctx->device);
     cudaFree(ctx->d_occ_raw); cudaFree(ctx->d_occ_dil);
-    cudaFree(ctx->d_raw); cudaFree(ctx->d_planes); cudaFree(ctx->d_dil); cudaFree(ctx->d_closed); cudaFree(ctx->d_word_base);
+    cudaFree(ctx->d_raw); cudaFree(ctx->d_planes); cudaFree(ctx->d_dil); cudaFree(ctx->d_open); cudaFree(ctx->d_closed); cudaFree(ctx->d_word_base);
     cudaFree(ctx->d_run_pos); cudaFree(ctx->d_run_end); cudaFree(ctx->d_parent); cudaFree(ctx->d_run_label); cudaFree(ctx->d_label_count); cudaFree(ctx->d_label_slot);
     cudaFree(ctx->d_root_count); cudaFree(ctx->d_scan_runs); cudaFree(ctx->d_scan_rank); cudaFree(ctx->d_cand_label); cudaFree(ctx->d_cand_rank); cudaFree(ctx->d_cand_sums);
     cudaFree(ctx->d_stage_in); cudaFree(ctx->d_stage_body);
@@ -219,6 +221,8 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     ALLOC(ctx->d_raw, ctx->cap_pad_words * 4, "raw mask");
     ALLOC(ctx->d_planes, 3 * ctx->cap_pad_words * 4, "morphology planes");
     ALLOC(ctx->d_dil, ctx->cap_pad_words * 4, "dilated mask");
+    ALLOC(ctx->d_open, ctx->cap_pad_words * 4, "opening scratch");
+    if ((e = cudaMemset(ctx->d_open, 0, ctx->cap_pad_words * 4)) != cudaSuccess) return bail(e, "opening scratch");
     ALLOC(ctx->d_closed, ctx->cap_words * 4, "closed mask");
     ctx->occ_cap = (size_t(max_ny) / 8 + 2) * (size_t(max_nz) / 4 + 2);
     ALLOC(ctx->d_occ_raw, ctx->occ_cap, "occupancy cells");
@@ -263,15 +267,17 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
     // per-device function attributes (dynamic shared memory above 48 KB, cluster size): every context sets them for
     // its own device, so one process can drive several GPUs
     if ((e = segment_init_device()) != cudaSuccess) return bail(e, "kernel attributes");
-    ctx->max_cluster = ccl_init_device();
-    if (const char* lc = getenv("MAMRI_LABEL_CLUSTER")) {          // experiments: 0 = scalable kernels only, N = cluster size
-        const int want = atoi(lc);
-        ctx->max_cluster = want < ctx->max_cluster ? (want < 0 ? 0 : want) : ctx->max_cluster;
+    // The single-cluster labelling kernel (ccl.cu: k_label_cluster) is kept as an experiment: on the B200 it measured
+    // slower than the scalable kernels even on small run tables (its 16 CTAs give every thread several runs to hook one
+    // after the other, and chains grow between them), so it is off unless MAMRI_LABEL_CLUSTER=<cluster size> asks for it.
+    ctx->max_cluster = 0;
+    {
+        const int probe = ccl_init_device();
+        if (const char* lc = getenv("MAMRI_LABEL_CLUSTER")) {
+            const int want = atoi(lc);
+            ctx->max_cluster = want < probe ? (want < 0 ? 0 : want) : probe;
+        }
     }
-    if ((e = cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "capture stream");
-    if ((e = cudaStreamCreateWithFlags(&ctx->cap_stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "capture stream");
-    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "events");
-    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "events");
     {
         const char* ng = getenv("MAMRI_NO_GRAPH");
         ctx->use_graph = !(ng && ng[0] == '1');
@@ -316,6 +322,8 @@ static int validate(mamri_ctx* ctx, const mamri_volume_desc* d, const mamri_para
     if (dtype_size(d->dtype) == 0) return fail(ctx, MAMRI_ERR_INVALID_ARG, "unsupported voxel type");
     if (p->close_radius < 0 || p->close_radius > MAMRI_RMAX)
         return fail(ctx, MAMRI_ERR_INVALID_ARG, "close_radius must be 0..3");
+    if (p->open_radius < 0 || p->open_radius > MAMRI_RMAX)
+        return fail(ctx, MAMRI_ERR_INVALID_ARG, "open_radius must be 0..3");
     if (p->connectivity != 6 && p->connectivity != 26) return fail(ctx, MAMRI_ERR_INVALID_ARG, "connectivity must be 6 or 26");
     for (int i = 0; i < 3; ++i)
         if (!(d->spacing[i] > 0.0)) return fail(ctx, MAMRI_ERR_INVALID_ARG, "spacing must be positive");
@@ -332,10 +340,12 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool f
     launch_counter() = 0;
     CK(cudaMemcpyAsync(ctx->d_args, ctx->h_args, sizeof(ScanArgs), cudaMemcpyHostToDevice, s));   // pointers + zeroed scalars
     if (prof) { ctx->n_fine = 0; CK(cudaEventRecord(ctx->ev[0], s)); }
-    CK(launch_threshold_pack(ctx, k.vol_aligned, desc->dtype, nx, ny, nz, params->lower, params->upper, params->close_radius, s));
+    const int geom_r = morph_geom_radius(params->open_radius, params->close_radius);
+    CK(launch_threshold_pack(ctx, k.vol_aligned, desc->dtype, nx, ny, nz, params->lower, params->upper, geom_r, s));
     if (prof) CK(cudaEventRecord(ctx->ev[1], s));
     const uint32_t* mask = ctx->d_closed;
-    if (params->close_radius > 0) CK(launch_closing(ctx, nx, ny, nz, params->close_radius, s));
+    CK(launch_opening(ctx, nx, ny, nz, params->open_radius, geom_r, s));
+    CK(launch_closing(ctx, nx, ny, nz, params->close_radius, geom_r, s));
     if (prof) CK(cudaEventRecord(ctx->ev[2], s));
     CK(launch_label(ctx, mask, desc, params, s));
     if (prof) CK(cudaEventRecord(ctx->ev[3], s));
@@ -402,7 +412,7 @@ static int detect_async_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, cons
     ctx->h_dyn->table_slots = d_table ? table_slots : 0u;
     ctx->h_dyn->gen = ++ctx->gen;            // generation 0 is the cleared state: never used
     if ((ctx->gen & 0x3FFFFFFFu) == 0) ctx->h_dyn->gen = ++ctx->gen;
-    CK(prepare_raw_apron(ctx, desc->nx, desc->ny, desc->nz, params->close_radius, s));
+    CK(prepare_raw_apron(ctx, desc->nx, desc->ny, desc->nz, morph_geom_radius(params->open_radius, params->close_radius), s));
     if (ctx->profile || !ctx->use_graph) {
         rc = enqueue_pipeline(ctx, k, ctx->profile, false, s);
         if (rc != MAMRI_OK) return rc;
@@ -668,6 +678,7 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
     const int nx = desc->nx, ny = desc->ny, nz = desc->nz;
     cudaStream_t H0 = pool->hbm;
     const int NC = pool->n_chains;
+    const int geom_r = morph_geom_radius(prm->open_radius, prm->close_radius);
     launch_counter() = 0;
     CKP(cudaMemcpyAsync(pool->d_args_all, pool->h_args_all, sizeof(ScanArgs) * m, cudaMemcpyHostToDevice, H0));
     CKP(cudaEventRecord(pool->fork, H0));
@@ -675,7 +686,7 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
     for (int i = 0; i < m; ++i) {
         cudaStream_t H = pool->chain[i % NC];
         TRACE(i, 0, H);
-        CKP(launch_threshold_pack(pool->ctx[i], k.vol_aligned, desc->dtype, nx, ny, nz, prm->lower, prm->upper, prm->close_radius, H));
+        CKP(launch_threshold_pack(pool->ctx[i], k.vol_aligned, desc->dtype, nx, ny, nz, prm->lower, prm->upper, geom_r, H));
         TRACE(i, 1, H);
         CKP(cudaEventRecord(pool->ev_thr[i], H));
     }
@@ -684,7 +695,8 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
         mamri_ctx* c = pool->ctx[i];
         cudaStream_t s = pool->streams[i];
         CKP(cudaStreamWaitEvent(s, pool->ev_thr[i], 0));
-        if (prm->close_radius > 0) CKP(launch_closing(c, nx, ny, nz, prm->close_radius, s));
+        CKP(launch_opening(c, nx, ny, nz, prm->open_radius, geom_r, s));
+        CKP(launch_closing(c, nx, ny, nz, prm->close_radius, geom_r, s));
         TRACE(i, 2, s);
         TRACE(i, 3, s);
         CKP(launch_label(c, c->d_closed, desc, prm, s));
@@ -729,7 +741,7 @@ static int pool_wave_launch(mamri_pool* pool, const GraphKey& k, const void* con
         d->table_slots = tables ? table_slots : 0u;
         d->gen = ++c->gen;
         if ((c->gen & 0x3FFFFFFFu) == 0) d->gen = ++c->gen;
-        CKP(prepare_raw_apron(c, k.desc.nx, k.desc.ny, k.desc.nz, k.prm.close_radius, cur));
+        CKP(prepare_raw_apron(c, k.desc.nx, k.desc.ny, k.desc.nz, morph_geom_radius(k.prm.open_radius, k.prm.close_radius), cur));
     }
     WaveGraph& w = pool->waves[m];
     if (!w.valid || memcmp(&w.key, &k, sizeof(k)) != 0) {

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
         else sc->n_runs = before + total;
     }
     ktrace(KT_RUNS_LB);
+    ktrace_last(KT_RUNS_LB2);
     uint32_t base = before + ex;
     uint32_t e_idx = base - open;                                        // ends before this thread = starts before - open runs
     uint32_t wb[RS_ITEMS];
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
     const uint32_t r0 = word_base[w0];
     const uint32_t r1 = (z + 1 < uint32_t(nz)) ? word_base[w0 + slice_words] : sc->n_runs;
     const uint32_t n = r1 - r0;
+    ktrace_both(KT_US_N);
     if (n == 0) return;
     uint32_t* P = (n <= SLICE_SMEM_RUNS) ? sp : parent + r0;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) P[i] = i;
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
         const int gx0 = int((wi - row * W) * 32 + (pos & 31u));
         join_run<CONN26>(word_base, run_pos, run_end, P, r0, W, i, gx0, int(run_end[r0 + i] - pos + 1u), (row - 1) * W);
     }
+    ktrace_both(KT_US_JOIN);
     // flatten by pointer jumping: a convex object leaves a chain as long as it is tall, which a per-run
     // walk would follow hop by hop; doubling reaches the root in log2(height) rounds
     bool again = true;
@@ -252,7 +255,9 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
         }
         again = __syncthreads_or(changed);
     }
+    ktrace_both(KT_US_FLAT);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) parent[r0 + i] = r0 + P[i];
+    ktrace_both(KT_US_END);
 }
 
 // Phase 2 -- global boundary merge between slices, with atomicMin on the roots.  Joining all slice
@@ -283,6 +288,7 @@ __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ wo
             if (y + 1 < uint32_t(ny)) join_run<true>(word_base, run_pos, run_end, parent, 0u, W, r, gx0, len, below + W);
         }
     }
+    ktrace_both(between_blocks ? KT_UZ2_END : KT_UZ1_END);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -376,6 +382,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_flatten_rank(uint32_t* parent, c
             if (is_root[k]) run_label[r0 + k * 32] = base + row_tot[k] + row_ex[k] + 1u;
     }
     cache.flush(root_count);
+    ktrace_both(KT_RANK_END);
 }
 
 

@@ -25,6 +25,8 @@ struct DevScalars {
     unsigned int ticket_rank;
     unsigned int done_select;        // CTAs of k_select that have finished (last one prepares the moment table)
     unsigned int done_stats;         // CTAs of k_stats that have finished their moment sums (last one finalises)
+    unsigned int ticket_close;       // tile tickets of k_close_fused
+    unsigned int reserved_[3];
     unsigned int cl_roots[16];       // k_label_cluster: roots found by each CTA of the cluster (rank exchange)
 };
 
@@ -83,6 +85,7 @@ struct mamri_ctx {
     uint32_t* d_raw;        // thresholded mask, bit-packed, zero-apron padded layout   [cap_pad_words]
     uint32_t* d_planes;     // morphology pass-A planes (x-z part of the ball)          [3 * cap_pad_words]
     uint32_t* d_dil;        // dilation on the r-grown domain, padded layout            [cap_pad_words]
+    uint32_t* d_open;       // erosion of an opening, padded layout; its apron is zero and never written [cap_pad_words]
     uint32_t* d_closed;     // closed mask, bit-packed [nz][ny][W]                      [cap_words]
     int raw_nx, raw_ny, raw_nz, raw_r;   // geometry d_raw's zero apron was last cleared for
     uint8_t* d_occ_raw;     // occupancy cells of the raw mask (set by threshold+pack, cleared by the erosion)  [occ_cap]
@@ -170,7 +173,10 @@ inline void prof_mark(mamri_ctx* c, cudaStream_t s, const char* name) {
 cudaError_t prepare_raw_apron(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s);
 cudaError_t launch_threshold_pack(mamri_ctx* c, int vol_aligned16, int dtype, int nx, int ny, int nz, double lo,
                                   double hi, int radius, cudaStream_t s);
-cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s);
+// geom_r = morph_geom_radius(open, close): the radius the padded layout (apron 2 geom_r) is built for
+int morph_geom_radius(int open_radius, int close_radius);
+cudaError_t launch_opening(mamri_ctx* c, int nx, int ny, int nz, int radius, int geom_r, cudaStream_t s);
+cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, int geom_r, cudaStream_t s);
 // run numbering + union-find + ranking + volume filter + body label (one cluster kernel or the scalable kernels)
 cudaError_t launch_label(mamri_ctx* c, const uint32_t* d_mask, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
 cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
@@ -287,7 +293,10 @@ __device__ __forceinline__ void pdl_wait() {
 // the earliest stamp per slot.  One scan in flight at a time; the production library compiles this away.
 enum KId { KT_THRESHOLD = 0, KT_CLOSE, KT_ERODE, KT_RUNS, KT_USLICE, KT_UZ1, KT_UZ2, KT_RANK, KT_SELECT, KT_LABEL,
            KT_STATS, KT_FINAL, KT_MAT, KT_END, KT_L_U1, KT_L_U2, KT_L_F, KT_L_FIX, KT_L_S, KT_L_END, KT_RUNS_LB, KT_RUNS_WR,
-           KT_CLOSE_LD, KT_CLOSE_DIL, KT_CLOSE_ERO, KT_STATS_FIN, KT_CLOSE_LAST, KT_RUNS_LAST, KT_THR_LAST, KT_SLOTS = 32 };
+           KT_CLOSE_LD, KT_CLOSE_DIL, KT_CLOSE_ERO, KT_STATS_FIN, KT_CLOSE_LAST, KT_RUNS_LAST, KT_THR_LAST,
+           // pairs (earliest CTA, latest CTA) of in-kernel phase stamps: ktrace_both(id) fills id and id + 1
+           KT_US_N = 29, KT_US_JOIN = 31, KT_US_FLAT = 33, KT_US_END = 35, KT_UZ1_END = 37, KT_UZ2_END = 39, KT_RANK_END = 41,
+           KT_SEL_END = 43, KT_RUNS_LB2 = 45, KT_SLOTS = 48 };
 #ifdef MAMRI_KTRACE
 static __device__ unsigned long long g_ktrace[KT_SLOTS];      // one copy per translation unit (no -rdc)
 __device__ __forceinline__ void ktrace(int id) {
@@ -305,6 +314,7 @@ __device__ __forceinline__ void ktrace_last(int id) {
         atomicMin(&g_ktrace[id], ~t);
     }
 }
+__device__ __forceinline__ void ktrace_both(int id) { ktrace(id); ktrace_last(id + 1); }
 // reset / min-merge of this translation unit's stamps (called by mamri_ktrace_reset / mamri_ktrace_read)
 #define KTRACE_TU(name)                                                                         \
     void ktrace_reset_##name() {                                                                \
@@ -320,6 +330,7 @@ __device__ __forceinline__ void ktrace_last(int id) {
 #else
 __device__ __forceinline__ void ktrace(int) {}
 __device__ __forceinline__ void ktrace_last(int) {}
+__device__ __forceinline__ void ktrace_both(int) {}
 #define KTRACE_TU(name)
 #endif
 

@@ -332,6 +332,7 @@ cudaError_t prepare_raw_apron(mamri_ctx* c, int nx, int ny, int nz, int radius, 
     if (c->raw_nx == nx && c->raw_ny == ny && c->raw_nz == nz && c->raw_r == radius) return cudaSuccess;
     const PadGeom g(nx, ny, nz, radius);
     cudaError_t e = cudaMemsetAsync(c->d_raw, 0, size_t(g.words) * 4, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_open, 0, size_t(g.words) * 4, s);   // same rule for the opening's scratch
     if (e != cudaSuccess) return e;
     c->raw_nx = nx; c->raw_ny = ny; c->raw_nz = nz; c->raw_r = radius;
     return cudaSuccess;
@@ -586,6 +587,7 @@ struct TileArgs {
     uint32_t occ_stride, cy, cz, oy, oz, dom_y, dom_z;
     uint8_t* occ_out;                   // one flag per tile of this pass: any output word non-zero
     uint32_t occ_tagged;                // occ_in holds scan tags (raw-mask cells) instead of 0/1 flags
+    uint32_t invert_out;                // padded output only: store the complement (inside the row's tail mask)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -716,6 +718,8 @@ __global__ void __launch_bounds__(1024) k_morph_tile(const uint32_t* __restrict_
                         if (xx == a.x_cnt - 1) v &= a.tail_mask;
                         dst[((zo - a.z_lo) * a.out_ny + (y0 + y - a.y_lo)) * a.out_w + xx] = v;
                     } else {
+                        if (a.invert_out) v = ~v;
+                        if (xx == a.x_cnt - 1) v &= a.tail_mask;
                         dst[zo * a.slice + (y0 + y) * a.Wp + xw] = v;
                         out_any |= v;
                     }
@@ -765,7 +769,7 @@ static cudaError_t closing_tile_r(mamri_ctx* c, int nx, int ny, int nz, uint32_t
     a.occ_in = occ ? c->d_occ_raw : nullptr;
     a.occ_stride = ncy; a.cy = OCC_CY; a.cz = OCC_CZ; a.oy = 2 * R; a.oz = 2 * R; a.dom_y = uint32_t(ny); a.dom_z = uint32_t(nz);
     a.occ_out = occ ? c->d_occ_dil : nullptr;
-    a.occ_tagged = 1;
+    a.occ_tagged = 1; a.invert_out = 0;
     const dim3 dil_grid = grid;
     LKS(k_morph_tile<R, false, false, SY>, grid, threads, smem, s, false, c->d_raw, c->d_dil, c->d_dyn, a);
     prof_mark(c, s, "dilate");
@@ -805,6 +809,7 @@ struct FusedArgs {
     uint32_t tail_mask;
     const uint8_t* occ;                 // occupancy cells of the raw mask (scan tags), NULL = read every tile
     uint32_t occ_stride;
+    uint32_t tiles_y, n_tiles;          // tiles along y / in all; CTAs draw them from DevScalars::ticket_close
 };
 
 // The strip walk: `col` points at (first source row of the strip, word column) of the first source slice of a
@@ -866,19 +871,15 @@ __device__ __forceinline__ void ball_walk(const uint32_t* col, uint32_t row_stri
 
 template <int R, int SYD, int SYE>
 __global__ void __launch_bounds__(512) k_close_fused(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
-                                                     const DynArgs* __restrict__ dyn, FusedArgs a) {
+                                                     const DynArgs* __restrict__ dyn, DevScalars* sc, FusedArgs a) {
     extern __shared__ __align__(128) uint32_t tile[];
+    __shared__ uint32_t s_ticket;
     const uint32_t SY_ = a.TY + 4 * R, SZ_ = a.TZ + 4 * R;          // source rows / slices held
     const uint32_t DY = a.TY + 2 * R, DZ = a.TZ + 2 * R;            // dilated rows / slices held
     uint32_t* s_src = tile;                                         // [SZ_][SY_][Wp]
     uint32_t* s_dil = tile + SZ_ * SY_ * a.Wp;                      // [DZ][DY][Wp]
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_dil + DZ * DY * a.Wp);
     const uint32_t bar_s = smem_u32(bar);
-    const uint32_t Y0 = blockIdx.x * a.TY, Z0 = blockIdx.y * a.TZ;  // first output row / slice (image coordinates)
-    const uint32_t py0 = Y0 + a.pad - 2 * R, pz0 = Z0 + a.pad - 2 * R;   // first source row / slice (padded coordinates)
-    const uint32_t rows_src = min(SY_, a.ny + 2 * a.pad - py0);     // rows / slices past the padded volume feed no output
-    const uint32_t n_sl = min(SZ_, a.nz + 2 * a.pad - pz0);
-    const uint32_t out_rows = min(a.TY, a.ny - Y0), out_sl = min(a.TZ, a.nz - Z0);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -886,79 +887,97 @@ __global__ void __launch_bounds__(512) k_close_fused(const uint32_t* __restrict_
     __syncthreads();
     pdl_wait();
     ktrace(KT_CLOSE);
-    if (a.occ) {
-        const uint8_t want = occ_tag(dyn->gen);
-        // source rows / slices of the tile in image coordinates, clipped to the image (the apron is air)
-        const int ya = max(int(Y0) - 2 * R, 0), yb = min(int(Y0 + a.TY) + 2 * R, int(a.ny));
-        const int za = max(int(Z0) - 2 * R, 0), zb = min(int(Z0 + a.TZ) + 2 * R, int(a.nz));
-        const int c0 = ya / int(OCC_CY), nyc = (yb - 1) / int(OCC_CY) - c0 + 1;
-        const int d0 = za / int(OCC_CZ), nzc = (zb - 1) / int(OCC_CZ) - d0 + 1;
-        int hit = 0;
-        for (int i = threadIdx.x; i < nyc * nzc; i += blockDim.x)
-            hit |= a.occ[(d0 + i / nyc) * a.occ_stride + c0 + i % nyc] == want;
-        if (!__syncthreads_or(hit)) {                               // air: the closing of nothing is nothing
-            const uint32_t per_slice = out_rows * a.W;
-            for (uint32_t i = threadIdx.x; i < per_slice * out_sl; i += blockDim.x) {
-                const uint32_t zo = i / per_slice;
-                dst[(size_t(Z0 + zo) * a.ny + Y0) * a.W + (i - zo * per_slice)] = 0u;
+    const uint8_t want = a.occ ? occ_tag(dyn->gen) : uint8_t(0);
+    uint32_t phase = 0;                                             // parity of the mbarrier phase the next fetch completes
+    // Persistent CTAs draw tiles from a ticket counter: most tiles of an MR volume are air and cost next to nothing, so
+    // the tiles that do hold something end up spread over all the CTAs instead of queueing behind each other in the
+    // launch order of a static grid (measured: the last CTA of a static grid finished 7 us after the first).
+    while (true) {
+        __syncthreads();                                            // everyone is done with the previous tile's shared memory
+        if (threadIdx.x == 0) s_ticket = atomicAdd(&sc->ticket_close, 1u);
+        __syncthreads();
+        const uint32_t t = s_ticket;
+        if (t >= a.n_tiles) break;
+        const uint32_t ty = t % a.tiles_y, tz = t / a.tiles_y;
+        const uint32_t Y0 = ty * a.TY, Z0 = tz * a.TZ;              // first output row / slice (image coordinates)
+        const uint32_t py0 = Y0 + a.pad - 2 * R, pz0 = Z0 + a.pad - 2 * R;   // first source row / slice (padded coordinates)
+        const uint32_t rows_src = min(SY_, a.ny + 2 * a.pad - py0); // rows / slices past the padded volume feed no output
+        const uint32_t n_sl = min(SZ_, a.nz + 2 * a.pad - pz0);
+        const uint32_t out_rows = min(a.TY, a.ny - Y0), out_sl = min(a.TZ, a.nz - Z0);
+        if (a.occ) {
+            // source rows / slices of the tile in image coordinates, clipped to the image (the apron is air)
+            const int ya = max(int(Y0) - 2 * R, 0), yb = min(int(Y0 + a.TY) + 2 * R, int(a.ny));
+            const int za = max(int(Z0) - 2 * R, 0), zb = min(int(Z0 + a.TZ) + 2 * R, int(a.nz));
+            const int c0 = ya / int(OCC_CY), nyc = (yb - 1) / int(OCC_CY) - c0 + 1;
+            const int d0 = za / int(OCC_CZ), nzc = (zb - 1) / int(OCC_CZ) - d0 + 1;
+            int hit = 0;
+            for (int i = threadIdx.x; i < nyc * nzc; i += blockDim.x)
+                hit |= a.occ[(d0 + i / nyc) * a.occ_stride + c0 + i % nyc] == want;
+            if (!__syncthreads_or(hit)) {                           // air: the closing of nothing is nothing
+                const uint32_t per_slice = out_rows * a.W;
+                for (uint32_t i = threadIdx.x; i < per_slice * out_sl; i += blockDim.x) {
+                    const uint32_t zo = i / per_slice;
+                    dst[(size_t(Z0 + zo) * a.ny + Y0) * a.W + (i - zo * per_slice)] = 0u;
+                }
+                continue;
             }
-            return;
         }
-    }
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = rows_src * a.Wp * 4u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes * n_sl) : "memory");
-        for (uint32_t k = 0; k < n_sl; ++k) {
-            const uint32_t* g = src + size_t(pz0 + k) * a.slice + py0 * a.Wp;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(s_src + k * SY_ * a.Wp)), "l"(g), "r"(bytes), "r"(bar_s) : "memory");
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = rows_src * a.Wp * 4u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes * n_sl) : "memory");
+            for (uint32_t k = 0; k < n_sl; ++k) {
+                const uint32_t* g = src + size_t(pz0 + k) * a.slice + py0 * a.Wp;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(s_src + k * SY_ * a.Wp)), "l"(g), "r"(bytes), "r"(bar_s) : "memory");
+            }
         }
-    }
-    {
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done) : "r"(bar_s) : "memory");
-    }
-    ktrace(KT_CLOSE_LD);
-    // ---- dilation: dilated row j (image row Y0 - R + j) folds source rows j .. j + 2R; same along the slices.
-    // Slices / rows past the data that was fetched hold stale shared memory; they only reach outputs that are dropped.
-    {
-        const uint32_t n_strips = DY / SYD;
-        const uint32_t cz = (DZ + a.zs_d - 1) / a.zs_d;
-        const uint32_t n_units = a.Wp * n_strips * a.zs_d;
-        for (uint32_t u = threadIdx.x; u < n_units; u += blockDim.x) {
-            const uint32_t xw = u % a.Wp, rest = u / a.Wp;
-            const uint32_t strip = rest % n_strips, q = rest / n_strips;
-            const uint32_t m0 = q * cz, m1 = min(m0 + cz, DZ);
-            if (m0 >= m1) continue;
-            uint32_t* out = s_dil + (strip * SYD) * a.Wp + xw;
-            ball_walk<R, false, SYD>(s_src + (strip * SYD) * a.Wp + xw, a.Wp, SY_ * a.Wp, m0, m1 + 2 * R, xw > 0, xw + 1 < a.Wp,
-                                     [&](uint32_t m, int y, uint32_t v) { out[m * DY * a.Wp + uint32_t(y) * a.Wp] = v; });
+        {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar_s), "r"(phase) : "memory");
+            phase ^= 1u;
         }
-    }
-    __syncthreads();
-    ktrace(KT_CLOSE_DIL);
-    // ---- erosion: output row y (image row Y0 + y) folds dilated rows y .. y + 2R
-    {
-        const uint32_t n_strips = a.TY / SYE;
-        const uint32_t cz = (a.TZ + a.zs_e - 1) / a.zs_e;
-        const uint32_t n_units = a.W * n_strips * a.zs_e;
-        for (uint32_t u = threadIdx.x; u < n_units; u += blockDim.x) {
-            const uint32_t xx = u % a.W, rest = u / a.W;
-            const uint32_t strip = rest % n_strips, q = rest / n_strips;
-            const uint32_t m0 = q * cz, m1 = min(min(m0 + cz, a.TZ), out_sl);
-            if (m0 >= m1 || strip * SYE >= out_rows) continue;
-            const uint32_t tail = (xx == a.W - 1) ? a.tail_mask : 0xFFFFFFFFu;
-            uint32_t* out = dst + (size_t(Z0) * a.ny + Y0 + strip * SYE) * a.W + xx;
-            const uint32_t rows_left = out_rows - strip * SYE;
-            ball_walk<R, true, SYE>(s_dil + (strip * SYE) * a.Wp + xx + 1, a.Wp, DY * a.Wp, m0, m1 + 2 * R, true, true,
-                                    [&](uint32_t m, int y, uint32_t v) {
-                                        if (uint32_t(y) < rows_left) out[size_t(m) * a.ny * a.W + uint32_t(y) * a.W] = v & tail;
-                                    });
+        ktrace(KT_CLOSE_LD);
+        // ---- dilation: dilated row j (image row Y0 - R + j) folds source rows j .. j + 2R; same along the slices.
+        // Slices / rows past the data that was fetched hold stale shared memory; they only reach outputs that are dropped.
+        {
+            const uint32_t n_strips = DY / SYD;
+            const uint32_t cz = (DZ + a.zs_d - 1) / a.zs_d;
+            const uint32_t n_units = a.Wp * n_strips * a.zs_d;
+            for (uint32_t u = threadIdx.x; u < n_units; u += blockDim.x) {
+                const uint32_t xw = u % a.Wp, rest = u / a.Wp;
+                const uint32_t strip = rest % n_strips, q = rest / n_strips;
+                const uint32_t m0 = q * cz, m1 = min(m0 + cz, DZ);
+                if (m0 >= m1) continue;
+                uint32_t* out = s_dil + (strip * SYD) * a.Wp + xw;
+                ball_walk<R, false, SYD>(s_src + (strip * SYD) * a.Wp + xw, a.Wp, SY_ * a.Wp, m0, m1 + 2 * R, xw > 0, xw + 1 < a.Wp,
+                                         [&](uint32_t m, int y, uint32_t v) { out[m * DY * a.Wp + uint32_t(y) * a.Wp] = v; });
+            }
         }
+        __syncthreads();
+        ktrace(KT_CLOSE_DIL);
+        // ---- erosion: output row y (image row Y0 + y) folds dilated rows y .. y + 2R
+        {
+            const uint32_t n_strips = a.TY / SYE;
+            const uint32_t cz = (a.TZ + a.zs_e - 1) / a.zs_e;
+            const uint32_t n_units = a.W * n_strips * a.zs_e;
+            for (uint32_t u = threadIdx.x; u < n_units; u += blockDim.x) {
+                const uint32_t xx = u % a.W, rest = u / a.W;
+                const uint32_t strip = rest % n_strips, q = rest / n_strips;
+                const uint32_t m0 = q * cz, m1 = min(min(m0 + cz, a.TZ), out_sl);
+                if (m0 >= m1 || strip * SYE >= out_rows) continue;
+                const uint32_t tail = (xx == a.W - 1) ? a.tail_mask : 0xFFFFFFFFu;
+                uint32_t* out = dst + (size_t(Z0) * a.ny + Y0 + strip * SYE) * a.W + xx;
+                const uint32_t rows_left = out_rows - strip * SYE;
+                ball_walk<R, true, SYE>(s_dil + (strip * SYE) * a.Wp + xx + 1, a.Wp, DY * a.Wp, m0, m1 + 2 * R, true, true,
+                                        [&](uint32_t m, int y, uint32_t v) {
+                                            if (uint32_t(y) < rows_left) out[size_t(m) * a.ny * a.W + uint32_t(y) * a.W] = v & tail;
+                                        });
+            }
+        }
+        ktrace(KT_CLOSE_ERO);
     }
-    ktrace(KT_CLOSE_ERO);
     ktrace_last(KT_CLOSE_LAST);
 }
 
@@ -979,14 +998,14 @@ static bool fused_plan(uint32_t Wp, uint32_t want_ty, uint32_t want_tz, uint32_t
 constexpr uint32_t FUSED_SMEM_MAX = 200u * 1024u;
 
 template <int R, int SYD, int SYE>
-static cudaError_t closing_fused_r(mamri_ctx* c, int nx, int ny, int nz, bool& done, cudaStream_t s) {
+static cudaError_t closing_fused_r(mamri_ctx* c, int nx, int ny, int nz, int geom_r, bool& done, cudaStream_t s) {
     static const int e_ty = [] { const char* e = getenv("MAMRI_CLOSE_TY"); return e ? atoi(e) : 16; }();
     static const int e_tz = [] { const char* e = getenv("MAMRI_CLOSE_TZ"); return e ? atoi(e) : 16; }();
     static const int e_zsd = [] { const char* e = getenv("MAMRI_CLOSE_ZSD"); return e ? atoi(e) : 1; }();
     static const int e_zse = [] { const char* e = getenv("MAMRI_CLOSE_ZSE"); return e ? atoi(e) : 1; }();
     static const int e_budget = [] { const char* e = getenv("MAMRI_CLOSE_SMEM_KB"); return e ? atoi(e) : 100; }();
     static const int use_occ = [] { const char* e = getenv("MAMRI_TILE_OCC"); return e ? atoi(e) : 1; }();
-    const PadGeom g(nx, ny, nz, R);
+    const PadGeom g(nx, ny, nz, geom_r);                 // the apron may be wider than this ball needs (opening before it)
     FusedArgs a;
     uint32_t smem = 0;
     done = false;
@@ -995,7 +1014,7 @@ static cudaError_t closing_fused_r(mamri_ctx* c, int nx, int ny, int nz, bool& d
     if (!fused_plan<R, SYD, SYE>(g.Wp, uint32_t(e_ty), uint32_t(e_tz), budget, a.TY, a.TZ, smem) &&
         !fused_plan<R, SYD, SYE>(g.Wp, uint32_t(e_ty), uint32_t(e_tz), FUSED_SMEM_MAX, a.TY, a.TZ, smem))
         return cudaSuccess;                                         // too wide: the caller takes the two-pass kernels
-    a.Wp = g.Wp; a.slice = g.slice; a.W = g.W; a.ny = uint32_t(ny); a.nz = uint32_t(nz); a.pad = 2 * R;
+    a.Wp = g.Wp; a.slice = g.slice; a.W = g.W; a.ny = uint32_t(ny); a.nz = uint32_t(nz); a.pad = 2 * uint32_t(geom_r);
     a.zs_d = uint32_t(e_zsd < 1 ? 1 : e_zsd); a.zs_e = uint32_t(e_zse < 1 ? 1 : e_zse);
     a.tail_mask = (nx % 32) ? (0xFFFFFFFFu >> (32 - nx % 32)) : 0xFFFFFFFFu;
     const uint32_t ncy = (uint32_t(ny) + OCC_CY - 1) / OCC_CY, ncz = (uint32_t(nz) + OCC_CZ - 1) / OCC_CZ;
@@ -1004,21 +1023,30 @@ static cudaError_t closing_fused_r(mamri_ctx* c, int nx, int ny, int nz, bool& d
     const uint32_t units_d = a.Wp * ((a.TY + 2 * R) / SYD) * a.zs_d, units_e = a.W * (a.TY / SYE) * a.zs_e;
     uint32_t threads = ((units_d > units_e ? units_d : units_e) + 31) / 32 * 32;
     if (threads > 512) threads = 512;
-    const dim3 grid((uint32_t(ny) + a.TY - 1) / a.TY, (uint32_t(nz) + a.TZ - 1) / a.TZ);
-    LKS(k_close_fused<R, SYD, SYE>, grid, threads, smem, s, false, c->d_raw, c->d_closed, c->d_dyn, a);
+    a.tiles_y = (uint32_t(ny) + a.TY - 1) / a.TY;
+    a.n_tiles = a.tiles_y * ((uint32_t(nz) + a.TZ - 1) / a.TZ);
+    // persistent CTAs: as many as fit the machine at this tile size (shared memory is what limits them), at most one per tile
+    static const int e_ctas = [] { const char* e = getenv("MAMRI_CLOSE_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    uint32_t per_sm = (227u * 1024u) / (smem + 1024u);
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    if (e_ctas > 0) per_sm = uint32_t(e_ctas);
+    uint32_t grid = 148u * per_sm;
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    LKS(k_close_fused<R, SYD, SYE>, grid, threads, smem, s, false, c->d_raw, c->d_closed, c->d_dyn, c->d_scalars, a);
     prof_mark(c, s, "close_fused");
     done = true;
     return cudaGetLastError();
 }
 
 template <int R>
-static cudaError_t closing_fused_dispatch(mamri_ctx* c, int nx, int ny, int nz, bool& done, cudaStream_t s) {
+static cudaError_t closing_fused_dispatch(mamri_ctx* c, int nx, int ny, int nz, int geom_r, bool& done, cudaStream_t s) {
     // strip heights of the two passes: 4 rows amortise the shifted loads best, 2 rows give more, shorter walks
     static const int syd = [] { const char* e = getenv("MAMRI_CLOSE_SYD"); return e ? atoi(e) : 4; }();
     static const int sye = [] { const char* e = getenv("MAMRI_CLOSE_SYE"); return e ? atoi(e) : 2; }();
-    if (syd == 4 && sye == 4 && R % 2 == 0) return closing_fused_r<R, 4, 4>(c, nx, ny, nz, done, s);
-    if (syd == 4) return closing_fused_r<R, 4, 2>(c, nx, ny, nz, done, s);
-    return closing_fused_r<R, 2, 2>(c, nx, ny, nz, done, s);
+    if (syd == 4 && sye == 4 && R % 2 == 0) return closing_fused_r<R, 4, 4>(c, nx, ny, nz, geom_r, done, s);
+    if (syd == 4) return closing_fused_r<R, 4, 2>(c, nx, ny, nz, geom_r, done, s);
+    return closing_fused_r<R, 2, 2>(c, nx, ny, nz, geom_r, done, s);
 }
 
 // Opt-in to more than 48 KB of dynamic shared memory is a per-device function attribute: set for every tile kernel
@@ -1042,13 +1070,19 @@ cudaError_t segment_init_device() {
 }
 
 template <int R, int SY>
-static cudaError_t closing_dispatch(mamri_ctx* c, int nx, int ny, int nz, cudaStream_t s) {
+static cudaError_t closing_dispatch(mamri_ctx* c, int nx, int ny, int nz, int geom_r, cudaStream_t s) {
     static const int use_planes = [] { const char* e = getenv("MAMRI_MORPH_PLANES"); return e ? atoi(e) : 0; }();
     static const int use_fused = [] { const char* e = getenv("MAMRI_CLOSE_FUSED"); return e ? atoi(e) : 1; }();
-    if (use_fused && !use_planes) {
+    // MAMRI_CLOSE_FUSED: 1 (default) = the fused kernel for volumes of up to 2^27 voxels -- a clinical scan, mostly air,
+    // where the launch it saves and the occupancy skip count -- and the two-pass kernels above that (a noisy high-
+    // resolution volume has foreground in every tile: the fused tile's halo of 2R is then redundant work, measured
+    // 159 us against 116 us on config C4); 2 = always fused, 0 = never.
+    const bool small = (unsigned long long)nx * ny * nz <= (1ull << 27);
+    if (((use_fused == 2 || (use_fused == 1 && small)) && !use_planes) || geom_r != R) {
         bool done = false;
-        const cudaError_t e = closing_fused_dispatch<R>(c, nx, ny, nz, done, s);
+        const cudaError_t e = closing_fused_dispatch<R>(c, nx, ny, nz, geom_r, done, s);
         if (e != cudaSuccess || done) return e;
+        if (geom_r != R) return cudaErrorInvalidValue;     // the two-pass kernels assume an apron of exactly 2R
     }
     uint32_t TY, TZ, smem;
     if (!use_planes && tile_plan<R, SY>(PadGeom(nx, ny, nz, R).Wp, TY, TZ, smem)) {
@@ -1061,11 +1095,97 @@ static cudaError_t closing_dispatch(mamri_ctx* c, int nx, int ny, int nz, cudaSt
     return closing_r<R>(c, nx, ny, nz, s);
 }
 
-cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, cudaStream_t s) {
+// Radius the padded layout is built for: the closing needs an apron of 2 Rc, an opening before it one of Ro.
+int morph_geom_radius(int open_radius, int close_radius) {
+    const int ro = (open_radius + 1) / 2;
+    return close_radius > ro ? close_radius : ro;
+}
+
+// Copies the interior of the padded raw mask into the plain [nz][ny][W] mask (opening without a closing after it).
+__global__ void __launch_bounds__(256) k_unpad(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t Wp, uint32_t slice,
+                                               uint32_t W, uint32_t ny, uint32_t n_words, uint32_t pad) {
+    pdl_wait();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) {
+        const uint32_t row = i / W, xw = i - row * W;
+        const uint32_t z = row / ny, y = row - z * ny;
+        dst[i] = src[(z + pad) * slice + (y + pad) * Wp + 1u + xw];
+    }
+}
+
+// `geom_r` = radius the padded layout was built for (morph_geom_radius); the mask ends up in c->d_closed.
+cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, int geom_r, cudaStream_t s) {
     switch (radius) {
-        case 1: return closing_dispatch<1, 4>(c, nx, ny, nz, s);
-        case 2: return closing_dispatch<2, 4>(c, nx, ny, nz, s);
-        case 3: return closing_dispatch<3, 4>(c, nx, ny, nz, s);
+        case 0: {
+            if (geom_r == 0) return cudaSuccess;                     // threshold wrote the plain mask itself
+            const PadGeom g(nx, ny, nz, geom_r);
+            const uint32_t n_words = g.W * uint32_t(ny) * uint32_t(nz);
+            uint32_t blocks = (n_words + 255) / 256;
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            LK(k_unpad, blocks, 256, s, false, c->d_raw, c->d_closed, g.Wp, g.slice, g.W, uint32_t(ny), n_words, 2u * uint32_t(geom_r));
+            prof_mark(c, s, "unpad");
+            return cudaGetLastError();
+        }
+        case 1: return closing_dispatch<1, 4>(c, nx, ny, nz, geom_r, s);
+        case 2: return closing_dispatch<2, 4>(c, nx, ny, nz, geom_r, s);
+        case 3: return closing_dispatch<3, 4>(c, nx, ny, nz, geom_r, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// opening (north_star "open/close"; the reference only closes): erosion with the outside of the image counted as
+// foreground, then dilation -- itk::BinaryMorphologicalOpeningImageFilter
+// ------------------------------------------------------------------------------------------------
+// With X' the complement of X inside the image (and 0 outside), erode(X; outside = 1) = complement of dilate(X'), so
+// the opening is two DILATIONS on the image domain of the padded layout (zero apron = the outside of both):
+//   raw <- ~raw (image only);  open <- ~dilate(raw) (image only) = the erosion;  raw <- dilate(open).
+// `d_open` is a buffer whose apron is zero and is never written.  The occupancy cells of the raw mask stay valid for
+// the closing that follows (an opening only removes voxels).
+__global__ void __launch_bounds__(256) k_invert_image(uint32_t* __restrict__ buf, uint32_t Wp, uint32_t slice, uint32_t W, uint32_t ny,
+                                                      uint32_t n_words, uint32_t pad, uint32_t tail_mask) {
+    pdl_wait();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) {
+        const uint32_t row = i / W, xw = i - row * W;
+        const uint32_t z = row / ny, y = row - z * ny;
+        uint32_t* p = buf + (z + pad) * slice + (y + pad) * Wp + 1u + xw;
+        *p = ~*p & (xw == W - 1 ? tail_mask : 0xFFFFFFFFu);
+    }
+}
+
+template <int R>
+static cudaError_t opening_r(mamri_ctx* c, int nx, int ny, int nz, int geom_r, cudaStream_t s) {
+    const PadGeom g(nx, ny, nz, geom_r);
+    const uint32_t pad = 2u * uint32_t(geom_r);
+    uint32_t TY, TZ, smem;
+    if (!tile_plan<R, 4>(g.Wp, TY, TZ, smem)) return cudaErrorInvalidValue;     // rows of more than ~8000 voxels
+    const uint32_t tail = (nx % 32) ? (0xFFFFFFFFu >> (32 - nx % 32)) : 0xFFFFFFFFu;
+    const uint32_t n_words = g.W * uint32_t(ny) * uint32_t(nz);
+    uint32_t blocks = (n_words + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    LK(k_invert_image, blocks, 256, s, false, c->d_raw, g.Wp, g.slice, g.W, uint32_t(ny), n_words, pad, tail);
+    prof_mark(c, s, "open_invert");
+    TileArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Wp = g.Wp; a.slice = g.slice; a.TY = TY; a.TZ = TZ;
+    a.x_lo = 1; a.x_cnt = g.W; a.y_lo = pad; a.y_cnt = uint32_t(ny); a.z_lo = pad; a.z_hi = pad + uint32_t(nz);
+    a.tail_mask = tail;
+    const uint32_t threads = ((a.x_cnt * (TY / 4) + 31) / 32) * 32;
+    const dim3 grid((a.y_cnt + TY - 1) / TY, (a.z_hi - a.z_lo + TZ - 1) / TZ);
+    a.invert_out = 1;
+    LKS(k_morph_tile<R, false, false, 4>, grid, threads, smem, s, false, c->d_raw, c->d_open, c->d_dyn, a);
+    prof_mark(c, s, "open_erode");
+    a.invert_out = 0;
+    LKS(k_morph_tile<R, false, false, 4>, grid, threads, smem, s, false, c->d_open, c->d_raw, c->d_dyn, a);
+    prof_mark(c, s, "open_dilate");
+    return cudaGetLastError();
+}
+
+cudaError_t launch_opening(mamri_ctx* c, int nx, int ny, int nz, int radius, int geom_r, cudaStream_t s) {
+    switch (radius) {
+        case 0: return cudaSuccess;
+        case 1: return opening_r<1>(c, nx, ny, nz, geom_r, s);
+        case 2: return opening_r<2>(c, nx, ny, nz, geom_r, s);
+        case 3: return opening_r<3>(c, nx, ny, nz, geom_r, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ par
         if (packed) atomicMax(&sc->body_packed, packed);
         if (cnt64) atomicAdd(&sc->n_foreground, cnt64);
     }
+    ktrace_both(KT_SEL_END);
     // The last CTA to finish clamps the candidate count, names the body's label in slot `max_markers`
     // and zeroes the moment sums of the slots in use.
     __shared__ bool last;
@@ -337,7 +338,11 @@ cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mam
 cudaError_t launch_stats(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
     const GeomArgs g = geom_args(desc, prm);
     const int W = (desc->nx + 31) / 32;
-    LK(k_stats, c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS, 256, s, false, c->d_run_pos, c->d_run_end, c->d_parent, c->d_run_label,
+    // at most one CTA per SM: the kernel runs beside `materialise`, which needs the thread slots more (on a table of
+    // millions of runs a full grid of these 128-register CTAs held materialise back by 0.1 ms)
+    int grid = c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS;
+    if (grid > 148) grid = 148;
+    LK(k_stats, grid, 256, s, false, c->d_run_pos, c->d_run_end, c->d_parent, c->d_run_label,
        c->d_label_slot, W, desc->ny, c->d_cand_sums, c->d_cand_label, c->d_cand_rank, c->d_label_count, c->max_markers, g, c->h_markers,
        c->h_summary, c->d_scalars, c->d_dyn);
     prof_mark(c, s, "stats");

@@ -32,9 +32,11 @@ class DetectParams:
     connectivity: int = 6
     min_volume: float = 50.0
     max_volume: float = 1500.0
+    open_radius: int = 0            # 0 = the reference (closing only); > 0: sitk.BinaryMorphologicalOpening first
 
     def to_c(self) -> Params:
-        return Params(self.lower, self.upper, self.close_radius, self.connectivity, self.min_volume, self.max_volume)
+        return Params(self.lower, self.upper, self.close_radius, self.connectivity, self.min_volume, self.max_volume,
+                      self.open_radius, 0)
 
 
 @dataclasses.dataclass
@@ -112,6 +114,7 @@ class DetectionResult:
     mask: Optional[torch.Tensor] = None          # uint8 [nz,ny,nx] closed mask (device)
     labels: Optional[torch.Tensor] = None        # uint32-valued int32 tensor [nz,ny,nx] (device)
     body_mask: Optional[object] = None           # uint8 [nz,ny,nx] (device tensor, or host array for detect_host)
+    status: int = 0                              # MAMRI_OK; batches: MAMRI_ERR_CAPACITY for a scan beyond the pool's capacity
 
     @property
     def marker_table(self) -> Optional[np.ndarray]:
@@ -214,6 +217,8 @@ class FiducialDetector:
             raise ValueError("volume must be a contiguous CUDA tensor [nz, ny, nx]")
         if volume.dtype not in _TORCH_DTYPES:
             raise ValueError(f"unsupported voxel type {volume.dtype}")
+        if volume.device.index != self.device:
+            raise ValueError(f"volume is on {volume.device}, this context runs on cuda:{self.device}")
         params = params or DetectParams()
         dev = volume.device
         shape = tuple(volume.shape)
@@ -499,11 +504,20 @@ def generate_phantom_cuda(ph, device: int = 0, out: Optional[torch.Tensor] = Non
 
 
 class BatchResult:
-    """Results of one batch, held as the C arrays `mamri_pool_detect` filled; a sequence of
-    `DetectionResult` built on demand (so the per-scan Python objects cost nothing unless they are read)."""
+    """Results of one batch: per-scan summaries and marker tables copied out of the C arrays `mamri_pool_detect` filled
+    (only the records in use, so a pool may keep a large marker capacity without a large per-batch cost); a sequence of
+    `DetectionResult` built on demand.  `status[i]` is the scan's device status: MAMRI_OK, or MAMRI_ERR_CAPACITY when
+    the scan found more runs / kept labels than the pool was created for -- that scan's result carries the status and
+    no markers, the other scans of the batch are unaffected (the reference never fails on many candidates, a noisy
+    scan just yields more control points; Mamri.py:1310-1317)."""
 
     def __init__(self, n, summaries, markers, max_m, outs):
-        self.n, self._summ, self._mk, self._max_m, self._outs = n, summaries, markers, max_m, outs
+        self.n, self._max_m, self._outs = n, max_m, outs
+        self._summ = np.frombuffer(summaries, dtype=np.dtype(Summary), count=n).copy()
+        mk = np.frombuffer(markers, dtype=np.dtype(Marker), count=n * max_m).reshape(n, max_m) if max_m else None
+        self.status = [int(v) for v in self._summ["device_status"]]
+        self._tables = [mk[i, :min(int(self._summ["n_markers"][i]), max_m)].copy() if (mk is not None and self.status[i] == 0)
+                        else np.zeros(0, dtype=np.dtype(Marker)) for i in range(n)]
         self._cache = {}
 
     def __len__(self):
@@ -518,40 +532,34 @@ class BatchResult:
             raise IndexError(i)
         if i not in self._cache:
             summ = self._summ[i]
-            k = min(int(summ.n_markers), self._max_m)
-            markers = _LazyMarkers(_marker_table(self._mk, k, first=i * self._max_m))
-            body = MarkerStats.from_c(summ.body) if summ.body_label else None
+            body = None
+            if int(summ["body_label"]) and self.status[i] == 0:
+                body = MarkerStats.from_c(Marker.from_buffer_copy(summ["body"].tobytes()))
             m, l, b = self._outs(i)
-            self._cache[i] = DetectionResult(n_labels=int(summ.n_labels), n_runs=int(summ.n_runs),
-                                             n_foreground=int(summ.n_foreground), markers=markers,
-                                             body_label=int(summ.body_label), body_count=int(summ.body_count), body=body,
-                                             mask=m, labels=l, body_mask=b)
+            self._cache[i] = DetectionResult(n_labels=int(summ["n_labels"]), n_runs=int(summ["n_runs"]),
+                                             n_foreground=int(summ["n_foreground"]), markers=_LazyMarkers(self._tables[i]),
+                                             body_label=int(summ["body_label"]), body_count=int(summ["body_count"]), body=body,
+                                             mask=m, labels=l, body_mask=b, status=self.status[i])
         return self._cache[i]
 
     def __iter__(self):
         return (self[i] for i in range(self.n))
 
     def ras_points(self) -> List[np.ndarray]:
-        """Per scan: [n_markers, 3] control points of "DetectedFiducials" (node order), straight from the C arrays."""
-        mk = np.frombuffer(self._mk, dtype=np.dtype(Marker)).reshape(self.n, self._max_m)
-        sm = np.frombuffer(self._summ, dtype=np.dtype(Summary))
-        return [np.array(mk[i, :min(int(sm["n_markers"][i]), self._max_m)]["centroid_ras"], dtype=np.float64).reshape(-1, 3)
-                for i in range(self.n)]
+        """Per scan: [n_markers, 3] control points of "DetectedFiducials" (node order)."""
+        return [np.array(t["centroid_ras"], dtype=np.float64).reshape(-1, 3) for t in self._tables]
 
     def table(self, slots: int = 32) -> np.ndarray:
         """[n, slots, 8] float64: label, count, volume_mm3, RAS x y z, n_labels, body_label (distributed.pack_table)."""
-        mk = np.frombuffer(self._mk, dtype=np.dtype(Marker)).reshape(self.n, self._max_m)[:, :slots]
-        sm = np.frombuffer(self._summ, dtype=np.dtype(Summary))
         t = np.zeros((self.n, slots, 8), dtype=np.float64)
-        k = min(slots, self._max_m)
-        valid = np.arange(k)[None, :] < np.minimum(sm["n_markers"], k)[:, None]
-        t[:, :k, 0] = mk["label"]
-        t[:, :k, 1] = mk["count"]
-        t[:, :k, 2] = mk["volume_mm3"]
-        t[:, :k, 3:6] = mk["centroid_ras"]
-        t[:, :k, 6] = sm["n_labels"][:, None]
-        t[:, :k, 7] = sm["body_label"][:, None]
-        t[:, :k][~valid] = 0.0
+        for i, mk in enumerate(self._tables):
+            k = min(slots, len(mk))
+            t[i, :k, 0] = mk["label"][:k]
+            t[i, :k, 1] = mk["count"][:k]
+            t[i, :k, 2] = mk["volume_mm3"][:k]
+            t[i, :k, 3:6] = mk["centroid_ras"][:k]
+            t[i, :k, 6] = self._summ["n_labels"][i]
+            t[i, :k, 7] = self._summ["body_label"][i]
         return t
 
 
@@ -565,7 +573,7 @@ class BatchDetector:
     current stream around `run` / `run_host` bracket all the work."""
 
     def __init__(self, dims_xyz: Sequence[int], device: int = 0, n_contexts: int = 4, max_runs: int = 0,
-                 max_markers: int = 64, materialise: bool = True):
+                 max_markers: int = 4096, materialise: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("mamri_pose_estimation_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self._lib = _capi.load()
@@ -609,6 +617,29 @@ class BatchDetector:
         view._owned = False                  # the pool destroys its contexts
         return view
 
+    def _scratch(self, n):
+        """Result arrays for n scans, allocated once per size (ctypes zero-fills what it allocates; at the default
+        capacity of 4096 markers per scan that would cost more than a batch of scans).  BatchResult copies out what
+        is in use before the arrays are reused."""
+        cache = self.__dict__.setdefault("_scratch_cache", {})
+        if n not in cache:
+            cache[n] = ((Summary * n)(), (Marker * (n * self.max_markers))())
+        return cache[n]
+
+    def _check_volumes(self, volumes):
+        v0 = volumes[0]
+        for v in volumes:
+            if not (v.is_cuda and v.is_contiguous() and v.dim() == 3 and v.dtype == v0.dtype and v.shape == v0.shape):
+                raise ValueError("volumes must be contiguous CUDA tensors [nz, ny, nx] of one shape and type")
+            if v.device.index != self.device:
+                raise ValueError(f"volume is on {v.device}, this pool runs on cuda:{self.device}")
+        return v0
+
+    def _finish(self, rc):
+        """A scan beyond the pool's capacity is reported per scan (BatchResult.status), everything else raises."""
+        if rc != _capi.MAMRI_ERR_CAPACITY:
+            _capi.check_pool(rc, self._pool)
+
     @staticmethod
     def _ptrs(items, n):
         arr = (C.c_void_p * n)()
@@ -621,23 +652,21 @@ class BatchDetector:
         """Device-resident scans in, marker tables out (mask + label volumes are materialised into the pool's
         ring of buffers, as the reference's `closed` / `labeled` temporaries are)."""
         n, k = len(volumes), self.n_contexts
-        v0 = volumes[0]
-        for v in volumes:
-            if not (v.is_cuda and v.is_contiguous() and v.dim() == 3 and v.dtype == v0.dtype and v.shape == v0.shape):
-                raise ValueError("volumes must be contiguous CUDA tensors [nz, ny, nx] of one shape and type")
+        v0 = self._check_volumes(volumes)
         d = _desc(tuple(v0.shape), _TORCH_DTYPES[v0.dtype], spacing, origin, direction)
         p = (params or DetectParams()).to_c()
-        summ = (Summary * n)()
-        mk = (Marker * (n * self.max_markers))()
+        summ, mk = self._scratch(n)
         vp = self._ptrs([v.data_ptr() for v in volumes], n)
         mp = self._ptrs([self.masks[i % k].data_ptr() for i in range(n)], n) if self.materialise else None
         lp = self._ptrs([self.labels[i % k].data_ptr() for i in range(n)], n) if self.materialise else None
         s = torch.cuda.current_stream(self.device)
         rc = self._lib.mamri_pool_detect(self._pool, C.byref(d), vp, n, C.byref(p), mp, lp, None, summ, mk,
                                          self.max_markers, s.cuda_stream)
-        _capi.check_pool(rc, self._pool)
+        self._finish(rc)
         masks, labels = self.masks, self.labels
-        return BatchResult(n, summ, mk, self.max_markers, lambda i: (masks[i % k], labels[i % k], None))
+        # the mask / label volumes live in a ring of n_contexts buffers: only the last n_contexts scans still own theirs
+        return BatchResult(n, summ, mk, self.max_markers,
+                           lambda i: (masks[i % k], labels[i % k], None) if i >= n - k else (None, None, None))
 
     def begin(self, volumes: Sequence[torch.Tensor], spacing, origin, direction=IDENTITY,
               params: Optional[DetectParams] = None, tables: Optional[torch.Tensor] = None) -> None:
@@ -648,10 +677,7 @@ class BatchDetector:
         n, k = len(volumes), self.n_contexts
         if not 1 <= n <= k:
             raise ValueError(f"begin/end handles 1..{k} scans per call")
-        v0 = volumes[0]
-        for v in volumes:
-            if not (v.is_cuda and v.is_contiguous() and v.dim() == 3 and v.dtype == v0.dtype and v.shape == v0.shape):
-                raise ValueError("volumes must be contiguous CUDA tensors [nz, ny, nx] of one shape and type")
+        v0 = self._check_volumes(volumes)
         tptr, slots = None, 0
         if tables is not None:
             if not (tables.is_cuda and tables.is_contiguous() and tables.dtype == torch.float64 and tables.dim() == 3
@@ -703,10 +729,9 @@ class BatchDetector:
             raise RuntimeError("no batch pending: call begin() first")
         n = self._begun[0]
         self._begun = None
-        summ = (Summary * n)()
-        mk = (Marker * (n * self.max_markers))()
+        summ, mk = self._scratch(n)
         rc = self._lib.mamri_pool_detect_end(self._pool, summ, mk, self.max_markers)
-        _capi.check_pool(rc, self._pool)
+        self._finish(rc)
         masks, labels, k = self.masks, self.labels, self.n_contexts
         body, self._begun_body = getattr(self, "_begun_body", None), None
         if body is not None:                         # begun with begin_host: no device volumes, host body masks if asked for
@@ -729,8 +754,7 @@ class BatchDetector:
                 raise ValueError("host volumes must share one shape and type")
         d = _desc(a0["shape"], a0["dtype"], spacing, origin, direction)
         p = (params or DetectParams()).to_c()
-        summ = (Summary * n)()
-        mk = (Marker * (n * self.max_markers))()
+        summ, mk = self._scratch(n)
         vp = self._ptrs([a["ptr"] for a, _ in views], n)
         bp = None
         if body_out is not None:
@@ -742,7 +766,7 @@ class BatchDetector:
         s = torch.cuda.current_stream(self.device)
         rc = self._lib.mamri_pool_detect_host(self._pool, C.byref(d), vp, n, C.byref(p), bp, summ, mk, self.max_markers,
                                               s.cuda_stream)
-        _capi.check_pool(rc, self._pool)
+        self._finish(rc)
         return BatchResult(n, summ, mk, self.max_markers,
                            lambda i: (None, None, body_out[i] if body_out is not None else None))
 

@@ -80,3 +80,91 @@ def marker_positions_ras(angles_rad: Sequence[float], base: np.ndarray,
         tf = world[name]
         out[name] = loc @ tf[:3, :3].T + tf[:3, 3]
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# robot_config.json -> mamri_robot (Mamri.py:1577-1613 _load_robot_definition, :816-819)
+# ------------------------------------------------------------------------------------------------
+def robot_from_definition(definition: Sequence[dict], articulated_chain: Sequence[str] = ARTICULATED_CHAIN,
+                          base_link: str = "Baseplate", effector_link: str = "Joint6", secondary_link: str = "Joint4",
+                          distance_tolerance: float = 5.0, secondary_weight: float = 0.05, apply_correction: bool = False):
+    """Fills a ``mamri_robot`` (ctypes mirror ``_capi.Robot``) from the list of link dictionaries the reference keeps in
+    ``robot_config.json`` -- same file order (``joint_detection`` iterates the links in this order, Mamri.py:1349), the
+    same keys (``name, parent, fixed_offset_to_parent{translate}, has_markers, local_marker_coords, arm_lengths,
+    articulation_axis, joint_limits``).  The articulated chain, the effector / secondary links and the two constants are
+    the reference's (Mamri.py:813, 819, 1414-1424, 1507).  A ``rotate`` entry in ``fixed_offset_to_parent`` (which
+    _load_robot_definition would apply, and the shipped file does not use) is rejected: ``mamri_link`` carries a
+    translation only."""
+    from . import _capi
+    if not 1 <= len(definition) <= _capi.MAX_LINKS:
+        raise ValueError(f"robot definition has {len(definition)} links; mamri_robot holds 1..{_capi.MAX_LINKS}")
+    names = [d["name"] for d in definition]
+    r = _capi.Robot()
+    r.n_links = len(definition)
+    for key, want in (("base_link", base_link), ("effector_link", effector_link)):
+        if want not in names:
+            raise ValueError(f"{key} {want!r} is not in the robot definition")
+        setattr(r, key, names.index(want))
+    r.secondary_link = names.index(secondary_link) if secondary_link in names else -1
+    r.distance_tolerance, r.secondary_weight = float(distance_tolerance), float(secondary_weight)
+    r.apply_correction = int(bool(apply_correction))
+    chain = list(articulated_chain)
+    if len(chain) > _capi.MAX_CHAIN:
+        raise ValueError(f"articulated chain longer than {_capi.MAX_CHAIN}")
+    for i, d in enumerate(definition):
+        l = r.links[i]
+        parent = d.get("parent")
+        if parent is None:
+            l.parent = -1
+        else:
+            if parent not in names[:i]:
+                raise ValueError(f"link {d['name']!r}: parent {parent!r} must come earlier in the file")
+            l.parent = names.index(parent)
+        axis = d.get("articulation_axis")
+        if axis not in _capi.AXIS_CODES:
+            raise ValueError(f"link {d['name']!r}: unknown articulation_axis {axis!r}")
+        l.axis = _capi.AXIS_CODES[axis]
+        off = d.get("fixed_offset_to_parent")
+        if isinstance(off, dict):
+            if off.get("rotate"):
+                raise ValueError(f"link {d['name']!r}: fixed_offset_to_parent.rotate is not supported (translation only)")
+            l.translate[:] = [float(v) for v in off.get("translate", (0.0, 0.0, 0.0))]
+        markers = d.get("local_marker_coords") if d.get("has_markers") else None
+        l.has_markers = int(bool(markers))
+        if markers:
+            if len(markers) != 3:
+                raise ValueError(f"link {d['name']!r}: exactly three markers per link (L-shape), got {len(markers)}")
+            l.marker_coords[:] = [float(v) for m in markers for v in m]
+            l.arm_lengths[:] = [float(v) for v in d["arm_lengths"]]
+        l.chain_index = chain.index(d["name"]) if d["name"] in chain else -1
+        lim = d.get("joint_limits")
+        if lim is not None:
+            l.limits_deg[:] = [float(lim[0]), float(lim[1])]
+    return r
+
+
+def load_robot_config(path: str, **kw):
+    """``robot_config.json`` (the reference's ``Mamri/Resources/Robot/robot_config.json``) -> ``mamri_robot``."""
+    import json
+    with open(path) as f:
+        return robot_from_definition(json.load(f), **kw)
+
+
+def default_definition() -> List[dict]:
+    """The constants of this module in robot_config.json's own shape (what ``mamri_default_robot`` hard-codes)."""
+    limits = {"Joint1": (-180, 180), "Joint2": (-120, 120), "Joint3": (-120, 120), "Joint4": (-180, 180),
+              "Joint5": (-120, 120), "Joint6": (-270, 270)}
+    out = []
+    for l in LINKS:
+        d = {"name": l["name"], "parent": l["parent"],
+             "fixed_offset_to_parent": {"translate": list(l["translate"])} if l["parent"] else None,
+             "has_markers": "markers" in l, "articulation_axis": l["axis"]}
+        if "markers" in l:
+            d["local_marker_coords"] = [list(m) for m in l["markers"]]
+            d["arm_lengths"] = list(l["arm_lengths"])
+        if l["name"] in limits:
+            d["joint_limits"] = list(limits[l["name"]])
+        out.append(d)
+    out.append({"name": "Needle", "parent": "Joint6", "fixed_offset_to_parent": {"translate": [-50.0, 0.0, 71.0]},
+                "has_markers": False, "articulation_axis": "TRANS_X", "joint_limits": [0, 0]})
+    return out

@@ -124,6 +124,36 @@ API int oracle_closing(const uint8_t* in, int nx, int ny, int nz, int r, uint8_t
     return 0;
 }
 
+/* ---- sitk.BinaryMorphologicalOpening(binary, [r]*3, sitkBall): north_star extension, not in the reference ----- */
+/* itk::BinaryMorphologicalOpeningImageFilter: BinaryErode with BoundaryToForeground = true (outside the image counts
+ * as foreground), then BinaryDilate (outside = background); no safe-border padding.  On a copy padded by r: the
+ * apron is 1 for the erosion and 0 for the dilation. */
+API int oracle_opening(const uint8_t* in, int nx, int ny, int nz, int r, uint8_t* out) {
+    const size_t n = (size_t)nx * ny * nz;
+    if (r <= 0) { memcpy(out, in, n); return 0; }
+    const int P = r;
+    const int px = nx + 2 * P, py = ny + 2 * P, pz = nz + 2 * P;
+    const size_t pn = (size_t)px * py * pz;
+    uint8_t* a = (uint8_t*)malloc(pn);
+    uint8_t* b = (uint8_t*)calloc(pn, 1);
+    if (!a || !b) { free(a); free(b); return -2; }
+    memset(a, 1, pn);                               /* outside = foreground for the erosion */
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            memcpy(a + ((size_t)(z + P) * py + (y + P)) * px + P, in + ((size_t)z * ny + y) * nx, (size_t)nx);
+    morph_pass(a, b, px, py, pz, r, P, 1);          /* erosion on the image domain; b stays 0 in the apron */
+    memset(a, 0, pn);
+    morph_pass(b, a, px, py, pz, r, P, 0);          /* dilation on the image domain, outside = background */
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            memcpy(out + ((size_t)z * ny + y) * nx, a + ((size_t)(z + P) * py + (y + P)) * px + P, (size_t)nx);
+    free(a);
+    free(b);
+    return 0;
+}
+
 /* ---- sitk.ConnectedComponent(closed)                       Mamri.py:1309 ------------------------------ */
 /* Raster scan; a voxel takes the smallest root among its already-visited neighbours (6: -x,-y,-z; 26: the 13
  * preceding neighbours), unions keep the smaller label; roots are then renumbered consecutively in increasing
@@ -221,12 +251,27 @@ API int oracle_label_sums(const uint32_t* labels, int nx, int ny, int nz, uint32
 
 /* ---- the whole of Mamri.py:1308-1309 on one volume ----------------------------------------------------- */
 /* closed: uint8[n]; labels: uint32[n]; sums: caller passes capacity max_labels*10 (returns -3 if too small). */
+API int oracle_detect2(const void* vol, int dtype, int nx, int ny, int nz, double lo, double hi, int open_radius, int radius,
+                       int conn, uint8_t* closed, uint32_t* labels, uint32_t* n_labels, uint64_t* sums, uint32_t max_labels);
+
 API int oracle_detect(const void* vol, int dtype, int nx, int ny, int nz, double lo, double hi, int radius, int conn,
                       uint8_t* closed, uint32_t* labels, uint32_t* n_labels, uint64_t* sums, uint32_t max_labels) {
+    return oracle_detect2(vol, dtype, nx, ny, nz, lo, hi, 0, radius, conn, closed, labels, n_labels, sums, max_labels);
+}
+
+API int oracle_detect2(const void* vol, int dtype, int nx, int ny, int nz, double lo, double hi, int open_radius, int radius,
+                       int conn, uint8_t* closed, uint32_t* labels, uint32_t* n_labels, uint64_t* sums, uint32_t max_labels) {
     const size_t n = (size_t)nx * ny * nz;
     uint8_t* bin = (uint8_t*)malloc(n);
     if (!bin) return -2;
     int rc = oracle_threshold(vol, dtype, n, lo, hi, bin);
+    if (rc == 0 && open_radius > 0) {
+        uint8_t* op = (uint8_t*)malloc(n);
+        if (!op) { free(bin); return -2; }
+        rc = oracle_opening(bin, nx, ny, nz, open_radius, op);
+        free(bin);
+        bin = op;
+    }
     if (rc == 0) rc = oracle_closing(bin, nx, ny, nz, radius, closed);
     free(bin);
     if (rc == 0) rc = oracle_ccl(closed, nx, ny, nz, conn, labels, n_labels);

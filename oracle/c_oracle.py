@@ -23,6 +23,11 @@ def load():
         lib.oracle_detect.restype = C.c_int
         lib.oracle_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                       C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32]
+        lib.oracle_detect2.restype = C.c_int
+        lib.oracle_detect2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                       C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32]
+        lib.oracle_opening.restype = C.c_int
+        lib.oracle_opening.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.oracle_closing.restype = C.c_int
         lib.oracle_closing.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.oracle_ccl.restype = C.c_int
@@ -49,7 +54,7 @@ def use_all_cores() -> int:
 
 
 def run_pipeline(vol: np.ndarray, lo=seg.INTENSITY_THRESHOLD, hi=seg.UPPER_THRESHOLD, close_radius=seg.CLOSE_RADIUS,
-                 connectivity=6, with_sums=True):
+                 connectivity=6, with_sums=True, open_radius=0):
     """threshold -> closing -> CCL (-> integer sums).  Returns (closed u8, labels u32, K, sums[K,10] or None, seconds)."""
     lib = load()
     vol = np.ascontiguousarray(vol)
@@ -58,8 +63,8 @@ def run_pipeline(vol: np.ndarray, lo=seg.INTENSITY_THRESHOLD, hi=seg.UPPER_THRES
     labels = np.empty(vol.shape, dtype=np.uint32)
     k = C.c_uint32(0)
     t0 = time.perf_counter()
-    rc = lib.oracle_detect(vol.ctypes.data, _DT[vol.dtype.name], nx, ny, nz, float(lo), float(hi), int(close_radius),
-                           int(connectivity), closed.ctypes.data, labels.ctypes.data, C.byref(k), None, 0)
+    rc = lib.oracle_detect2(vol.ctypes.data, _DT[vol.dtype.name], nx, ny, nz, float(lo), float(hi), int(open_radius),
+                            int(close_radius), int(connectivity), closed.ctypes.data, labels.ctypes.data, C.byref(k), None, 0)
     if rc != 0:
         raise RuntimeError(f"oracle_detect failed: {rc}")
     sums = None
@@ -75,9 +80,9 @@ def run_pipeline(vol: np.ndarray, lo=seg.INTENSITY_THRESHOLD, hi=seg.UPPER_THRES
 
 def detect_fiducials(vol: np.ndarray, geom: seg.Geometry, lo=seg.INTENSITY_THRESHOLD, hi=seg.UPPER_THRESHOLD,
                      close_radius=seg.CLOSE_RADIUS, connectivity=6, min_vol=seg.MIN_VOLUME_THRESHOLD,
-                     max_vol=seg.MAX_VOLUME_THRESHOLD, want_body_mask=True) -> seg.Detection:
+                     max_vol=seg.MAX_VOLUME_THRESHOLD, want_body_mask=True, open_radius=0) -> seg.Detection:
     """Mamri.py:1308-1323 via the C oracle; statistics finalised exactly like oracle.segmentation."""
-    closed, labels, k, sums, _ = run_pipeline(vol, lo, hi, close_radius, connectivity)
+    closed, labels, k, sums, _ = run_pipeline(vol, lo, hi, close_radius, connectivity, open_radius=open_radius)
     counts = sums[:, 0].astype(np.int64) if k else np.zeros(0, dtype=np.int64)
     kept, body = seg.select_candidates(counts, geom.voxel_volume(), min_vol, max_vol)
     stats = []

@@ -97,6 +97,46 @@ def test_random_masks_all_radii(cuda_lib, radius):
             _compare(res, counts, ora, geom, check_axes=False)
 
 
+@pytest.mark.parametrize("open_radius", [1, 2, 3])
+def test_opening_then_closing(cuda_lib, open_radius):
+    """mamri_params.open_radius (north_star "open/close"; sitk.BinaryMorphologicalOpening): dense random masks, objects
+    touching every face (the erosion counts the outside as foreground), ragged rows, every closing radius after it --
+    including none, and a closing ball smaller than half the opening ball (wider apron than the closing needs)."""
+    from mamri_pose_estimation_b200.detector import DetectParams
+    rng = np.random.default_rng(300 + open_radius)
+    for dims, p in (((45, 22, 19), 0.75), ((64, 16, 12), 0.9), ((33, 31, 30), 0.97), ((128, 24, 16), 0.85)):
+        nx, ny, nz = dims
+        vol = (rng.random((nz, ny, nx)) < p).astype(np.uint8) * 200
+        vol[:, :, :2] = 200                                   # a slab on the x = 0 face
+        geom = seg.Geometry((0.7, 0.9, 1.3), (1.0, -2.0, 3.0), (1, 0, 0, 0, 1, 0, 0, 0, 1))
+        for close_radius in (0, 1, 2, 3):
+            prm = DetectParams(lower=1, upper=255, close_radius=close_radius, open_radius=open_radius, connectivity=6,
+                               min_volume=3.0, max_volume=400.0)
+            ora = seg.detect_fiducials(vol, geom, lo=1, hi=255, close_radius=close_radius, open_radius=open_radius,
+                                       connectivity=6, min_vol=3.0, max_vol=400.0)
+            res, counts = _run_gpu(vol, geom, prm, max_markers=8192)
+            _compare(res, counts, ora, geom, check_axes=False)
+
+
+def test_opening_on_a_phantom_and_state_between_scans(cuda_lib):
+    """Opening removes the noise specks of a phantom before the closing; the same context then runs a scan without
+    opening and a different geometry (the opening's scratch apron must be zero again)."""
+    from mamri_pose_estimation_b200.detector import DetectParams, FiducialDetector
+    import torch
+    det = FiducialDetector((96, 64, 48))
+    for dims, seed, orad in (((96, 64, 48), 31, 1), ((96, 64, 48), 32, 0), ((70, 50, 40), 33, 2), ((96, 64, 48), 34, 1)):
+        ph = phantom.small_phantom(dims=dims, seed=seed, sigma=24.0, touch_border=True)
+        vol = phantom.generate(ph)
+        geom = seg.Geometry(ph.spacing, ph.origin, ph.direction)
+        ora = seg.detect_fiducials(vol, geom, open_radius=orad, min_vol=20.0, max_vol=600.0)
+        res = det.detect(torch.from_numpy(vol).cuda(), spacing=geom.spacing, origin=geom.origin, direction=geom.direction,
+                         params=DetectParams(open_radius=orad, min_volume=20.0, max_volume=600.0), want_mask=True, want_labels=True)
+        assert np.array_equal(res.mask.cpu().numpy(), ora.closed)
+        assert np.array_equal(res.labels.cpu().numpy().view(np.uint32), ora.labels)
+        assert [m.label for m in res.markers] == [f["id"] for f in ora.fiducials]
+    det.close()
+
+
 @pytest.mark.parametrize("dtype", ["uint8", "int16", "uint16", "int32", "float32", "float64"])
 def test_voxel_types(cuda_lib, dtype):
     from mamri_pose_estimation_b200.detector import DetectParams

@@ -1,4 +1,5 @@
 """Host-side logic that needs no GPU: phantom generator, Philox, sharding, table packing."""
+import os
 import types
 
 import numpy as np
@@ -83,3 +84,36 @@ def test_ijk_to_ras_geometry_conversion():
     assert np.allclose(lps, ras * np.array([-1.0, -1.0, 1.0]), atol=1e-9)
     d = np.array(node.direction).reshape(3, 3)
     assert np.allclose(d @ d.T, np.eye(3), atol=1e-12)
+
+
+def _robots_equal(a, b):
+    import ctypes as C
+    return bytes(C.string_at(C.addressof(a), C.sizeof(a))) == bytes(C.string_at(C.addressof(b), C.sizeof(b)))
+
+
+def test_robot_config_loader_reproduces_the_default_robot(cuda_lib, tmp_path):
+    """mamri_robot filled from a robot_config.json (Mamri.py:1577-1613) == mamri_default_robot, field for field: from
+    this module's own constants written out in the file's shape, and -- where the reference tree is present (the build
+    container; never at run time on the GPU box) -- from the reference's file itself."""
+    import ctypes as C
+    import json
+    from mamri_pose_estimation_b200 import _capi, robot
+    ref = _capi.Robot()
+    cuda_lib.mamri_default_robot(C.byref(ref))
+    path = tmp_path / "robot_config.json"
+    path.write_text(json.dumps(robot.default_definition()))
+    mine = robot.load_robot_config(str(path))
+    assert _robots_equal(mine, ref)
+    assert robot.load_robot_config(str(path), apply_correction=True).apply_correction == 1
+    real = "/root/reference/Mamri/Resources/Robot/robot_config.json"
+    if os.path.exists(real):
+        assert _robots_equal(robot.load_robot_config(real), ref)
+    # malformed files are rejected, not guessed at
+    bad = robot.default_definition()
+    bad[1]["fixed_offset_to_parent"]["rotate"] = [["x", 90.0]]
+    with pytest.raises(ValueError):
+        robot.robot_from_definition(bad)
+    bad = robot.default_definition()
+    bad[2]["parent"] = "Joint5"
+    with pytest.raises(ValueError):
+        robot.robot_from_definition(bad)

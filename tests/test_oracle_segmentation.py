@@ -120,3 +120,37 @@ def test_properties_random(seed, radius, conn):
         cnt, sums, moms = seg.integer_sums(lab, k)
         nz, ny, nx = dims
         assert (sums[:, 0] <= cnt * (nx - 1)).all() and (sums[:, 1] <= cnt * (ny - 1)).all()
+
+
+@pytest.mark.parametrize("radius", [1, 2, 3])
+@pytest.mark.parametrize("p", [0.5, 0.8, 0.97])
+def test_opening_three_restatements_agree(radius, p):
+    """sitk.BinaryMorphologicalOpening (mamri_params.open_radius): scipy-based, definitional and C restatements agree;
+    opening is anti-extensive and idempotent; the outside of the image counts as foreground for its erosion, so a full
+    volume stays full (plain scipy binary_opening with border_value=0 would eat its rim)."""
+    import ctypes as C
+    from oracle import c_oracle
+    rng = np.random.default_rng(radius * 17 + int(p * 100))
+    m = (rng.random((13, 18, 23)) < p).astype(np.uint8)
+    a = seg.binary_opening(m, radius)
+    assert np.array_equal(a, bf.opening_itk_pipeline(m, radius))
+    c = np.empty_like(m)
+    assert c_oracle.load().oracle_opening(m.ctypes.data, 23, 18, 13, radius, c.ctypes.data) == 0
+    assert np.array_equal(a, c)
+    assert (a <= m).all()
+    assert np.array_equal(seg.binary_opening(a, radius), a)
+    full = np.ones((9, 10, 11), dtype=np.uint8)
+    assert seg.binary_opening(full, radius).all()
+    assert not ndimage.binary_opening(full, structure=seg.ball_structure(radius)).all()
+
+
+def test_detect_with_opening_matches_c_oracle():
+    from oracle import c_oracle
+    ph = phantom.small_phantom(dims=(48, 40, 32), seed=77, sigma=24.0, touch_border=True)
+    vol = phantom.generate(ph)
+    geom = seg.Geometry(ph.spacing, ph.origin, ph.direction)
+    for orad in (1, 2):
+        a = seg.detect_fiducials(vol, geom, open_radius=orad, min_vol=20.0, max_vol=600.0)
+        b = c_oracle.detect_fiducials(vol, geom, open_radius=orad, min_vol=20.0, max_vol=600.0)
+        assert np.array_equal(a.closed, b.closed) and np.array_equal(a.labels, b.labels) and a.fiducials == b.fiducials
+        assert (a.closed <= seg.detect_fiducials(vol, geom, min_vol=20.0, max_vol=600.0).closed).all()   # both operators are increasing

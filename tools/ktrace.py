@@ -26,7 +26,11 @@ from mamri_pose_estimation_b200.detector import DetectParams, FiducialDetector, 
 NAMES = ["threshold", "close", "erode", "runs_scan", "union_slices", "union_z1", "union_z2", "flatten_rank", "select",
          "label_cluster", "stats", "final", "materialise", "end", "label.U1", "label.U2", "label.F", "label.FIX", "label.S",
          "label.end", "runs.lookback", "runs.write", "close.loaded", "close.dilated", "close.eroded", "stats.finalise",
-         "close.lastCTA", "runs.lastCTA", "threshold.lastCTA"]
+         "close.lastCTA", "runs.lastCTA", "threshold.lastCTA",
+         "uslice.n", "uslice.n.last", "uslice.join", "uslice.join.last", "uslice.flat", "uslice.flat.last", "uslice.end", "uslice.end.last",
+         "uz1.end", "uz1.end.last", "uz2.end", "uz2.end.last", "rank.end", "rank.end.last", "select.end", "select.end.last",
+         "runs.lookback.last"]
+LAST = {11, 13, 26, 27, 28, 30, 32, 34, 36, 38, 40, 42, 44, 45}      # slots written by ktrace_last (complemented)
 
 
 def main():
@@ -47,7 +51,7 @@ def main():
               out_mask=mask, out_labels=lab)
     for _ in range(4):                                   # warm-up: sizes the grids, captures the graph
         r = det.detect(vol, **kw)
-    buf = (C.c_uint64 * 32)()
+    buf = (C.c_uint64 * 48)()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rows, totals = [], []
     for _ in range(a.reps):
@@ -60,9 +64,9 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         totals.append(e0.elapsed_time(e1) * 1e3)
-        lib.mamri_ktrace_read(buf, 32)
+        lib.mamri_ktrace_read(buf, 48)
         row = [int(v) for v in buf]
-        for j in (11, 13, 26, 27, 28):                               # KT_FINAL / KT_END hold the complement of the LAST stamp (ktrace_last)
+        for j in LAST:                               # KT_FINAL / KT_END hold the complement of the LAST stamp (ktrace_last)
             if row[j] != (1 << 64) - 1:
                 row[j] = ~row[j] & ((1 << 64) - 1)
         rows.append(row)
