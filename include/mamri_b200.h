@@ -17,11 +17,15 @@
  *   - "d_" pointers are device memory owned by the caller, "h_" pointers host;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *   - a context is not thread-safe and serves one scan at a time; use one per
- *     (device, stream).  No allocation happens on the hot calls.
+ *     (device, stream).  The device-buffer calls never allocate.  The host-buffer
+ *     calls keep device staging buffers that grow on the first call at a size
+ *     (mamri_reserve_staging sizes them ahead of time); the pose / collision calls
+ *     keep a scratch buffer that grows with the batch size the same way.
  */
 #ifndef MAMRI_B200_H
 #define MAMRI_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -139,6 +143,16 @@ MAMRI_API int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc, 
  * out when h_body_out != NULL.  This is the call a MamriLogic adapter makes. */
 MAMRI_API int mamri_detect_host_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* h_volume,
                             const mamri_params* params, uint8_t* h_body_out, void* stream);
+/* The body labelmap at 1 bit per voxel instead of uint8 (8x fewer bytes over the link to the host, which is what bounds
+ * the host-buffer calls): [nz][ny][W] 32-bit words, W = ceil(nx / 32), bit k of word w of a row = voxel x = 32 w + k.
+ * _bits_async: device output (d_body_bits_out may be NULL); _host_bits_async: host output. */
+MAMRI_API int mamri_detect_bits_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* d_volume,
+                            const mamri_params* params, uint8_t* d_mask_out, uint32_t* d_labels_out,
+                            uint32_t* d_body_bits_out, void* stream);
+MAMRI_API int mamri_detect_host_bits_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* h_volume,
+                                 const mamri_params* params, uint32_t* h_body_bits_out, void* stream);
+/* Sizes the device staging buffers of the host-buffer calls (volume in, body labelmap out) ahead of the first call. */
+MAMRI_API int mamri_reserve_staging(mamri_ctx* ctx, size_t volume_bytes, size_t body_bytes);
 /* Waits for the pending detect, then writes the summary and up to max_markers markers
  * (ascending label).  "No markers" is MAMRI_OK with n_markers == 0 (Mamri.py:1312). */
 MAMRI_API int mamri_detect_collect(mamri_ctx* ctx, mamri_summary* summary, mamri_marker* h_markers,
@@ -184,6 +198,9 @@ MAMRI_API int mamri_pool_detect_begin(mamri_pool* pool, const mamri_volume_desc*
  * this one drains.  Ended by mamri_pool_detect_end. */
 MAMRI_API int mamri_pool_detect_host_begin(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes,
                                  int32_t n, const mamri_params* params, uint8_t* const* h_body_out, void* stream);
+/* Same with the body labelmaps at 1 bit per voxel (see mamri_detect_host_bits_async). */
+MAMRI_API int mamri_pool_detect_host_bits_begin(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes,
+                                      int32_t n, const mamri_params* params, uint32_t* const* h_body_bits_out, void* stream);
 MAMRI_API int mamri_pool_detect_end(mamri_pool* pool, mamri_summary* summaries, mamri_marker* markers,
                           uint32_t max_markers_per_scan);
 /* Same from/to HOST buffers (pinned for full PCIe speed): the H2D copy of scan i+1 overlaps the

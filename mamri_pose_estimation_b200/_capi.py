@@ -104,6 +104,12 @@ SIGNATURES = {
                                           C.c_uint32, C.c_void_p]),
     "mamri_pool_detect_host_begin": (C.c_int, [C.c_void_p, C.POINTER(VolumeDesc), C.POINTER(C.c_void_p), C.c_int32,
                                                C.POINTER(Params), C.POINTER(C.c_void_p), C.c_void_p]),
+    "mamri_pool_detect_host_bits_begin": (C.c_int, [C.c_void_p, C.POINTER(VolumeDesc), C.POINTER(C.c_void_p), C.c_int32,
+                                                    C.POINTER(Params), C.POINTER(C.c_void_p), C.c_void_p]),
+    "mamri_detect_bits_async": (C.c_int, [C.c_void_p, C.POINTER(VolumeDesc), C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "mamri_detect_host_bits_async": (C.c_int, [C.c_void_p, C.POINTER(VolumeDesc), C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]),
+    "mamri_reserve_staging": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "mamri_pool_detect_end": (C.c_int, [C.c_void_p, C.POINTER(Summary), C.POINTER(Marker), C.c_uint32]),
     "mamri_pool_detect_host": (C.c_int, [C.c_void_p, C.POINTER(VolumeDesc), C.POINTER(C.c_void_p), C.c_int32,
                                          C.POINTER(Params), C.POINTER(C.c_void_p), C.POINTER(Summary), C.POINTER(Marker),

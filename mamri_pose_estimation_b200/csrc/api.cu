@@ -350,7 +350,7 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool f
     CK(launch_label(ctx, mask, desc, params, s));
     if (prof) CK(cudaEventRecord(ctx->ev[3], s));
     const bool outputs = k.has_mask || k.has_labels || k.has_body;
-    const bool forked = fork && outputs;
+    const bool forked = fork && (outputs || k.has_body_bits);
     // Statistics (marker table + summary, written straight into the pinned host buffers) and the per-voxel outputs
     // both depend on the labels only.  The statistics kernel goes FIRST, on the second branch: its few CTAs take their
     // slots before `materialise` floods the machine with thousands of CTAs (launched after it, a small kernel only
@@ -364,6 +364,7 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool f
         CK(launch_stats(ctx, desc, params, s));
     }
     if (prof) CK(cudaEventRecord(ctx->ev[4], s));
+    if (k.has_body_bits) CK(launch_body_bits(ctx, mask, nx, ny, nz, s));
     if (outputs) CK(launch_materialise(ctx, mask, nx, ny, nz, k.outs_aligned, s));
     if (prof) CK(cudaEventRecord(ctx->ev[5], s));
     if (forked) CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
@@ -373,17 +374,23 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool f
 
 static int detect_async_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* d_volume,
                              const mamri_params* params, uint8_t* d_mask_out, uint32_t* d_labels_out,
-                             uint8_t* d_body_out, double* d_table, uint32_t table_slots, void* stream);
+                             uint8_t* d_body_out, uint32_t* d_body_bits_out, double* d_table, uint32_t table_slots, void* stream);
 
 extern "C" int mamri_detect_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* d_volume,
                                   const mamri_params* params, uint8_t* d_mask_out, uint32_t* d_labels_out,
                                   uint8_t* d_body_out, void* stream) {
-    return detect_async_impl(ctx, desc, d_volume, params, d_mask_out, d_labels_out, d_body_out, nullptr, 0, stream);
+    return detect_async_impl(ctx, desc, d_volume, params, d_mask_out, d_labels_out, d_body_out, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int mamri_detect_bits_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* d_volume,
+                                       const mamri_params* params, uint8_t* d_mask_out, uint32_t* d_labels_out,
+                                       uint32_t* d_body_bits_out, void* stream) {
+    return detect_async_impl(ctx, desc, d_volume, params, d_mask_out, d_labels_out, nullptr, d_body_bits_out, nullptr, 0, stream);
 }
 
 static int detect_async_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* d_volume,
                              const mamri_params* params, uint8_t* d_mask_out, uint32_t* d_labels_out,
-                             uint8_t* d_body_out, double* d_table, uint32_t table_slots, void* stream) {
+                             uint8_t* d_body_out, uint32_t* d_body_bits_out, double* d_table, uint32_t table_slots, void* stream) {
     if (!ctx) return MAMRI_ERR_INVALID_ARG;
     int rc = validate(ctx, desc, params);
     if (rc != MAMRI_OK) return rc;
@@ -399,6 +406,7 @@ static int detect_async_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, cons
     k.outs_aligned = ((reinterpret_cast<uintptr_t>(d_labels_out) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(d_mask_out) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_body_out) & 15u) == 0);
     k.has_mask = d_mask_out != nullptr; k.has_labels = d_labels_out != nullptr; k.has_body = d_body_out != nullptr;
+    k.has_body_bits = d_body_bits_out != nullptr;
     k.run_ctas = ctx->run_ctas = run_grid_class(ctx->run_ctas, ctx->last_n_runs);
     ctx->slice_threads = slice_threads_class(ctx->slice_threads, ctx->last_n_runs, desc->nz);
     k.slice_threads = ctx->slice_threads < 0 ? -ctx->slice_threads : ctx->slice_threads;
@@ -408,6 +416,7 @@ static int detect_async_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, cons
     ctx->h_dyn->mask_out = d_mask_out;
     ctx->h_dyn->labels_out = d_labels_out;
     ctx->h_dyn->body_out = d_body_out;
+    ctx->h_dyn->body_bits_out = d_body_bits_out;
     ctx->h_dyn->table_out = d_table;
     ctx->h_dyn->table_slots = d_table ? table_slots : 0u;
     ctx->h_dyn->gen = ++ctx->gen;            // generation 0 is the cleared state: never used
@@ -447,37 +456,63 @@ static int detect_async_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, cons
     return MAMRI_OK;
 }
 
-extern "C" int mamri_detect_host_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* h_volume,
-                                       const mamri_params* params, uint8_t* h_body_out, void* stream) {
+// Host-buffer form: H2D copy of the volume into the context's staging buffer, the scan, D2H copy of the body labelmap
+// (uint8, or 1 bit per voxel).  The staging buffers are sized on the first call at a size (mamri_reserve_staging does
+// it ahead of time); a call that has to grow them synchronises the stream first.
+static int detect_host_impl(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* h_volume, const mamri_params* params,
+                            uint8_t* h_body_out, uint32_t* h_body_bits_out, void* stream) {
     if (!ctx) return MAMRI_ERR_INVALID_ARG;
     int rc = validate(ctx, desc, params);
     if (rc != MAMRI_OK) return rc;
     if (!h_volume) return fail(ctx, MAMRI_ERR_INVALID_ARG, "volume pointer is NULL");
+    if (h_body_out && h_body_bits_out) return fail(ctx, MAMRI_ERR_INVALID_ARG, "ask for the body labelmap as uint8 or as bits, not both");
     if (ctx->pending) return fail(ctx, MAMRI_ERR_STATE, "a detect is already pending on this context; collect it first");
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = size_t(desc->nx) * desc->ny * desc->nz;
     const size_t in_bytes = n * dtype_size(desc->dtype);
-    if (ctx->stage_in_bytes < in_bytes) {            // first host call at this size: grow the staging buffer
+    const size_t body_bytes = h_body_out ? n : (h_body_bits_out ? size_t((desc->nx + 31) / 32) * desc->ny * desc->nz * 4 : 0);
+    if (ctx->stage_in_bytes < in_bytes || ctx->stage_body_bytes < body_bytes) {
         CK(cudaStreamSynchronize(s));
-        cudaFree(ctx->d_stage_in);
-        ctx->d_stage_in = nullptr; ctx->stage_in_bytes = 0;
-        CK(cudaMalloc(&ctx->d_stage_in, in_bytes));
-        ctx->stage_in_bytes = in_bytes;
-    }
-    if (h_body_out && ctx->stage_body_bytes < n) {
-        CK(cudaStreamSynchronize(s));
-        cudaFree(ctx->d_stage_body);
-        ctx->d_stage_body = nullptr; ctx->stage_body_bytes = 0;
-        CK(cudaMalloc((void**)&ctx->d_stage_body, n));
-        ctx->stage_body_bytes = n;
+        rc = mamri_reserve_staging(ctx, in_bytes, body_bytes);
+        if (rc != MAMRI_OK) return rc;
     }
     CK(cudaMemcpyAsync(ctx->d_stage_in, h_volume, in_bytes, cudaMemcpyHostToDevice, s));
-    rc = mamri_detect_async(ctx, desc, ctx->d_stage_in, params, nullptr, nullptr, h_body_out ? ctx->d_stage_body : nullptr,
-                            stream);
+    rc = detect_async_impl(ctx, desc, ctx->d_stage_in, params, nullptr, nullptr, h_body_out ? ctx->d_stage_body : nullptr,
+                           h_body_bits_out ? reinterpret_cast<uint32_t*>(ctx->d_stage_body) : nullptr, nullptr, 0, stream);
     if (rc != MAMRI_OK) return rc;
-    if (h_body_out) CK(cudaMemcpyAsync(h_body_out, ctx->d_stage_body, n, cudaMemcpyDeviceToHost, s));
+    if (body_bytes) CK(cudaMemcpyAsync(h_body_out ? static_cast<void*>(h_body_out) : static_cast<void*>(h_body_bits_out), ctx->d_stage_body,
+                                       body_bytes, cudaMemcpyDeviceToHost, s));
     return MAMRI_OK;
+}
+
+extern "C" int mamri_reserve_staging(mamri_ctx* ctx, size_t volume_bytes, size_t body_bytes) {
+    if (!ctx) return MAMRI_ERR_INVALID_ARG;
+    if (ctx->pending) return fail(ctx, MAMRI_ERR_STATE, "collect the pending detect first");
+    DeviceGuard g(ctx->device);
+    if (ctx->stage_in_bytes < volume_bytes) {
+        cudaFree(ctx->d_stage_in);
+        ctx->d_stage_in = nullptr; ctx->stage_in_bytes = 0;
+        CK(cudaMalloc(&ctx->d_stage_in, volume_bytes));
+        ctx->stage_in_bytes = volume_bytes;
+    }
+    if (ctx->stage_body_bytes < body_bytes) {
+        cudaFree(ctx->d_stage_body);
+        ctx->d_stage_body = nullptr; ctx->stage_body_bytes = 0;
+        CK(cudaMalloc((void**)&ctx->d_stage_body, body_bytes));
+        ctx->stage_body_bytes = body_bytes;
+    }
+    return MAMRI_OK;
+}
+
+extern "C" int mamri_detect_host_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* h_volume,
+                                       const mamri_params* params, uint8_t* h_body_out, void* stream) {
+    return detect_host_impl(ctx, desc, h_volume, params, h_body_out, nullptr, stream);
+}
+
+extern "C" int mamri_detect_host_bits_async(mamri_ctx* ctx, const mamri_volume_desc* desc, const void* h_volume,
+                                            const mamri_params* params, uint32_t* h_body_bits_out, void* stream) {
+    return detect_host_impl(ctx, desc, h_volume, params, nullptr, h_body_bits_out, stream);
 }
 
 extern "C" int mamri_detect_collect(mamri_ctx* ctx, mamri_summary* summary, mamri_marker* h_markers, uint32_t max_markers) {
@@ -737,6 +772,7 @@ static int pool_wave_launch(mamri_pool* pool, const GraphKey& k, const void* con
         d->mask_out = mask_out ? mask_out[first + i] : nullptr;
         d->labels_out = labels_out ? labels_out[first + i] : nullptr;
         d->body_out = body_out ? body_out[first + i] : nullptr;
+        d->body_bits_out = nullptr;
         d->table_out = tables ? tables + size_t(first + i) * table_slots * 8 : nullptr;
         d->table_slots = tables ? table_slots : 0u;
         d->gen = ++c->gen;
@@ -936,7 +972,7 @@ extern "C" int mamri_pool_detect_begin(mamri_pool* pool, const mamri_volume_desc
         for (int i = 0; i < n; ++i) {
             if (cudaStreamWaitEvent(pool->streams[i], pool->fork, 0) != cudaSuccess) return pfail(MAMRI_ERR_CUDA, "forking failed");
             const int rc = detect_async_impl(pool->ctx[i], desc, d_volumes[i], params, d_mask_out ? d_mask_out[i] : nullptr,
-                                             d_labels_out ? d_labels_out[i] : nullptr, d_body_out ? d_body_out[i] : nullptr,
+                                             d_labels_out ? d_labels_out[i] : nullptr, d_body_out ? d_body_out[i] : nullptr, nullptr,
                                              d_tables ? d_tables + size_t(i) * table_slots * 8 : nullptr, table_slots, pool->streams[i]);
             if (rc != MAMRI_OK) {
                 snprintf(pool->err, sizeof(pool->err), "scan %d: %s", i, mamri_last_error(pool->ctx[i]));
@@ -952,8 +988,8 @@ extern "C" int mamri_pool_detect_begin(mamri_pool* pool, const mamri_volume_desc
     return MAMRI_OK;
 }
 
-extern "C" int mamri_pool_detect_host_begin(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes,
-                                            int32_t n, const mamri_params* params, uint8_t* const* h_body_out, void* stream) {
+static int pool_host_begin(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes, int32_t n,
+                           const mamri_params* params, uint8_t* const* h_body_out, uint32_t* const* h_body_bits_out, void* stream) {
     if (!pool) return MAMRI_ERR_INVALID_ARG;
     auto pfail = [&](int code, const char* msg) { snprintf(pool->err, sizeof(pool->err), "%s", msg); return code; };
     if (n < 1 || n > pool->k || !h_volumes) return pfail(MAMRI_ERR_INVALID_ARG, "begin/end handles 1..n_contexts scans per call");
@@ -965,8 +1001,8 @@ extern "C" int mamri_pool_detect_host_begin(mamri_pool* pool, const mamri_volume
     if (cudaEventRecord(pool->fork, cur) != cudaSuccess) return pfail(MAMRI_ERR_CUDA, "recording the fork event failed");
     for (int i = 0; i < n; ++i) {                     // scan i: H2D, kernels, body-mask D2H on stream i
         if (cudaStreamWaitEvent(pool->streams[i], pool->fork, 0) != cudaSuccess) return pfail(MAMRI_ERR_CUDA, "forking failed");
-        const int rc = mamri_detect_host_async(pool->ctx[i], desc, h_volumes[i], params, h_body_out ? h_body_out[i] : nullptr,
-                                               pool->streams[i]);
+        const int rc = detect_host_impl(pool->ctx[i], desc, h_volumes[i], params, h_body_out ? h_body_out[i] : nullptr,
+                                        h_body_bits_out ? h_body_bits_out[i] : nullptr, pool->streams[i]);
         if (rc != MAMRI_OK) {
             snprintf(pool->err, sizeof(pool->err), "scan %d: %s", i, mamri_last_error(pool->ctx[i]));
             for (int j = 0; j < i; ++j) { mamri_summary tmp; mamri_detect_collect(pool->ctx[j], &tmp, nullptr, 0); }
@@ -978,6 +1014,16 @@ extern "C" int mamri_pool_detect_host_begin(mamri_pool* pool, const mamri_volume
     }
     pool->pending_n = n;
     return MAMRI_OK;
+}
+
+extern "C" int mamri_pool_detect_host_begin(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes,
+                                            int32_t n, const mamri_params* params, uint8_t* const* h_body_out, void* stream) {
+    return pool_host_begin(pool, desc, h_volumes, n, params, h_body_out, nullptr, stream);
+}
+
+extern "C" int mamri_pool_detect_host_bits_begin(mamri_pool* pool, const mamri_volume_desc* desc, const void* const* h_volumes,
+                                                 int32_t n, const mamri_params* params, uint32_t* const* h_body_bits_out, void* stream) {
+    return pool_host_begin(pool, desc, h_volumes, n, params, nullptr, h_body_bits_out, stream);
 }
 
 extern "C" int mamri_pool_detect_end(mamri_pool* pool, mamri_summary* summaries, mamri_marker* markers,

@@ -887,4 +887,47 @@ cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// body labelmap at 1 bit per voxel (DynArgs::body_bits_out): what a host caller gets back instead of the uint8
+// labelmap when the link to the host is the bottleneck (8x fewer bytes; Mamri.py:1323 `largest_object_img`)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_body_bits(const uint32_t* __restrict__ mask, const uint32_t* __restrict__ word_base,
+                                                   const uint32_t* __restrict__ run_label, int W, uint32_t n_words,
+                                                   const DynArgs* __restrict__ dyn, const DevScalars* sc) {
+    pdl_wait();
+    uint32_t* __restrict__ bits = dyn->body_bits_out;
+    if (!bits) return;
+    const unsigned long long bp = sc->body_packed;
+    const uint32_t body = (sc->status == MAMRI_OK && (bp >> 32) != 0ull) ? 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull) : 0u;
+    for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += gridDim.x * blockDim.x) {
+        const uint32_t m = mask[wi];
+        uint32_t out = 0;
+        if (m && body) {
+            const uint32_t prev = (wi % uint32_t(W)) ? mask[wi - 1] : 0u;
+            const uint32_t starts = run_starts(m, prev), base = word_base[wi];
+            uint32_t rem = m;
+            while (rem) {                                           // one piece of set bits = part of one run
+                const int b = __ffs(rem) - 1;
+                const uint32_t t = m >> b;
+                const int len = (t == (0xFFFFFFFFu >> b)) ? 32 - b : __ffs(~t) - 1;
+                const uint32_t seg = (len == 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << b;
+                if (run_label[run_id_in_word(base, starts, b)] == body) out |= seg;
+                rem &= ~seg;
+            }
+        }
+        bits[wi] = out;
+    }
+}
+
+cudaError_t launch_body_bits(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, cudaStream_t s) {
+    const int W = (nx + 31) / 32;
+    const uint32_t n_words = uint32_t(W) * ny * nz;
+    uint32_t blocks = (n_words + 255u) / 256u;
+    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    if (blocks == 0) blocks = 1;
+    LK(k_body_bits, blocks, 256, s, false, d_mask, c->d_word_base, c->d_run_label, W, n_words, c->d_dyn, c->d_scalars);
+    prof_mark(c, s, "body_bits");
+    return cudaGetLastError();
+}
+
 KTRACE_TU(ccl)

@@ -45,6 +45,7 @@ struct DynArgs {
     uint8_t* mask_out;
     uint32_t* labels_out;
     uint8_t* body_out;
+    uint32_t* body_bits_out;         // NULL or the body labelmap at 1 bit per voxel, [nz][ny][ceil(nx/32)] words
     uint32_t gen;                    // launch generation (tags the look-back states of the single-pass scans)
     uint32_t table_slots;            // rows of table_out
     double* table_out;               // NULL or [table_slots][8]: fixed-size marker table of the scan, written by the
@@ -63,7 +64,7 @@ struct ScanArgs {
 struct GraphKey {
     mamri_volume_desc desc;
     mamri_params prm;
-    int vol_aligned, outs_aligned, has_mask, has_labels, has_body;
+    int vol_aligned, outs_aligned, has_mask, has_labels, has_body, has_body_bits;
     int run_ctas;                    // grid of the per-run kernels (sized from the previous scans' run counts)
     int slice_threads;               // threads of the per-slice union-find CTAs (same source)
     int label_cluster;               // 0: labelling by the scalable multi-kernel path; N > 0: one cluster of N CTAs
@@ -186,6 +187,7 @@ cudaError_t segment_init_device();
 int ccl_init_device();               // returns the largest cluster size the labelling kernel can use (0 = none)
 cudaError_t launch_materialise(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, int outs_aligned,
                                cudaStream_t s);
+cudaError_t launch_body_bits(mamri_ctx* c, const uint32_t* d_mask, int nx, int ny, int nz, cudaStream_t s);
 cudaError_t launch_entry_search(mamri_ctx* c, const float* d_points, const float* d_normals, long long n,
                                 const double target[3], double radius, double wx, double wy, double cutoff,
                                 int n_path_samples, const uint8_t* d_path_mask, int mnx, int mny, int mnz,

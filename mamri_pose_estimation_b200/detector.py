@@ -255,25 +255,37 @@ class FiducialDetector:
         return self.collect()
 
     # ------------------------------------------------------------------ host-buffer path (the drop-in call)
+    def reserve_staging(self, volume_bytes: int, body_bytes: int = 0) -> None:
+        """Sizes the device staging buffers of the host-buffer calls ahead of the first call (mamri_reserve_staging)."""
+        check(self._lib.mamri_reserve_staging(self._ctx, int(volume_bytes), int(body_bytes)), self._ctx)
+
     def detect_host_async(self, volume, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), direction=IDENTITY,
-                          params: Optional[DetectParams] = None, body_out=None,
+                          params: Optional[DetectParams] = None, body_out=None, body_bits_out=None,
                           stream: Optional[torch.cuda.Stream] = None) -> None:
         """`volume`: C-contiguous host array [nz, ny, nx] (numpy, or a pinned CPU torch tensor for full PCIe
-        speed).  `body_out`: optional host uint8 buffer of the same shape receiving the body mask."""
+        speed).  `body_out`: optional host uint8 buffer of the same shape receiving the body mask;
+        `body_bits_out`: instead, a host int32/uint32 buffer [nz, ny, ceil(nx/32)] receiving it at 1 bit per voxel
+        (8x fewer bytes back over PCIe; `unpack_body_bits` expands it)."""
         arr, keep = _host_view(volume)
         params = params or DetectParams()
         d = _desc(arr["shape"], arr["dtype"], spacing, origin, direction)
         p = params.to_c()
         body_ptr, keep_b = (None, None)
+        if body_out is not None and body_bits_out is not None:
+            raise ValueError("ask for the body mask as uint8 (body_out) or bit-packed (body_bits_out), not both")
         if body_out is not None:
             b, keep_b = _host_view(body_out)
             if b["dtype"] != "uint8" or tuple(b["shape"]) != tuple(arr["shape"]):
                 raise ValueError("body_out must be uint8 with the volume's shape")
             body_ptr = b["ptr"]
         s = stream or torch.cuda.current_stream(self.device)
-        rc = self._lib.mamri_detect_host_async(self._ctx, C.byref(d), arr["ptr"], C.byref(p), body_ptr, s.cuda_stream)
+        if body_bits_out is not None:
+            bptr, keep_b = _bits_view(body_bits_out, arr["shape"])
+            rc = self._lib.mamri_detect_host_bits_async(self._ctx, C.byref(d), arr["ptr"], C.byref(p), bptr, s.cuda_stream)
+        else:
+            rc = self._lib.mamri_detect_host_async(self._ctx, C.byref(d), arr["ptr"], C.byref(p), body_ptr, s.cuda_stream)
         check(rc, self._ctx)
-        self._pending = (None, None, body_out, (keep, keep_b))
+        self._pending = (None, None, body_out if body_out is not None else body_bits_out, (keep, keep_b))
 
     def detect_host(self, volume, **kw) -> DetectionResult:
         self.detect_host_async(volume, **kw)
@@ -487,6 +499,33 @@ def _host_view(a):
     return {"ptr": arr.ctypes.data, "shape": arr.shape, "dtype": arr.dtype.name}, arr
 
 
+def body_bits_shape(shape_zyx) -> tuple:
+    nz, ny, nx = (int(v) for v in shape_zyx)
+    return (nz, ny, (nx + 31) // 32)
+
+
+def _bits_view(a, shape_zyx):
+    """Pointer of a host buffer for the bit-packed body mask: 32-bit words [nz, ny, ceil(nx/32)]."""
+    want = body_bits_shape(shape_zyx)
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda or not a.is_contiguous() or a.dtype not in (torch.int32, torch.uint32) or tuple(a.shape) != want:
+            raise ValueError(f"body_bits_out must be a contiguous CPU int32 tensor of shape {want}")
+        return a.data_ptr(), a
+    arr = np.asarray(a)
+    if not arr.flags["C_CONTIGUOUS"] or arr.dtype.itemsize != 4 or arr.dtype.kind not in "iu" or tuple(arr.shape) != want:
+        raise ValueError(f"body_bits_out must be a C-contiguous 32-bit integer array of shape {want}")
+    return arr.ctypes.data, arr
+
+
+def unpack_body_bits(bits, shape_zyx) -> np.ndarray:
+    """uint8 [nz, ny, nx] labelmap (what `largest_object_img` is, Mamri.py:1323) from the bit-packed form the
+    `*_bits` calls return: bit k of word w of a row is voxel x = 32 w + k."""
+    nz, ny, nx = (int(v) for v in shape_zyx)
+    words = bits.numpy() if isinstance(bits, torch.Tensor) else np.asarray(bits)
+    by = np.ascontiguousarray(words).view(np.uint8).reshape(nz, ny, -1)
+    return np.unpackbits(by, axis=2, bitorder="little")[:, :, :nx]
+
+
 def generate_phantom_cuda(ph, device: int = 0, out: Optional[torch.Tensor] = None,
                           stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
     """Creates the phantom described by `ph` (phantom.Phantom) directly in HBM; uint16 [nz, ny, nx]."""
@@ -696,9 +735,10 @@ class BatchDetector:
         self._begun = (n, volumes, tables)           # keep the buffers alive until end()
 
     def begin_host(self, volumes: Sequence, spacing, origin, direction=IDENTITY, params: Optional[DetectParams] = None,
-                   body_out: Optional[Sequence] = None) -> None:
+                   body_out: Optional[Sequence] = None, body_bits_out: Optional[Sequence] = None) -> None:
         """First half of `run_host` for up to n_contexts scans: every scan's H2D copy, kernels and body-mask D2H are
-        enqueued; `end()` waits."""
+        enqueued; `end()` waits.  `body_bits_out`: host buffers for the body masks at 1 bit per voxel instead of
+        `body_out`'s uint8 (see FiducialDetector.detect_host_async)."""
         n = len(volumes)
         if not 1 <= n <= self.n_contexts:
             raise ValueError(f"begin/end handles 1..{self.n_contexts} scans per call")
@@ -718,7 +758,15 @@ class BatchDetector:
                     raise ValueError("body_out must be uint8 with the volume's shape")
             bp = self._ptrs([b["ptr"] for b, _ in bviews], n)
         s = torch.cuda.current_stream(self.device)
-        rc = self._lib.mamri_pool_detect_host_begin(self._pool, C.byref(d), vp, n, C.byref(p), bp, s.cuda_stream)
+        if body_bits_out is not None:
+            if body_out is not None:
+                raise ValueError("ask for the body masks as uint8 or bit-packed, not both")
+            bviews = [_bits_view(b, a0["shape"]) for b in body_bits_out]
+            bp = self._ptrs([ptr for ptr, _ in bviews], n)
+            rc = self._lib.mamri_pool_detect_host_bits_begin(self._pool, C.byref(d), vp, n, C.byref(p), bp, s.cuda_stream)
+            body_out = body_bits_out
+        else:
+            rc = self._lib.mamri_pool_detect_host_begin(self._pool, C.byref(d), vp, n, C.byref(p), bp, s.cuda_stream)
         _capi.check_pool(rc, self._pool)
         self._begun = (n, views, bviews)
         self._begun_body = body_out if body_out is not None else ()
@@ -808,7 +856,7 @@ class BatchPipeline:
         return s
 
     def submit_host(self, volumes: Sequence, spacing, origin, direction=IDENTITY, params: Optional[DetectParams] = None,
-                    body_out: Optional[Sequence] = None) -> torch.cuda.Stream:
+                    body_out: Optional[Sequence] = None, body_bits_out: Optional[Sequence] = None) -> torch.cuda.Stream:
         """`submit` for HOST buffers (pinned for full PCIe speed): the next batch's copies start feeding the link while
         the previous batch's last scans still compute and drain."""
         i = self._next
@@ -818,7 +866,7 @@ class BatchPipeline:
         s = self.streams[i]
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
-            self.pools[i].begin_host(volumes, spacing, origin, direction, params, body_out=body_out)
+            self.pools[i].begin_host(volumes, spacing, origin, direction, params, body_out=body_out, body_bits_out=body_bits_out)
         self._in_flight.append(i)
         return s
 

@@ -397,3 +397,54 @@ def test_host_pipeline_matches_run_host(cuda_lib):
     r = bp.result()
     assert r[0].body_mask is None and r[0].mask is None
     bp.close()
+
+
+@pytest.mark.gpu
+def test_bit_packed_body_mask_equals_uint8_body_mask(cuda_lib):
+    """The *_bits calls return the body labelmap at 1 bit per voxel (8x fewer bytes over PCIe): unpacked, it is the
+    uint8 labelmap of the plain calls and of the oracle -- single context, device output, pool and pipeline; ragged
+    rows (nx % 32 != 0) included; an empty scan gives an all-zero mask."""
+    import ctypes as C
+    import torch
+    from mamri_pose_estimation_b200.detector import (BatchPipeline, DetectParams, FiducialDetector, body_bits_shape,
+                                                     unpack_body_bits, _desc)
+    for dims, seed in (((96, 80, 48), 12), ((70, 45, 33), 13)):
+        ph = phantom.small_phantom(dims=dims, n_fiducials=5, seed=seed)
+        vol = phantom.generate(ph)
+        ora = seg.detect_fiducials(vol, _geom(ph))
+        nx, ny, nz = dims
+        det = FiducialDetector(dims)
+        det.reserve_staging(vol.nbytes, int(np.prod(body_bits_shape(vol.shape))) * 4)
+        bits = np.full(body_bits_shape(vol.shape), -1, dtype=np.int32)
+        res = det.detect_host(vol, spacing=ph.spacing, origin=ph.origin, direction=ph.direction, body_bits_out=bits)
+        assert res.body_label == ora.body_label
+        assert np.array_equal(unpack_body_bits(bits, vol.shape), ora.body_mask)
+        # device-resident form through the C ABI
+        d_bits = torch.full(body_bits_shape(vol.shape), -1, dtype=torch.int32, device="cuda")
+        d = _desc(vol.shape, "uint16", ph.spacing, ph.origin, ph.direction)
+        p = DetectParams().to_c()
+        dv = torch.from_numpy(vol).cuda()
+        rc = cuda_lib.mamri_detect_bits_async(det._ctx, C.byref(d), dv.data_ptr(), C.byref(p), None, None, d_bits.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        det._pending = (None, None, None, None)
+        det.collect()
+        assert np.array_equal(unpack_body_bits(d_bits.cpu(), vol.shape), ora.body_mask)
+        # empty scan
+        bits[:] = -1
+        det.detect_host(np.zeros_like(vol), spacing=ph.spacing, origin=ph.origin, direction=ph.direction, body_bits_out=bits)
+        assert not bits.any()
+        det.close()
+    # pool / pipeline
+    ph = phantom.small_phantom(dims=(96, 80, 48), n_fiducials=5, seed=14)
+    vols = [phantom.generate(phantom.small_phantom(dims=(96, 80, 48), n_fiducials=5, seed=14 + i)) for i in range(3)]
+    bp = BatchPipeline((96, 80, 48), n_contexts=4, depth=2)
+    hv = [torch.from_numpy(v).pin_memory() for v in vols]
+    hb = [torch.empty(body_bits_shape(vols[0].shape), dtype=torch.int32).pin_memory() for _ in vols]
+    bp.submit_host(hv, ph.spacing, ph.origin, ph.direction, body_bits_out=hb)
+    r = bp.result()
+    for i, v in enumerate(vols):
+        ora = seg.detect_fiducials(v, _geom(ph))
+        assert r[i].body_label == ora.body_label
+        assert np.array_equal(unpack_body_bits(hb[i], v.shape), ora.body_mask if ora.body_mask is not None else np.zeros_like(v, dtype=np.uint8))
+    bp.close()
