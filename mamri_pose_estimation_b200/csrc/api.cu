@@ -278,6 +278,10 @@ extern "C" int mamri_create(mamri_ctx** out, int device, int32_t max_nx, int32_t
             ctx->max_cluster = want < probe ? (want < 0 ? 0 : want) : probe;
         }
     }
+    if ((e = cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "capture stream");
+    if ((e = cudaStreamCreateWithFlags(&ctx->cap_stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "capture stream");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "events");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "events");
     {
         const char* ng = getenv("MAMRI_NO_GRAPH");
         ctx->use_graph = !(ng && ng[0] == '1');
