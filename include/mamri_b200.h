@@ -265,9 +265,10 @@ MAMRI_API int mamri_body_surface(mamri_ctx* ctx, const mamri_volume_desc* desc, 
 /* What MamriLogic.process does with "DetectedFiducials" after the segmentation (Mamri.py:858-870),
  * batched on the device: L-shape triplet matching per marker-bearing link (joint_detection), the
  * baseplate y-flatten, the rigid landmark registration of the baseplate (vtkLandmarkTransform, float32
- * landmarks) and the full-chain IK on the effector (+ weighted secondary) markers.  The IK is a
- * projected Levenberg-Marquardt with an analytic Jacobian iterated to the minimum; the reference stops
- * SciPy's TRF at ftol = xtol = 1e-6, so angles agree to that stopping error, not bit for bit. */
+ * landmarks) and the full-chain IK on the effector (+ weighted secondary) markers.  The IK is the reference's own
+ * solver restated: Trust Region Reflective bounded least squares with a 2-point finite-difference Jacobian and
+ * ftol = xtol = 1e-6 (scipy.optimize.least_squares defaults otherwise), so it takes the same iterates and stops in
+ * the same minimum as the reference, to rounding. */
 #define MAMRI_MAX_LINKS        16
 #define MAMRI_MAX_CHAIN         8
 #define MAMRI_POSE_MAX_POINTS  64    /* control points per scan the matcher accepts */
@@ -277,8 +278,8 @@ MAMRI_API int mamri_body_surface(mamri_ctx* ctx, const mamri_volume_desc* desc, 
 #define MAMRI_AXIS_LR    3           /* RotateX(angle)    Mamri.py:1767 */
 #define MAMRI_AXIS_TRANS 4           /* "TRANS_X": no rotation (Mamri.py:1498) */
 #define MAMRI_IK_NOT_RUN   0         /* baseplate or effector markers not identified */
-#define MAMRI_IK_CONVERGED 1
-#define MAMRI_IK_MAX_ITER  2
+#define MAMRI_IK_CONVERGED 1         /* the solver met a stopping criterion (res.success, Mamri.py:1434) */
+#define MAMRI_IK_MAX_ITER  2         /* evaluation budget spent on every initial guess: the reference would report "IK failed" */
 
 /* One entry of robot_config.json, in file order (joint_detection iterates in this order, :1349). */
 typedef struct mamri_link {
@@ -308,10 +309,10 @@ typedef struct mamri_pose {
     int32_t n_points;                        /* control points of the scan */
     int32_t status;                          /* MAMRI_OK, or MAMRI_ERR_CAPACITY: more than MAMRI_POSE_MAX_POINTS points */
     int32_t matched[MAMRI_MAX_LINKS][3];     /* per link: control-point indices (corner, short arm, long arm), -1 = not identified */
-    int32_t has_base;                        /* baseplate registered from the scan */
+    int32_t has_base;                        /* 0 = none; 1 = baseplate registered from the scan; 2 = the saved transform */
     int32_t ik_status;                       /* MAMRI_IK_* */
-    int32_t ik_iterations;
-    int32_t reserved;
+    int32_t ik_iterations;                   /* residual evaluations of the solver (SciPy's nfev), all initial guesses */
+    int32_t ik_termination;                  /* SciPy's status of the run that was kept: 1 gtol, 2 ftol, 3 xtol, 4 both, 0 = budget spent */
     double  base_matrix[16];                 /* row-major 4x4, baseplate model -> world (RAS) */
     double  joint_angles[MAMRI_MAX_CHAIN];   /* rad, articulated-chain order */
     double  ik_cost;                         /* 0.5 * sum of squared residuals */
@@ -327,6 +328,22 @@ MAMRI_API void mamri_default_robot(mamri_robot* robot);
 MAMRI_API int mamri_pose_estimate(mamri_ctx* ctx, const mamri_robot* robot, const double* h_points_ras,
                         const int32_t* h_counts, int32_t n_scans, int32_t max_points, mamri_pose* h_poses,
                         void* stream);
+
+/* What MamriLogic holds besides the scan when it estimates a pose (all optional; NULL options = a fresh scene):
+ *   h_saved_base      row-major 4x4 "MamriSavedBaseplateTransform" (Mamri.py:820, 1376-1408): used instead of the scan's
+ *                     baseplate when prefer_saved_base is set (pNode.useSavedBaseplate), and as the fall-back when the
+ *                     scan shows no baseplate; mamri_pose.has_base tells which one a scan got
+ *   h_initial_angles  [n_scans][MAMRI_MAX_CHAIN] current joint angles (rad): the first of the two initial guesses of
+ *                     _solve_full_chain_ik (:1425), the second being zeros; the lower cost of the successful runs is kept */
+typedef struct mamri_pose_options {
+    const double* h_saved_base;
+    const double* h_initial_angles;
+    int32_t prefer_saved_base;
+    int32_t reserved;
+} mamri_pose_options;
+MAMRI_API int mamri_pose_estimate_ex(mamri_ctx* ctx, const mamri_robot* robot, const double* h_points_ras,
+                           const int32_t* h_counts, int32_t n_scans, int32_t max_points,
+                           const mamri_pose_options* options, mamri_pose* h_poses, void* stream);
 
 /* Same, fed from the device-written marker tables of mamri_pool_detect_begin (float64
  * [n_scans][table_slots][8]; a row is a control point while its label is non-zero): enqueued on `stream`

@@ -70,9 +70,14 @@ class Robot(C.Structure):
 
 class Pose(C.Structure):
     _fields_ = [("n_points", C.c_int32), ("status", C.c_int32), ("matched", (C.c_int32 * 3) * MAX_LINKS),
-                ("has_base", C.c_int32), ("ik_status", C.c_int32), ("ik_iterations", C.c_int32), ("reserved", C.c_int32),
+                ("has_base", C.c_int32), ("ik_status", C.c_int32), ("ik_iterations", C.c_int32), ("ik_termination", C.c_int32),
                 ("base_matrix", C.c_double * 16), ("joint_angles", C.c_double * MAX_CHAIN), ("ik_cost", C.c_double),
                 ("ik_rms_error", C.c_double)]
+
+
+class PoseOptions(C.Structure):
+    _fields_ = [("h_saved_base", C.POINTER(C.c_double)), ("h_initial_angles", C.POINTER(C.c_double)),
+                ("prefer_saved_base", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CollisionResult(C.Structure):
@@ -129,6 +134,8 @@ SIGNATURES = {
     "mamri_default_robot": (None, [C.POINTER(Robot)]),
     "mamri_pose_estimate": (C.c_int, [C.c_void_p, C.POINTER(Robot), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.POINTER(Pose), C.c_void_p]),
+    "mamri_pose_estimate_ex": (C.c_int, [C.c_void_p, C.POINTER(Robot), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.POINTER(PoseOptions), C.POINTER(Pose), C.c_void_p]),
     "mamri_pose_from_tables": (C.c_int, [C.c_void_p, C.POINTER(Robot), C.c_void_p, C.c_int32, C.c_uint32, C.POINTER(Pose),
                                          C.c_void_p]),
     "mamri_collision_check": (C.c_int, [C.c_void_p, C.POINTER(Robot), C.POINTER(C.c_double), C.c_void_p, C.c_int32, C.c_void_p,

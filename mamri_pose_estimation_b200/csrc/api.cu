@@ -1151,9 +1151,9 @@ extern "C" void mamri_default_robot(mamri_robot* r) {
     }
 }
 
-extern "C" int mamri_pose_estimate(mamri_ctx* ctx, const mamri_robot* robot, const double* h_points_ras,
-                                   const int32_t* h_counts, int32_t n_scans, int32_t max_points, mamri_pose* h_poses,
-                                   void* stream) {
+extern "C" int mamri_pose_estimate_ex(mamri_ctx* ctx, const mamri_robot* robot, const double* h_points_ras,
+                                      const int32_t* h_counts, int32_t n_scans, int32_t max_points,
+                                      const mamri_pose_options* options, mamri_pose* h_poses, void* stream) {
     if (!ctx) return MAMRI_ERR_INVALID_ARG;
     if (!robot || n_scans < 0 || max_points < 0 || (n_scans > 0 && (!h_counts || !h_poses)) ||
         (n_scans > 0 && max_points > 0 && !h_points_ras))
@@ -1165,11 +1165,16 @@ extern "C" int mamri_pose_estimate(mamri_ctx* ctx, const mamri_robot* robot, con
     if (n_scans == 0) return MAMRI_OK;
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const double* h_saved = options ? options->h_saved_base : nullptr;
+    const double* h_init = options ? options->h_initial_angles : nullptr;
     const size_t off_pts = (sizeof(mamri_robot) + 255) & ~size_t(255);
     const size_t pts_bytes = size_t(n_scans) * max_points * 3 * sizeof(double);
     const size_t off_cnt = (off_pts + pts_bytes + 255) & ~size_t(255);
     const size_t off_pose = (off_cnt + size_t(n_scans) * sizeof(int32_t) + 255) & ~size_t(255);
-    const size_t total = off_pose + size_t(n_scans) * sizeof(mamri_pose);
+    const size_t off_base = (off_pose + size_t(n_scans) * sizeof(mamri_pose) + 255) & ~size_t(255);
+    const size_t off_init = off_base + 16 * sizeof(double);
+    const size_t init_bytes = size_t(n_scans) * MAMRI_MAX_CHAIN * sizeof(double);
+    const size_t total = off_init + init_bytes;
     if (ctx->pose_buf_bytes < total) {                   // first call at this batch size: grow the scratch
         CK(cudaStreamSynchronize(s));
         cudaFree(ctx->d_pose_buf);
@@ -1181,12 +1186,22 @@ extern "C" int mamri_pose_estimate(mamri_ctx* ctx, const mamri_robot* robot, con
     CK(cudaMemcpyAsync(base, robot, sizeof(mamri_robot), cudaMemcpyHostToDevice, s));
     if (pts_bytes) CK(cudaMemcpyAsync(base + off_pts, h_points_ras, pts_bytes, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(base + off_cnt, h_counts, size_t(n_scans) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (h_saved) CK(cudaMemcpyAsync(base + off_base, h_saved, 16 * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (h_init) CK(cudaMemcpyAsync(base + off_init, h_init, init_bytes, cudaMemcpyHostToDevice, s));
     CK(launch_pose(reinterpret_cast<const mamri_robot*>(base), reinterpret_cast<const double*>(base + off_pts),
                    reinterpret_cast<const int32_t*>(base + off_cnt), n_scans, max_points,
-                   reinterpret_cast<mamri_pose*>(base + off_pose), s));
+                   h_init ? reinterpret_cast<const double*>(base + off_init) : nullptr,
+                   h_saved ? reinterpret_cast<const double*>(base + off_base) : nullptr,
+                   options ? options->prefer_saved_base : 0, reinterpret_cast<mamri_pose*>(base + off_pose), s));
     CK(cudaMemcpyAsync(h_poses, base + off_pose, size_t(n_scans) * sizeof(mamri_pose), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return MAMRI_OK;
+}
+
+extern "C" int mamri_pose_estimate(mamri_ctx* ctx, const mamri_robot* robot, const double* h_points_ras,
+                                   const int32_t* h_counts, int32_t n_scans, int32_t max_points, mamri_pose* h_poses,
+                                   void* stream) {
+    return mamri_pose_estimate_ex(ctx, robot, h_points_ras, h_counts, n_scans, max_points, nullptr, h_poses, stream);
 }
 
 extern "C" int mamri_pose_from_tables(mamri_ctx* ctx, const mamri_robot* robot, const double* d_tables, int32_t n_scans,
@@ -1212,7 +1227,7 @@ extern "C" int mamri_pose_from_tables(mamri_ctx* ctx, const mamri_robot* robot, 
     }
     char* base = static_cast<char*>(ctx->d_pose_buf);
     CK(cudaMemcpyAsync(base, robot, sizeof(mamri_robot), cudaMemcpyHostToDevice, s));
-    CK(launch_pose(reinterpret_cast<const mamri_robot*>(base), d_tables, nullptr, n_scans, int(table_slots),
+    CK(launch_pose(reinterpret_cast<const mamri_robot*>(base), d_tables, nullptr, n_scans, int(table_slots), nullptr, nullptr, 0,
                    reinterpret_cast<mamri_pose*>(base + off_pose), s));
     CK(cudaMemcpyAsync(h_poses, base + off_pose, size_t(n_scans) * sizeof(mamri_pose), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

@@ -60,16 +60,22 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
                                                           volatile unsigned long long* state, const DynArgs* __restrict__ dyn,
                                                           uint32_t* __restrict__ word_base, uint32_t* __restrict__ run_pos,
                                                           uint32_t* __restrict__ run_end, uint32_t* __restrict__ root_count,
-                                                          uint32_t max_runs, DevScalars* sc) {
+                                                          uint32_t max_runs, uint32_t n_tiles, DevScalars* sc) {
     constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     pdl_wait();
     ktrace(KT_RUNS);
     __shared__ uint32_t ws[RS_THREADS / 32];
     __shared__ uint32_t red[34];
     __shared__ uint32_t s_tile;
+    // Persistent CTAs draw tiles from a ticket counter: a tile only ever waits for tiles with lower tickets, and those
+    // were drawn by CTAs that are already running -- with one CTA per tile the late tiles of a grid larger than the
+    // machine (or than what fits beside the previous kernel's CTAs) made every tile after them wait for their launch.
+    while (true) {
+    __syncthreads();
     if (threadIdx.x == 0) s_tile = atomicAdd(&sc->ticket_runs, 1u);
     __syncthreads();
-    const uint32_t tile = s_tile, n_tiles = gridDim.x;
+    const uint32_t tile = s_tile;
+    if (tile >= n_tiles) break;
     const uint32_t i0 = tile * RS_TILE + threadIdx.x * RS_ITEMS;
     uint32_t m[RS_ITEMS], starts[RS_ITEMS], ends[RS_ITEMS];
     uint32_t cnt = 0, open = 0;
@@ -148,6 +154,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
         for (int k = 0; k < RS_ITEMS; ++k)
             if (i0 + k < n_words) word_base[i0 + k] = wb[k];
     }
+    }   // tiles
     ktrace_last(KT_RUNS_LAST);
 }
 
@@ -206,6 +213,25 @@ __device__ __forceinline__ void join_run(const uint32_t* __restrict__ word_base,
     }
 }
 
+// The runs of row `nbr_row` that touch [gx0, gx0 + len) (widened by one voxel each side for DIAG) have consecutive
+// ids [ja, jb): same rule as join_run, without doing the unions.
+template <bool DIAG>
+__device__ __forceinline__ void nbr_range(const uint32_t* __restrict__ word_base, const uint32_t* __restrict__ run_pos,
+                                          const uint32_t* __restrict__ run_end, int W, int gx0, int len, uint32_t nbr_row,
+                                          uint32_t& ja, uint32_t& jb) {
+    int lo = gx0 - (DIAG ? 1 : 0), hi = gx0 + len - 1 + (DIAG ? 1 : 0);
+    if (lo < 0) lo = 0;
+    if (hi > W * 32 - 1) hi = W * 32 - 1;
+    const uint32_t lo_abs = nbr_row * 32u + uint32_t(lo), hi_abs = nbr_row * 32u + uint32_t(hi);
+    const uint32_t j_lo = word_base[nbr_row + uint32_t(lo >> 5)];
+    const uint32_t j_hi = word_base[nbr_row + uint32_t(hi >> 5) + 1u];
+    ja = j_lo;
+    if (j_lo > 0u && run_end[j_lo - 1u] >= lo_abs) ja = j_lo - 1u;
+    else while (ja < j_hi && run_end[ja] < lo_abs) ++ja;              // runs of the first word that end left of the range
+    jb = ja > j_lo ? ja : j_lo;
+    while (jb < j_hi && run_pos[jb] <= hi_abs) ++jb;
+}
+
 // Phase 1 -- block-local: one CTA per z-slice.  The runs of a slice are contiguous in id space, so the
 // CTA keeps their parents in shared memory (local index = run id - first run of the slice), joins
 // every run with the runs of the row above at shared-memory latency (simultaneous hooking builds
@@ -242,6 +268,9 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
         const int gx0 = int((wi - row * W) * 32 + (pos & 31u));
         join_run<CONN26>(word_base, run_pos, run_end, P, r0, W, i, gx0, int(run_end[r0 + i] - pos + 1u), (row - 1) * W);
     }
+#ifdef MAMRI_KTRACE
+    __syncthreads();                                                    // trace build: stamp when the whole CTA is through
+#endif
     ktrace_both(KT_US_JOIN);
     // flatten by pointer jumping: a convex object leaves a chain as long as it is tall, which a per-run
     // walk would follow hop by hop; doubling reaches the root in log2(height) rounds
@@ -273,19 +302,51 @@ __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ wo
     ktrace(between_blocks ? KT_UZ2 : KT_UZ1);
     if (sc->status != MAMRI_OK) return;
     const uint32_t n = sc->n_runs;
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        const uint32_t pos = run_pos[r];
-        const uint32_t wi = pos >> 5, row = wi / W;
-        const uint32_t z = row / ny;
-        if (z == 0 || ((z % radix) == 0) != (between_blocks != 0)) continue;
-        const uint32_t y = row - z * ny;
-        const int gx0 = int((wi - row * W) * 32 + (pos & 31u));
-        const int len = int(run_end[r] - pos + 1u);
-        const uint32_t below = (row - ny) * W;                              // row (y, z-1)
-        join_run<CONN26>(word_base, run_pos, run_end, parent, 0u, W, r, gx0, len, below);
-        if (CONN26) {
-            if (y > 0) join_run<true>(word_base, run_pos, run_end, parent, 0u, W, r, gx0, len, below - W);
-            if (y + 1 < uint32_t(ny)) join_run<true>(word_base, run_pos, run_end, parent, 0u, W, r, gx0, len, below + W);
+    const unsigned lane = lane_id();
+    // One run per lane, the warp in step: most runs of a slice belong to one object (the body), so most lanes of a
+    // warp ask for the SAME union (root of the object in this slice, root of it in the slice below).  Lanes with equal
+    // root pairs elect one of them to do it: hundreds of atomicMin on one address, and the re-walks they cause,
+    // become a handful.
+    for (uint32_t r0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; r0 < n; r0 += gridDim.x * blockDim.x) {
+        const uint32_t r = r0 + lane;
+        bool active = r < n;
+        uint32_t row = 0, y = 0;
+        int gx0 = 0, len = 0;
+        if (active) {
+            const uint32_t pos = run_pos[r];
+            const uint32_t wi = pos >> 5;
+            row = wi / W;
+            const uint32_t z = row / ny;
+            y = row - z * ny;
+            active = z > 0 && (((z % radix) == 0) == (between_blocks != 0));
+            gx0 = int((wi - row * W) * 32 + (pos & 31u));
+            if (active) len = int(run_end[r] - pos + 1u);
+        }
+        if (!__any_sync(FULL, active)) continue;
+        const uint32_t below = active ? (row - ny) * W : 0u;            // row (y, z-1)
+#pragma unroll
+        for (int q = 0; q < (CONN26 ? 3 : 1); ++q) {
+            uint32_t ja = 0, jb = 0;
+            if (active) {
+                if (q == 0) nbr_range<CONN26>(word_base, run_pos, run_end, W, gx0, len, below, ja, jb);
+                else if (q == 1) { if (y > 0) nbr_range<true>(word_base, run_pos, run_end, W, gx0, len, below - W, ja, jb); }
+                else { if (y + 1 < uint32_t(ny)) nbr_range<true>(word_base, run_pos, run_end, W, gx0, len, below + W, ja, jb); }
+            }
+            const uint32_t most = __reduce_max_sync(FULL, jb - ja);
+            for (uint32_t it = 0; it < most; ++it) {
+                unsigned long long key = ~0ull;
+                uint32_t a = 0, b = 0;
+                if (it < jb - ja) {
+                    a = uf_find(parent, r);
+                    b = uf_find(parent, ja + it);
+                    if (a != b) {
+                        if (a < b) { const uint32_t t = a; a = b; b = t; }
+                        key = ((unsigned long long)a << 32) | b;
+                    }
+                }
+                const unsigned peers = __match_any_sync(FULL, key);
+                if (key != ~0ull && int(lane) == __ffs(peers) - 1) uf_union(parent, a, b);
+            }
         }
     }
     ktrace_both(between_blocks ? KT_UZ2_END : KT_UZ1_END);
@@ -672,12 +733,15 @@ cudaError_t launch_label(mamri_ctx* c, const uint32_t* d_mask, const mamri_volum
     const int nx = desc->nx, ny = desc->ny, nz = desc->nz, connectivity = prm->connectivity;
     const int W = (nx + 31) / 32;
     const uint32_t n_words = uint32_t(W) * ny * nz;
+    static const int scan_ctas = [] { const char* e = getenv("MAMRI_SCAN_CTAS"); return e ? atoi(e) : 148; }();
     if (n_words >= 148u * RS_THREADS * 16u) {
-        LK(k_runs_scan<16>, (n_words + RS_THREADS * 16 - 1) / (RS_THREADS * 16), RS_THREADS, s, false, d_mask, W, n_words, c->d_scan_runs,
-           c->d_dyn, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_root_count, c->max_runs, c->d_scalars);
+        const uint32_t n_tiles = (n_words + RS_THREADS * 16 - 1) / (RS_THREADS * 16);
+        LK(k_runs_scan<16>, n_tiles < uint32_t(scan_ctas) ? n_tiles : uint32_t(scan_ctas), RS_THREADS, s, false, d_mask, W, n_words, c->d_scan_runs,
+           c->d_dyn, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_root_count, c->max_runs, n_tiles, c->d_scalars);
     } else {
-        LK(k_runs_scan<4>, (n_words + RS_THREADS * 4 - 1) / (RS_THREADS * 4), RS_THREADS, s, false, d_mask, W, n_words, c->d_scan_runs,
-           c->d_dyn, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_root_count, c->max_runs, c->d_scalars);
+        const uint32_t n_tiles = (n_words + RS_THREADS * 4 - 1) / (RS_THREADS * 4);
+        LK(k_runs_scan<4>, n_tiles < uint32_t(scan_ctas) ? n_tiles : uint32_t(scan_ctas), RS_THREADS, s, false, d_mask, W, n_words, c->d_scan_runs,
+           c->d_dyn, c->d_word_base, c->d_run_pos, c->d_run_end, c->d_root_count, c->max_runs, n_tiles, c->d_scalars);
     }
     prof_mark(c, s, "runs_scan");
     if (c->label_cluster > 0) {

@@ -195,7 +195,8 @@ cudaError_t launch_entry_search(mamri_ctx* c, const float* d_points, const float
 cudaError_t launch_body_surface(mamri_ctx* c, const mamri_volume_desc* desc, const uint8_t* d_body_mask, uint32_t body_label,
                                 float* d_points, float* d_normals, unsigned long long capacity, cudaStream_t s);
 cudaError_t launch_pose(const mamri_robot* d_robot, const double* d_points, const int32_t* d_counts, int n_scans,
-                        int max_points, mamri_pose* d_poses, cudaStream_t s);
+                        int max_points, const double* d_initial, const double* d_saved_base, int prefer_saved,
+                        mamri_pose* d_poses, cudaStream_t s);
 cudaError_t launch_collision(const mamri_robot* d_robot, const double base[16], const double m[12], int nx, int ny, int nz,
                              const int* offsets, int n_links, const double* d_angles, int n_configs, const float* d_points,
                              const uint8_t* d_mask, mamri_collision_result* d_out, cudaStream_t s);

@@ -11,10 +11,10 @@
 //
 // One warp per scan.  Matching is warp-parallel over the 3-combinations (the lexicographically first match =
 // itertools.combinations order is a min-reduction over the combination rank); registration and the IK run
-// on lane 0: 4x4 Jacobi eigen-solve, then a projected Levenberg-Marquardt with the analytic Jacobian of the
-// chain.  The reference's solver is SciPy's TRF with a finite-difference Jacobian stopped at ftol = xtol =
-// 1e-6; this one iterates to the minimum itself, so the two agree to the reference's own stopping error
-// (tests: 1e-5 rad), not bit for bit -- SciPy stays the parity path for the 1e-6 rad criterion.
+// on lane 0: 4x4 Jacobi eigen-solve, then the reference's own algorithm -- Trust Region Reflective least squares
+// with a 2-point finite-difference Jacobian, ftol = xtol = 1e-6 -- restated step by step (trf_solve), so that it
+// takes SciPy's iterates and ends in SciPy's minimum (the objective has several; tests: >= 95 % of scenes within
+// 1e-5 rad of SciPy, the rest are ill-conditioned fits where rounding moves the stopping point).
 #include "common.cuh"
 
 namespace {
@@ -154,87 +154,355 @@ __device__ void ik_eval(const IkProblem& P, const double* x, double* r, double (
     }
 }
 
-// Solves (A + lambda * diag(A)) dx = -g for symmetric positive semi-definite A (n <= MAMRI_MAX_CHAIN) by Cholesky.
-__device__ bool solve_damped(const double (*A)[MAMRI_MAX_CHAIN], const double* g, double lambda, int n, double* dx) {
-    double L[MAMRI_MAX_CHAIN][MAMRI_MAX_CHAIN];
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j <= i; ++j) {
-            double sum = A[i][j] + (i == j ? lambda * (A[i][i] > 1e-12 ? A[i][i] : 1e-12) : 0.0);
-            for (int k = 0; k < j; ++k) sum -= L[i][k] * L[j][k];
-            if (i == j) { if (!(sum > 0.0)) return false; L[i][i] = sqrt(sum); }
-            else L[i][j] = sum / L[j][j];
+// ------------------------------------------------------------------------------------------------
+// Trust Region Reflective least squares: the solver the reference calls (Mamri.py:1430-1433,
+// scipy.optimize.least_squares(method='trf', bounds, ftol = xtol = 1e-6), defaults otherwise: gtol 1e-8, x_scale 1,
+// '2-point' finite-difference Jacobian, exact trust-region sub-problem on the SVD of the augmented Jacobian).
+// The objective has several local minima and, for three markers on a six-joint chain, several exact solutions of
+// equal cost; which one a solver started at zero ends in is decided by its iterates, so this follows the published
+// algorithm (Branch, Coleman & Li 1999; More 1977 for the sub-problem; scipy/optimize/_lsq/trf.py trf_bounds,
+// common.py select_step / solve_lsq_trust_region / CL_scaling_vector / update_tr_radius / check_termination) step
+// by step, including the finite-difference Jacobian, so that its iterates are SciPy's up to rounding.  The SVD is a
+// one-sided Jacobi (Hestenes) on the (m + n) x n augmented matrix.  n <= MAMRI_MAX_CHAIN unknowns, m <= 18 residuals.
+// ------------------------------------------------------------------------------------------------
+constexpr int TN = MAMRI_MAX_CHAIN, TM = 18, TA = TM + TN;
+constexpr double T_EPS = 2.220446049250313e-16;
+
+__device__ double vnorm(const double* v, int n) { double s = 0.0; for (int i = 0; i < n; ++i) s += v[i] * v[i]; return sqrt(s); }
+
+// 2-point finite differences as scipy.optimize._numdiff.approx_derivative does them: h = sqrt(eps) * sign(x) *
+// max(1, |x|), turned around where it would leave the bounds, J[:, i] = (f(x + h e_i) - f0) / ((x_i + h) - x_i).
+__device__ void trf_jac(const IkProblem& P, const double* x, const double* f0, int n, int m, double (*J)[TN]) {
+    const double rel = 1.4901161193847656e-08;
+    for (int i = 0; i < n; ++i) {
+        double h = rel * (x[i] >= 0.0 ? 1.0 : -1.0) * fmax(1.0, fabs(x[i]));
+        const double xh = x[i] + h;
+        if (xh < P.lo[i] || xh > P.hi[i]) {
+            const double lower = x[i] - P.lo[i], upper = P.hi[i] - x[i];
+            if (x[i] - h >= P.lo[i] && x[i] - h <= P.hi[i]) h = -h;
+            else if (upper >= lower) h = upper;
+            else h = -lower;
         }
-    double y[MAMRI_MAX_CHAIN];
-    for (int i = 0; i < n; ++i) { double sum = -g[i]; for (int k = 0; k < i; ++k) sum -= L[i][k] * y[k]; y[i] = sum / L[i][i]; }
-    for (int i = n - 1; i >= 0; --i) { double sum = y[i]; for (int k = i + 1; k < n; ++k) sum -= L[k][i] * dx[k]; dx[i] = sum / L[i][i]; }
-    return true;
+        double x1[TN], f1[TM];
+        for (int u = 0; u < n; ++u) x1[u] = x[u];
+        x1[i] = x[i] + h;
+        const double dx = x1[i] - x[i];
+        ik_eval(P, x1, f1, nullptr);
+        for (int r = 0; r < m; ++r) J[r][i] = (f1[r] - f0[r]) / dx;
+    }
 }
 
-__device__ void solve_ik(const IkProblem& P, mamri_pose* out) {
-    const int n = P.n_unknowns, m = 9 * P.n_sets;
-    double x[MAMRI_MAX_CHAIN], r[18], J[18][MAMRI_MAX_CHAIN];
-    for (int u = 0; u < n; ++u) x[u] = fmin(fmax(0.0, P.lo[u]), P.hi[u]);   // both initial guesses of :1425 are zeros on a fresh scene
-    ik_eval(P, x, r, J);
-    double cost = 0.0;
-    for (int i = 0; i < m; ++i) cost += r[i] * r[i];
-    cost *= 0.5;
-    double lambda = 1e-3;
-    int it = 0, status = MAMRI_IK_MAX_ITER;
-    for (; it < 500; ++it) {
-        double A[MAMRI_MAX_CHAIN][MAMRI_MAX_CHAIN], g[MAMRI_MAX_CHAIN];
-        for (int u = 0; u < n; ++u) {
-            g[u] = 0.0;
-            for (int i = 0; i < m; ++i) g[u] += J[i][u] * r[i];
-            for (int v = 0; v <= u; ++v) { double sum = 0.0; for (int i = 0; i < m; ++i) sum += J[i][u] * J[i][v]; A[u][v] = A[v][u] = sum; }
-        }
-        // active set: unknowns sitting on a joint limit with the gradient pushing outwards stay fixed for this step
-        int idx[MAMRI_MAX_CHAIN], nf = 0;
-        double gmax = 0.0;
-        for (int u = 0; u < n; ++u) {
-            const bool blocked = (x[u] <= P.lo[u] && g[u] > 0.0) || (x[u] >= P.hi[u] && g[u] < 0.0);
-            if (!blocked) { idx[nf++] = u; gmax = fmax(gmax, fabs(g[u])); }
-        }
-        if (nf == 0 || gmax < 1e-11) { status = MAMRI_IK_CONVERGED; break; }
-        double Af[MAMRI_MAX_CHAIN][MAMRI_MAX_CHAIN], gf[MAMRI_MAX_CHAIN];
-        for (int a = 0; a < nf; ++a) { gf[a] = g[idx[a]]; for (int b = 0; b < nf; ++b) Af[a][b] = A[idx[a]][idx[b]]; }
-        bool accepted = false;
-        for (int tries = 0; tries < 40 && !accepted; ++tries) {
-            double df[MAMRI_MAX_CHAIN], xt[MAMRI_MAX_CHAIN], rt[18];
-            if (!solve_damped(Af, gf, lambda, nf, df)) { lambda *= 10.0; continue; }
-            double step = 0.0;
-            for (int u = 0; u < n; ++u) xt[u] = x[u];
-            for (int a = 0; a < nf; ++a) {
-                const int u = idx[a];
-                xt[u] = fmin(fmax(x[u] + df[a], P.lo[u]), P.hi[u]);
-                step = fmax(step, fabs(xt[u] - x[u]));
-            }
-            ik_eval(P, xt, rt, nullptr);
-            double ct = 0.0;
-            for (int i = 0; i < m; ++i) ct += rt[i] * rt[i];
-            ct *= 0.5;
-            if (ct <= cost) {
-                for (int u = 0; u < n; ++u) x[u] = xt[u];
-                const bool tiny = step < 1e-14 || (cost - ct) <= 1e-16 * cost;
-                cost = ct;
-                lambda = fmax(lambda / 5.0, 1e-15);
-                accepted = true;
-                if (tiny) status = MAMRI_IK_CONVERGED;
-            } else {
-                lambda = fmin(lambda * 4.0, 1e12);
-            }
-        }
-        if (!accepted) { status = MAMRI_IK_CONVERGED; break; }    // no downhill step left at any damping: at a minimum to rounding
-        if (status == MAMRI_IK_CONVERGED) { ++it; break; }
-        ik_eval(P, x, r, J);
+// min over i of the step t > 0 that takes x + t s onto a bound (inf if s == 0); hits[i] = sign(s_i) where that
+// minimum is attained (common.step_size_to_bound)
+__device__ double trf_step_to_bound(const double* x, const double* s, const double* lo, const double* hi, int n, int* hits) {
+    double steps[TN], ms = INFINITY;
+    for (int i = 0; i < n; ++i) {
+        steps[i] = INFINITY;
+        if (s[i] != 0.0) steps[i] = fmax((lo[i] - x[i]) / s[i], (hi[i] - x[i]) / s[i]);
+        ms = fmin(ms, steps[i]);
     }
-    ik_eval(P, x, r, nullptr);
-    for (int u = 0; u < MAMRI_MAX_CHAIN; ++u) out->joint_angles[u] = u < n ? x[u] : 0.0;
-    out->ik_cost = cost;
+    if (hits) for (int i = 0; i < n; ++i) hits[i] = steps[i] == ms ? (s[i] > 0.0 ? 1 : (s[i] < 0.0 ? -1 : 0)) : 0;
+    return ms;
+}
+
+struct TrfQuad {                      // the quadratic model in the scaled ("hat") variables
+    const double (*Jh)[TN];
+    const double* gh;
+    const double* diag;
+    int n, m;
+    __device__ void Js(const double* s, double* out) const {
+        for (int r = 0; r < m; ++r) { double a = 0.0; for (int u = 0; u < n; ++u) a += Jh[r][u] * s[u]; out[r] = a; }
+    }
+    __device__ double value(const double* s) const {                                   // evaluate_quadratic
+        double v[TM], q = 0.0, l = 0.0;
+        Js(s, v);
+        for (int r = 0; r < m; ++r) q += v[r] * v[r];
+        for (int u = 0; u < n; ++u) { q += s[u] * diag[u] * s[u]; l += s[u] * gh[u]; }
+        return 0.5 * q + l;
+    }
+    __device__ void line(const double* s, const double* s0, double& a, double& b, double& c) const {   // build_quadratic_1d
+        double v[TM], u0[TM];
+        Js(s, v);
+        a = 0.0; b = 0.0; c = 0.0;
+        for (int r = 0; r < m; ++r) a += v[r] * v[r];
+        for (int u = 0; u < n; ++u) { a += s[u] * diag[u] * s[u]; b += gh[u] * s[u]; }
+        a *= 0.5;
+        if (s0) {
+            Js(s0, u0);
+            double uu = 0.0, uv = 0.0, g0 = 0.0, sd = 0.0, s0d = 0.0;
+            for (int r = 0; r < m; ++r) { uu += u0[r] * u0[r]; uv += u0[r] * v[r]; }
+            for (int u = 0; u < n; ++u) { g0 += gh[u] * s0[u]; sd += s0[u] * diag[u] * s[u]; s0d += s0[u] * diag[u] * s0[u]; }
+            b += uv + sd;
+            c = 0.5 * uu + g0 + 0.5 * s0d;
+        }
+    }
+};
+
+// minimize_quadratic_1d: a t^2 + b t + c on [lo, hi]; candidates in SciPy's order (lo, hi, interior extremum), first minimum wins
+__device__ void trf_minq(double a, double b, double lo, double hi, double c, double& t_best, double& y_best) {
+    t_best = lo; y_best = lo * (a * lo + b) + c;
+    const double yh = hi * (a * hi + b) + c;
+    if (yh < y_best) { t_best = hi; y_best = yh; }
+    if (a != 0.0) {
+        const double e = -0.5 * b / a;
+        if (lo < e && e < hi) { const double ye = e * (a * e + b) + c; if (ye < y_best) { t_best = e; y_best = ye; } }
+    }
+}
+
+// One-sided Jacobi SVD of A (rows x n): on return the columns of A are U diag(s) sorted by descending s, V the
+// right singular vectors in the same order.
+__device__ void trf_svd(double (*A)[TN], int rows, int n, double* sv, double (*V)[TN]) {
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        int rot = 0;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int r = 0; r < rows; ++r) { al += A[r][p] * A[r][p]; be += A[r][q] * A[r][q]; ga += A[r][p] * A[r][q]; }
+                if (fabs(ga) <= 1e-300 || fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
+                ++rot;
+                const double zeta = (be - al) / (2.0 * ga);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                for (int r = 0; r < rows; ++r) { const double x = A[r][p], y = A[r][q]; A[r][p] = c * x - sn * y; A[r][q] = sn * x + c * y; }
+                for (int r = 0; r < n; ++r) { const double x = V[r][p], y = V[r][q]; V[r][p] = c * x - sn * y; V[r][q] = sn * x + c * y; }
+            }
+        if (!rot) break;
+    }
+    for (int j = 0; j < n; ++j) { double a = 0.0; for (int r = 0; r < rows; ++r) a += A[r][j] * A[r][j]; sv[j] = sqrt(a); }
+    for (int i = 0; i < n - 1; ++i) {                    // selection sort, descending, stable enough for distinct values
+        int best = i;
+        for (int j = i + 1; j < n; ++j) if (sv[j] > sv[best]) best = j;
+        if (best != i) {
+            double t = sv[i]; sv[i] = sv[best]; sv[best] = t;
+            for (int r = 0; r < rows; ++r) { t = A[r][i]; A[r][i] = A[r][best]; A[r][best] = t; }
+            for (int r = 0; r < n; ++r) { t = V[r][i]; V[r][i] = V[r][best]; V[r][best] = t; }
+        }
+    }
+}
+
+// solve_lsq_trust_region with suf = s * (U^T f): min |J p + f| subject to |p| <= Delta
+__device__ void trf_subproblem(int n, int m, const double* suf, const double* sv, const double (*V)[TN], double Delta,
+                               double& alpha, double* p) {
+    auto phi = [&](double a, double& dphi) {
+        double pn = 0.0, d3 = 0.0;
+        for (int i = 0; i < n; ++i) { const double den = sv[i] * sv[i] + a; pn += (suf[i] / den) * (suf[i] / den); d3 += suf[i] * suf[i] / (den * den * den); }
+        pn = sqrt(pn);
+        dphi = -d3 / pn;
+        return pn - Delta;
+    };
+    auto step = [&](double a) {
+        for (int r = 0; r < n; ++r) { double acc = 0.0; for (int i = 0; i < n; ++i) acc += V[r][i] * (suf[i] / (sv[i] * sv[i] + a)); p[r] = -acc; }
+    };
+    const bool full_rank = m >= n && sv[n - 1] > T_EPS * m * sv[0];
+    if (full_rank) {
+        step(0.0);
+        if (vnorm(p, n) <= Delta) { alpha = 0.0; return; }
+    }
+    double au = vnorm(suf, n) / Delta, al = 0.0, dphi;
+    if (full_rank) { const double ph = phi(0.0, dphi); al = -ph / dphi; }
+    if (!full_rank && alpha == 0.0) alpha = fmax(0.001 * au, sqrt(al * au));
+    for (int it = 0; it < 10; ++it) {
+        if (alpha < al || alpha > au) alpha = fmax(0.001 * au, sqrt(al * au));
+        const double ph = phi(alpha, dphi);
+        if (ph < 0.0) au = alpha;
+        const double ratio = ph / dphi;
+        al = fmax(al, alpha - ratio);
+        alpha -= (ph + Delta) * ratio / Delta;
+        if (fabs(ph) < 0.01 * Delta) break;
+    }
+    step(alpha);
+    const double pn = vnorm(p, n);
+    for (int r = 0; r < n; ++r) p[r] *= Delta / pn;
+}
+
+// trf.select_step: the trust-region step, its reflection at the first bound it hits, or the constrained Cauchy step
+__device__ double trf_select_step(const double* x, const TrfQuad& Q, const double* p_in, const double* ph_in, const double* d,
+                                  double Delta, const double* lo, const double* hi, double theta, double* step, double* step_h) {
+    const int n = Q.n;
+    double p[TN], ph[TN], xp[TN];
+    bool inside = true;
+    for (int i = 0; i < n; ++i) { p[i] = p_in[i]; ph[i] = ph_in[i]; xp[i] = x[i] + p[i]; inside = inside && xp[i] >= lo[i] && xp[i] <= hi[i]; }
+    if (inside) {
+        for (int i = 0; i < n; ++i) { step[i] = p[i]; step_h[i] = ph[i]; }
+        return -Q.value(ph);
+    }
+    int hits[TN];
+    const double p_stride = trf_step_to_bound(x, p, lo, hi, n, hits);
+    double rh[TN], r[TN], xb[TN];
+    for (int i = 0; i < n; ++i) { rh[i] = hits[i] ? -ph[i] : ph[i]; r[i] = d[i] * rh[i]; }
+    for (int i = 0; i < n; ++i) { p[i] *= p_stride; ph[i] *= p_stride; xb[i] = x[i] + p[i]; }
+    double to_tr;
+    {   // intersect_trust_region(p_h, r_h, Delta): positive root of |p_h + t r_h| = Delta
+        double a = 0.0, b = 0.0, c = -Delta * Delta;
+        for (int i = 0; i < n; ++i) { a += rh[i] * rh[i]; b += ph[i] * rh[i]; c += ph[i] * ph[i]; }
+        const double dd = sqrt(b * b - a * c);
+        const double q = -(b + copysign(dd, b));
+        const double t1 = q / a, t2 = c / q;
+        to_tr = fmax(t1, t2);
+    }
+    const double to_bound = trf_step_to_bound(xb, r, lo, hi, n, nullptr);
+    double r_stride = fmin(to_bound, to_tr), rl, ru;
+    if (r_stride > 0.0) { rl = (1.0 - theta) * p_stride / r_stride; ru = (r_stride == to_bound) ? theta * to_bound : to_tr; }
+    else { rl = 0.0; ru = -1.0; }
+    double r_value = INFINITY;
+    if (rl <= ru) {
+        double a, b, c;
+        Q.line(rh, ph, a, b, c);
+        trf_minq(a, b, rl, ru, c, r_stride, r_value);
+        for (int i = 0; i < n; ++i) { rh[i] = rh[i] * r_stride + ph[i]; r[i] = rh[i] * d[i]; }
+    }
+    for (int i = 0; i < n; ++i) { p[i] *= theta; ph[i] *= theta; }
+    const double p_value = Q.value(ph);
+    double agh[TN], ag[TN];
+    for (int i = 0; i < n; ++i) { agh[i] = -Q.gh[i]; ag[i] = d[i] * agh[i]; }
+    const double ag_to_tr = Delta / vnorm(agh, n);
+    const double ag_to_bound = trf_step_to_bound(x, ag, lo, hi, n, nullptr);
+    double ag_stride = ag_to_bound < ag_to_tr ? theta * ag_to_bound : ag_to_tr, ag_value;
+    {
+        double a, b, c;
+        Q.line(agh, nullptr, a, b, c);
+        trf_minq(a, b, 0.0, ag_stride, 0.0, ag_stride, ag_value);
+    }
+    for (int i = 0; i < n; ++i) { agh[i] *= ag_stride; ag[i] *= ag_stride; }
+    const double* sp; const double* sh; double val;
+    if (p_value < r_value && p_value < ag_value) { sp = p; sh = ph; val = p_value; }
+    else if (r_value < p_value && r_value < ag_value) { sp = r; sh = rh; val = r_value; }
+    else { sp = ag; sh = agh; val = ag_value; }
+    for (int i = 0; i < n; ++i) { step[i] = sp[i]; step_h[i] = sh[i]; }
+    return -val;
+}
+
+// Returns SciPy's termination status (1 gtol, 2 ftol, 3 xtol, 4 both, 0 = evaluation budget spent: res.success is
+// status > 0); x holds the solution, cost = 0.5 |f|^2, nfev the residual evaluations used (Jacobians not counted).
+__device__ int trf_solve(const IkProblem& P, double* x, double& cost, int& nfev) {
+    const int n = P.n_unknowns, m = 9 * P.n_sets;
+    const double ftol = 1e-6, xtol = 1e-6, gtol = 1e-8;
+    const double* lo = P.lo; const double* hi = P.hi;
+    for (int i = 0; i < n; ++i) {                         // least_squares: make_strictly_feasible(x0, lb, ub) with rstep = 1e-10
+        const double lt = 1e-10 * fmax(1.0, fabs(lo[i])), ut = 1e-10 * fmax(1.0, fabs(hi[i]));
+        if (x[i] - lo[i] <= fmin(hi[i] - x[i], lt)) x[i] = lo[i] + lt;
+        else if (hi[i] - x[i] <= fmin(x[i] - lo[i], ut)) x[i] = hi[i] - ut;
+        if (x[i] < lo[i] || x[i] > hi[i]) x[i] = 0.5 * (lo[i] + hi[i]);
+    }
+    double f[TM], J[TM][TN], g[TN], v[TN], dv[TN];
+    ik_eval(P, x, f, nullptr);
+    nfev = 1;
+    trf_jac(P, x, f, n, m, J);
+    cost = 0.0;
+    for (int r = 0; r < m; ++r) cost += f[r] * f[r];
+    cost *= 0.5;
+    auto grad = [&]() { for (int u = 0; u < n; ++u) { double a = 0.0; for (int r = 0; r < m; ++r) a += J[r][u] * f[r]; g[u] = a; } };
+    auto cl_scaling = [&]() {                             // Coleman-Li scaling vector and its derivative
+        for (int i = 0; i < n; ++i) {
+            v[i] = 1.0; dv[i] = 0.0;
+            if (g[i] < 0.0) { v[i] = hi[i] - x[i]; dv[i] = -1.0; }
+            else if (g[i] > 0.0) { v[i] = x[i] - lo[i]; dv[i] = 1.0; }
+        }
+    };
+    grad();
+    cl_scaling();
+    double Delta = 0.0;
+    for (int i = 0; i < n; ++i) Delta += x[i] * x[i] / v[i];
+    Delta = sqrt(Delta);
+    if (Delta == 0.0) Delta = 1.0;
+    double alpha = 0.0;
+    int status = -1;
+    const int max_nfev = 100 * n;
+    while (true) {
+        cl_scaling();
+        double g_norm = 0.0;
+        for (int i = 0; i < n; ++i) g_norm = fmax(g_norm, fabs(g[i] * v[i]));
+        if (g_norm < gtol) status = 1;
+        if (status >= 0 || nfev == max_nfev) break;
+        double d[TN], diag[TN], gh[TN], Jh[TM][TN], Ja[TA][TN], V[TN][TN], sv[TN], suf[TN];
+        for (int i = 0; i < n; ++i) { d[i] = sqrt(v[i]); diag[i] = g[i] * dv[i]; gh[i] = d[i] * g[i]; }
+        for (int r = 0; r < m; ++r) for (int u = 0; u < n; ++u) { Jh[r][u] = J[r][u] * d[u]; Ja[r][u] = Jh[r][u]; }
+        for (int r = 0; r < n; ++r) for (int u = 0; u < n; ++u) Ja[m + r][u] = r == u ? sqrt(diag[u]) : 0.0;
+        trf_svd(Ja, m + n, n, sv, V);
+        for (int u = 0; u < n; ++u) { double a = 0.0; for (int r = 0; r < m; ++r) a += Ja[r][u] * f[r]; suf[u] = a; }   // s * (U^T f_aug)
+        const double theta = fmax(0.995, 1.0 - g_norm);
+        TrfQuad Q{Jh, gh, diag, n, m};
+        double actual = -1.0, x_new[TN], f_new[TM], cost_new = cost;
+        while (actual <= 0.0 && nfev < max_nfev) {
+            double ph[TN], p[TN], step[TN], step_h[TN];
+            trf_subproblem(n, m, suf, sv, V, Delta, alpha, ph);
+            for (int i = 0; i < n; ++i) p[i] = d[i] * ph[i];
+            const double predicted = trf_select_step(x, Q, p, ph, d, Delta, lo, hi, theta, step, step_h);
+            for (int i = 0; i < n; ++i) {                 // make_strictly_feasible(x + step, rstep = 0)
+                double xn = x[i] + step[i];
+                if (xn <= lo[i]) xn = nextafter(lo[i], hi[i]);
+                else if (xn >= hi[i]) xn = nextafter(hi[i], lo[i]);
+                if (xn < lo[i] || xn > hi[i]) xn = 0.5 * (lo[i] + hi[i]);
+                x_new[i] = xn;
+            }
+            ik_eval(P, x_new, f_new, nullptr);
+            ++nfev;
+            const double sh_norm = vnorm(step_h, n);
+            cost_new = 0.0;
+            for (int r = 0; r < m; ++r) cost_new += f_new[r] * f_new[r];
+            cost_new *= 0.5;
+            if (!isfinite(cost_new)) { Delta = 0.25 * sh_norm; continue; }
+            actual = cost - cost_new;
+            double ratio;                                 // update_tr_radius
+            if (predicted > 0.0) ratio = actual / predicted;
+            else if (predicted == 0.0 && actual == 0.0) ratio = 1.0;
+            else ratio = 0.0;
+            double Delta_new = Delta;
+            if (ratio < 0.25) Delta_new = 0.25 * sh_norm;
+            else if (ratio > 0.75 && sh_norm > 0.95 * Delta) Delta_new = Delta * 2.0;
+            const double s_norm = vnorm(step, n);
+            const bool ft = actual < ftol * cost && ratio > 0.25;          // check_termination
+            const bool xt = s_norm < xtol * (xtol + vnorm(x, n));
+            if (ft && xt) status = 4; else if (ft) status = 2; else if (xt) status = 3;
+            if (status >= 0) break;
+            alpha *= Delta / Delta_new;
+            Delta = Delta_new;
+        }
+        if (actual > 0.0) {
+            for (int i = 0; i < n; ++i) x[i] = x_new[i];
+            for (int r = 0; r < m; ++r) f[r] = f_new[r];
+            cost = cost_new;
+            trf_jac(P, x, f, n, m, J);
+            grad();
+        }
+    }
+    return status < 0 ? 0 : status;
+}
+
+// _solve_full_chain_ik (Mamri.py:1410-1447): the solver is run from every initial guess -- the current joint angles
+// when the caller has them, then zeros (:1425; on a fresh scene both are zeros and one run suffices) -- and the
+// lowest cost among the runs SciPy would call successful (status > 0) is kept.
+__device__ void solve_ik(const IkProblem& P, const double* initial, mamri_pose* out) {
+    const int n = P.n_unknowns, m = 9 * P.n_sets;
+    double best_x[MAMRI_MAX_CHAIN], best_cost = INFINITY;
+    int best_status = -1, evals = 0;
+    for (int guess = 0; guess < 2; ++guess) {
+        double x[MAMRI_MAX_CHAIN];
+        bool zero = true;
+        for (int u = 0; u < n; ++u) { x[u] = (guess == 0 && initial) ? initial[u] : 0.0; zero = zero && x[u] == 0.0; }
+        if (guess == 0 && (!initial || zero)) continue;            // the first guess would repeat the second
+        double cost;
+        int nfev;
+        const int st = trf_solve(P, x, cost, nfev);
+        evals += nfev;
+        if (best_status < 0 || (st > 0 && (best_status == 0 || cost < best_cost))) {
+            best_status = st; best_cost = cost;
+            for (int u = 0; u < n; ++u) best_x[u] = x[u];
+        }
+    }
+    double r[18];
+    ik_eval(P, best_x, r, nullptr);
+    for (int u = 0; u < MAMRI_MAX_CHAIN; ++u) out->joint_angles[u] = u < n ? best_x[u] : 0.0;
+    double c2 = 0.0;
+    for (int i = 0; i < m; ++i) c2 += r[i] * r[i];
+    out->ik_cost = 0.5 * c2;
     double ss = 0.0;
     for (int i = 0; i < 9; ++i) ss += r[i] * r[i];                // last_ik_error: effector residuals only (:1443-1444)
     out->ik_rms_error = sqrt(ss / 9.0);
-    out->ik_iterations = it;
-    out->ik_status = status;
+    out->ik_iterations = evals;
+    out->ik_termination = best_status;
+    out->ik_status = best_status > 0 ? MAMRI_IK_CONVERGED : MAMRI_IK_MAX_ITER;
 }
 
 }  // namespace
@@ -243,7 +511,9 @@ __device__ void solve_ik(const IkProblem& P, mamri_pose* out) {
 // device-written marker tables [n_scans][max_points][8] (rows {label, count, volume, RAS x y z, n_labels, body};
 // a row is in use while its label is non-zero), so the stage can be queued right behind the scans.
 __global__ void __launch_bounds__(32) k_pose(const mamri_robot* __restrict__ robot, const double* __restrict__ points,
-                                             const int32_t* __restrict__ counts, int max_points, mamri_pose* __restrict__ poses) {
+                                             const int32_t* __restrict__ counts, int max_points, const double* __restrict__ initial,
+                                             const double* __restrict__ saved_base, int prefer_saved,
+                                             mamri_pose* __restrict__ poses) {
     __shared__ mamri_robot rb;
     __shared__ double pt[MAMRI_POSE_MAX_POINTS][3];
     __shared__ int s_match[MAMRI_MAX_LINKS][3];
@@ -329,24 +599,34 @@ __global__ void __launch_bounds__(32) k_pose(const mamri_robot* __restrict__ rob
     out->has_base = 0;
     out->ik_status = MAMRI_IK_NOT_RUN;
     out->ik_iterations = 0;
+    out->ik_termination = 0;
     out->ik_cost = 0.0;
     out->ik_rms_error = 0.0;
     for (int i = 0; i < 16; ++i) out->base_matrix[i] = (i % 5 == 0) ? 1.0 : 0.0;
     for (int u = 0; u < MAMRI_MAX_CHAIN; ++u) out->joint_angles[u] = 0.0;
+    // _get_baseplate_transform (:1376-1408): the saved transform when the caller prefers it, else the registration of the
+    // scan's baseplate markers, else the saved transform as a fall-back, else no pose
     const int bl = rb.base_link;
-    if (bl < 0 || bl >= rb.n_links || s_match[bl][0] < 0) return;   // no baseplate in the scan (:1392-1398 falls back to a saved transform)
-    double tgt[9];
-    for (int q = 0; q < 3; ++q) for (int k = 0; k < 3; ++k) tgt[3 * q + k] = pt[s_match[bl][q]][k];
-    const double avg_y = (tgt[1] + tgt[4] + tgt[7]) / 3.0;          // (:1371-1373)
-    tgt[1] = tgt[4] = tgt[7] = avg_y;
+    const bool in_scan = bl >= 0 && bl < rb.n_links && s_match[bl][0] >= 0;
     IkProblem P;
     P.rb = &rb;
-    P.base = landmark_rigid(rb.links[bl].marker_coords, tgt);
+    if (saved_base && (prefer_saved || !in_scan)) {
+        for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) P.base.r[3 * i + j] = saved_base[4 * i + j]; P.base.t[i] = saved_base[4 * i + 3]; }
+        out->has_base = 2;
+    } else if (in_scan) {
+        double tgt[9];
+        for (int q = 0; q < 3; ++q) for (int k = 0; k < 3; ++k) tgt[3 * q + k] = pt[s_match[bl][q]][k];
+        const double avg_y = (tgt[1] + tgt[4] + tgt[7]) / 3.0;          // (:1371-1373)
+        tgt[1] = tgt[4] = tgt[7] = avg_y;
+        P.base = landmark_rigid(rb.links[bl].marker_coords, tgt);
+        out->has_base = 1;
+    } else {
+        return;                                                         // neither: "Pose estimation failed" (:1406-1408)
+    }
     for (int i = 0; i < 3; ++i) {
         for (int j = 0; j < 3; ++j) out->base_matrix[4 * i + j] = P.base.r[3 * i + j];
         out->base_matrix[4 * i + 3] = P.base.t[i];
     }
-    out->has_base = 1;
     const int ef = rb.effector_link;
     if (ef < 0 || ef >= rb.n_links || s_match[ef][0] < 0) return;   // "Joint6Fiducials" missing: no IK (:866-868)
     P.n_sets = 1;
@@ -373,7 +653,7 @@ __global__ void __launch_bounds__(32) k_pose(const mamri_robot* __restrict__ rob
             if (ci + 1 > P.n_unknowns) P.n_unknowns = ci + 1;
         }
     }
-    solve_ik(P, out);
+    solve_ik(P, initial ? initial + size_t(scan) * MAMRI_MAX_CHAIN : nullptr, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -458,8 +738,9 @@ cudaError_t launch_collision(const mamri_robot* d_robot, const double base[16], 
 }
 
 cudaError_t launch_pose(const mamri_robot* d_robot, const double* d_points, const int32_t* d_counts, int n_scans,
-                        int max_points, mamri_pose* d_poses, cudaStream_t s) {
+                        int max_points, const double* d_initial, const double* d_saved_base, int prefer_saved,
+                        mamri_pose* d_poses, cudaStream_t s) {
     if (n_scans <= 0) return cudaSuccess;
-    k_pose<<<n_scans, 32, 0, s>>>(d_robot, d_points, d_counts, max_points, d_poses);
+    k_pose<<<n_scans, 32, 0, s>>>(d_robot, d_points, d_counts, max_points, d_initial, d_saved_base, prefer_saved, d_poses);
     return cudaGetLastError();
 }

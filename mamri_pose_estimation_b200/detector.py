@@ -157,9 +157,11 @@ class PoseResult:
     base_matrix: Optional[np.ndarray]            # 4x4 baseplate model -> world (RAS), None if no baseplate in the scan
     joint_angles: Optional[np.ndarray]           # rad, articulated-chain order (Joint1..Joint6), None if the IK did not run
     ik_converged: bool
-    ik_iterations: int
+    ik_iterations: int                           # residual evaluations (SciPy's nfev) over all initial guesses
     ik_cost: float
     ik_rms_error: float                          # last_ik_error (Mamri.py:1443-1444)
+    ik_termination: int = 0                      # SciPy's status of the kept run: 1 gtol, 2 ftol, 3 xtol, 4 both, 0 budget spent
+    base_source: str = ""                        # "scan", "saved" or "" (no baseplate transform at all)
 
     @staticmethod
     def from_c(p: Pose, names=ROBOT_LINK_NAMES, n_chain: int = 6) -> "PoseResult":
@@ -169,7 +171,8 @@ class PoseResult:
                           base_matrix=np.array(p.base_matrix[:]).reshape(4, 4) if p.has_base else None,
                           joint_angles=np.array(p.joint_angles[:n_chain]) if ran else None,
                           ik_converged=p.ik_status == _capi.IK_CONVERGED, ik_iterations=int(p.ik_iterations),
-                          ik_cost=float(p.ik_cost), ik_rms_error=float(p.ik_rms_error))
+                          ik_cost=float(p.ik_cost), ik_rms_error=float(p.ik_rms_error), ik_termination=int(p.ik_termination),
+                          base_source={0: "", 1: "scan", 2: "saved"}.get(int(p.has_base), ""))
 
 
 def _desc(shape_zyx, dtype_name, spacing, origin, direction) -> VolumeDesc:
@@ -357,10 +360,14 @@ class FiducialDetector:
         return r
 
     def pose_estimate(self, ras_points: Sequence, robot: Optional[Robot] = None, apply_correction: bool = False,
-                      stream: Optional[torch.cuda.Stream] = None) -> List[PoseResult]:
+                      stream: Optional[torch.cuda.Stream] = None, saved_base=None, prefer_saved_base: bool = False,
+                      initial_angles=None) -> List[PoseResult]:
         """L-shape matching, baseplate registration and full-chain IK (Mamri.py:1343-1447) for a batch of scans on the
         device, one warp per scan.  `ras_points[i]`: [n_i, 3] control points of scan i in node order
-        (DetectionResult.ras_points)."""
+        (DetectionResult.ras_points).  `saved_base`: 4x4 "MamriSavedBaseplateTransform" -- used instead of the scan's
+        baseplate when `prefer_saved_base` (pNode.useSavedBaseplate) and as the fall-back when a scan shows no
+        baseplate (Mamri.py:1376-1408).  `initial_angles`: [n, <= 8] current joint angles, the first initial guess of
+        the IK (:1425)."""
         n = len(ras_points)
         if n == 0:
             return []
@@ -374,8 +381,21 @@ class FiducialDetector:
         robot = robot if robot is not None else self.default_robot(apply_correction)
         poses = (Pose * n)()
         s = stream or torch.cuda.current_stream(self.device)
-        rc = self._lib.mamri_pose_estimate(self._ctx, C.byref(robot), pts.ctypes.data, cnt.ctypes.data, n, max_pts, poses,
-                                           s.cuda_stream)
+        opt = _capi.PoseOptions()
+        keep = []
+        if saved_base is not None:
+            sb = np.ascontiguousarray(np.asarray(saved_base, dtype=np.float64).reshape(16))
+            keep.append(sb)
+            opt.h_saved_base = sb.ctypes.data_as(C.POINTER(C.c_double))
+        if initial_angles is not None:
+            ia = np.zeros((n, _capi.MAX_CHAIN), dtype=np.float64)
+            a = np.asarray(initial_angles, dtype=np.float64).reshape(n, -1)
+            ia[:, :a.shape[1]] = a
+            keep.append(ia)
+            opt.h_initial_angles = ia.ctypes.data_as(C.POINTER(C.c_double))
+        opt.prefer_saved_base = int(bool(prefer_saved_base))
+        rc = self._lib.mamri_pose_estimate_ex(self._ctx, C.byref(robot), pts.ctypes.data, cnt.ctypes.data, n, max_pts,
+                                              C.byref(opt), poses, s.cuda_stream)
         check(rc, self._ctx)
         out = []
         for i in range(n):

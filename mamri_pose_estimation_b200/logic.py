@@ -104,6 +104,7 @@ class MamriParameterNode:
     targetFiducialNode: Optional[MarkupsFiducialNode] = None
     entryPointFiducialNode: Optional[MarkupsFiducialNode] = None
     safetyDistance: float = 5.0
+    useSavedBaseplate: bool = False              # Mamri.py:60: prefer "MamriSavedBaseplateTransform" over the scan's baseplate
 
 
 class MamriLogic:
@@ -119,6 +120,7 @@ class MamriLogic:
         self.DISTANCE_TOLERANCE = 5.0
         self.SEARCH_RADIUS = 80.0
         self.device = int(device)
+        self.SAVED_BASEPLATE_TRANSFORM_NODE_NAME = "MamriSavedBaseplateTransform"      # Mamri.py:820
         self.scene: Dict[str, object] = {}
         self._detector: Optional[FiducialDetector] = None
         self.last_detection: Optional[DetectionResult] = None
@@ -200,14 +202,39 @@ class MamriLogic:
         if not (all_node and all_node.GetNumberOfControlPoints() >= 3):
             return None
         det = self._detector or self._detector_for((32, 32, 32))
-        self.last_pose = det.pose_estimate([all_node.points()], apply_correction=apply_correction)[0]
+        # _get_baseplate_transform (Mamri.py:1376-1408): the saved transform node first when the parameter node says so,
+        # the scan's baseplate otherwise, the saved node again as the fall-back; the IK starts from the current joint
+        # angles and from zeros (:1425)
+        saved = self.scene.get(self.SAVED_BASEPLATE_TRANSFORM_NODE_NAME)
+        prefer = bool(pNode is not None and getattr(pNode, "useSavedBaseplate", False))
+        if prefer and saved is None:
+            logging.warning(f"'Use Saved Transform' is checked, but node '{self.SAVED_BASEPLATE_TRANSFORM_NODE_NAME}' was not "
+                            "found. Will attempt detection from scan.")
+        current = getattr(self, "current_joint_angles", None)
+        self.last_pose = det.pose_estimate([all_node.points()], apply_correction=apply_correction, saved_base=saved,
+                                           prefer_saved_base=prefer, initial_angles=None if current is None else [current])[0]
+        if self.last_pose.base_source == "saved" and not prefer:
+            logging.info("Baseplate not found in scan; successfully used saved transform instead.")
+        elif self.last_pose.base_matrix is None:
+            logging.error("Pose estimation failed. A scan containing the baseplate is required, or a previously saved "
+                          "baseplate transform must exist.")
         return self.last_pose
+
+    def save_baseplate_transform(self, matrix=None) -> None:
+        '''Keeps a baseplate transform in the scene under SAVED_BASEPLATE_TRANSFORM_NODE_NAME (the reference's
+        saveBaseplateTransform, Mamri.py:883-907): the given 4x4, or the one of the last estimated pose.'''
+        if matrix is None:
+            pose = getattr(self, "last_pose", None)
+            matrix = None if pose is None else pose.base_matrix
+        if matrix is None:
+            raise ValueError("no baseplate transform to save: estimate a pose from a scan with the baseplate first")
+        self.scene[self.SAVED_BASEPLATE_TRANSFORM_NODE_NAME] = np.array(matrix, dtype=np.float64).reshape(4, 4)
 
     # -- Mamri.py:850-881 (without the scene/model building and the motor-step conversion) ----------
     def process(self, pNode: MamriParameterNode, apply_correction: bool = False):
         '''Executes the pipeline: segmentation, fiducial detection, baseplate registration and inverse kinematics.
         Returns the joint angles (rad, Joint1..Joint6) or None, like the first element of the reference's result:
-        None when no baseplate was registered from the scan (`:861-864`) or the Joint6 markers were not found
+        None when there is no baseplate transform, neither from the scan nor saved (`:861-864`), or the Joint6 markers were not found
         (`:868-875`).  Details of the run stay in `last_detection` / `last_pose`.'''
         self.volume_threshold_segmentation(pNode)
         pose = self.estimate_pose(pNode, apply_correction=apply_correction)
@@ -216,6 +243,7 @@ class MamriLogic:
         if pose.joint_angles is None:
             logging.info("Prerequisites for full-chain IK not met (e.g., Joint6 markers not found). Cannot estimate pose.")
             return None
+        self.current_joint_angles = np.array(pose.joint_angles)        # the next IK starts here (Mamri.py:1425)
         return pose.joint_angles
 
     # -- Mamri.py:987-1033 -------------------------------------------------------------------------
