@@ -1069,8 +1069,11 @@ extern "C" int mamri_entry_search(mamri_ctx* ctx, const float* d_points, const f
     if (!ctx) return MAMRI_ERR_INVALID_ARG;
     if (!result || !target) return fail(ctx, MAMRI_ERR_INVALID_ARG, "result/target is NULL");
     if (n < 0 || (n > 0 && (!d_points || !d_normals))) return fail(ctx, MAMRI_ERR_INVALID_ARG, "bad candidate arrays");
-    if (n_path_samples > 0 && d_path_mask && (!mask_desc || !ras_to_index))
-        return fail(ctx, MAMRI_ERR_INVALID_ARG, "path sampling needs mask_desc and ras_to_index");
+    if (n_path_samples < 0) return fail(ctx, MAMRI_ERR_INVALID_ARG, "n_path_samples must not be negative");
+    if (n_path_samples > 0 && (!d_path_mask || !mask_desc || !ras_to_index))
+        return fail(ctx, MAMRI_ERR_INVALID_ARG, "path sampling (n_path_samples > 0) needs d_path_mask, mask_desc and ras_to_index");
+    if (n_path_samples > 0 && (mask_desc->nx <= 0 || mask_desc->ny <= 0 || mask_desc->nz <= 0))
+        return fail(ctx, MAMRI_ERR_INVALID_ARG, "path mask dimensions must be positive");
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (n == 0) {
@@ -1079,7 +1082,7 @@ extern "C" int mamri_entry_search(mamri_ctx* ctx, const float* d_points, const f
         result->distance = INFINITY;
         return MAMRI_OK;
     }
-    const bool sample = n_path_samples > 0 && d_path_mask;
+    const bool sample = n_path_samples > 0;
     CK(launch_entry_search(ctx, d_points, d_normals, n, target, radius, wx, wy, cutoff, sample ? n_path_samples : 0,
                            sample ? d_path_mask : nullptr, sample ? mask_desc->nx : 0, sample ? mask_desc->ny : 0,
                            sample ? mask_desc->nz : 0, ras_to_index, path_free_value, s));

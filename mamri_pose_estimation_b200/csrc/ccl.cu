@@ -55,6 +55,48 @@ __device__ __forceinline__ uint32_t block_excl_scan_w(uint32_t v, uint32_t* ws /
     return off + inc - v;
 }
 
+// Words of one thread's part of a tile, and the run starts / ends in them.  A run starts where a set bit follows a
+// clear one and ends where a clear one follows a set one (row ends cut runs); the j-th start and the j-th end in raster
+// order belong to the same run, so lengths need no walk along the run: starts go to run_pos, ends to run_end, both
+// indexed by the same scan.  `open` = a run is open across the thread's first word (its end belongs to an earlier start).
+template <int RS_ITEMS>
+__device__ __forceinline__ uint32_t load_runs(const uint32_t* __restrict__ mask, uint32_t i0, uint32_t n_words, int W,
+                                              uint32_t (&m)[RS_ITEMS], uint32_t (&starts)[RS_ITEMS], uint32_t (&ends)[RS_ITEMS],
+                                              uint32_t& open, bool want_ends) {
+    if (i0 + RS_ITEMS <= n_words) {
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; k += 4) {
+            const uint4 q = *reinterpret_cast<const uint4*>(mask + i0 + k);
+            m[k] = q.x; m[k + 1] = q.y; m[k + 2] = q.z; m[k + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k) m[k] = (i0 + k < n_words) ? mask[i0 + k] : 0u;
+    }
+    const uint32_t xw0 = i0 % uint32_t(W);
+    uint32_t prev = (m[0] != 0u && i0 > 0) ? mask[i0 - 1] : 0u;
+    const uint32_t after = (want_ends && m[RS_ITEMS - 1] != 0u && i0 + RS_ITEMS < n_words) ? mask[i0 + RS_ITEMS] : 0u;
+    uint32_t xw = xw0, cnt = 0;
+    open = (xw0 != 0u && (prev >> 31) && (m[0] & 1u)) ? 1u : 0u;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const bool row_first = xw == 0u, row_last = xw + 1u == uint32_t(W);
+        uint32_t nxt = after;
+        if (k + 1 < RS_ITEMS) nxt = m[(k + 1) % RS_ITEMS];
+        starts[k] = run_starts(m[k], row_first ? 0u : prev);
+        ends[k] = m[k] & ~((m[k] >> 1) | (row_last ? 0u : (nxt << 31)));
+        cnt += __popc(starts[k]);
+        prev = m[k];
+        if (++xw == uint32_t(W)) xw = 0;
+    }
+    return cnt;
+}
+
+// Two phases over a CTA's tiles (tile = blockIdx.x + k gridDim.x), so that no tile's prefix waits for another tile's
+// table writes: (A) every tile's run count is published as soon as its words have been counted; (B) each tile sums
+// the counts before it (one CTA-wide look-back over values that phase A of all CTAs has published, or is about to,
+// without waiting for anything), re-reads its words from L2 and writes word_base and the run table.  With one CTA per
+// tile, or tiles handed out by a ticket, the late tiles of a big mask wait for the full duration of the earlier ones.
 template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
                                                           volatile unsigned long long* state, const DynArgs* __restrict__ dyn,
@@ -66,95 +108,72 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
     ktrace(KT_RUNS);
     __shared__ uint32_t ws[RS_THREADS / 32];
     __shared__ uint32_t red[34];
-    __shared__ uint32_t s_tile;
-    // Persistent CTAs draw tiles from a ticket counter: a tile only ever waits for tiles with lower tickets, and those
-    // were drawn by CTAs that are already running -- with one CTA per tile the late tiles of a grid larger than the
-    // machine (or than what fits beside the previous kernel's CTAs) made every tile after them wait for their launch.
-    while (true) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_tile = atomicAdd(&sc->ticket_runs, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= n_tiles) break;
-    const uint32_t i0 = tile * RS_TILE + threadIdx.x * RS_ITEMS;
-    uint32_t m[RS_ITEMS], starts[RS_ITEMS], ends[RS_ITEMS];
-    uint32_t cnt = 0, open = 0;
-    if (i0 + RS_ITEMS <= n_words) {
+    const uint32_t gen = dyn->gen;
+    // ---- phase A: counts
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t m[RS_ITEMS], starts[RS_ITEMS], ends[RS_ITEMS], open;
+        uint32_t cnt = load_runs<RS_ITEMS>(mask, tile * RS_TILE + threadIdx.x * RS_ITEMS, n_words, W, m, starts, ends, open, false);
 #pragma unroll
-        for (int k = 0; k < RS_ITEMS; k += 4) {
-            const uint4 q = *reinterpret_cast<const uint4*>(mask + i0 + k);
-            m[k] = q.x; m[k + 1] = q.y; m[k + 2] = q.z; m[k + 3] = q.w;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+        __syncthreads();                                               // ws is free again
+        if (lane_id() == 0) ws[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < RS_THREADS / 32; ++w) total += ws[w];
+            state[tile] = scan_pack(gen, total, 1u);
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < RS_ITEMS; ++k) m[k] = (i0 + k < n_words) ? mask[i0 + k] : 0u;
-    }
-    {
-        // a run starts where a set bit follows a clear one and ends where a clear one follows a set one (row ends
-        // cut runs); the j-th start and the j-th end in raster order belong to the same run, so lengths need no walk
-        // along the run: starts go to run_pos, ends to run_end, both indexed by the same scan
-        const uint32_t xw0 = i0 % uint32_t(W);
-        const bool any_first = m[0] != 0u, any_last = m[RS_ITEMS - 1] != 0u;
-        uint32_t prev = (any_first && i0 > 0) ? mask[i0 - 1] : 0u;
-        const uint32_t after = (any_last && i0 + RS_ITEMS < n_words) ? mask[i0 + RS_ITEMS] : 0u;
-        uint32_t xw = xw0;
-        open = (xw0 != 0u && (prev >> 31) && (m[0] & 1u)) ? 1u : 0u;      // a run is open across this thread's first word
-#pragma unroll
-        for (int k = 0; k < RS_ITEMS; ++k) {
-            const bool row_first = xw == 0u, row_last = xw + 1u == uint32_t(W);
-            uint32_t nxt = after;
-            if (k + 1 < RS_ITEMS) nxt = m[(k + 1) % RS_ITEMS];
-            starts[k] = run_starts(m[k], row_first ? 0u : prev);
-            ends[k] = m[k] & ~((m[k] >> 1) | (row_last ? 0u : (nxt << 31)));
-            cnt += __popc(starts[k]);
-            prev = m[k];
-            if (++xw == uint32_t(W)) xw = 0;
-        }
-    }
-    uint32_t total;
-    const uint32_t ex = block_excl_scan_w<RS_THREADS / 32>(cnt, ws, total);
-    const uint32_t before = scan_lookback_cta(state, tile, total, dyn->gen, red);
-    if (threadIdx.x == 0 && tile == n_tiles - 1) {      // grand total: every later stage keys off n_runs / status
-        if (before + total > max_runs) { sc->status = MAMRI_ERR_CAPACITY; sc->n_runs = 0; }
-        else sc->n_runs = before + total;
     }
     ktrace(KT_RUNS_LB);
-    ktrace_last(KT_RUNS_LB2);
-    uint32_t base = before + ex;
-    uint32_t e_idx = base - open;                                        // ends before this thread = starts before - open runs
-    uint32_t wb[RS_ITEMS];
+    // ---- phase B: prefixes and tables
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t i0 = tile * RS_TILE + threadIdx.x * RS_ITEMS;
+        uint32_t m[RS_ITEMS], starts[RS_ITEMS], ends[RS_ITEMS], open;
+        const uint32_t cnt = load_runs<RS_ITEMS>(mask, i0, n_words, W, m, starts, ends, open, true);
+        __syncthreads();
+        uint32_t total;
+        const uint32_t ex = block_excl_scan_w<RS_THREADS / 32>(cnt, ws, total);
+        const uint32_t before = scan_prefix_cta(state, tile, total, gen, red);
+        if (threadIdx.x == 0 && tile == n_tiles - 1) {  // grand total: every later stage keys off n_runs / status
+            if (before + total > max_runs) { sc->status = MAMRI_ERR_CAPACITY; sc->n_runs = 0; }
+            else sc->n_runs = before + total;
+        }
+        uint32_t base = before + ex;
+        uint32_t e_idx = base - open;                                    // ends before this thread = starts before - open runs
+        uint32_t wb[RS_ITEMS];
 #pragma unroll
-    for (int k = 0; k < RS_ITEMS; ++k) {
-        wb[k] = base;
-        const uint32_t bit0 = (i0 + uint32_t(k)) * 32u;
-        uint32_t st = starts[k];
-        while (st) {
-            const int b = __ffs(st) - 1;
-            st &= st - 1;
-            if (base < max_runs) {
-                run_pos[base] = bit0 + uint32_t(b);
-                root_count[base] = 0u;                                   // accumulated on the roots by the labelling
+        for (int k = 0; k < RS_ITEMS; ++k) {
+            wb[k] = base;
+            const uint32_t bit0 = (i0 + uint32_t(k)) * 32u;
+            uint32_t st = starts[k];
+            while (st) {
+                const int b = __ffs(st) - 1;
+                st &= st - 1;
+                if (base < max_runs) {
+                    run_pos[base] = bit0 + uint32_t(b);
+                    root_count[base] = 0u;                               // accumulated on the roots by the labelling
+                }
+                ++base;
             }
-            ++base;
+            uint32_t en = ends[k];
+            while (en) {
+                const int b = __ffs(en) - 1;
+                en &= en - 1;
+                if (e_idx < max_runs) run_end[e_idx] = bit0 + uint32_t(b);
+                ++e_idx;
+            }
         }
-        uint32_t en = ends[k];
-        while (en) {
-            const int b = __ffs(en) - 1;
-            en &= en - 1;
-            if (e_idx < max_runs) run_end[e_idx] = bit0 + uint32_t(b);
-            ++e_idx;
+        if (i0 + RS_ITEMS <= n_words) {
+#pragma unroll
+            for (int k = 0; k < RS_ITEMS; k += 4)
+                *reinterpret_cast<uint4*>(word_base + i0 + k) = make_uint4(wb[k], wb[k + 1], wb[k + 2], wb[k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < RS_ITEMS; ++k)
+                if (i0 + k < n_words) word_base[i0 + k] = wb[k];
         }
     }
-    if (i0 + RS_ITEMS <= n_words) {
-#pragma unroll
-        for (int k = 0; k < RS_ITEMS; k += 4)
-            *reinterpret_cast<uint4*>(word_base + i0 + k) = make_uint4(wb[k], wb[k + 1], wb[k + 2], wb[k + 3]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < RS_ITEMS; ++k)
-            if (i0 + k < n_words) word_base[i0 + k] = wb[k];
-    }
-    }   // tiles
     ktrace_last(KT_RUNS_LAST);
 }
 
@@ -259,30 +278,63 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
     ktrace_both(KT_US_N);
     if (n == 0) return;
     uint32_t* P = (n <= SLICE_SMEM_RUNS) ? sp : parent + r0;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) P[i] = i;
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t pos = run_pos[r0 + i];
-        const uint32_t wi = pos >> 5, row = wi / W;
-        if (row == z * ny) continue;                                        // y == 0: no row above in this slice
-        const int gx0 = int((wi - row * W) * 32 + (pos & 31u));
-        join_run<CONN26>(word_base, run_pos, run_end, P, r0, W, i, gx0, int(run_end[r0 + i] - pos + 1u), (row - 1) * W);
+    // (1) Every run points at the first run of the row above that touches it (a smaller id), or at itself: a forest,
+    // built with plain stores -- no atomics, no root walks.  Hooking root under root while the other threads do the
+    // same leaves chains as long as the object is tall, and the late warps walk them hop by hop.
+    constexpr int KEEP = 2;
+    uint32_t ja_[KEEP], jb_[KEEP];
+    bool more = false;
+    {
+        int k = 0;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x, ++k) {
+            const uint32_t pos = run_pos[r0 + i];
+            const uint32_t wi = pos >> 5, row = wi / W;
+            uint32_t ja = 0, jb = 0;
+            if (row != z * ny) {                                            // y == 0: no row above in this slice
+                const int gx0 = int((wi - row * W) * 32 + (pos & 31u));
+                nbr_range<CONN26>(word_base, run_pos, run_end, W, gx0, int(run_end[r0 + i] - pos + 1u), (row - 1) * W, ja, jb);
+            }
+            P[i] = ja < jb ? ja - r0 : i;
+            more = more || jb - ja > 1u;
+            if (k < KEEP) { ja_[k] = ja; jb_[k] = jb; }
+        }
     }
 #ifdef MAMRI_KTRACE
     __syncthreads();                                                    // trace build: stamp when the whole CTA is through
 #endif
     ktrace_both(KT_US_JOIN);
-    // flatten by pointer jumping: a convex object leaves a chain as long as it is tall, which a per-run
-    // walk would follow hop by hop; doubling reaches the root in log2(height) rounds
-    bool again = true;
-    while (again) {
-        __syncthreads();
-        bool changed = false;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t p = P[i], pp = P[p];   // a concurrent update of P[p] still yields an ancestor
-            if (pp != p) { P[i] = pp; changed = true; }
+    // (2) flatten by pointer jumping: log2(height) rounds
+    auto flatten = [&]() {
+        bool again = true;
+        while (again) {
+            __syncthreads();
+            bool changed = false;
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t p = P[i], pp = P[p];   // a concurrent update of P[p] still yields an ancestor
+                if (pp != p) { P[i] = pp; changed = true; }
+            }
+            again = __syncthreads_or(changed);
         }
-        again = __syncthreads_or(changed);
+    };
+    flatten();
+    // (3) the runs that touch more than one run of the row above join the trees of the others (two branches of an object
+    // meeting): real unions, on trees that are flat now; flatten again if there were any
+    if (__syncthreads_or(more)) {
+        int k = 0;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x, ++k) {
+            uint32_t ja, jb;
+            if (k < KEEP) { ja = ja_[k]; jb = jb_[k]; }
+            else {
+                const uint32_t pos = run_pos[r0 + i];
+                const uint32_t wi = pos >> 5, row = wi / W;
+                ja = jb = 0;
+                if (row != z * ny)
+                    nbr_range<CONN26>(word_base, run_pos, run_end, W, int((wi - row * W) * 32 + (pos & 31u)),
+                                      int(run_end[r0 + i] - pos + 1u), (row - 1) * W, ja, jb);
+            }
+            for (uint32_t j = ja + 1; j < jb; ++j) uf_union(P, i, j - r0);
+        }
+        flatten();
     }
     ktrace_both(KT_US_FLAT);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) parent[r0 + i] = r0 + P[i];
@@ -398,9 +450,11 @@ __global__ void __launch_bounds__(FR_THREADS) k_flatten_rank(uint32_t* parent, c
             uint32_t key = MAMRI_NONE, v[1] = {0u};
             is_root[k] = 0;
             if (r < n) {
-                uint32_t x = r, p = parent[x];
-                while (p != x) { x = p; p = parent[x]; }
-                parent[r] = x;                                       // roots stay fixed points: concurrent walkers stay correct
+                // path halving on the way up: the slice roots of a tall object hang in chains of up to 2 * radix hops after
+                // the two merge rounds, and every run of the object walks them at the same time -- whoever gets there
+                // first shortens the way for the others (roots stay fixed points: concurrent walkers stay correct)
+                const uint32_t x = uf_find(parent, r);
+                parent[r] = x;
                 is_root[k] = (x == r);
                 key = x;
                 v[0] = run_end[r] - run_pos[r] + 1u;

@@ -337,8 +337,10 @@ class FiducialDetector:
         tgt = (C.c_double * 3)(*[float(v) for v in target])
         res = EntryResult()
         md, m2i, mptr = None, None, None
-        if n_path_samples and path_mask is not None:
-            if not (path_mask.is_cuda and path_mask.is_contiguous() and path_mask.dtype == torch.uint8):
+        if n_path_samples:
+            if path_mask is None or ras_to_index is None:
+                raise ValueError("needle-path sampling (n_path_samples > 0) needs path_mask and ras_to_index")
+            if not (path_mask.is_cuda and path_mask.is_contiguous() and path_mask.dtype == torch.uint8 and path_mask.dim() == 3):
                 raise ValueError("path_mask must be a contiguous uint8 CUDA tensor [nz, ny, nx]")
             md = C.byref(_desc(tuple(path_mask.shape), "uint8", (1, 1, 1), (0, 0, 0), IDENTITY))
             m2i = (C.c_double * 12)(*[float(v) for v in np.asarray(ras_to_index, dtype=np.float64).reshape(12)])

@@ -1,5 +1,6 @@
 """Golden fixtures of the stages around the segmentation (tests/golden/stages/*.npz, made by
 tests/golden/make_golden_stages.py): the oracles on CPU, and the CUDA path on the GPU, must reproduce them."""
+import math
 import os
 
 import numpy as np
@@ -70,10 +71,10 @@ def test_cuda_reproduces_stage_goldens(cuda_lib):
     assert np.array_equal(pts.cpu().numpy(), g["points"]) and np.array_equal(nrm.cpu().numpy(), g["normals"])
     r = det.entry_search(pts, nrm, g["target"])
     assert r["index"] == int(g["entry_index"]) and r["distance"] == float(g["entry_distance"])
-    # matching + registration (+ IK where the device solver ends in SciPy's basin)
+    # matching + registration + IK (the device solver is SciPy's algorithm restated: it ends where SciPy does)
     g = np.load(os.path.join(DIR, "p1_pose_12_scans.npz"))
     poses = det.pose_estimate([g["points"][i, :g["counts"][i]] for i in range(len(g["counts"]))])
-    agree = 0
+    agree, n_ik = 0, 0
     for i, p in enumerate(poses):
         m = -np.ones((16, 3), dtype=np.int32)
         for jn, ids in p.identified.items():
@@ -83,12 +84,11 @@ def test_cuda_reproduces_stage_goldens(cuda_lib):
         if p.base_matrix is not None:
             assert np.abs(p.base_matrix - g["base"][i]).max() < 1e-9
         assert (p.joint_angles is not None) == bool(g["has_ik"][i])
-        if p.joint_angles is not None and np.abs(p.joint_angles - g["scipy_angles"][i]).max() < 0.05:
-            agree += 1
-            # SciPy stops at ftol = xtol = 1e-6: a few 1e-5 rad short of the minimum where the fit is good, ~1e-3 in the
-            # flat valleys of scenes whose markers do not fit the model
-            assert np.abs(p.joint_angles - g["scipy_angles"][i]).max() < (1e-4 if p.ik_cost < 10.0 else 1e-2)
-    assert agree >= 2
+        if p.joint_angles is not None:
+            n_ik += 1
+            # same iterates as SciPy: 1e-5 rad where the markers fit the model, 1e-2 in the flat valleys of a misfit
+            agree += bool(np.abs(p.joint_angles - g["scipy_angles"][i]).max() < (1e-5 if p.ik_cost < 10.0 else 1e-2))
+    assert agree >= math.ceil(0.95 * n_ik), (agree, n_ik)
     # collision sampling
     g = np.load(os.path.join(DIR, "k1_collision_24_configs.npz"))
     body = _unpack(g["body_bits"], g["shape"])

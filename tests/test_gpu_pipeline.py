@@ -448,3 +448,49 @@ def test_bit_packed_body_mask_equals_uint8_body_mask(cuda_lib):
         assert r[i].body_label == ora.body_label
         assert np.array_equal(unpack_body_bits(hb[i], v.shape), ora.body_mask if ora.body_mask is not None else np.zeros_like(v, dtype=np.uint8))
     bp.close()
+
+
+@pytest.mark.gpu
+def test_entry_search_at_config_c5_size(cuda_lib):
+    """BASELINE config C5 at full size on one GPU: 1,048,576 skin-surface candidates; the winner (index and float64
+    distance) is bit-identical to the reference loop restated in NumPy (Mamri.py:1008-1023), with and without sharding
+    the candidates into blocks and reducing the block winners the way distributed.gather_entry_results does."""
+    import torch
+    from mamri_pose_estimation_b200.detector import FiducialDetector
+    n = 1 << 20
+    pts, nrm, tgt = phantom.surface_candidates(n)
+    wi, wd = kin.find_entry_point(pts, nrm, tgt)
+    det = FiducialDetector((64, 64, 64))
+    p, q = torch.from_numpy(pts).cuda(), torch.from_numpy(nrm).cuda()
+    r = det.entry_search(p, q, tgt)
+    assert r["index"] == wi and r["distance"] == wd and wi >= 0
+    best = (float("inf"), -1)
+    for lo in range(0, n, n // 8):                            # 8 blocks, as 8 ranks would hold them
+        b = det.entry_search(p[lo:lo + n // 8].contiguous(), q[lo:lo + n // 8].contiguous(), tgt)
+        if b["index"] >= 0 and (b["distance"], b["index"] + lo) < best:
+            best = (b["distance"], b["index"] + lo)
+    assert best == (wd, wi)
+    # argument errors are reported, not guessed around
+    with pytest.raises(ValueError):
+        det.entry_search(p, q, tgt, n_path_samples=8)
+    det.close()
+
+
+@pytest.mark.gpu
+def test_one_process_two_devices(cuda_lib):
+    """One process driving two GPUs (mamri_create takes any device): the opt-in to more than 48 KB of dynamic shared
+    memory is per device, so a context created on the second device must run the tile kernels too."""
+    import torch
+    from mamri_pose_estimation_b200.detector import FiducialDetector
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    ph = phantom.config_c2()
+    vol = phantom.generate(phantom.small_phantom(dims=(512, 64, 48), seed=5))        # rows of 512 voxels: > 48 KB tiles
+    sm = phantom.small_phantom(dims=(512, 64, 48), seed=5)
+    ora = seg.detect_fiducials(vol, _geom(sm))
+    for dev in (0, 1):
+        det = FiducialDetector((512, 64, 48), device=dev)
+        res = det.detect(torch.from_numpy(vol).to(f"cuda:{dev}"), spacing=sm.spacing, origin=sm.origin, direction=sm.direction,
+                         want_mask=True, want_labels=True)
+        assert np.array_equal(res.mask.cpu().numpy(), ora.closed) and np.array_equal(res.labels.cpu().numpy().view(np.uint32), ora.labels)
+        det.close()
