@@ -450,11 +450,12 @@ __global__ void __launch_bounds__(FR_THREADS) k_flatten_rank(uint32_t* parent, c
             uint32_t key = MAMRI_NONE, v[1] = {0u};
             is_root[k] = 0;
             if (r < n) {
-                // path halving on the way up: the slice roots of a tall object hang in chains of up to 2 * radix hops after
-                // the two merge rounds, and every run of the object walks them at the same time -- whoever gets there
-                // first shortens the way for the others (roots stay fixed points: concurrent walkers stay correct)
-                const uint32_t x = uf_find(parent, r);
-                parent[r] = x;
+                // plain walk, and only parent[r] is written: a walker that shortened other nodes' paths on its way (path
+                // halving) could overwrite a parent[r'] that its owner has already set to the root with a nearer ancestor,
+                // and the filter pass relies on parent[] holding roots
+                uint32_t x = r, p = parent[x];
+                while (p != x) { x = p; p = parent[x]; }
+                parent[r] = x;                                       // roots stay fixed points: concurrent walkers stay correct
                 is_root[k] = (x == r);
                 key = x;
                 v[0] = run_end[r] - run_pos[r] + 1u;

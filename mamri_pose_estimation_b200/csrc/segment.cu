@@ -825,6 +825,7 @@ __device__ __forceinline__ void ball_walk(const uint32_t* col, uint32_t row_stri
     for (int y = 0; y < SY; ++y)
 #pragma unroll
         for (int j = 0; j < RING; ++j) acc[y][j] = NEUTRAL;
+#pragma unroll 1
     for (uint32_t k = k0; k < k1; ++k) {
         uint32_t Q[NC][SY];
 #pragma unroll
@@ -1037,7 +1038,7 @@ static cudaError_t closing_fused_r(mamri_ctx* c, int nx, int ny, int nz, int geo
     if (e_ctas > 0) per_sm = uint32_t(e_ctas);
     uint32_t grid = 148u * per_sm;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    static const int specialise = [] { const char* e = getenv("MAMRI_CLOSE_SPECIALISE"); return e ? atoi(e) : 1; }();
+    static const int specialise = [] { const char* e = getenv("MAMRI_CLOSE_SPECIALISE"); return e ? atoi(e) : 0; }();
     if (specialise && R == 2 && SYD == 4 && SYE == 2 && a.TY == 16 && a.TZ == 16 && (a.Wp == 12 || a.Wp == 20 || a.Wp == 36)) {
         // the reference's radius on rows of 256 / 512 / 1024 voxels: strides known at compile time
         if (a.Wp == 12) LKS(k_close_fused<2, 4, 2, 12, 16, 16>, grid, threads, smem, s, false, c->d_raw, c->d_closed, c->d_dyn, c->d_scalars, a);
