@@ -34,7 +34,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 // RS_TILE words (16 consecutive words per thread, 128-bit loads), scans its run-start counts, gets
 // the count of all earlier tiles by decoupled look-back and writes its part of both tables.
 // Tiles of RS_THREADS x ITEMS words: 16 words per thread on large masks (few, large tiles), 4 on small ones (enough
-// CTAs to use the machine).  The prefix of a tile comes from a CTA-wide look-back (scan_lookback_cta).
+// CTAs to use the machine).
 constexpr int RS_THREADS = 512;
 
 template <int WARPS>
@@ -94,8 +94,8 @@ __device__ __forceinline__ uint32_t load_runs(const uint32_t* __restrict__ mask,
 
 // Two phases over a CTA's tiles (tile = blockIdx.x + k gridDim.x), so that no tile's prefix waits for another tile's
 // table writes: (A) every tile's run count is published as soon as its words have been counted; (B) each tile sums
-// the counts before it (one CTA-wide look-back over values that phase A of all CTAs has published, or is about to,
-// without waiting for anything), re-reads its words from L2 and writes word_base and the run table.  With one CTA per
+// the counts before it (values that phase A of all CTAs has published, or is about to, without waiting for
+// anything), re-reads its words from L2 and writes word_base and the run table.  With one CTA per
 // tile, or tiles handed out by a ticket, the late tiles of a big mask wait for the full duration of the earlier ones.
 template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __restrict__ mask, int W, uint32_t n_words,
@@ -131,10 +131,33 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
         const uint32_t i0 = tile * RS_TILE + threadIdx.x * RS_ITEMS;
         uint32_t m[RS_ITEMS], starts[RS_ITEMS], ends[RS_ITEMS], open;
         const uint32_t cnt = load_runs<RS_ITEMS>(mask, i0, n_words, W, m, starts, ends, open, true);
+        // prefix of the tile = sum of the published counts of all earlier tiles (each thread reads a share of them; a
+        // count of this launch that is not there yet is about to be: phase A waits for nothing), exclusive scan of the
+        // threads' own counts: one exchange through shared memory serves both
+        uint32_t acc = 0;
+        {
+            const unsigned long long g30 = gen & 0x3FFFFFFFu;
+            for (uint32_t idx = threadIdx.x; idx < tile; idx += blockDim.x) {
+                unsigned long long v;
+                do { v = state[idx]; } while ((v >> 34) != g30);
+                acc += uint32_t(v >> 2);
+            }
+        }
+        const uint32_t inc = warp_incl_scan(cnt);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        __syncthreads();                                               // ws / red are free again
+        if (lane_id() == 31) ws[threadIdx.x >> 5] = inc;
+        if (lane_id() == 0) red[threadIdx.x >> 5] = acc;
         __syncthreads();
-        uint32_t total;
-        const uint32_t ex = block_excl_scan_w<RS_THREADS / 32>(cnt, ws, total);
-        const uint32_t before = scan_prefix_cta(state, tile, total, gen, red);
+        uint32_t ex = inc - cnt, total = 0, before = 0;
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) {
+            const uint32_t t = ws[w];
+            if (w < int(threadIdx.x >> 5)) ex += t;
+            total += t;
+            before += red[w];
+        }
         if (threadIdx.x == 0 && tile == n_tiles - 1) {  // grand total: every later stage keys off n_runs / status
             if (before + total > max_runs) { sc->status = MAMRI_ERR_CAPACITY; sc->n_runs = 0; }
             else sc->n_runs = before + total;

@@ -383,108 +383,6 @@ __device__ __forceinline__ uint32_t scan_lookback(volatile unsigned long long* s
     return excl;
 }
 
-// Same, called by EVERY thread of the CTA (blockDim.x a multiple of 32, at most 1024): one window covers blockDim.x
-// earlier tiles, so with no more tiles than threads -- all of them resident -- the prefix is one round trip to L2 and
-// one block reduction instead of a chain of 32-tile windows.  `red` is shared scratch of 34 words.
-__device__ __forceinline__ uint32_t scan_lookback_cta(volatile unsigned long long* state, uint32_t tile, uint32_t total,
-                                                      uint32_t gen, uint32_t* red) {
-    const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5, nw = blockDim.x >> 5;
-    if (tile == 0) {
-        if (tid == 0) state[0] = scan_pack(gen, total, 2u);
-        return 0u;
-    }
-    if (tid == 0) state[tile] = scan_pack(gen, total, 1u);
-    const unsigned long long g30 = gen & 0x3FFFFFFFu;
-    uint32_t excl = 0;
-    int pos = int(tile);
-    while (true) {
-        const int idx = pos - 1 - int(tid);
-        uint32_t flag = 2u, val = 0u;                    // before the first tile: inclusive prefix 0
-        if (idx >= 0) {
-            unsigned long long v;
-            do {
-                v = state[idx];
-                flag = ((v >> 34) == g30) ? uint32_t(v & 3u) : 0u;
-            } while (flag == 0u);
-            val = uint32_t(v >> 2);
-        }
-        if (tid == 0) red[33] = 0xFFFFFFFFu;
-        __syncthreads();
-        // nearest earlier tile with an inclusive prefix = smallest thread index that saw flag 2
-        const unsigned incl = __ballot_sync(FULL, flag == 2u);
-        if (lane == 0 && incl) atomicMin(&red[33], wid * 32u + uint32_t(__ffs(incl) - 1));
-        __syncthreads();
-        const uint32_t first = red[33];
-        uint32_t c = tid <= first ? val : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-        if (lane == 0) red[wid] = c;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t t = lane < nw ? red[lane] : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-            if (lane == 0) red[32] = t;
-        }
-        __syncthreads();
-        excl += red[32];
-        if (first != 0xFFFFFFFFu) break;
-        pos -= int(blockDim.x);
-    }
-    if (tid == 0) state[tile] = scan_pack(gen, excl + total, 2u);
-    return excl;
-}
-
-// Same for a two-phase scan whose tiles have all published their own totals (flag 1) in a first phase: returns the sum
-// of the totals of the earlier tiles and publishes the tile's inclusive prefix (flag 2), which lets the tiles more than
-// blockDim.x after it stop their look-back there.
-__device__ __forceinline__ uint32_t scan_prefix_cta(volatile unsigned long long* state, uint32_t tile, uint32_t total,
-                                                    uint32_t gen, uint32_t* red) {
-    const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5, nw = blockDim.x >> 5;
-    if (tile == 0) {
-        if (tid == 0) state[0] = scan_pack(gen, total, 2u);
-        return 0u;
-    }
-    const unsigned long long g30 = gen & 0x3FFFFFFFu;
-    uint32_t excl = 0;
-    int pos = int(tile);
-    while (true) {
-        const int idx = pos - 1 - int(tid);
-        uint32_t flag = 2u, val = 0u;                    // before the first tile: inclusive prefix 0
-        if (idx >= 0) {
-            unsigned long long v;
-            do {
-                v = state[idx];
-                flag = ((v >> 34) == g30) ? uint32_t(v & 3u) : 0u;
-            } while (flag == 0u);
-            val = uint32_t(v >> 2);
-        }
-        if (tid == 0) red[33] = 0xFFFFFFFFu;
-        __syncthreads();
-        const unsigned incl = __ballot_sync(FULL, flag == 2u);
-        if (lane == 0 && incl) atomicMin(&red[33], wid * 32u + uint32_t(__ffs(incl) - 1));
-        __syncthreads();
-        const uint32_t first = red[33];
-        uint32_t c = tid <= first ? val : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-        if (lane == 0) red[wid] = c;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t t = lane < nw ? red[lane] : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-            if (lane == 0) red[32] = t;
-        }
-        __syncthreads();
-        excl += red[32];
-        if (first != 0xFFFFFFFFu) break;
-        pos -= int(blockDim.x);
-    }
-    if (tid == 0) state[tile] = scan_pack(gen, excl + total, 2u);
-    return excl;
-}
-
 // ------------------------------------------------------------------------------------------------
 // aggregation: warp shuffles first, then a per-CTA shared-memory cache, then global atomics
 // ------------------------------------------------------------------------------------------------

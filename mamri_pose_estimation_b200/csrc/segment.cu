@@ -825,7 +825,6 @@ __device__ __forceinline__ void ball_walk(const uint32_t* col, uint32_t row_stri
     for (int y = 0; y < SY; ++y)
 #pragma unroll
         for (int j = 0; j < RING; ++j) acc[y][j] = NEUTRAL;
-#pragma unroll 1
     for (uint32_t k = k0; k < k1; ++k) {
         uint32_t Q[NC][SY];
 #pragma unroll
@@ -870,15 +869,14 @@ __device__ __forceinline__ void ball_walk(const uint32_t* col, uint32_t row_stri
     }
 }
 
-// WP / TYC / TZC: padded row length and tile shape as compile-time constants (0 = take them from the arguments).  With
-// them every shared-memory address of the strip walks is base + immediate; with run-time strides a fifth of the
-// kernel's instructions were integer multiply-adds computing addresses (ncu source view, round 2).
-template <int R, int SYD, int SYE, int WP = 0, int TYC = 0, int TZC = 0>
+// (Strides and tile shape are run-time values on purpose: variants with the padded row length and the tile shape as
+// template constants -- every shared-memory address base + immediate, a fifth fewer instructions -- measured 13 us
+// SLOWER in the dilation pass on the B200, so they were dropped.)
+template <int R, int SYD, int SYE>
 __global__ void __launch_bounds__(512) k_close_fused(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
                                                      const DynArgs* __restrict__ dyn, DevScalars* sc, FusedArgs a) {
     extern __shared__ __align__(128) uint32_t tile[];
     __shared__ uint32_t s_ticket;
-    if (WP) { a.Wp = WP; a.TY = TYC; a.TZ = TZC; }                  // constants from here on
     const uint32_t SY_ = a.TY + 4 * R, SZ_ = a.TZ + 4 * R;          // source rows / slices held
     const uint32_t DY = a.TY + 2 * R, DZ = a.TZ + 2 * R;            // dilated rows / slices held
     uint32_t* s_src = tile;                                         // [SZ_][SY_][Wp]
@@ -1038,15 +1036,7 @@ static cudaError_t closing_fused_r(mamri_ctx* c, int nx, int ny, int nz, int geo
     if (e_ctas > 0) per_sm = uint32_t(e_ctas);
     uint32_t grid = 148u * per_sm;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    static const int specialise = [] { const char* e = getenv("MAMRI_CLOSE_SPECIALISE"); return e ? atoi(e) : 0; }();
-    if (specialise && R == 2 && SYD == 4 && SYE == 2 && a.TY == 16 && a.TZ == 16 && (a.Wp == 12 || a.Wp == 20 || a.Wp == 36)) {
-        // the reference's radius on rows of 256 / 512 / 1024 voxels: strides known at compile time
-        if (a.Wp == 12) LKS(k_close_fused<2, 4, 2, 12, 16, 16>, grid, threads, smem, s, false, c->d_raw, c->d_closed, c->d_dyn, c->d_scalars, a);
-        else if (a.Wp == 20) LKS(k_close_fused<2, 4, 2, 20, 16, 16>, grid, threads, smem, s, false, c->d_raw, c->d_closed, c->d_dyn, c->d_scalars, a);
-        else LKS(k_close_fused<2, 4, 2, 36, 16, 16>, grid, threads, smem, s, false, c->d_raw, c->d_closed, c->d_dyn, c->d_scalars, a);
-    } else {
-        LKS(k_close_fused<R, SYD, SYE>, grid, threads, smem, s, false, c->d_raw, c->d_closed, c->d_dyn, c->d_scalars, a);
-    }
+    LKS(k_close_fused<R, SYD, SYE>, grid, threads, smem, s, false, c->d_raw, c->d_closed, c->d_dyn, c->d_scalars, a);
     prof_mark(c, s, "close_fused");
     done = true;
     return cudaGetLastError();
@@ -1072,11 +1062,6 @@ static cudaError_t tile_attrs_r() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_close_fused<R, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(FUSED_SMEM_MAX));
     if constexpr (R % 2 == 0)
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_close_fused<R, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(FUSED_SMEM_MAX));
-    if constexpr (R == 2) {
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_close_fused<2, 4, 2, 12, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(FUSED_SMEM_MAX));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_close_fused<2, 4, 2, 20, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(FUSED_SMEM_MAX));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_close_fused<2, 4, 2, 36, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(FUSED_SMEM_MAX));
-    }
     return e;
 }
 
