@@ -294,7 +294,7 @@ def run_native(args):
     sp, org, dr = specs[0].spacing, specs[0].origin, specs[0].direction
     params = DetectParams()
     n_ctx = int(os.environ.get("MAMRI_BENCH_CONTEXTS", "8"))
-    depth = 2 if S <= n_ctx else 1
+    depth = int(os.environ.get("MAMRI_BENCH_DEPTH", "2")) if S <= n_ctx else 1      # pools alternating (batches in flight)
     bp = BatchPipeline(DIMS, device=local, n_contexts=n_ctx, depth=depth)
     bd = bp.pools[0]
     # the single exchange of the path: the scans' last kernels write their fixed-size marker tables into gather_in,
@@ -320,11 +320,11 @@ def run_native(args):
             if use_gather:
                 with torch.cuda.stream(st):
                     works.append(dist.all_gather_into_tensor(gather_out[slot], gather_in[slot], async_op=True))
-        submit(0)
-        res = None
+        res, submitted = None, 0
         for k in range(n):
-            if k + 1 < n:
-                submit(k + 1)
+            while submitted < n and bp.pending() < depth:
+                submit(submitted)
+                submitted += 1
             res = bp.result()
             if use_gather:
                 works.pop(0).wait()
@@ -398,15 +398,15 @@ def run_native(args):
                     gather_in[0].copy_(torch.from_numpy(pack_table(r)), non_blocking=True)
                     dist.all_gather_into_tensor(gather_out[0], gather_in[0])
             return r
-        bp.submit_host(h_vols, sp, org, dr, params, **{body_kw: bodies[0]})
-        r = None
+        r, submitted = None, 0
         for k in range(n):
-            if k + 1 < n:
-                bp.submit_host(h_vols, sp, org, dr, params, **{body_kw: bodies[(k + 1) % 2]})
+            while submitted < n and bp.pending() < depth:
+                bp.submit_host(h_vols, sp, org, dr, params, **{body_kw: bodies[submitted % depth]})
+                submitted += 1
             r = bp.result()
             if use_gather:                              # host-packed tables on this path (the marker tables are on the host anyway)
-                gather_in[k % 2].copy_(torch.from_numpy(pack_table(r)), non_blocking=True)
-                dist.all_gather_into_tensor(gather_out[k % 2], gather_in[k % 2])
+                gather_in[k % depth].copy_(torch.from_numpy(pack_table(r)), non_blocking=True)
+                dist.all_gather_into_tensor(gather_out[k % depth], gather_in[k % depth])
         return r
 
     e2e_steps = max(4, min(args.steps, 30))

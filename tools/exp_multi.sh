@@ -17,7 +17,7 @@ import json, sys
 O, N = sys.argv[1], sys.argv[2]
 for name in (f"bench_n{N}", f"bench_nogather_n{N}", f"bench_u8_n{N}"):
     try:
-        d = json.load(open(f"{O}/{name}.json"))
+        d = json.loads(open(f"{O}/{name}.json").read().strip().splitlines()[-1])
         print(name, "value", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 4), "ranks", d["rank_ms_per_step"], "e2e", round(d["e2e"]["value"], 2),
               "ceil", round(d["e2e"]["copy_ceiling"]["value"], 2), "frac", round(d["e2e"]["frac_of_copy_ceiling"], 3),
               "C3", {k: d["configs"]["C3"][k] for k in ("ms_per_batch", "scans_per_s", "gathered_equals_single_gpu")},
