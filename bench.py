@@ -302,6 +302,8 @@ def run_native(args):
     gather_in = [torch.zeros((S, MAX_TABLE, 8), dtype=torch.float64, device=dev) for _ in range(depth)]
     gather_out = [torch.zeros((world * S, MAX_TABLE, 8), dtype=torch.float64, device=dev) for _ in range(depth)]
     use_gather = world > 1 and not no_gather
+    gstream = torch.cuda.Stream(device=dev)
+    gather_done = [torch.cuda.Event() for _ in range(depth)]
 
     def run_steps(n):
         """n steps, software-pipelined over the two pools: batch k+1 is enqueued before batch k is collected."""
@@ -312,22 +314,26 @@ def run_native(args):
                     gather_in[0].copy_(torch.from_numpy(pack_table(res)), non_blocking=True)
                     dist.all_gather_into_tensor(gather_out[0], gather_in[0])
             return res, 0
-        works = []
-
         def submit(k):
             slot = k % depth
+            if use_gather:
+                bp.streams[slot].wait_event(gather_done[slot])       # the tables of this slot's previous batch have been gathered
             st = bp.submit(vols, sp, org, dr, params, tables=gather_in[slot] if use_gather else None)
             if use_gather:
-                with torch.cuda.stream(st):
-                    works.append(dist.all_gather_into_tensor(gather_out[slot], gather_in[slot], async_op=True))
+                # the all-gather runs on a stream of its own behind the batch: the pool's stream is free for its next
+                # batch, and a rank that is a little late does not hold up the others' scans, only their gather
+                gstream.wait_stream(st)
+                with torch.cuda.stream(gstream):
+                    dist.all_gather_into_tensor(gather_out[slot], gather_in[slot])
+                    gather_done[slot].record(gstream)
         res, submitted = None, 0
         for k in range(n):
             while submitted < n and bp.pending() < depth:
                 submit(submitted)
                 submitted += 1
             res = bp.result()
-            if use_gather:
-                works.pop(0).wait()
+        if use_gather:
+            torch.cuda.current_stream().wait_stream(gstream)            # the timed region ends when the last gather has
         return res, (n - 1) % depth
 
     # ---------------- device-resident throughput (the contract's `value`)
@@ -391,12 +397,10 @@ def run_native(args):
         """n end-to-end steps, software-pipelined over the two pools like run_steps: the next batch's H2D copies start
         while the previous batch's last scans still compute and drain (the PCIe link never idles between steps)."""
         if depth == 1:
-            for _ in range(n):
-                bd.begin_host(h_vols, sp, org, dr, params, **{body_kw: bodies[0]})
-                r = bd.end()
-                if use_gather:
-                    gather_in[0].copy_(torch.from_numpy(pack_table(r)), non_blocking=True)
-                    dist.all_gather_into_tensor(gather_out[0], gather_in[0])
+            for _ in range(n):                          # more scans than contexts: chunks of n_ctx, one after the other
+                for first in range(0, S, n_ctx):
+                    bd.begin_host(h_vols[first:first + n_ctx], sp, org, dr, params, **{body_kw: bodies[0][first:first + n_ctx]})
+                    r = bd.end()
             return r
         r, submitted = None, 0
         for k in range(n):

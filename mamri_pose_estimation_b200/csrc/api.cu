@@ -717,11 +717,15 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
     const int nx = desc->nx, ny = desc->ny, nz = desc->nz;
     cudaStream_t H0 = pool->hbm;
     const int NC = pool->n_chains;
+    // MAMRI_WAVE_MAT_CHAINS=1 (experiment): the materialise kernels get chains of their own (NC more streams) instead of
+    // queueing behind the wave's thresholds on the same chains
+    static const int mat_chains = [] { const char* e = getenv("MAMRI_WAVE_MAT_CHAINS"); return e ? atoi(e) : 0; }();
+    const int MC = (mat_chains && NC <= 2) ? NC : 0;                   // first materialise chain = chain[MC ? NC : 0]
     const int geom_r = morph_geom_radius(prm->open_radius, prm->close_radius);
     launch_counter() = 0;
     CKP(cudaMemcpyAsync(pool->d_args_all, pool->h_args_all, sizeof(ScanArgs) * m, cudaMemcpyHostToDevice, H0));
     CKP(cudaEventRecord(pool->fork, H0));
-    for (int c = 0; c < NC; ++c) CKP(cudaStreamWaitEvent(pool->chain[c], pool->fork, 0));
+    for (int c = 0; c < NC + MC; ++c) CKP(cudaStreamWaitEvent(pool->chain[c], pool->fork, 0));
     for (int i = 0; i < m; ++i) {
         cudaStream_t H = pool->chain[i % NC];
         TRACE(i, 0, H);
@@ -749,14 +753,14 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
     }
     if (outputs)
         for (int i = 0; i < m; ++i) {
-            cudaStream_t H = pool->chain[i % NC];
+            cudaStream_t H = pool->chain[(MC ? NC : 0) + i % NC];
             CKP(cudaStreamWaitEvent(H, pool->ev_sel[i], 0));
             TRACE(i, 5, H);
             CKP(launch_materialise(pool->ctx[i], pool->ctx[i]->d_closed, nx, ny, nz, k.outs_aligned, H));
             TRACE(i, 6, H);
         }
     for (int i = 0; i < m; ++i) CKP(cudaStreamWaitEvent(H0, pool->ev_done[i], 0));
-    for (int c = 0; c < NC; ++c) {
+    for (int c = 0; c < NC + MC; ++c) {
         CKP(cudaEventRecord(pool->ev_chain[c], pool->chain[c]));
         CKP(cudaStreamWaitEvent(H0, pool->ev_chain[c], 0));
     }

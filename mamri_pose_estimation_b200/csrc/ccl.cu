@@ -127,17 +127,20 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
     }
     ktrace(KT_RUNS_LB);
     // ---- phase B: prefixes and tables
+    uint32_t carry = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t i0 = tile * RS_TILE + threadIdx.x * RS_ITEMS;
         uint32_t m[RS_ITEMS], starts[RS_ITEMS], ends[RS_ITEMS], open;
         const uint32_t cnt = load_runs<RS_ITEMS>(mask, i0, n_words, W, m, starts, ends, open, true);
-        // prefix of the tile = sum of the published counts of all earlier tiles (each thread reads a share of them; a
-        // count of this launch that is not there yet is about to be: phase A waits for nothing), exclusive scan of the
-        // threads' own counts: one exchange through shared memory serves both
+        // prefix of the tile = runs before the CTA's previous tile and in it (`carry`, known from the round before) + the
+        // published counts of the tiles since then -- at most gridDim.x - 1 values, one per thread (a count of this
+        // launch that is not there yet is about to be: phase A waits for nothing).  Summing ALL earlier counts for every
+        // tile made thousands of CTAs-times-tiles read the same few cache lines: 108 us of the 127 on a 2048-tile mask.
         uint32_t acc = 0;
         {
             const unsigned long long g30 = gen & 0x3FFFFFFFu;
-            for (uint32_t idx = threadIdx.x; idx < tile; idx += blockDim.x) {
+            const uint32_t first = tile >= gridDim.x ? tile - gridDim.x + 1u : 0u;
+            for (uint32_t idx = first + threadIdx.x; idx < tile; idx += blockDim.x) {
                 unsigned long long v;
                 do { v = state[idx]; } while ((v >> 34) != g30);
                 acc += uint32_t(v >> 2);
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
         if (lane_id() == 31) ws[threadIdx.x >> 5] = inc;
         if (lane_id() == 0) red[threadIdx.x >> 5] = acc;
         __syncthreads();
-        uint32_t ex = inc - cnt, total = 0, before = 0;
+        uint32_t ex = inc - cnt, total = 0, before = carry;
 #pragma unroll
         for (int w = 0; w < RS_THREADS / 32; ++w) {
             const uint32_t t = ws[w];
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
             total += t;
             before += red[w];
         }
+        carry = before + total;                                          // runs up to and including this tile
         if (threadIdx.x == 0 && tile == n_tiles - 1) {  // grand total: every later stage keys off n_runs / status
             if (before + total > max_runs) { sc->status = MAMRI_ERR_CAPACITY; sc->n_runs = 0; }
             else sc->n_runs = before + total;
