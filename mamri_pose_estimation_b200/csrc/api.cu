@@ -359,6 +359,7 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool f
     // both depend on the labels only.  The statistics kernel goes FIRST, on the second branch: its few CTAs take their
     // slots before `materialise` floods the machine with thousands of CTAs (launched after it, a small kernel only
     // gets in when that grid has drained -- measured: it then ran after materialise instead of beside it).
+    CK(launch_stats_early(ctx, desc, params, s));          // run tables of a noisy scan: the sums first (stats.cu)
     if (forked) {
         CK(cudaEventRecord(ctx->ev_fork, s));
         CK(cudaStreamWaitEvent(ctx->cap_stream2, ctx->ev_fork, 0));
@@ -736,13 +737,17 @@ static int enqueue_wave(mamri_pool* pool, const GraphKey& k, int m) {
     const bool outputs = k.has_mask || k.has_labels || k.has_body;
     for (int i = 0; i < m; ++i) {
         mamri_ctx* c = pool->ctx[i];
-        cudaStream_t s = pool->streams[i];
+        // MAMRI_WAVE_MID_CHAINS=n: the latency-bound middles of the wave's scans queue on n streams in scan order instead
+        // of all sharing the machine, so that the first scans' labels are final early (0 = one stream per scan)
+        static const int mid_chains = [] { const char* e = getenv("MAMRI_WAVE_MID_CHAINS"); return e ? atoi(e) : 0; }();
+        cudaStream_t s = pool->streams[mid_chains > 0 ? i % mid_chains : i];
         CKP(cudaStreamWaitEvent(s, pool->ev_thr[i], 0));
         CKP(launch_opening(c, nx, ny, nz, prm->open_radius, geom_r, s));
         CKP(launch_closing(c, nx, ny, nz, prm->close_radius, geom_r, s));
         TRACE(i, 2, s);
         TRACE(i, 3, s);
         CKP(launch_label(c, c->d_closed, desc, prm, s));
+        CKP(launch_stats_early(c, desc, prm, s));
         TRACE(i, 4, s);
         CKP(cudaEventRecord(pool->ev_sel[i], s));
         // statistics + tables (straight into the pinned host buffers) right behind the labels, before the wave's

@@ -134,8 +134,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_runs_scan(const uint32_t* __rest
         const uint32_t cnt = load_runs<RS_ITEMS>(mask, i0, n_words, W, m, starts, ends, open, true);
         // prefix of the tile = runs before the CTA's previous tile and in it (`carry`, known from the round before) + the
         // published counts of the tiles since then -- at most gridDim.x - 1 values, one per thread (a count of this
-        // launch that is not there yet is about to be: phase A waits for nothing).  Summing ALL earlier counts for every
-        // tile made thousands of CTAs-times-tiles read the same few cache lines: 108 us of the 127 on a 2048-tile mask.
+        // launch that is not there yet is about to be: phase A waits for nothing), instead of all the earlier counts.
+        // Measured on the 2048-tile mask of config C4: phase B is ~102 us either way (7 us per tile and CTA: the loads of
+        // the words, the counts, two barriers and the table stores in sequence, 16 warps per SM); staging the table
+        // entries in shared memory for whole-sector stores was slower (127 us), so the entries are written straight out.
         uint32_t acc = 0;
         {
             const unsigned long long g30 = gen & 0x3FFFFFFFu;
@@ -734,6 +736,8 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_label_cluster(LabelArgs a) {
             const uint32_t root = ld_vol(a.parent + r);
             if (root != r) {
                 a.run_label[r] = ld_vol(a.run_label + root);
+                const double vol = double(ld_vol(a.root_count + root)) * a.voxel_volume;   // as k_select
+                a.label_slot[r] = (vol >= a.min_volume && vol <= a.max_volume) ? MAMRI_SLOT_OF_ROOT : MAMRI_NONE;
             } else {
                 const uint32_t cnt = ld_vol(a.root_count + r), label = ld_vol(a.run_label + r);
                 a.label_count[label - 1u] = cnt;
@@ -815,7 +819,19 @@ cudaError_t launch_label(mamri_ctx* c, const uint32_t* d_mask, const mamri_volum
     const int nx = desc->nx, ny = desc->ny, nz = desc->nz, connectivity = prm->connectivity;
     const int W = (nx + 31) / 32;
     const uint32_t n_words = uint32_t(W) * ny * nz;
-    static const int scan_ctas = [] { const char* e = getenv("MAMRI_SCAN_CTAS"); return e ? atoi(e) : 148; }();
+    // Phase B of the run scan spins on counts that phase A of OTHER CTAs publishes, so the whole grid has to be resident
+    // at once: never more CTAs than the occupancy calculator says fit on the device next to each other.
+    static const int scan_ctas = [] {
+        const char* e = getenv("MAMRI_SCAN_CTAS");
+        int want = e ? atoi(e) : 296, per_sm = 0, dev = 0, sms = 148;
+        int a = 0, b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_runs_scan<16>, RS_THREADS, 0) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_runs_scan<4>, RS_THREADS, 0) == cudaSuccess)
+            per_sm = a < b ? a : b;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int cap = (per_sm > 0 ? per_sm : 1) * sms;
+        return want < 1 ? 1 : (want > cap ? cap : want);
+    }();
     if (n_words >= 148u * RS_THREADS * 16u) {
         const uint32_t n_tiles = (n_words + RS_THREADS * 16 - 1) / (RS_THREADS * 16);
         LK(k_runs_scan<16>, n_tiles < uint32_t(scan_ctas) ? n_tiles : uint32_t(scan_ctas), RS_THREADS, s, false, d_mask, W, n_words, c->d_scan_runs,

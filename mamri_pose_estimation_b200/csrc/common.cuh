@@ -12,6 +12,7 @@
 #define MAMRI_SCAN_CTAS 592          // 148 SMs x 4: CTA count of the chunked scans
 #define MAMRI_RUN_CTAS (148 * 8)     // largest CTA count of the per-run kernels (grid-stride over the run table)
 #define MAMRI_NONE 0xFFFFFFFFu
+#define MAMRI_SLOT_OF_ROOT 0xFFFFFFFEu   // label_slot of a non-root run whose label passed the volume filter: the slot is on its root
 
 // Device-side scalars of one scan (one cudaMemsetAsync clears them).
 struct DevScalars {
@@ -99,7 +100,7 @@ struct mamri_ctx {
     uint32_t* d_run_label;  // final label of each run                  [max_runs]
     uint32_t* d_root_count; // voxels of the component rooted at each run (roots only) [max_runs]
     uint32_t* d_label_count;// voxels per label                         [max_runs]
-    uint32_t* d_label_slot; // marker-table slot of each ROOT run / NONE [max_runs]
+    uint32_t* d_label_slot; // marker-table slot of each ROOT run / NONE; other runs: SLOT_OF_ROOT / NONE [max_runs]
     unsigned long long* d_scan_runs;  // look-back states of k_runs_scan     [tiles of cap_words]
     unsigned long long* d_scan_rank;  // look-back states of k_flatten_rank  [tiles of max_runs]
     uint32_t gen;
@@ -181,6 +182,7 @@ cudaError_t launch_closing(mamri_ctx* c, int nx, int ny, int nz, int radius, int
 // run numbering + union-find + ranking + volume filter + body label (one cluster kernel or the scalable kernels)
 cudaError_t launch_label(mamri_ctx* c, const uint32_t* d_mask, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
 cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
+cudaError_t launch_stats_early(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);   // before the fork (big run tables)
 cudaError_t launch_stats(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
 // per-device function attributes (dynamic shared memory opt-in, non-portable cluster size); called by mamri_create
 cudaError_t segment_init_device();

@@ -42,6 +42,10 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ par
             const uint32_t root = parent[r];
             if (root != r) {
                 run_label[r] = run_label[root];                   // roots were ranked by k_flatten_rank
+                // the filter's verdict on the run's component (the count on the root is final): the statistics kernel
+                // then knows from the run's own entry whether it has anything to fetch from the root
+                const double vol = double(root_count[root]) * g.voxel_volume;
+                label_slot[r] = (vol >= g.min_volume && vol <= g.max_volume) ? MAMRI_SLOT_OF_ROOT : MAMRI_NONE;
             } else {
                 const uint32_t cnt = root_count[r], label = run_label[r];
                 label_count[label - 1u] = cnt;
@@ -208,7 +212,12 @@ __device__ void make_marker(mamri_marker& m, uint32_t label, unsigned long long 
 //            (DynArgs::table_out, rows of {label, count, volume_mm3, RAS x y z, n_labels, body_label}: the layout
 //            distributed.pack_table builds on the host) when the caller asked for it.
 // It runs beside `materialise` on the second branch of the graph.
-__global__ void __launch_bounds__(256) k_stats(const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_end,
+// MODE 0: all three in one launch (the usual scan: the kernel hides beside `materialise`).  MODE 1: ranks + moments only,
+// compiled for 4 CTAs per SM (<= 64 registers), MODE 2: the finalisation alone, one CTA, launched behind MODE 1 -- for
+// run tables of millions of entries, where the one-launch form kept half of every SM's register file (the float64
+// eigen-decomposition needs 124 registers per thread) for 0.3 ms and `materialise` beside it ran at half occupancy.
+template <int MODE>
+__global__ void __launch_bounds__(256, MODE == 1 ? 4 : 1) k_stats(const uint32_t* __restrict__ run_pos, const uint32_t* __restrict__ run_end,
                                                const uint32_t* __restrict__ parent, const uint32_t* __restrict__ run_label,
                                                const uint32_t* __restrict__ label_slot, int W, int ny,
                                                unsigned long long* sums, const uint32_t* __restrict__ cand_label,
@@ -218,64 +227,95 @@ __global__ void __launch_bounds__(256) k_stats(const uint32_t* __restrict__ run_
     __shared__ CtaCache<9, unsigned long long, 16> cache;
     __shared__ bool last;
     pdl_wait();
-    ktrace(KT_STATS);
-    cache.init();
+    if (MODE != 2) ktrace(KT_STATS);
     const bool ok = sc->status == MAMRI_OK;
     const uint32_t n = ok ? sc->n_runs : 0u;
     const uint32_t n_all = sc->n_cand;
     const uint32_t n_kept = ok ? (n_all < max_markers ? n_all : max_markers) : 0u;
     const unsigned long long bp = sc->body_packed;
     const uint32_t body = (ok && (bp >> 32) != 0ull) ? 0xFFFFFFFFu - uint32_t(bp & 0xFFFFFFFFull) : 0u;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    // ---- ranks of the kept labels
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_kept; i += stride) {
-        const uint32_t lab = cand_label[i];
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < n_kept; ++j) rank += cand_label[j] < lab;
-        cand_rank[i] = rank;
-    }
-    // ---- moments
-    for (uint32_t r0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < n; r0 += stride) {
-        const uint32_t r = r0 + lane_id();
-        uint32_t key = MAMRI_NONE;
-        unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (r < n) {
-            key = label_slot[parent[r]];
-            if (key == MAMRI_NONE && body != 0u && run_label[r] == body) key = max_markers;   // the body has the extra slot
-            if (key != MAMRI_NONE) {
-                const uint32_t pos = run_pos[r];
-                const uint32_t wi = pos >> 5, row = wi / W;
-                const long long z = row / ny, y = row - uint32_t(z) * ny;
-                const long long xs = (long long)(wi - row * W) * 32 + (pos & 31u);
-                const long long len = (long long)(run_end[r] - pos) + 1, xe = xs + len - 1;
-                const unsigned long long sx = (unsigned long long)((xs + xe) * len / 2);
-                v[0] = sx;                                              // sum x
-                v[1] = (unsigned long long)(len * y);                   // sum y
-                v[2] = (unsigned long long)(len * z);                   // sum z
-                v[3] = sum_sq_upto(xe) - sum_sq_upto(xs - 1);           // sum xx
-                v[4] = (unsigned long long)(len * y * y);               // sum yy
-                v[5] = (unsigned long long)(len * z * z);               // sum zz
-                v[6] = sx * (unsigned long long)y;                      // sum xy
-                v[7] = sx * (unsigned long long)z;                      // sum xz
-                v[8] = (unsigned long long)(len * y * z);               // sum yz
+    if (MODE != 2) {
+        cache.init();
+        const uint32_t stride = gridDim.x * blockDim.x;
+        // ---- ranks of the kept labels
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_kept; i += stride) {
+            const uint32_t lab = cand_label[i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n_kept; ++j) rank += cand_label[j] < lab;
+            cand_rank[i] = rank;
+        }
+        // ---- moments: a warp takes ST_U x 32 consecutive runs per trip; whether a run counts is in its own entries
+        // (slot, label: two coalesced loads), only the runs of kept labels go to their root for the slot
+        // The body's runs (most of a clinical scan's table, every fifth warp trip of a noisy one) are summed in registers
+        // over the thread's whole loop and combined once at the end; only the markers' runs go through the warp-level
+        // combine for every trip.
+        constexpr int ST_U = 4;
+        unsigned long long bsum[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t r0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * ST_U; r0 < n; r0 += stride * ST_U) {
+            uint32_t key[ST_U], lab[ST_U];
+#pragma unroll
+            for (int u = 0; u < ST_U; ++u) {
+                const uint32_t r = r0 + u * 32 + lane_id();
+                key[u] = r < n ? label_slot[r] : MAMRI_NONE;      // a root's slot, SLOT_OF_ROOT for the other runs of a kept label
+                lab[u] = r < n ? run_label[r] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < ST_U; ++u)
+                if (key[u] == MAMRI_SLOT_OF_ROOT) key[u] = label_slot[parent[r0 + u * 32 + lane_id()]];
+#pragma unroll
+            for (int u = 0; u < ST_U; ++u) {
+                const uint32_t r = r0 + u * 32 + lane_id();
+                uint32_t k = key[u];
+                if (k == MAMRI_NONE && body != 0u && lab[u] == body) k = max_markers;   // the body has the extra slot
+                if (!__any_sync(FULL, k != MAMRI_NONE)) continue;
+                unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                if (k != MAMRI_NONE) {
+                    const uint32_t pos = run_pos[r];
+                    const uint32_t wi = pos >> 5, row = wi / W;
+                    const long long z = row / ny, y = row - uint32_t(z) * ny;
+                    const long long xs = (long long)(wi - row * W) * 32 + (pos & 31u);
+                    const long long len = (long long)(run_end[r] - pos) + 1, xe = xs + len - 1;
+                    const unsigned long long sx = (unsigned long long)((xs + xe) * len / 2);
+                    v[0] = sx;                                              // sum x
+                    v[1] = (unsigned long long)(len * y);                   // sum y
+                    v[2] = (unsigned long long)(len * z);                   // sum z
+                    v[3] = sum_sq_upto(xe) - sum_sq_upto(xs - 1);           // sum xx
+                    v[4] = (unsigned long long)(len * y * y);               // sum yy
+                    v[5] = (unsigned long long)(len * z * z);               // sum zz
+                    v[6] = sx * (unsigned long long)y;                      // sum xy
+                    v[7] = sx * (unsigned long long)z;                      // sum xz
+                    v[8] = (unsigned long long)(len * y * z);               // sum yz
+                    if (k == max_markers) {
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) bsum[i] += v[i];
+                        k = MAMRI_NONE;
+                    }
+                }
+                warp_agg_add(k, v, cache, sums);
             }
         }
-        warp_agg_add(key, v, cache, sums);
+        warp_agg_add(bsum[4] | bsum[5] | bsum[0] | bsum[1] | bsum[2] ? max_markers : MAMRI_NONE, bsum, cache, sums);
+        cache.flush(sums);
     }
-    cache.flush(sums);
-    // ---- the last CTA to get here finalises
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(&sc->done_stats, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
+    if (MODE == 1) return;
+    // ---- the last CTA to get here finalises (MODE 2: the only CTA, behind the kernel that made the sums)
+    if (MODE == 0) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(&sc->done_stats, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!last) return;
+        __threadfence();
+    }
     ktrace(KT_STATS_FIN);
     double* __restrict__ table = dyn->table_out;
     const uint32_t slots = table ? dyn->table_slots : 0u;
     const double body_d = double(body);
     const uint32_t n_labels = sc->n_labels;
-    for (uint32_t i = threadIdx.x; i < n_kept; i += blockDim.x) {
+    // MODE 2 may be launched with several CTAs: the markers are dealt over all of them, CTA 0 does the rest
+    const uint32_t m_first = MODE == 2 ? blockIdx.x * blockDim.x + threadIdx.x : threadIdx.x;
+    const uint32_t m_step = MODE == 2 ? gridDim.x * blockDim.x : blockDim.x;
+    for (uint32_t i = m_first; i < n_kept; i += m_step) {
         const uint32_t lab = __ldcg(cand_label + i), rank = __ldcg(cand_rank + i);
         unsigned long long s9[9];
         for (int k = 0; k < 9; ++k) s9[k] = __ldcg(sums + i * 9u + k);
@@ -289,6 +329,7 @@ __global__ void __launch_bounds__(256) k_stats(const uint32_t* __restrict__ run_
             row[6] = double(n_labels); row[7] = body_d;
         }
     }
+    if (MODE == 2 && blockIdx.x != 0) return;
     for (uint32_t i = n_kept * 8 + threadIdx.x; i < slots * 8; i += blockDim.x) table[i] = 0.0;   // unused rows
     if (threadIdx.x == blockDim.x - 1) {                     // the body: a thread of another warp than marker 0's
         mamri_marker m;
@@ -335,18 +376,44 @@ cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mam
 }
 
 // Moments of the kept labels + body, and the marker table / summary (independent of `materialise`).
+// Usual scan: ONE launch (k_stats<0>) on the graph's side branch, hidden beside `materialise`.  Run tables of >= 150 k
+// entries (noisy scans): the sums are made by a full grid BEFORE `materialise` (launch_stats_early, ~0.03 ms alone) and
+// only the finalisation runs beside it -- beside `materialise` the sums' loads queue behind its stores and the kernel
+// only finishes when `materialise` does (measured on config C4), while its CTAs cost `materialise` its occupancy.
+#define MAMRI_STATS_ARGS c->d_run_pos, c->d_run_end, c->d_parent, c->d_run_label, c->d_label_slot, W, desc->ny, c->d_cand_sums, \
+                         c->d_cand_label, c->d_cand_rank, c->d_label_count, c->max_markers, g, c->h_markers, c->h_summary, c->d_scalars, c->d_dyn
+static bool stats_split(const mamri_ctx* c) {
+    static const int split_env = [] { const char* e = getenv("MAMRI_STATS_SPLIT"); return e ? atoi(e) : 1; }();
+    return split_env >= 2 || (split_env == 1 && c->run_ctas >= 592);
+}
+
+cudaError_t launch_stats_early(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
+    if (!stats_split(c)) return cudaSuccess;
+    const GeomArgs g = geom_args(desc, prm);
+    const int W = (desc->nx + 31) / 32;
+    static const int early_ctas = [] { const char* e = getenv("MAMRI_STATS_EARLY_CTAS"); return e ? atoi(e) : 0; }();
+    const int grid = early_ctas > 0 ? early_ctas : (c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS);
+    LK(k_stats<1>, grid, 256, s, false, MAMRI_STATS_ARGS);
+    prof_mark(c, s, "stats_moments");
+    return cudaGetLastError();
+}
+
 cudaError_t launch_stats(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
     const GeomArgs g = geom_args(desc, prm);
     const int W = (desc->nx + 31) / 32;
-    // at most one CTA per SM: the kernel runs beside `materialise`, which needs the thread slots more (on a table of
-    // millions of runs a full grid of these 128-register CTAs held materialise back by 0.1 ms)
-    int grid = c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS;
-    if (grid > 148) grid = 148;
-    LK(k_stats, grid, 256, s, false, c->d_run_pos, c->d_run_end, c->d_parent, c->d_run_label,
-       c->d_label_slot, W, desc->ny, c->d_cand_sums, c->d_cand_label, c->d_cand_rank, c->d_label_count, c->max_markers, g, c->h_markers,
-       c->h_summary, c->d_scalars, c->d_dyn);
+    if (stats_split(c)) {
+        int fin = int((c->max_markers + 127u) / 128u);             // one marker per thread: the float64 eigen-decomposition
+        fin = fin < 1 ? 1 : (fin > 64 ? 64 : fin);                 // is a ~20 us dependent chain
+        LK(k_stats<2>, fin, 128, s, false, MAMRI_STATS_ARGS);
+    } else {
+        // at most one CTA per SM: the kernel runs beside `materialise`, which needs the thread slots more
+        int grid = c->run_ctas > 0 ? c->run_ctas : MAMRI_RUN_CTAS;
+        if (grid > 148) grid = 148;
+        LK(k_stats<0>, grid, 256, s, false, MAMRI_STATS_ARGS);
+    }
     prof_mark(c, s, "stats");
     return cudaGetLastError();
 }
+#undef MAMRI_STATS_ARGS
 
 KTRACE_TU(stats)
