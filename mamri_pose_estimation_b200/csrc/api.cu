@@ -359,13 +359,16 @@ static int enqueue_pipeline(mamri_ctx* ctx, const GraphKey& k, bool prof, bool f
     // both depend on the labels only.  The statistics kernel goes FIRST, on the second branch: its few CTAs take their
     // slots before `materialise` floods the machine with thousands of CTAs (launched after it, a small kernel only
     // gets in when that grid has drained -- measured: it then ran after materialise instead of beside it).
-    CK(launch_stats_early(ctx, desc, params, s));          // run tables of a noisy scan: the sums first (stats.cu)
+    const bool early_beside = stats_early_beside();        // experiment knob (stats.cu): the sums of a noisy scan on the side branch too
+    if (!early_beside) CK(launch_stats_early(ctx, desc, params, s));          // run tables of a noisy scan: the sums first (stats.cu)
     if (forked) {
         CK(cudaEventRecord(ctx->ev_fork, s));
         CK(cudaStreamWaitEvent(ctx->cap_stream2, ctx->ev_fork, 0));
+        if (early_beside) CK(launch_stats_early(ctx, desc, params, ctx->cap_stream2));
         CK(launch_stats(ctx, desc, params, ctx->cap_stream2));
         CK(cudaEventRecord(ctx->ev_join, ctx->cap_stream2));
     } else {
+        if (early_beside) CK(launch_stats_early(ctx, desc, params, s));
         CK(launch_stats(ctx, desc, params, s));
     }
     if (prof) CK(cudaEventRecord(ctx->ev[4], s));

@@ -223,10 +223,22 @@ __device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
     return x;
 }
 
+// Two finds at once: the hops of the two chains are independent loads, so they travel together (one round trip per
+// pair of hops instead of two).  Same path halving as uf_find.
+__device__ __forceinline__ void uf_find2(uint32_t* parent, uint32_t& x, uint32_t& y) {
+    volatile uint32_t* vp = parent;
+    uint32_t px = vp[x], py = vp[y];
+    while (px != x || py != y) {
+        const uint32_t gx = px != x ? vp[px] : px;
+        const uint32_t gy = py != y ? vp[py] : py;
+        if (px != x) { if (gx != px) vp[x] = gx; x = px; px = gx; }
+        if (py != y) { if (gy != py) vp[y] = gy; y = py; py = gy; }
+    }
+}
+
 __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
     while (true) {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
+        uf_find2(parent, a, b);
         if (a == b) return;
         if (a < b) { uint32_t t = a; a = b; b = t; }       // hook the larger root under the smaller
         uint32_t old = atomicMin(&parent[a], b);
@@ -287,7 +299,7 @@ __device__ __forceinline__ void nbr_range(const uint32_t* __restrict__ word_base
 // trip), flattens, and publishes parent[run] = slice-local root as a global id.  Slices with more runs
 // than fit fall back to the same code on the global array.
 constexpr int SLICE_THREADS = 512;
-constexpr uint32_t SLICE_SMEM_RUNS = 12000;      // 48 KB static shared memory
+constexpr uint32_t SLICE_SMEM_RUNS = 11776;      // 46 KB of parents + 1.4 KB of flags: under the 48 KB of static shared memory
 
 template <bool CONN26>
 __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* __restrict__ word_base,
@@ -297,6 +309,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
     pdl_wait();
     ktrace(KT_USLICE);
     __shared__ uint32_t sp[SLICE_SMEM_RUNS];
+    __shared__ uint32_t sflag[SLICE_SMEM_RUNS / 32];                    // runs that touch more than one run of the row above
     if (sc->status != MAMRI_OK) return;
     const uint32_t z = blockIdx.x;
     const uint32_t slice_words = uint32_t(W) * ny;
@@ -306,7 +319,12 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
     const uint32_t n = r1 - r0;
     ktrace_both(KT_US_N);
     if (n == 0) return;
-    uint32_t* P = (n <= SLICE_SMEM_RUNS) ? sp : parent + r0;
+    const bool in_smem = n <= SLICE_SMEM_RUNS;
+    uint32_t* P = in_smem ? sp : parent + r0;
+    if (in_smem) {
+        for (uint32_t i = threadIdx.x; i < (n + 31u) / 32u; i += blockDim.x) sflag[i] = 0u;
+        __syncthreads();
+    }
     // (1) Every run points at the first run of the row above that touches it (a smaller id), or at itself: a forest,
     // built with plain stores -- no atomics, no root walks.  Hooking root under root while the other threads do the
     // same leaves chains as long as the object is tall, and the late warps walk them hop by hop.
@@ -324,7 +342,10 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
                 nbr_range<CONN26>(word_base, run_pos, run_end, W, gx0, int(run_end[r0 + i] - pos + 1u), (row - 1) * W, ja, jb);
             }
             P[i] = ja < jb ? ja - r0 : i;
-            more = more || jb - ja > 1u;
+            if (jb - ja > 1u) {
+                more = true;
+                if (in_smem && k >= KEEP) atomicOr(&sflag[i >> 5], 1u << (i & 31u));
+            }
             if (k < KEEP) { ja_[k] = ja; jb_[k] = jb; }
         }
     }
@@ -354,6 +375,10 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_union_slices(const uint32_t* 
             uint32_t ja, jb;
             if (k < KEEP) { ja = ja_[k]; jb = jb_[k]; }
             else {
+                // a thread with more than KEEP runs (noisy slices: a dozen per thread) looks the neighbours up again --
+                // but only for the flagged runs, a few per slice: without the flags this second pass over every run cost
+                // as much as the first (dependent loads from the run table) on every slice that holds an object
+                if (in_smem && !((sflag[i >> 5] >> (i & 31u)) & 1u)) continue;
                 const uint32_t pos = run_pos[r0 + i];
                 const uint32_t wi = pos >> 5, row = wi / W;
                 ja = jb = 0;
@@ -394,14 +419,14 @@ __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ wo
         uint32_t row = 0, y = 0;
         int gx0 = 0, len = 0;
         if (active) {
-            const uint32_t pos = run_pos[r];
+            const uint32_t pos = run_pos[r], end = run_end[r];       // both in flight together (coalesced)
             const uint32_t wi = pos >> 5;
             row = wi / W;
             const uint32_t z = row / ny;
             y = row - z * ny;
             active = z > 0 && (((z % radix) == 0) == (between_blocks != 0));
             gx0 = int((wi - row * W) * 32 + (pos & 31u));
-            if (active) len = int(run_end[r] - pos + 1u);
+            len = int(end - pos + 1u);
         }
         if (!__any_sync(FULL, active)) continue;
         const uint32_t below = active ? (row - ny) * W : 0u;            // row (y, z-1)
@@ -418,8 +443,8 @@ __global__ void __launch_bounds__(256) k_union_z(const uint32_t* __restrict__ wo
                 unsigned long long key = ~0ull;
                 uint32_t a = 0, b = 0;
                 if (it < jb - ja) {
-                    a = uf_find(parent, r);
-                    b = uf_find(parent, ja + it);
+                    a = r; b = ja + it;
+                    uf_find2(parent, a, b);
                     if (a != b) {
                         if (a < b) { const uint32_t t = a; a = b; b = t; }
                         key = ((unsigned long long)a << 32) | b;
@@ -472,25 +497,32 @@ __global__ void __launch_bounds__(FR_THREADS) k_flatten_rank(uint32_t* parent, c
         const uint32_t tile = s_tile;
         if (tile >= n_tiles) break;
         const uint32_t r0 = tile * FR_TILE + (threadIdx.x >> 5) * (32 * FR_ITEMS) + lane_id();
-        uint32_t roots = 0, is_root[FR_ITEMS];
+        // The FR_ITEMS root walks of a lane advance together (one dependent load per chain and round, all in flight at
+        // once) instead of one after the other.  Plain walks, and only parent[r] is written: a walker that shortened
+        // other nodes' paths on its way (path halving) could overwrite a parent[r'] that its owner has already set to the
+        // root with a nearer ancestor, and the filter pass relies on parent[] holding roots.
+        uint32_t x[FR_ITEMS], p[FR_ITEMS], len[FR_ITEMS];
 #pragma unroll
         for (int k = 0; k < FR_ITEMS; ++k) {
             const uint32_t r = r0 + k * 32;                          // warp-contiguous: coalesced, one key per lane
-            uint32_t key = MAMRI_NONE, v[1] = {0u};
-            is_root[k] = 0;
-            if (r < n) {
-                // plain walk, and only parent[r] is written: a walker that shortened other nodes' paths on its way (path
-                // halving) could overwrite a parent[r'] that its owner has already set to the root with a nearer ancestor,
-                // and the filter pass relies on parent[] holding roots
-                uint32_t x = r, p = parent[x];
-                while (p != x) { x = p; p = parent[x]; }
-                parent[r] = x;                                       // roots stay fixed points: concurrent walkers stay correct
-                is_root[k] = (x == r);
-                key = x;
-                v[0] = run_end[r] - run_pos[r] + 1u;
-            }
+            x[k] = r;
+            p[k] = r < n ? parent[r] : r;                            // past the table: a fixed point, nothing to walk
+            len[k] = r < n ? run_end[r] - run_pos[r] + 1u : 0u;
+        }
+        bool more;
+        do {
+            more = false;
+#pragma unroll
+            for (int k = 0; k < FR_ITEMS; ++k)
+                if (p[k] != x[k]) { x[k] = p[k]; p[k] = parent[x[k]]; more = true; }
+        } while (more);
+        uint32_t roots = 0, is_root[FR_ITEMS];
+#pragma unroll
+        for (int k = 0; k < FR_ITEMS; ++k) {
+            const uint32_t r = r0 + k * 32;
+            is_root[k] = (r < n && x[k] == r) ? 1u : 0u;
+            if (r < n && !is_root[k]) parent[r] = x[k];              // roots stay fixed points: concurrent walkers stay correct
             roots += is_root[k];
-            warp_agg_add(key, v, cache, root_count);
         }
         // rank: items are ordered (warp, k, lane) inside the tile, so scan per k-row
         uint32_t row_tot[FR_ITEMS], row_ex[FR_ITEMS];
@@ -512,6 +544,15 @@ __global__ void __launch_bounds__(FR_THREADS) k_flatten_rank(uint32_t* parent, c
             const uint32_t t = ws[w];
             if (w < int(wid)) off += t;
             total += t;
+        }
+        // the tile's own total is published BEFORE the voxel counts are combined: the tiles behind this one find it
+        // there when they look back, instead of waiting for this tile's aggregation as well
+        if (threadIdx.x == 0) state[tile] = scan_pack(dyn->gen, total, tile == 0 ? 2u : 1u);
+#pragma unroll
+        for (int k = 0; k < FR_ITEMS; ++k) {
+            const uint32_t r = r0 + k * 32;
+            uint32_t v[1] = {len[k]};
+            warp_agg_add(r < n ? x[k] : MAMRI_NONE, v, cache, root_count);
         }
         if (threadIdx.x < 32) {
             const uint32_t before = scan_lookback(state, tile, total, dyn->gen);

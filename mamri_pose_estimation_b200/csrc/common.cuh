@@ -184,6 +184,7 @@ cudaError_t launch_label(mamri_ctx* c, const uint32_t* d_mask, const mamri_volum
 cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
 cudaError_t launch_stats_early(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);   // before the fork (big run tables)
 cudaError_t launch_stats(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s);
+bool stats_early_beside();     // MAMRI_STATS_SPLIT=3: the early sums run beside `materialise` instead of before it
 // per-device function attributes (dynamic shared memory opt-in, non-portable cluster size); called by mamri_create
 cudaError_t segment_init_device();
 int ccl_init_device();               // returns the largest cluster size the labelling kernel can use (0 = none)

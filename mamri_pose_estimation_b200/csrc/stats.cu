@@ -36,28 +36,41 @@ __global__ void __launch_bounds__(256) k_select(const uint32_t* __restrict__ par
     // per-thread body bid and foreground count over all of the thread's runs: one pair of atomics per warp at the
     // end (a noisy scan has millions of one-voxel components, every one of them a root that bids)
     unsigned long long packed = 0ull, cnt64 = 0ull;
-    for (uint32_t r0 = warp0; r0 < n; r0 += stride) {
-        const uint32_t r = r0 + lane;
-        if (r < n) {
-            const uint32_t root = parent[r];
-            if (root != r) {
-                run_label[r] = run_label[root];                   // roots were ranked by k_flatten_rank
+    // SEL_U runs per thread and trip: their parents, then their roots' entries, travel together (a noisy table is ten
+    // trips per thread, each one two dependent loads deep)
+    constexpr int SEL_U = 4;
+    for (uint32_t r0 = warp0; r0 < n; r0 += stride * SEL_U) {
+        uint32_t root[SEL_U], cnt[SEL_U], lab[SEL_U];
+#pragma unroll
+        for (int u = 0; u < SEL_U; ++u) {
+            const uint32_t r = r0 + u * stride + lane;
+            root[u] = r < n ? parent[r] : MAMRI_NONE;
+        }
+#pragma unroll
+        for (int u = 0; u < SEL_U; ++u)
+            if (root[u] != MAMRI_NONE) { cnt[u] = root_count[root[u]]; lab[u] = run_label[root[u]]; }
+#pragma unroll
+        for (int u = 0; u < SEL_U; ++u) {
+            const uint32_t r = r0 + u * stride + lane;
+            if (root[u] == MAMRI_NONE) continue;
+            const double vol = double(cnt[u]) * g.voxel_volume;           // GetPhysicalSize
+            const bool keep = vol >= g.min_volume && vol <= g.max_volume; // inclusive bounds
+            if (root[u] != r) {
+                run_label[r] = lab[u];                                    // roots were ranked by k_flatten_rank
                 // the filter's verdict on the run's component (the count on the root is final): the statistics kernel
                 // then knows from the run's own entry whether it has anything to fetch from the root
-                const double vol = double(root_count[root]) * g.voxel_volume;
-                label_slot[r] = (vol >= g.min_volume && vol <= g.max_volume) ? MAMRI_SLOT_OF_ROOT : MAMRI_NONE;
+                label_slot[r] = keep ? MAMRI_SLOT_OF_ROOT : MAMRI_NONE;
             } else {
-                const uint32_t cnt = root_count[r], label = run_label[r];
-                label_count[label - 1u] = cnt;
-                cnt64 += cnt;
-                const double vol = double(cnt) * g.voxel_volume;        // GetPhysicalSize
+                const uint32_t label = lab[u];
+                label_count[label - 1u] = cnt[u];
+                cnt64 += cnt[u];
                 uint32_t slot = MAMRI_NONE;
-                if (vol >= g.min_volume && vol <= g.max_volume) {         // inclusive bounds
+                if (keep) {
                     slot = atomicAdd(&sc->n_cand, 1u);
                     if (slot < max_markers) cand_label[slot] = label; else slot = MAMRI_NONE;
                 } else {
                     // max(..., key=GetPhysicalSize) returns the FIRST maximum -> lowest label on ties
-                    const unsigned long long bid = ((unsigned long long)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - label);
+                    const unsigned long long bid = ((unsigned long long)cnt[u] << 32) | (unsigned long long)(0xFFFFFFFFu - label);
                     packed = bid > packed ? bid : packed;
                 }
                 label_slot[r] = slot;
@@ -200,6 +213,24 @@ __device__ void make_marker(mamri_marker& m, uint32_t label, unsigned long long 
     }
 }
 
+// Exact integer sums of one x-run [pos .. end] (linear bit positions in the [nz][ny][W*32] mask): x, y, z, xx, yy, zz, xy, xz, yz.
+__device__ __forceinline__ void run_sums(uint32_t pos, uint32_t end, int W, int ny, unsigned long long (&v)[9]) {
+    const uint32_t wi = pos >> 5, row = wi / W;
+    const long long z = row / ny, y = row - uint32_t(z) * ny;
+    const long long xs = (long long)(wi - row * W) * 32 + (pos & 31u);
+    const long long len = (long long)(end - pos) + 1, xe = xs + len - 1;
+    const unsigned long long sx = (unsigned long long)((xs + xe) * len / 2);
+    v[0] = sx;                                              // sum x
+    v[1] = (unsigned long long)(len * y);                   // sum y
+    v[2] = (unsigned long long)(len * z);                   // sum z
+    v[3] = sum_sq_upto(xe) - sum_sq_upto(xs - 1);           // sum xx
+    v[4] = (unsigned long long)(len * y * y);               // sum yy
+    v[5] = (unsigned long long)(len * z * z);               // sum zz
+    v[6] = sx * (unsigned long long)y;                      // sum xy
+    v[7] = sx * (unsigned long long)z;                      // sum xz
+    v[8] = (unsigned long long)(len * y * z);               // sum yz
+}
+
 // Turns the sums into the marker table and the summary.  One kernel does three things:
 //   ranks    every kept label's place in GetLabels order = number of kept labels below it (slots are claimed by
 //            atomics in arbitrary order); spread over the whole grid, it only needs the slot table
@@ -238,60 +269,111 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 4 : 1) k_stats(const uint32_t
         cache.init();
         const uint32_t stride = gridDim.x * blockDim.x;
         // ---- ranks of the kept labels
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_kept; i += stride) {
+        // one warp per kept label, the lanes share the comparisons (coalesced loads of the slot table): with one thread
+        // per label the first few CTAs walked the whole table serially, n_kept dependent iterations on the critical path
+        for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_kept; i += stride >> 5) {
             const uint32_t lab = cand_label[i];
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < n_kept; ++j) rank += cand_label[j] < lab;
-            cand_rank[i] = rank;
+            uint32_t below = 0;
+            for (uint32_t j = lane_id(); j < n_kept; j += 32) below += cand_label[j] < lab ? 1u : 0u;
+            below = __reduce_add_sync(FULL, below);
+            if (lane_id() == 0) cand_rank[i] = below;
         }
         // ---- moments: a warp takes ST_U x 32 consecutive runs per trip; whether a run counts is in its own entries
         // (slot, label: two coalesced loads), only the runs of kept labels go to their root for the slot
         // The body's runs (most of a clinical scan's table, every fifth warp trip of a noisy one) are summed in registers
         // over the thread's whole loop and combined once at the end; only the markers' runs go through the warp-level
         // combine for every trip.
-        constexpr int ST_U = 4;
+        constexpr int ST_U = MODE == 1 ? 8 : 4;        // noisy table: latency-bound on 3 dependent loads per trip, so twice the runs in flight
         unsigned long long bsum[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (uint32_t r0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * ST_U; r0 < n; r0 += stride * ST_U) {
             uint32_t key[ST_U], lab[ST_U];
+            if constexpr (MODE == 1) {
+                // the parents travel with the slots (coalesced, mostly unused) instead of after them: one dependent load less
+                uint32_t par[ST_U];
 #pragma unroll
-            for (int u = 0; u < ST_U; ++u) {
-                const uint32_t r = r0 + u * 32 + lane_id();
-                key[u] = r < n ? label_slot[r] : MAMRI_NONE;      // a root's slot, SLOT_OF_ROOT for the other runs of a kept label
-                lab[u] = r < n ? run_label[r] : 0u;
+                for (int u = 0; u < ST_U; ++u) {
+                    const uint32_t r = r0 + u * 32 + lane_id();
+                    key[u] = r < n ? label_slot[r] : MAMRI_NONE;
+                    lab[u] = r < n ? run_label[r] : 0u;
+                    par[u] = r < n ? parent[r] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < ST_U; ++u)
+                    if (key[u] == MAMRI_SLOT_OF_ROOT) key[u] = label_slot[par[u]];
+            } else {
+#pragma unroll
+                for (int u = 0; u < ST_U; ++u) {
+                    const uint32_t r = r0 + u * 32 + lane_id();
+                    key[u] = r < n ? label_slot[r] : MAMRI_NONE;      // a root's slot, SLOT_OF_ROOT for the other runs of a kept label
+                    lab[u] = r < n ? run_label[r] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < ST_U; ++u)
+                    if (key[u] == MAMRI_SLOT_OF_ROOT) key[u] = label_slot[parent[r0 + u * 32 + lane_id()]];
             }
 #pragma unroll
             for (int u = 0; u < ST_U; ++u)
-                if (key[u] == MAMRI_SLOT_OF_ROOT) key[u] = label_slot[parent[r0 + u * 32 + lane_id()]];
+                if (key[u] == MAMRI_NONE && body != 0u && lab[u] == body) key[u] = max_markers;   // the body has the extra slot
+            if constexpr (MODE == 1) {
+                // Noisy table (millions of runs, a thousand kept labels whose runs sit between the specks' runs): the runs
+                // that count are ~10 % of the table, a few per 32 consecutive runs and of several labels.  Combining them by
+                // shuffles (9 values x 5 rounds per distinct label) cost ~1800 instructions per trip, and the sums of a
+                // 32-run row were computed with three or four lanes active.  So: the warp compacts the runs that count of
+                // its ST_U x 32 into shared memory (ballot + popc), one lane per run computes the sums (one dense pass),
+                // the body's go to the thread's registers and the markers' straight to the table (fire-and-forget
+                // reductions in L2, spread over a thousand rows).
+                __shared__ uint32_t st_k[8][ST_U * 32], st_r[8][ST_U * 32];
+                const unsigned wid = threadIdx.x >> 5, lane = lane_id();
+                uint32_t cnt = 0;
 #pragma unroll
-            for (int u = 0; u < ST_U; ++u) {
-                const uint32_t r = r0 + u * 32 + lane_id();
-                uint32_t k = key[u];
-                if (k == MAMRI_NONE && body != 0u && lab[u] == body) k = max_markers;   // the body has the extra slot
-                if (!__any_sync(FULL, k != MAMRI_NONE)) continue;
-                unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                if (k != MAMRI_NONE) {
-                    const uint32_t pos = run_pos[r];
-                    const uint32_t wi = pos >> 5, row = wi / W;
-                    const long long z = row / ny, y = row - uint32_t(z) * ny;
-                    const long long xs = (long long)(wi - row * W) * 32 + (pos & 31u);
-                    const long long len = (long long)(run_end[r] - pos) + 1, xe = xs + len - 1;
-                    const unsigned long long sx = (unsigned long long)((xs + xe) * len / 2);
-                    v[0] = sx;                                              // sum x
-                    v[1] = (unsigned long long)(len * y);                   // sum y
-                    v[2] = (unsigned long long)(len * z);                   // sum z
-                    v[3] = sum_sq_upto(xe) - sum_sq_upto(xs - 1);           // sum xx
-                    v[4] = (unsigned long long)(len * y * y);               // sum yy
-                    v[5] = (unsigned long long)(len * z * z);               // sum zz
-                    v[6] = sx * (unsigned long long)y;                      // sum xy
-                    v[7] = sx * (unsigned long long)z;                      // sum xz
-                    v[8] = (unsigned long long)(len * y * z);               // sum yz
+                for (int u = 0; u < ST_U; ++u) {
+                    const bool take = key[u] != MAMRI_NONE;
+                    const unsigned bal = __ballot_sync(FULL, take);
+                    if (take) {
+                        const uint32_t j = cnt + __popc(bal & ((1u << lane) - 1u));
+                        st_k[wid][j] = key[u];
+                        st_r[wid][j] = r0 + u * 32 + lane;
+                    }
+                    cnt += __popc(bal);
+                }
+                __syncwarp();
+                for (uint32_t j = lane; j < cnt; j += 32) {
+                    const uint32_t k = st_k[wid][j], r = st_r[wid][j];
+                    unsigned long long v[9];
+                    run_sums(run_pos[r], run_end[r], W, ny, v);
                     if (k == max_markers) {
 #pragma unroll
                         for (int i = 0; i < 9; ++i) bsum[i] += v[i];
-                        k = MAMRI_NONE;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) atomicAdd(sums + size_t(k) * 9u + i, v[i]);
                     }
                 }
-                warp_agg_add(k, v, cache, sums);
+                __syncwarp();
+            } else {
+                // the extents of the runs that count, all ST_U loads in flight before the first is used
+                uint32_t rpos[ST_U], rend[ST_U];
+#pragma unroll
+                for (int u = 0; u < ST_U; ++u) {
+                    const uint32_t r = r0 + u * 32 + lane_id();
+                    rpos[u] = rend[u] = 0u;
+                    if (key[u] != MAMRI_NONE) { rpos[u] = run_pos[r]; rend[u] = run_end[r]; }
+                }
+#pragma unroll
+                for (int u = 0; u < ST_U; ++u) {
+                    uint32_t k = key[u];
+                    if (!__any_sync(FULL, k != MAMRI_NONE)) continue;
+                    unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    if (k != MAMRI_NONE) {
+                        run_sums(rpos[u], rend[u], W, ny, v);
+                        if (k == max_markers) {
+#pragma unroll
+                            for (int i = 0; i < 9; ++i) bsum[i] += v[i];
+                            k = MAMRI_NONE;
+                        }
+                    }
+                    warp_agg_add(k, v, cache, sums);
+                }
             }
         }
         warp_agg_add(bsum[4] | bsum[5] | bsum[0] | bsum[1] | bsum[2] ? max_markers : MAMRI_NONE, bsum, cache, sums);
@@ -382,10 +464,15 @@ cudaError_t launch_select(mamri_ctx* c, const mamri_volume_desc* desc, const mam
 // only finishes when `materialise` does (measured on config C4), while its CTAs cost `materialise` its occupancy.
 #define MAMRI_STATS_ARGS c->d_run_pos, c->d_run_end, c->d_parent, c->d_run_label, c->d_label_slot, W, desc->ny, c->d_cand_sums, \
                          c->d_cand_label, c->d_cand_rank, c->d_label_count, c->max_markers, g, c->h_markers, c->h_summary, c->d_scalars, c->d_dyn
-static bool stats_split(const mamri_ctx* c) {
+static int stats_split_env() {
     static const int split_env = [] { const char* e = getenv("MAMRI_STATS_SPLIT"); return e ? atoi(e) : 1; }();
-    return split_env >= 2 || (split_env == 1 && c->run_ctas >= 592);
+    return split_env;
 }
+static bool stats_split(const mamri_ctx* c) {
+    const int e = stats_split_env();
+    return e == 2 || ((e == 1 || e == 3) && c->run_ctas >= 592);
+}
+bool stats_early_beside() { return stats_split_env() == 3; }
 
 cudaError_t launch_stats_early(mamri_ctx* c, const mamri_volume_desc* desc, const mamri_params* prm, cudaStream_t s) {
     if (!stats_split(c)) return cudaSuccess;

@@ -1,0 +1,9 @@
+#!/bin/bash
+# k_stats<1> with direct reductions for the kept runs (noisy run tables): parity on C4 + timeline
+set -u
+O=gpurun_out/r2q
+mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_pipeline.py -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest.log
+for c in c3 c4; do timeout 120 python tools/serial_latency.py --config $c --reps 30 2>&1 | sed 's/.*bare C ABI/  '$c' bare/'; done
+timeout 120 python tools/serial_latency.py --config c4 --conn 26 --reps 30 2>&1 | sed 's/.*bare C ABI/  c4-26 bare/'
+timeout 120 python tools/ktrace.py --config c4 --reps 10 > $O/kt_c4.log 2>&1; echo "== c4"; cat $O/kt_c4.log | grep -E "^ +(select|select.end.last|stats|materialise|stats.finalise|final|end) "
