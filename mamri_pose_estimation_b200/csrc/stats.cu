@@ -337,17 +337,24 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 4 : 1) k_stats(const uint32_t
                     cnt += __popc(bal);
                 }
                 __syncwarp();
-                for (uint32_t j = lane; j < cnt; j += 32) {
-                    const uint32_t k = st_k[wid][j], r = st_r[wid][j];
-                    unsigned long long v[9];
-                    run_sums(run_pos[r], run_end[r], W, ny, v);
-                    if (k == max_markers) {
+                for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {                  // cnt is the same in every lane
+                    const uint32_t j = j0 + lane;
+                    uint32_t k = MAMRI_NONE;
+                    unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    if (j < cnt) {
+                        k = st_k[wid][j];
+                        const uint32_t r = st_r[wid][j];
+                        run_sums(run_pos[r], run_end[r], W, ny, v);
+                        if (k == max_markers) {
 #pragma unroll
-                        for (int i = 0; i < 9; ++i) bsum[i] += v[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) atomicAdd(sums + size_t(k) * 9u + i, v[i]);
+                            for (int i = 0; i < 9; ++i) bsum[i] += v[i];
+                            k = MAMRI_NONE;
+                        }
                     }
+                    // neighbours in the compacted list are mostly runs of ONE marker (its run in consecutive rows): the lanes
+                    // of a label are summed by shuffles first.  One reduction per run instead made the few hundred runs of a
+                    // big marker queue on the same L2 line, ~10 ns each: 40 us for the CTAs that held the biggest ones
+                    warp_agg_add(k, v, cache, sums);
                 }
                 __syncwarp();
             } else {
