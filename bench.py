@@ -502,6 +502,16 @@ def run_native(args):
                                         "how": "30 scans one after the other through the bare C ABI (graph launch, "
                                                "result synchronisation and collect included), CUDA events around the loop",
                                         "stage_sum_ms": sum(acc.values())}}}
+        # the stages between the two streaming kernels: what they have to move (1 bit per voxel volumes, 4 bytes per mask
+        # word of run bases, the run table) against the time they take alone -- latency-bound by design
+        n_words = n_vox // 32
+        mid_bytes = {"closing": 2 * n_vox // 8,                                           # raw mask in, closed mask out
+                     "ccl": n_vox // 8 + 4 * n_words + 5 * 4 * r0.n_runs,                 # mask in; word_base + 5 run-table columns out
+                     "stats_filter": 7 * 4 * r0.n_runs}                                   # run-table columns in
+        roof["stages"] = {k: {"ms": acc[k], "algorithmic_bytes": b, "achieved": b / (acc[k] * 1e-3) / 1e9,
+                              "frac": b / (acc[k] * 1e-3) / 1e9 / peak,
+                              "bound": "latency: dependent L2 loads / atomics on 1 bit/voxel data and the run table, not HBM"}
+                          for k, b in mid_bytes.items() if acc.get(k)}
         if not args.no_cpu_baseline:
             parity = oracle_parity(lone, r0)
             configs["C2"]["parity"] = parity
