@@ -219,3 +219,19 @@ def test_random_geometry_sweep(cuda_lib):
         if ora.body_label:
             assert np.array_equal(res.body_mask.cpu().numpy(), ora.body_mask), tag
     det.close()
+
+
+def test_split_statistics_path_on_small_scans(cuda_lib):
+    """The statistics kernels of noisy run tables (k_stats<1> + k_stats<2>: compacted runs, one dense pass, shuffle combine)
+    are only selected by scans of >= 150 k runs, i.e. by the full-size C4 test alone.  MAMRI_STATS_SPLIT=2 forces them for
+    every scan; the library reads its knobs once per process, hence the child process running parity cases of this file."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MAMRI_STATS_SPLIT="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "small_phantoms or random_geometry_sweep or one_context_across or empty_and_full"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
