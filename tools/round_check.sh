@@ -22,8 +22,11 @@ for c in c1 c2 c3 c4; do timeout 180 python tools/ktrace.py --config $c --reps 2
 timeout 180 python tools/ktrace.py --config c4 --conn 26 --reps 10 > $O/ktrace_c4_conn26.txt 2>&1
 for c in c1 c2 c3 c4; do timeout 180 python tools/serial_latency.py --config $c --reps 30; done > $O/serial.txt 2>&1
 timeout 180 python tools/profile_one.py --config c4 --scans 2 > $O/plain_c4.log 2>&1; echo "plain c4 rc=$?"
-timeout 1500 ncu --set full --clock-control none -k regex:'k_threshold|k_close|k_morph|k_runs|k_union|k_flatten|k_select|k_stats|k_materialise' -s 11 -c 11 -o $O/full_c4 -f \
+timeout 1500 ncu --set full --clock-control none -k regex:'k_threshold|k_close|k_morph|k_runs|k_union|k_flatten|k_select|k_stats|k_materialise' -s 12 -c 12 -o $O/full_c4 -f \
     python tools/profile_one.py --config c4 --scans 2 > $O/ncu_full_c4.log 2>&1; echo "ncu full c4 rc=$?"
-timeout 1500 ncu --set full --clock-control none -k regex:'k_threshold|k_close|k_morph|k_runs|k_union|k_flatten|k_select|k_stats|k_materialise' -s 11 -c 11 -o $O/full_c4_conn26 -f \
+timeout 1500 ncu --set full --clock-control none -k regex:'k_threshold|k_close|k_morph|k_runs|k_union|k_flatten|k_select|k_stats|k_materialise' -s 12 -c 12 -o $O/full_c4_conn26 -f \
     python tools/profile_one.py --config c4 --scans 2 --conn 26 > $O/ncu_full_c4_26.log 2>&1; echo "ncu full c4/26 rc=$?"
 cat $O/serial.txt
+
+# NOTE: the three .ncu-rep files together are ~64 MiB, gpurun's limit for what it copies back: if the call reports
+# "gpurun_out/ not copied back", use tools/round_final.sh (no C4/26 capture) and empty gpurun_out/ here first.
