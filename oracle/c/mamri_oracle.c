@@ -7,8 +7,9 @@
  * not available here; this file restates ITK 5.x semantics and is cross-checked bit for
  * bit against oracle/segmentation.py and oracle/bruteforce.py by tests/test_oracle_c.py.
  *
- * Layout: x fastest, linear index = x + nx*(y + ny*z).  OpenMP over rows where the stage allows it;
- * the labelling and statistics passes are sequential scans.
+ * Layout: x fastest, linear index = x + nx*(y + ny*z).  Every stage is threaded with OpenMP: threshold and morphology
+ * over rows, the labelling over slabs of slices that are merged along their faces (as ITK threads it), the statistics
+ * over rows with atomic adds of per-run sums.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -165,13 +166,8 @@ static uint32_t uf_find(uint32_t* p, uint32_t x) {
     return r;
 }
 
-API int oracle_ccl(const uint8_t* mask, int nx, int ny, int nz, int conn, uint32_t* labels, uint32_t* n_labels) {
-    const size_t n = (size_t)nx * ny * nz;
-    size_t cap = 1 << 16, used = 1;
-    uint32_t* parent = (uint32_t*)malloc(cap * sizeof(uint32_t));
-    if (!parent) return -2;
-    parent[0] = 0;
-    int offs[13][3];
+/* Offsets of the already-visited neighbours in raster order: 3 for face connectivity, 13 for 26-connectivity. */
+static int ccl_offsets(int conn, int offs[13][3]) {
     int no = 0;
     if (conn == 6) {
         int t[3][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, -1}};
@@ -184,8 +180,19 @@ API int oracle_ccl(const uint8_t* mask, int nx, int ny, int nz, int conn, uint32
                     if (dz == 0 && (dy > 0 || (dy == 0 && dx >= 0))) continue;
                     offs[no][0] = dx; offs[no][1] = dy; offs[no][2] = dz; ++no;
                 }
-    } else { free(parent); return -1; }
-    for (int z = 0; z < nz; ++z)
+    }
+    return no;
+}
+
+/* Raster scan of the slices [z0, z1): provisional labels 1, 2, ... local to the slab (neighbours below z0 are not
+ * looked at), union-find in *parent_io (grown as needed).  Returns the number of entries used (labels + 1), 0 on
+ * allocation failure. */
+static size_t ccl_scan_slab(const uint8_t* mask, int nx, int ny, int z0, int z1, int offs[13][3], int no, uint32_t* labels,
+                            uint32_t** parent_io, size_t* cap_io) {
+    uint32_t* parent = *parent_io;
+    size_t cap = *cap_io, used = 1;
+    parent[0] = 0;
+    for (int z = z0; z < z1; ++z)
         for (int y = 0; y < ny; ++y)
             for (int x = 0; x < nx; ++x) {
                 const size_t i = ((size_t)z * ny + y) * nx + x;
@@ -193,7 +200,7 @@ API int oracle_ccl(const uint8_t* mask, int nx, int ny, int nz, int conn, uint32
                 uint32_t best = 0;
                 for (int k = 0; k < no; ++k) {
                     const int X = x + offs[k][0], Y = y + offs[k][1], Z = z + offs[k][2];
-                    if (X < 0 || X >= nx || Y < 0 || Y >= ny || Z < 0) continue;
+                    if (X < 0 || X >= nx || Y < 0 || Y >= ny || Z < z0) continue;
                     const uint32_t l = labels[((size_t)Z * ny + Y) * nx + X];
                     if (!l) continue;
                     const uint32_t rt = uf_find(parent, l);
@@ -206,7 +213,7 @@ API int oracle_ccl(const uint8_t* mask, int nx, int ny, int nz, int conn, uint32
                     if (used == cap) {
                         cap *= 2;
                         uint32_t* np_ = (uint32_t*)realloc(parent, cap * sizeof(uint32_t));
-                        if (!np_) { free(parent); return -2; }
+                        if (!np_) { *parent_io = parent; *cap_io = cap / 2; return 0; }
                         parent = np_;
                     }
                     best = (uint32_t)used;
@@ -214,6 +221,22 @@ API int oracle_ccl(const uint8_t* mask, int nx, int ny, int nz, int conn, uint32
                 }
                 labels[i] = best;
             }
+    *parent_io = parent;
+    *cap_io = cap;
+    return used;
+}
+
+/* One slab = the whole volume: the sequential scan (kept as the cross-check of the slab-parallel form below). */
+API int oracle_ccl_serial(const uint8_t* mask, int nx, int ny, int nz, int conn, uint32_t* labels, uint32_t* n_labels) {
+    const size_t n = (size_t)nx * ny * nz;
+    int offs[13][3];
+    const int no = ccl_offsets(conn, offs);
+    if (!no) return -1;
+    size_t cap = 1 << 16;
+    uint32_t* parent = (uint32_t*)malloc(cap * sizeof(uint32_t));
+    if (!parent) return -2;
+    const size_t used = ccl_scan_slab(mask, nx, ny, 0, nz, offs, no, labels, &parent, &cap);
+    if (!used) { free(parent); return -2; }
     uint32_t* final_ = (uint32_t*)calloc(used, sizeof(uint32_t));
     if (!final_) { free(parent); return -2; }
     uint32_t k = 0;
@@ -221,7 +244,6 @@ API int oracle_ccl(const uint8_t* mask, int nx, int ny, int nz, int conn, uint32
         if (parent[l] == l) final_[l] = ++k;          /* roots in increasing provisional order */
     for (size_t l = 1; l < used; ++l)
         if (parent[l] != l) final_[l] = final_[uf_find(parent, (uint32_t)l)];
-#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n; ++i)
         if (labels[i]) labels[i] = final_[labels[i]];
     *n_labels = k;
@@ -230,22 +252,113 @@ API int oracle_ccl(const uint8_t* mask, int nx, int ny, int nz, int conn, uint32
     return 0;
 }
 
+/* The same labelling threaded the way itk::ConnectedComponentImageFilter is (slabs of slices scanned independently, then
+ * merged along the slab faces): provisional labels of slab t come after those of slab t-1, inside a slab in raster order of
+ * creation, and unions keep the smaller label -- so a component's root is still the label created at its first voxel in
+ * raster order and the consecutive renumbering gives ITK's numbering, identical to the sequential scan. */
+#define CCL_MAX_SLABS 256
+API int oracle_ccl(const uint8_t* mask, int nx, int ny, int nz, int conn, uint32_t* labels, uint32_t* n_labels) {
+    const size_t n = (size_t)nx * ny * nz;
+    int offs[13][3];
+    const int no = ccl_offsets(conn, offs);
+    if (!no) return -1;
+    int T = oracle_num_threads();
+    if (T > nz) T = nz;
+    if (T > CCL_MAX_SLABS) T = CCL_MAX_SLABS;
+    if (T <= 1 || n < ((size_t)1 << 16)) return oracle_ccl_serial(mask, nx, ny, nz, conn, labels, n_labels);
+    uint32_t* par[CCL_MAX_SLABS];
+    size_t cap[CCL_MAX_SLABS], used[CCL_MAX_SLABS], off[CCL_MAX_SLABS + 1];
+    int zs[CCL_MAX_SLABS + 1];
+    for (int t = 0; t <= T; ++t) zs[t] = (int)((long long)nz * t / T);
+    int fail = 0;
+    for (int t = 0; t < T; ++t) {
+        cap[t] = 1 << 14;
+        par[t] = (uint32_t*)malloc(cap[t] * sizeof(uint32_t));
+        if (!par[t]) fail = 1;
+    }
+    if (!fail) {
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+        for (int t = 0; t < T; ++t) used[t] = ccl_scan_slab(mask, nx, ny, zs[t], zs[t + 1], offs, no, labels, &par[t], &cap[t]);
+        for (int t = 0; t < T; ++t) if (!used[t]) fail = 1;
+    }
+    if (fail) { for (int t = 0; t < T; ++t) free(par[t]); return -2; }
+    /* global provisional label of local label l of slab t: off[t] + l   (l >= 1; off[0] = 0) */
+    off[0] = 0;
+    for (int t = 0; t < T; ++t) off[t + 1] = off[t] + (used[t] - 1);
+    const size_t total = off[T] + 1;
+    if (total > 0xFFFFFFFFull) { for (int t = 0; t < T; ++t) free(par[t]); return -2; }
+    uint32_t* parent = (uint32_t*)malloc(total * sizeof(uint32_t));
+    uint32_t* final_ = (uint32_t*)calloc(total, sizeof(uint32_t));
+    if (!parent || !final_) { free(parent); free(final_); for (int t = 0; t < T; ++t) free(par[t]); return -2; }
+    parent[0] = 0;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t) {
+        for (size_t l = 1; l < used[t]; ++l) parent[off[t] + l] = (uint32_t)(off[t] + par[t][l]);
+        free(par[t]);
+    }
+    /* merge along the slab faces: every voxel of a slab's first slice with its neighbours in the slice below */
+    for (int t = 1; t < T; ++t) {
+        const int z = zs[t];
+        if (z >= nz || z == 0) continue;
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                const size_t i = ((size_t)z * ny + y) * nx + x;
+                if (!labels[i]) continue;
+                const uint32_t a0 = (uint32_t)(off[t] + labels[i]);
+                for (int k = 0; k < no; ++k) {
+                    if (offs[k][2] != -1) continue;
+                    const int X = x + offs[k][0], Y = y + offs[k][1];
+                    if (X < 0 || X >= nx || Y < 0 || Y >= ny) continue;
+                    const uint32_t lb = labels[((size_t)(z - 1) * ny + Y) * nx + X];
+                    if (!lb) continue;
+                    uint32_t ra = uf_find(parent, a0), rb = uf_find(parent, (uint32_t)(off[t - 1] + lb));
+                    if (ra == rb) continue;
+                    if (ra < rb) parent[rb] = ra; else parent[ra] = rb;   /* the smaller label stays the root */
+                }
+            }
+    }
+    uint32_t k = 0;
+    for (size_t l = 1; l < total; ++l)
+        if (parent[l] == l) final_[l] = ++k;          /* roots in increasing provisional order */
+    for (size_t l = 1; l < total; ++l)
+        if (parent[l] != l) final_[l] = final_[uf_find(parent, (uint32_t)l)];
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t) {
+        const size_t i0 = (size_t)zs[t] * ny * nx, i1 = (size_t)zs[t + 1] * ny * nx;
+        for (size_t i = i0; i < i1; ++i)
+            if (labels[i]) labels[i] = final_[off[t] + labels[i]];
+    }
+    *n_labels = k;
+    free(final_);
+    free(parent);
+    return 0;
+}
+
 /* ---- LabelShapeStatisticsImageFilter: exact integer sums per label     Mamri.py:1309 -------------------- */
-/* sums[l*10 + ..] = count, sx, sy, sz, sxx, syy, szz, sxy, sxz, syz for label l+1 */
+/* sums[l*10 + ..] = count, sx, sy, sz, sxx, syy, szz, sxy, sxz, syz for label l+1.  Threaded over rows; a thread sums
+ * each x-run of one label privately and adds it to the table with atomics (integer sums: the order does not matter). */
 API int oracle_label_sums(const uint32_t* labels, int nx, int ny, int nz, uint32_t n_labels, uint64_t* sums) {
     memset(sums, 0, (size_t)n_labels * 10 * sizeof(uint64_t));
-    for (int z = 0; z < nz; ++z)
-        for (int y = 0; y < ny; ++y) {
-            const uint32_t* row = labels + ((size_t)z * ny + y) * nx;
-            for (int x = 0; x < nx; ++x) {
-                const uint32_t l = row[x];
-                if (!l) continue;
-                uint64_t* s = sums + (size_t)(l - 1) * 10;
-                const uint64_t X = (uint64_t)x, Y = (uint64_t)y, Z = (uint64_t)z;
-                s[0] += 1; s[1] += X; s[2] += Y; s[3] += Z;
-                s[4] += X * X; s[5] += Y * Y; s[6] += Z * Z; s[7] += X * Y; s[8] += X * Z; s[9] += Y * Z;
+    const long long rows = (long long)ny * nz;
+#pragma omp parallel for schedule(static)
+    for (long long r = 0; r < rows; ++r) {
+        const int z = (int)(r / ny), y = (int)(r - (long long)z * ny);
+        const uint32_t* row = labels + (size_t)r * nx;
+        const uint64_t Y = (uint64_t)y, Z = (uint64_t)z;
+        int x = 0;
+        while (x < nx) {
+            const uint32_t l = row[x];
+            if (!l) { ++x; continue; }
+            uint64_t c = 0, sx = 0, sxx = 0;
+            while (x < nx && row[x] == l) { const uint64_t X = (uint64_t)x; c += 1; sx += X; sxx += X * X; ++x; }
+            uint64_t* s = sums + (size_t)(l - 1) * 10;
+            const uint64_t v[10] = {c, sx, c * Y, c * Z, sxx, c * Y * Y, c * Z * Z, sx * Y, sx * Z, c * Y * Z};
+            for (int j = 0; j < 10; ++j) {
+#pragma omp atomic
+                s[j] += v[j];
             }
         }
+    }
     return 0;
 }
 

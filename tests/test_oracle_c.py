@@ -37,3 +37,37 @@ def test_c_threshold_types(dtype):
     vol = rng.integers(0, 200, size=(5, 6, 40)).astype(dtype)
     closed, labels, k, sums, _ = c_oracle.run_pipeline(vol, lo=64.5, hi=65535, close_radius=0)
     assert np.array_equal(closed, seg.binary_threshold(vol, 64.5, 65535))
+
+
+@pytest.mark.parametrize("conn", [6, 26])
+@pytest.mark.parametrize("threads", [2, 3, 8])
+def test_slab_parallel_labelling_equals_the_sequential_scan(conn, threads):
+    """oracle_ccl threads the scan over slabs of slices and merges them along their faces (as ITK does); the labels must
+    be the sequential scan's, bit for bit, for any number of slabs -- noisy masks, objects crossing every slab face."""
+    import ctypes as C
+    lib = c_oracle.load()
+    lib.oracle_ccl_serial.restype = C.c_int
+    lib.oracle_ccl_serial.argtypes = lib.oracle_ccl.argtypes
+    before = c_oracle.num_threads()
+    try:
+        lib.oracle_set_num_threads(threads)
+        rng = np.random.default_rng(100 * conn + threads)
+        for dims, p in (((41, 37, 45), 0.32), ((64, 48, 40), 0.18), ((33, 20, 64), 0.5), ((130, 9, 57), 0.27)):
+            nz, ny, nx = dims[2], dims[1], dims[0]
+            m = (rng.random((nz, ny, nx)) < p).astype(np.uint8)
+            m[:, ny // 2, nx // 3] = 1                                   # a column through every slab face
+            a, b = np.empty(m.shape, np.uint32), np.empty(m.shape, np.uint32)
+            ka, kb = C.c_uint32(0), C.c_uint32(0)
+            assert lib.oracle_ccl(m.ctypes.data, nx, ny, nz, conn, a.ctypes.data, C.byref(ka)) == 0
+            assert lib.oracle_ccl_serial(m.ctypes.data, nx, ny, nz, conn, b.ctypes.data, C.byref(kb)) == 0
+            assert ka.value == kb.value and np.array_equal(a, b)
+            ref, k_ref = seg.connected_components(m, conn)
+            assert k_ref == ka.value and np.array_equal(a, ref)
+            # threaded sums against a direct NumPy evaluation
+            sums = np.zeros((ka.value, 10), np.uint64)
+            assert lib.oracle_label_sums(a.ctypes.data, nx, ny, nz, ka.value, sums.ctypes.data) == 0
+            cnt, sidx, smom = seg.integer_sums(a, ka.value)
+            want = np.concatenate([cnt[:, None], sidx, smom], axis=1).astype(np.uint64)
+            assert np.array_equal(sums, want)
+    finally:
+        lib.oracle_set_num_threads(before)
